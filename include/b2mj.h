@@ -1,0 +1,131 @@
+/* b2mj.h -- C ABI of the B200-native batched physics path.
+ *
+ * Drop-in boundary for the one hot path of ChenDavidTimothy/mujoco-template.  The
+ * reference has no FFI of its own: its "operator API" for this path is the set of
+ * third-party `mujoco` symbols it calls.  Each entry point below names the reference
+ * call site(s) it replaces (paths relative to the reference repo root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes, no torch / C++ types.
+ *  - All state arrays are SoA with the env index fastest: element (k, e) of an array
+ *    with leading dimension `dim` lives at  base[k * nenv + e].  Precision is fixed per
+ *    batch (B2_F64 or B2_F32); pointers are `void*` and must match it.
+ *  - Pointers may be device memory or page-locked host memory mapped into the device
+ *    address space (the single-env `Env` uses the latter for zero-copy NumPy views).
+ *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
+ *    default stream) unless stated otherwise.  The library never allocates in b2_step.
+ *  - Every function returns B2_OK (0) or a negative error code; b2_last_error() returns
+ *    a thread-local message.  There is no CPU fallback: without a CUDA device every
+ *    compute entry point fails with B2_ERR_CUDA.
+ */
+#ifndef B2MJ_H
+#define B2MJ_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_OK 0
+#define B2_ERR_ARG (-1)      /* -> ConfigError */
+#define B2_ERR_BLOB (-2)     /* -> ConfigError (malformed / version mismatch) */
+#define B2_ERR_CAPACITY (-3) /* -> ConfigError (model larger than any compiled size class) */
+#define B2_ERR_CUDA (-4)     /* -> TemplateError */
+#define B2_ERR_LINEARIZE (-5) /* -> LinearizationError */
+
+#define B2_F64 64
+#define B2_F32 32
+
+/* per-env status bits written to b2_state.flags (replaces upstream's silent
+ * mj_checkPos/Vel/Acc auto-reset) */
+#define B2_FLAG_BAD_QPOS 1
+#define B2_FLAG_BAD_QVEL 2
+#define B2_FLAG_BAD_QACC 4
+#define B2_FLAG_OVERFLOW 8 /* contact / constraint-row capacity of the size class exceeded */
+
+/* Jacobian kinds for b2_jacobian (reference mujoco_template/jacobians.py:12-23) */
+#define B2_JAC_SITE 0
+#define B2_JAC_BODY 1
+#define B2_JAC_BODYCOM 2
+#define B2_JAC_SUBTREECOM 3
+
+typedef struct b2_model b2_model; /* opaque: compiled model constants (mj.MjModel's role) */
+typedef struct b2_batch b2_batch; /* opaque: nenv envs of one model on one device (mj.MjData's role) */
+
+/* SoA state of a batch; qacc_warmstart and flags may be NULL.  (mj.MjData.qpos/qvel/ctrl/
+ * qacc_warmstart, reference mujoco_template/state_utils.py:9-31) */
+typedef struct b2_state {
+  void* qpos;           /* (nq, nenv) */
+  void* qvel;           /* (nv, nenv) */
+  void* ctrl;           /* (nu, nenv) */
+  void* qacc_warmstart; /* (nv, nenv) or NULL (treated as zeros, not written) */
+  int* flags;           /* (nenv) int32 status bits, OR-ed in; or NULL */
+} b2_state;
+
+/* optional derived outputs of the forward pass that PRECEDES the last integration
+ * (MuJoCo semantics: derived arrays lag the state by one step).  Any pointer may be NULL.
+ * (mj.MjData.xpos/xipos/geom_xpos/site_xpos/subtree_com/qacc read by
+ *  reference mujoco_template/observations.py:132-164 and logging.py probes) */
+typedef struct b2_derived {
+  void* xpos;        /* (nbody*3, nenv) */
+  void* xquat;       /* (nbody*4, nenv) */
+  void* xipos;       /* (nbody*3, nenv) */
+  void* geom_xpos;   /* (ngeom*3, nenv) */
+  void* site_xpos;   /* (nsite*3, nenv) */
+  void* subtree_com; /* (nbody*3, nenv) */
+  void* qacc;        /* (nv, nenv) */
+  void* qfrc_bias;   /* (nv, nenv) */
+  int* ncon;         /* (nenv) active contacts */
+  int* nefc;         /* (nenv) constraint rows */
+  int* solver_iter;  /* (nenv) Newton iterations */
+} b2_derived;
+
+/* Replaces mj.MjModel.from_xml_path/from_xml_string (reference mujoco_template/model.py:22-31):
+ * the host compiler (mujoco_template/mjcf.py) produces `blob`; see include/b2_model_layout.h. */
+int b2_model_create(const void* blob, size_t nbytes, b2_model** out);
+void b2_model_destroy(b2_model* model);
+/* update the actuator-disable mask (opt.disableactuator, reference model.py:77-105); nu ints */
+int b2_model_set_actuator_disabled(b2_model* model, const int* disabled, int nu);
+
+/* Replaces mj.MjData(model) (reference model.py:14-20).  Allocates scratch only. */
+int b2_batch_create(const b2_model* model, int nenv, int device, int precision, b2_batch** out);
+void b2_batch_destroy(b2_batch* batch);
+
+/* Replaces mj.mj_step (reference mujoco_template/model.py:56-57, driven by env.py:190):
+ * advances every env `nsteps` steps with ctrl held constant.  `derived` may be NULL. */
+int b2_step(b2_batch* batch, const b2_state* state, int nsteps, const b2_derived* derived, void* stream);
+
+/* Replaces mj.mj_forward (reference model.py:53-54, env.py:157): no integration. */
+int b2_forward(b2_batch* batch, const b2_state* state, const b2_derived* derived, void* stream);
+
+/* Replaces mj.mjd_transitionFD(model, data, eps, centered, A, B, None, None)
+ * (reference mujoco_template/linearization.py:16-35).  A: (2nv, 2nv, nenv), B: (2nv, nu, nenv),
+ * element (r, c, e) at base[(r * ncols + c) * nenv + e].  State is not modified. */
+int b2_linearize(b2_batch* batch, const b2_state* state, double eps, int centered, void* A, void* B, void* stream);
+
+/* Replaces mj.mj_jacSite / mj_jacBody / mj_jacBodyCom / mj_jacSubtreeCom
+ * (reference mujoco_template/jacobians.py:44,55,67,79).  jacp/jacr: (3, nv, nenv); jacr may be NULL. */
+int b2_jacobian(b2_batch* batch, const b2_state* state, int kind, int objid, void* jacp, void* jacr, void* stream);
+
+/* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */
+int b2_integrate_pos(b2_batch* batch, void* qpos, const void* qvel, double dt, void* stream);
+int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void* qpos1, const void* qpos2, void* stream);
+
+/* End-to-end variant with HOST buffers (pageable or pinned): copies qpos/qvel/ctrl[/warm]
+ * host->device, runs `nsteps` steps (optionally one linearization first, as
+ * reference env.py:178-190 does per control tick), copies qpos/qvel[/warm][/A,B] back, and
+ * synchronises.  A/B may be NULL.  Used by bench.py's e2e leg. */
+int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int linearize, double eps, void* host_A,
+                 void* host_B, void* stream);
+
+int b2_stream_synchronize(b2_batch* batch, void* stream);
+/* number of kernels launched by this library in the calling process (bench gpu_launches) */
+long long b2_launch_count(void);
+/* size class the model was mapped to: 0 tiny, 1 small, 2 large */
+int b2_batch_size_class(const b2_batch* batch);
+const char* b2_last_error(void);
+const char* b2_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,236 @@
+// C-ABI of the B200-native batched physics path (see include/b2mj.h for the contract and the
+// reference call sites each entry point replaces).  Host-only logic: model bookkeeping,
+// constant-bank residency, launches, and the host-buffer (e2e) variant.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b2mj.h"
+#include "b2_kernels.h"
+#include "b2_model_dev.cuh"
+
+namespace {
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+std::atomic<unsigned long long> g_serial{1};
+std::mutex g_mu;
+// which model image currently sits in constant memory: [device][precision 0/1][size class]
+unsigned long long g_resident[16][2][3];
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(B2_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+}  // namespace
+
+struct b2_model {
+  std::vector<unsigned char> blob;
+  b2m_view v;
+  std::vector<int> disabled;
+  int cls;
+  unsigned long long serial;
+};
+
+struct b2_batch {
+  const b2_model* model;
+  int nenv, device, precision;
+  size_t esz;
+  // device staging for b2_step_host
+  void *d_qpos = nullptr, *d_qvel = nullptr, *d_ctrl = nullptr, *d_warm = nullptr, *d_A = nullptr, *d_B = nullptr;
+};
+
+extern "C" {
+
+const char* b2_last_error(void) { return g_err.c_str(); }
+const char* b2_version(void) { return "b2mj 0.1 (sm_100a lane engine)"; }
+long long b2_launch_count(void) { return g_launches.load(); }
+
+int b2_model_create(const void* blob, size_t nbytes, b2_model** out) {
+  if (!blob || !out) return fail(B2_ERR_ARG, "b2_model_create: null argument");
+  b2_model* m = new (std::nothrow) b2_model();
+  if (!m) return fail(B2_ERR_ARG, "out of host memory");
+  m->blob.assign((const unsigned char*)blob, (const unsigned char*)blob + nbytes);
+  int rc = b2m_view_init(&m->v, m->blob.data(), nbytes);
+  if (rc) { delete m; return fail(B2_ERR_BLOB, "b2_model_create: malformed model blob (code " + std::to_string(rc) + ")"); }
+  const b2m_view& v = m->v;
+  if (b2::model_fits<b2::DimsTiny>(v)) m->cls = 0;
+  else if (b2::model_fits<b2::DimsSmall>(v)) m->cls = 1;
+  else if (b2::model_fits<b2::DimsLarge>(v)) m->cls = 2;
+  else { delete m; return fail(B2_ERR_CAPACITY, "b2_model_create: model exceeds the largest compiled size class"); }
+  m->disabled.assign(v.actuator_disabled, v.actuator_disabled + v.nu);
+  m->serial = g_serial.fetch_add(1);
+  *out = m;
+  return B2_OK;
+}
+void b2_model_destroy(b2_model* m) { delete m; }
+
+int b2_model_set_actuator_disabled(b2_model* m, const int* disabled, int nu) {
+  if (!m || (nu && !disabled) || nu != m->v.nu) return fail(B2_ERR_ARG, "b2_model_set_actuator_disabled: bad arguments");
+  m->disabled.assign(disabled, disabled + nu);
+  m->serial = g_serial.fetch_add(1);  // forces a constant-bank refresh
+  return B2_OK;
+}
+
+int b2_batch_create(const b2_model* model, int nenv, int device, int precision, b2_batch** out) {
+  if (!model || !out || nenv < 1) return fail(B2_ERR_ARG, "b2_batch_create: bad arguments");
+  if (precision != B2_F64 && precision != B2_F32) return fail(B2_ERR_ARG, "b2_batch_create: precision must be 64 or 32");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(B2_ERR_CUDA, "b2_batch_create: no CUDA device (this path has no CPU fallback)");
+  if (device < 0 || device >= ndev || device >= 16) return fail(B2_ERR_ARG, "b2_batch_create: device index out of range");
+  b2_batch* b = new (std::nothrow) b2_batch();
+  if (!b) return fail(B2_ERR_ARG, "out of host memory");
+  b->model = model; b->nenv = nenv; b->device = device; b->precision = precision; b->esz = precision == B2_F64 ? 8 : 4;
+  *out = b;
+  return B2_OK;
+}
+void b2_batch_destroy(b2_batch* b) {
+  if (!b) return;
+  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B};
+  for (void* q : p) if (q) cudaFree(q);
+  delete b;
+}
+int b2_batch_size_class(const b2_batch* b) { return b ? b->model->cls : -1; }
+
+}  // extern "C"
+
+// make sure this batch's model is the image resident in constant memory on its device
+static int ensure_resident(b2_batch* b, void* stream) {
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const int pi = b->precision == B2_F64 ? 0 : 1;
+  std::lock_guard<std::mutex> lock(g_mu);
+  if (g_resident[b->device][pi][b->model->cls] == b->model->serial) return B2_OK;
+  // kernels of another model may still be reading the constant bank on other streams
+  e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
+  int rc = pi == 0 ? b2::b2k_upload_f64(b->model->cls, &b->model->v, b->model->disabled.data(), stream)
+                   : b2::b2k_upload_f32(b->model->cls, &b->model->v, b->model->disabled.data(), stream);
+  if (rc) return cuda_fail((cudaError_t)rc, "constant-bank model upload");
+  g_resident[b->device][pi][b->model->cls] = b->model->serial;
+  return B2_OK;
+}
+
+#define B2_CHECK_STATE(fn)                                                                         \
+  if (!b || !st || !st->qpos || !st->qvel || (b->model->v.nu && !st->ctrl)) return fail(B2_ERR_ARG, fn ": null batch/state pointer")
+
+extern "C" {
+
+int b2_step(b2_batch* b, const b2_state* st, int nsteps, const b2_derived* derived, void* stream) {
+  B2_CHECK_STATE("b2_step");
+  if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step: nsteps must be >= 1");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
+                              : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_step launch") : B2_OK;
+}
+
+int b2_forward(b2_batch* b, const b2_state* st, const b2_derived* derived, void* stream) {
+  B2_CHECK_STATE("b2_forward");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, 0, stream)
+                              : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, 0, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_forward launch") : B2_OK;
+}
+
+int b2_linearize(b2_batch* b, const b2_state* st, double eps, int centered, void* A, void* B, void* stream) {
+  B2_CHECK_STATE("b2_linearize");
+  if (!(eps > 0)) return fail(B2_ERR_LINEARIZE, "b2_linearize: eps must be > 0");
+  if (!A && !B) return fail(B2_ERR_ARG, "b2_linearize: A and B are both NULL");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  const int ncol = 2 * b->model->v.nv + b->model->v.nu;
+  rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream)
+                              : b2::b2k_linearize_f32(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_linearize launch") : B2_OK;
+}
+
+int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp, void* jacr, void* stream) {
+  if (!b || !st || !st->qpos) return fail(B2_ERR_ARG, "b2_jacobian: null batch/state pointer");
+  const b2m_view& v = b->model->v;
+  const int limit = kind == B2_JAC_SITE ? v.nsite : v.nbody;
+  if (kind < B2_JAC_SITE || kind > B2_JAC_SUBTREECOM || objid < 0 || objid >= limit)
+    return fail(B2_ERR_ARG, "b2_jacobian: kind/objid out of range");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_jacobian_f64(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream)
+                              : b2::b2k_jacobian_f32(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_jacobian launch") : B2_OK;
+}
+
+int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {
+  if (!b || !qpos || !qvel) return fail(B2_ERR_ARG, "b2_integrate_pos: null pointer");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_integrate_pos_f64(b->model->cls, qpos, qvel, dt, b->nenv, stream)
+                              : b2::b2k_integrate_pos_f32(b->model->cls, qpos, qvel, dt, b->nenv, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_integrate_pos launch") : B2_OK;
+}
+
+int b2_differentiate_pos(b2_batch* b, void* out, double dt, const void* q1, const void* q2, void* stream) {
+  if (!b || !out || !q1 || !q2) return fail(B2_ERR_ARG, "b2_differentiate_pos: null pointer");
+  if (dt == 0) return fail(B2_ERR_ARG, "b2_differentiate_pos: dt must be nonzero");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_differentiate_pos_f64(b->model->cls, out, dt, q1, q2, b->nenv, stream)
+                              : b2::b2k_differentiate_pos_f32(b->model->cls, out, dt, q1, q2, b->nenv, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_differentiate_pos launch") : B2_OK;
+}
+
+int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, double eps, void* host_A, void* host_B, void* stream) {
+  if (!b || !hs || !hs->qpos || !hs->qvel || (b->model->v.nu && !hs->ctrl)) return fail(B2_ERR_ARG, "b2_step_host: null pointer");
+  if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step_host: nsteps must be >= 1");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const b2m_view& v = b->model->v;
+  const size_t N = (size_t)b->nenv, es = b->esz, nx = 2 * (size_t)v.nv;
+  const size_t bq = v.nq * N * es, bv = v.nv * N * es, bu = (v.nu ? v.nu : 1) * N * es, bA = nx * nx * N * es, bB = nx * (v.nu ? v.nu : 1) * N * es;
+  auto need = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
+  if ((e = need(&b->d_qpos, bq)) || (e = need(&b->d_qvel, bv)) || (e = need(&b->d_ctrl, bu)) || (e = need(&b->d_warm, bv)))
+    return cuda_fail(e, "b2_step_host: cudaMalloc");
+  if (linearize && ((e = need(&b->d_A, bA)) || (e = need(&b->d_B, bB)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((e = cudaMemcpyAsync(b->d_qpos, hs->qpos, bq, cudaMemcpyHostToDevice, s)) ||
+      (e = cudaMemcpyAsync(b->d_qvel, hs->qvel, bv, cudaMemcpyHostToDevice, s)) ||
+      (v.nu && (e = cudaMemcpyAsync(b->d_ctrl, hs->ctrl, v.nu * N * es, cudaMemcpyHostToDevice, s))))
+    return cuda_fail(e, "b2_step_host: H2D copy");
+  if (hs->qacc_warmstart) e = cudaMemcpyAsync(b->d_warm, hs->qacc_warmstart, bv, cudaMemcpyHostToDevice, s);
+  else e = cudaMemsetAsync(b->d_warm, 0, bv, s);
+  if (e) return cuda_fail(e, "b2_step_host: warm-start copy");
+  b2_state ds = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, nullptr};
+  int rc;
+  if (linearize && (rc = b2_linearize(b, &ds, eps, 1, b->d_A, b->d_B, stream))) return rc;
+  if ((rc = b2_step(b, &ds, nsteps, nullptr, stream))) return rc;
+  if ((e = cudaMemcpyAsync(hs->qpos, b->d_qpos, bq, cudaMemcpyDeviceToHost, s)) ||
+      (e = cudaMemcpyAsync(hs->qvel, b->d_qvel, bv, cudaMemcpyDeviceToHost, s)))
+    return cuda_fail(e, "b2_step_host: D2H copy");
+  if (hs->qacc_warmstart && (e = cudaMemcpyAsync(hs->qacc_warmstart, b->d_warm, bv, cudaMemcpyDeviceToHost, s)))
+    return cuda_fail(e, "b2_step_host: D2H copy");
+  if (linearize && host_A && (e = cudaMemcpyAsync(host_A, b->d_A, bA, cudaMemcpyDeviceToHost, s))) return cuda_fail(e, "b2_step_host: D2H A");
+  if (linearize && host_B && v.nu && (e = cudaMemcpyAsync(host_B, b->d_B, nx * v.nu * N * es, cudaMemcpyDeviceToHost, s)))
+    return cuda_fail(e, "b2_step_host: D2H B");
+  e = cudaStreamSynchronize(s);
+  return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
+}
+
+int b2_stream_synchronize(b2_batch* b, void* stream) {
+  if (b) cudaSetDevice(b->device);
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  return e ? cuda_fail(e, "cudaStreamSynchronize") : B2_OK;
+}
+
+}  // extern "C"

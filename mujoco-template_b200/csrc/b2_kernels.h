@@ -1,0 +1,18 @@
+// Host-callable launchers exported by the per-precision kernel translation units.
+#pragma once
+#include "../../include/b2_model_layout.h"
+#include "../../include/b2mj.h"
+
+namespace b2 {
+#define B2_DECL(SUF)                                                                                                       \
+  int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
+  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);                  \
+  int b2k_linearize##SUF(int cls, const b2_state* st, int N, int ncol, double eps, int centered, void* A, void* B,         \
+                         void* stream);                                                                                    \
+  int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
+  int b2k_integrate_pos##SUF(int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \
+  int b2k_differentiate_pos##SUF(int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream);
+B2_DECL(_f64)
+B2_DECL(_f32)
+#undef B2_DECL
+}  // namespace b2

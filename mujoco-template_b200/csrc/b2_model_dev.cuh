@@ -1,0 +1,116 @@
+// Device-side model constants: one POD struct per (precision, size class) living in
+// __constant__ memory, so every model read is a uniform constant-bank operand.
+// Filled on the host from the compiled-model blob (include/b2_model_layout.h), which
+// replaces the reference's mj.MjModel (reference mujoco_template/model.py:14-25).
+#pragma once
+#include "../../include/b2_model_layout.h"
+
+namespace b2 {
+
+// Compile-time capacities.  A model is mapped to the smallest class that holds it.
+struct DimsTiny {   // pendulum, cartpole, the reference test fixture
+  static constexpr int NB = 4, NJ = 4, NQ = 4, NV = 4, NU = 2, NG = 4, NS = 2, NT = 1, NW = 2, NPAIR = 4, NCON = 8, NEFC = 36;
+  static constexpr int ID = 0;
+};
+struct DimsSmall {  // drone: one free body with many geoms
+  static constexpr int NB = 4, NJ = 4, NQ = 10, NV = 8, NU = 8, NG = 12, NS = 8, NT = 1, NW = 2, NPAIR = 12, NCON = 24, NEFC = 100;
+  static constexpr int ID = 1;
+};
+struct DimsLarge {  // humanoid
+  static constexpr int NB = 20, NJ = 24, NQ = 32, NV = 32, NU = 24, NG = 24, NS = 4, NT = 4, NW = 8, NPAIR = 176, NCON = 48, NEFC = 160;
+  static constexpr int ID = 2;
+};
+
+enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
+enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4, GEOM_BOX = 6 };
+enum { TRN_JOINT = 0, TRN_SITE = 4 };
+enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT_PYR = 3 };
+
+template <typename T, class D>
+struct DevModel {
+  int nq, nv, nu, nbody, njnt, ngeom, nsite, ntendon, npair, integrator, iterations, ls_iterations, has_fluid, has_dofdamping;
+  T timestep, gravity[3], wind[3], density, viscosity, tolerance, ls_tolerance, meaninertia;
+  // bodies
+  int body_parentid[D::NB], body_rootid[D::NB], body_jntnum[D::NB], body_jntadr[D::NB], body_dofnum[D::NB], body_dofadr[D::NB];
+  T body_pos[3 * D::NB], body_quat[4 * D::NB], body_ipos[3 * D::NB], body_iquat[4 * D::NB], body_mass[D::NB];
+  T body_subtreemass[D::NB], body_inertia[3 * D::NB], body_invweight0[2 * D::NB];
+  // joints
+  int jnt_type[D::NJ], jnt_qposadr[D::NJ], jnt_dofadr[D::NJ], jnt_bodyid[D::NJ], jnt_limited[D::NJ];
+  T jnt_pos[3 * D::NJ], jnt_axis[3 * D::NJ], jnt_stiffness[D::NJ], jnt_range[2 * D::NJ], jnt_margin[D::NJ];
+  T jnt_solref[2 * D::NJ], jnt_solimp[5 * D::NJ], qpos0[D::NQ], qpos_spring[D::NQ];
+  // dofs
+  int dof_bodyid[D::NV], dof_jntid[D::NV], dof_parentid[D::NV];
+  T dof_armature[D::NV], dof_damping[D::NV], dof_invweight0[D::NV];
+  // geoms / sites
+  int geom_type[D::NG], geom_bodyid[D::NG];
+  T geom_size[3 * D::NG], geom_rbound[D::NG], geom_pos[3 * D::NG], geom_quat[4 * D::NG];
+  int site_bodyid[D::NS];
+  T site_pos[3 * D::NS], site_quat[4 * D::NS];
+  // fixed tendons
+  int tendon_adr[D::NT], tendon_num[D::NT], tendon_limited[D::NT], wrap_jntid[D::NW];
+  T tendon_range[2 * D::NT], tendon_margin[D::NT], tendon_solref[2 * D::NT], tendon_solimp[5 * D::NT], tendon_invweight0[D::NT];
+  T tendon_stiffness[D::NT], tendon_damping[D::NT], tendon_lengthspring[2 * D::NT], wrap_coef[D::NW];
+  // actuators
+  int actuator_trntype[D::NU], actuator_trnid[D::NU], actuator_ctrllimited[D::NU], actuator_forcelimited[D::NU], actuator_disabled[D::NU];
+  T actuator_gear[6 * D::NU], actuator_ctrlrange[2 * D::NU], actuator_forcerange[2 * D::NU], actuator_gainprm[D::NU], actuator_biasprm[3 * D::NU];
+  // collision candidates with pre-mixed contact parameters
+  int pair_geom1[D::NPAIR], pair_geom2[D::NPAIR], pair_dim[D::NPAIR];
+  T pair_margin[D::NPAIR], pair_gap[D::NPAIR], pair_friction[2 * D::NPAIR], pair_solref[2 * D::NPAIR], pair_solimp[5 * D::NPAIR];
+};
+
+template <class D>
+inline bool model_fits(const b2m_view& v) {
+  return v.nbody <= D::NB && v.njnt <= D::NJ && v.nq <= D::NQ && v.nv <= D::NV && v.nu <= D::NU && v.ngeom <= D::NG &&
+         v.nsite <= D::NS && v.ntendon <= D::NT && v.nwrap <= D::NW && v.npair <= D::NPAIR;
+}
+
+template <typename T, typename S>
+inline void fill(T* dst, const S* src, int n) {
+  for (int i = 0; i < n; i++) dst[i] = (T)src[i];
+}
+
+template <typename T, class D>
+inline void fill_dev_model(DevModel<T, D>& m, const b2m_view& v, const int* actuator_disabled) {
+  memset(&m, 0, sizeof(m));
+  m.nq = v.nq; m.nv = v.nv; m.nu = v.nu; m.nbody = v.nbody; m.njnt = v.njnt; m.ngeom = v.ngeom; m.nsite = v.nsite;
+  m.ntendon = v.ntendon; m.npair = v.npair; m.integrator = v.integrator; m.iterations = v.iterations;
+  m.ls_iterations = v.ls_iterations; m.has_fluid = v.has_fluid; m.has_dofdamping = v.has_dofdamping;
+  m.timestep = (T)v.timestep; fill(m.gravity, v.gravity, 3); fill(m.wind, v.wind, 3);
+  m.density = (T)v.density; m.viscosity = (T)v.viscosity; m.tolerance = (T)v.tolerance; m.ls_tolerance = (T)v.ls_tolerance;
+  m.meaninertia = (T)v.meaninertia;
+  int nb = v.nbody, nj = v.njnt, nv = v.nv, ng = v.ngeom, ns = v.nsite, nt = v.ntendon, nu = v.nu, np = v.npair;
+  fill(m.body_parentid, v.body_parentid, nb); fill(m.body_rootid, v.body_rootid, nb); fill(m.body_jntnum, v.body_jntnum, nb);
+  fill(m.body_jntadr, v.body_jntadr, nb); fill(m.body_dofnum, v.body_dofnum, nb); fill(m.body_dofadr, v.body_dofadr, nb);
+  fill(m.body_pos, v.body_pos, 3 * nb); fill(m.body_quat, v.body_quat, 4 * nb); fill(m.body_ipos, v.body_ipos, 3 * nb);
+  fill(m.body_iquat, v.body_iquat, 4 * nb); fill(m.body_mass, v.body_mass, nb); fill(m.body_subtreemass, v.body_subtreemass, nb);
+  fill(m.body_inertia, v.body_inertia, 3 * nb); fill(m.body_invweight0, v.body_invweight0, 2 * nb);
+  fill(m.jnt_type, v.jnt_type, nj); fill(m.jnt_qposadr, v.jnt_qposadr, nj); fill(m.jnt_dofadr, v.jnt_dofadr, nj);
+  fill(m.jnt_bodyid, v.jnt_bodyid, nj); fill(m.jnt_limited, v.jnt_limited, nj);
+  fill(m.jnt_pos, v.jnt_pos, 3 * nj); fill(m.jnt_axis, v.jnt_axis, 3 * nj); fill(m.jnt_stiffness, v.jnt_stiffness, nj);
+  fill(m.jnt_range, v.jnt_range, 2 * nj); fill(m.jnt_margin, v.jnt_margin, nj); fill(m.jnt_solref, v.jnt_solref, 2 * nj);
+  fill(m.jnt_solimp, v.jnt_solimp, 5 * nj); fill(m.qpos0, v.qpos0, v.nq); fill(m.qpos_spring, v.qpos_spring, v.nq);
+  fill(m.dof_bodyid, v.dof_bodyid, nv); fill(m.dof_jntid, v.dof_jntid, nv); fill(m.dof_parentid, v.dof_parentid, nv);
+  fill(m.dof_armature, v.dof_armature, nv); fill(m.dof_damping, v.dof_damping, nv); fill(m.dof_invweight0, v.dof_invweight0, nv);
+  fill(m.geom_type, v.geom_type, ng); fill(m.geom_bodyid, v.geom_bodyid, ng); fill(m.geom_size, v.geom_size, 3 * ng);
+  fill(m.geom_rbound, v.geom_rbound, ng); fill(m.geom_pos, v.geom_pos, 3 * ng); fill(m.geom_quat, v.geom_quat, 4 * ng);
+  fill(m.site_bodyid, v.site_bodyid, ns); fill(m.site_pos, v.site_pos, 3 * ns); fill(m.site_quat, v.site_quat, 4 * ns);
+  fill(m.tendon_adr, v.tendon_adr, nt); fill(m.tendon_num, v.tendon_num, nt); fill(m.tendon_limited, v.tendon_limited, nt);
+  fill(m.wrap_jntid, v.wrap_jntid, v.nwrap); fill(m.wrap_coef, v.wrap_coef, v.nwrap);
+  fill(m.tendon_range, v.tendon_range, 2 * nt); fill(m.tendon_margin, v.tendon_margin, nt); fill(m.tendon_solref, v.tendon_solref, 2 * nt);
+  fill(m.tendon_solimp, v.tendon_solimp, 5 * nt); fill(m.tendon_invweight0, v.tendon_invweight0, nt);
+  fill(m.tendon_stiffness, v.tendon_stiffness, nt); fill(m.tendon_damping, v.tendon_damping, nt);
+  fill(m.tendon_lengthspring, v.tendon_lengthspring, 2 * nt);
+  fill(m.actuator_trntype, v.actuator_trntype, nu); fill(m.actuator_trnid, v.actuator_trnid, nu);
+  fill(m.actuator_ctrllimited, v.actuator_ctrllimited, nu); fill(m.actuator_forcelimited, v.actuator_forcelimited, nu);
+  fill(m.actuator_disabled, actuator_disabled ? actuator_disabled : v.actuator_disabled, nu);
+  fill(m.actuator_gear, v.actuator_gear, 6 * nu); fill(m.actuator_ctrlrange, v.actuator_ctrlrange, 2 * nu);
+  fill(m.actuator_forcerange, v.actuator_forcerange, 2 * nu); fill(m.actuator_gainprm, v.actuator_gainprm, nu);
+  fill(m.actuator_biasprm, v.actuator_biasprm, 3 * nu);
+  fill(m.pair_geom1, v.pair_geom1, np); fill(m.pair_geom2, v.pair_geom2, np); fill(m.pair_dim, v.pair_dim, np);
+  fill(m.pair_margin, v.pair_margin, np); fill(m.pair_gap, v.pair_gap, np); fill(m.pair_solref, v.pair_solref, 2 * np);
+  fill(m.pair_solimp, v.pair_solimp, 5 * np);
+  // only friction[0] (tangential) and friction[2] are distinct for condim<=3; keep the two used values
+  for (int p = 0; p < np; p++) { m.pair_friction[2 * p] = (T)v.pair_friction[5 * p]; m.pair_friction[2 * p + 1] = (T)v.pair_friction[5 * p + 1]; }
+}
+
+}  // namespace b2

@@ -1,0 +1,160 @@
+"""ctypes binding of the C-ABI in ``include/b2mj.h`` (``libb2mj.so``).
+
+This is the only place Python touches native code.  There is no CPU fallback: if the
+library is missing, or a compute call is made without a CUDA device, the call raises.
+Status codes map 1:1 onto the reference's exception hierarchy
+(reference ``mujoco_template/exceptions.py:4-21``).
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .exceptions import ConfigError, LinearizationError, TemplateError
+
+B2_F64, B2_F32 = 64, 32
+JAC_SITE, JAC_BODY, JAC_BODYCOM, JAC_SUBTREECOM = 0, 1, 2, 3
+FLAG_BAD_QPOS, FLAG_BAD_QVEL, FLAG_BAD_QACC, FLAG_OVERFLOW = 1, 2, 4, 8
+
+_LIB_PATH = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "libb2mj.so"))
+_lib: C.CDLL | None = None
+
+# every symbol include/b2mj.h declares (tests check the shared object exports all of them)
+EXPORTED_SYMBOLS = (
+    "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
+    "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
+    "b2_differentiate_pos", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_batch_size_class", "b2_last_error", "b2_version",
+)
+
+
+class State(C.Structure):
+    _fields_ = [("qpos", C.c_void_p), ("qvel", C.c_void_p), ("ctrl", C.c_void_p),
+                ("qacc_warmstart", C.c_void_p), ("flags", C.c_void_p)]
+
+
+class Derived(C.Structure):
+    _fields_ = [("xpos", C.c_void_p), ("xquat", C.c_void_p), ("xipos", C.c_void_p), ("geom_xpos", C.c_void_p),
+                ("site_xpos", C.c_void_p), ("subtree_com", C.c_void_p), ("qacc", C.c_void_p),
+                ("qfrc_bias", C.c_void_p), ("ncon", C.c_void_p), ("nefc", C.c_void_p), ("solver_iter", C.c_void_p)]
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load libb2mj.so (built in-tree by ``__graft_entry__.build()`` / ``csrc/Makefile``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise TemplateError(
+            f"native library not found: {_LIB_PATH}. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C mujoco-template_b200/csrc). There is no CPU fallback for the physics path.")
+    L = C.CDLL(_LIB_PATH)
+    vp, i, d = C.c_void_p, C.c_int, C.c_double
+    L.b2_last_error.restype = C.c_char_p
+    L.b2_version.restype = C.c_char_p
+    L.b2_launch_count.restype = C.c_longlong
+    L.b2_model_create.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
+    L.b2_model_destroy.argtypes = [vp]
+    L.b2_model_destroy.restype = None
+    L.b2_model_set_actuator_disabled.argtypes = [vp, C.POINTER(i), i]
+    L.b2_batch_create.argtypes = [vp, i, i, i, C.POINTER(vp)]
+    L.b2_batch_destroy.argtypes = [vp]
+    L.b2_batch_destroy.restype = None
+    L.b2_batch_size_class.argtypes = [vp]
+    L.b2_step.argtypes = [vp, C.POINTER(State), i, C.POINTER(Derived), vp]
+    L.b2_forward.argtypes = [vp, C.POINTER(State), C.POINTER(Derived), vp]
+    L.b2_linearize.argtypes = [vp, C.POINTER(State), d, i, vp, vp, vp]
+    L.b2_jacobian.argtypes = [vp, C.POINTER(State), i, i, vp, vp, vp]
+    L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
+    L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
+    L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
+    L.b2_stream_synchronize.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    """Translate a C status code into the reference's exception types."""
+    if rc == 0:
+        return
+    msg = lib().b2_last_error().decode("utf-8", "replace")
+    if rc in (-1, -2, -3):
+        raise ConfigError(msg)
+    if rc == -5:
+        raise LinearizationError(msg)
+    raise TemplateError(msg)
+
+
+def launch_count() -> int:
+    return int(lib().b2_launch_count())
+
+
+class NativeModel:
+    """Owns a ``b2_model*``."""
+
+    def __init__(self, blob: bytes):
+        self._L = lib()
+        h = C.c_void_p()
+        check(self._L.b2_model_create(blob, len(blob), C.byref(h)))
+        self.handle = h
+
+    def set_actuator_disabled(self, disabled) -> None:
+        arr = (C.c_int * len(disabled))(*[int(bool(x)) for x in disabled])
+        check(self._L.b2_model_set_actuator_disabled(self.handle, arr, len(disabled)))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._L.b2_model_destroy(h)
+            self.handle = None
+
+
+class NativeBatch:
+    """Owns a ``b2_batch*`` (nenv envs of one model on one device)."""
+
+    def __init__(self, model: NativeModel, nenv: int, device: int = 0, precision: int = B2_F64):
+        self._L = lib()
+        self.model = model
+        h = C.c_void_p()
+        check(self._L.b2_batch_create(model.handle, int(nenv), int(device), int(precision), C.byref(h)))
+        self.handle = h
+        self.nenv = int(nenv)
+
+    @property
+    def size_class(self) -> int:
+        return int(self._L.b2_batch_size_class(self.handle))
+
+    def step(self, state: State, nsteps: int, derived: Derived | None, stream: int = 0) -> None:
+        check(self._L.b2_step(self.handle, C.byref(state), int(nsteps), C.byref(derived) if derived is not None else None, stream))
+
+    def forward(self, state: State, derived: Derived | None, stream: int = 0) -> None:
+        check(self._L.b2_forward(self.handle, C.byref(state), C.byref(derived) if derived is not None else None, stream))
+
+    def linearize(self, state: State, eps: float, centered: bool, A: int, B: int, stream: int = 0) -> None:
+        check(self._L.b2_linearize(self.handle, C.byref(state), float(eps), int(bool(centered)), A, B, stream))
+
+    def jacobian(self, state: State, kind: int, objid: int, jacp: int, jacr: int | None, stream: int = 0) -> None:
+        check(self._L.b2_jacobian(self.handle, C.byref(state), int(kind), int(objid), jacp, jacr, stream))
+
+    def integrate_pos(self, qpos: int, qvel: int, dt: float, stream: int = 0) -> None:
+        check(self._L.b2_integrate_pos(self.handle, qpos, qvel, float(dt), stream))
+
+    def differentiate_pos(self, out: int, dt: float, qpos1: int, qpos2: int, stream: int = 0) -> None:
+        check(self._L.b2_differentiate_pos(self.handle, out, float(dt), qpos1, qpos2, stream))
+
+    def step_host(self, state: State, nsteps: int, linearize: bool, eps: float, A: int | None, B: int | None, stream: int = 0) -> None:
+        check(self._L.b2_step_host(self.handle, C.byref(state), int(nsteps), int(bool(linearize)), float(eps), A, B, stream))
+
+    def synchronize(self, stream: int = 0) -> None:
+        check(self._L.b2_stream_synchronize(self.handle, stream))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._L.b2_batch_destroy(h)
+            self.handle = None

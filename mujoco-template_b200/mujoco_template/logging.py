@@ -1,0 +1,165 @@
+"""State/control recorder producing the reference's CSV schema.
+
+Column order (reference ``mujoco_template/logging.py:81-178``): ``time_s``; then for every joint
+in id order its qpos columns followed by its qvel columns (free joints are labelled
+``pos_x..quat_z`` / ``lin_x..ang_z``, hinge/slide carry no component suffix); then
+``ctrl[<actuator>]`` per actuator (``ctrl[none]`` when ``nu == 0``); then probe columns.
+"""
+
+from __future__ import annotations
+
+from collections.abc import Callable, Iterator, Sequence
+from dataclasses import dataclass
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from . import _mj as mj
+from .exceptions import ConfigError
+from .runtime import TrajectoryLogger
+
+_QPOS_LABELS = {
+    mj.mjtJoint.mjJNT_FREE: ("pos_x", "pos_y", "pos_z", "quat_w", "quat_x", "quat_y", "quat_z"),
+    mj.mjtJoint.mjJNT_BALL: ("quat_w", "quat_x", "quat_y", "quat_z"),
+    mj.mjtJoint.mjJNT_SLIDE: ("",),
+    mj.mjtJoint.mjJNT_HINGE: ("",),
+}
+_QVEL_LABELS = {
+    mj.mjtJoint.mjJNT_FREE: ("lin_x", "lin_y", "lin_z", "ang_x", "ang_y", "ang_z"),
+    mj.mjtJoint.mjJNT_BALL: ("ang_x", "ang_y", "ang_z"),
+    mj.mjtJoint.mjJNT_SLIDE: ("",),
+    mj.mjtJoint.mjJNT_HINGE: ("",),
+}
+
+
+@dataclass(frozen=True)
+class DataProbe:
+    """Extra CSV column: ``extractor(env, result)`` must return a scalar (or ``None`` for an empty cell)."""
+
+    name: str
+    extractor: Callable[[Any, Any], Any]
+
+
+def _labels(table: dict, joint_type: int, count: int) -> Sequence[str]:
+    known = table.get(joint_type)
+    if known is None or len(known) != count:
+        return [f"c{i}" if count > 1 else "" for i in range(count)]
+    return known
+
+
+class StateControlRecorder:
+    """StepHook that logs time, generalized coordinates, velocities, controls and probes."""
+
+    def __init__(self, env: Any, *, log_path: str | Path | None = None, store_rows: bool = True,
+                 probes: Sequence[DataProbe] = ()) -> None:
+        self._env = env
+        self._model = env.model
+        self._store_rows = bool(store_rows)
+        self._rows: list[tuple[object, ...]] = []
+        self._probes = self._validate_probes(probes)
+        self._columns, self._qpos_indices, self._qvel_indices, self._ctrl_columns = self._schema()
+        self._has_actuators = self._model.nu > 0
+        self._column_index_map = {name: i for i, name in enumerate(self._columns)}
+        self._logger = TrajectoryLogger(log_path, self._columns, self._format_row)
+
+    @staticmethod
+    def _validate_probes(probes: Sequence[DataProbe]) -> tuple[DataProbe, ...]:
+        seen: set[str] = set()
+        for probe in probes:
+            if not isinstance(probe, DataProbe):
+                raise ConfigError("All probes must be instances of DataProbe.")
+            if not probe.name:
+                raise ConfigError("Probe names must be non-empty strings.")
+            if probe.name in seen:
+                raise ConfigError(f"Duplicate probe name detected: {probe.name}")
+            if not callable(probe.extractor):
+                raise ConfigError(f"Probe '{probe.name}' extractor must be callable.")
+            seen.add(probe.name)
+        return tuple(probes)
+
+    def _schema(self):
+        m = self._model
+        columns = ["time_s"]
+        qpos_idx: list[int] = []
+        qvel_idx: list[int] = []
+        for j in range(m.njnt):
+            name = mj.mj_id2name(m, mj.mjtObj.mjOBJ_JOINT, j) or f"joint_{j}"
+            jtype = int(m.jnt_type[j])
+            q0 = int(m.jnt_qposadr[j])
+            q1 = int(m.jnt_qposadr[j + 1]) if j + 1 < m.njnt else int(m.nq)
+            v0 = int(m.jnt_dofadr[j])
+            v1 = int(m.jnt_dofadr[j + 1]) if j + 1 < m.njnt else int(m.nv)
+            for idx, comp in zip(range(q0, q1), _labels(_QPOS_LABELS, jtype, q1 - q0)):
+                columns.append(f"qpos[{name}].{comp}" if comp else f"qpos[{name}]")
+                qpos_idx.append(idx)
+            for idx, comp in zip(range(v0, v1), _labels(_QVEL_LABELS, jtype, v1 - v0)):
+                columns.append(f"qvel[{name}].{comp}" if comp else f"qvel[{name}]")
+                qvel_idx.append(idx)
+        if m.nu > 0:
+            ctrl_cols = tuple(f"ctrl[{mj.mj_id2name(m, mj.mjtObj.mjOBJ_ACTUATOR, a) or f'actuator_{a}'}]" for a in range(m.nu))
+        else:
+            ctrl_cols = ("ctrl[none]",)
+        columns.extend(ctrl_cols)
+        columns.extend(p.name for p in self._probes)
+        return tuple(columns), qpos_idx, qvel_idx, ctrl_cols
+
+    @property
+    def columns(self) -> tuple[str, ...]:
+        return self._columns
+
+    @property
+    def column_index(self) -> dict[str, int]:
+        return dict(self._column_index_map)
+
+    @property
+    def rows(self) -> list[tuple[object, ...]]:
+        return self._rows
+
+    def __enter__(self) -> "StateControlRecorder":
+        self._logger.__enter__()
+        return self
+
+    def __exit__(self, exc_type, exc, exc_tb) -> None:
+        self._logger.__exit__(exc_type, exc, exc_tb)
+
+    def close(self) -> None:
+        self._logger.close()
+
+    def _format_row(self, result: Any) -> tuple[object, ...]:
+        data, m = self._env.data, self._model
+        if len(self._qpos_indices) != m.nq:
+            raise ConfigError("Internal recorder error: qpos index coverage mismatch.")
+        if len(self._qvel_indices) != m.nv:
+            raise ConfigError("Internal recorder error: qvel index coverage mismatch.")
+        row: list[object] = [float(data.time)]
+        row += [float(data.qpos[i]) for i in self._qpos_indices]
+        row += [float(data.qvel[i]) for i in self._qvel_indices]
+        if self._has_actuators:
+            row += [float(data.ctrl[a]) for a in range(m.nu)]
+        else:
+            row.append("")
+        for probe in self._probes:
+            value = probe.extractor(self._env, result)
+            if isinstance(value, np.ndarray):
+                if value.size != 1:
+                    raise ConfigError(f"Probe '{probe.name}' returned array with {value.size} elements; expected scalar.")
+                value = float(value.item())
+            elif isinstance(value, (list, tuple)):
+                raise ConfigError(f"Probe '{probe.name}' returned a non-scalar sequence; expected scalar-compatible value.")
+            elif value is None:
+                value = ""
+            row.append(value)
+        return tuple(row)
+
+    def __call__(self, result: Any) -> None:
+        row = self._logger.log(result)
+        if self._store_rows:
+            self._rows.append(row)
+
+    def as_dicts(self) -> Iterator[dict[str, object]]:
+        for row in self._rows:
+            yield {name: row[i] for name, i in self._column_index_map.items()}
+
+
+__all__ = ["DataProbe", "StateControlRecorder"]

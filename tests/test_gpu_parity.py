@@ -1,0 +1,311 @@
+"""GPU parity tests proper: CUDA path (through the C-ABI) vs the CPU oracle on seeded inputs.
+
+Tolerances (BASELINE.json north_star): FP64 per-step relative error <= 1e-9 on qpos/qvel;
+(A, B) relative error <= 1e-6.
+"""
+import numpy as np
+import pytest
+
+from conftest import MODEL_NAMES, load_model, oracle_for, random_states
+
+pytestmark = pytest.mark.gpu
+
+STEP_RTOL = 1e-9
+AB_RTOL = 1e-6
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
+
+
+def _batch(model, n):
+    import torch
+    from mujoco_template import _mj as mj
+
+    assert torch.cuda.is_available()
+    return mj.BatchData(model, n)
+
+
+def _upload(data, qpos, qvel, ctrl, warm=None):
+    import torch
+
+    data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=data.qpos.device))
+    data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=data.qpos.device))
+    data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=data.qpos.device))
+    if warm is None:
+        data.qacc_warmstart.zero_()
+    else:
+        data.qacc_warmstart.copy_(torch.as_tensor(warm.T.copy(), device=data.qpos.device))
+
+
+N_ENVS = {"pendulum": 96, "cartpole": 96, "drone": 64, "humanoid": 24}
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_step_parity_per_step(name):
+    """Every step from a shared state: GPU step == oracle step to <= 1e-9 relative."""
+    from mujoco_template import _mj as mj
+
+    model = load_model(name)
+    n = N_ENVS[name]
+    qpos, qvel, ctrl = random_states(model, name, n, seed=1)
+    warm = np.zeros((n, model.nv))
+    data = _batch(model, n)
+    om, od = oracle_for(model)
+    nsteps = 40 if name != "humanoid" else 25
+    worst = 0.0
+    for s in range(nsteps):
+        _upload(data, qpos, qvel, ctrl, warm)
+        mj.mj_step(model, data)
+        gq, gv, gw = data.qpos.cpu().numpy().T, data.qvel.cpu().numpy().T, data.qacc_warmstart.cpu().numpy().T
+        for e in range(n):
+            od.reset()
+            od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]; od.qacc_warmstart[:] = warm[e]
+            od.step()
+            qpos[e] = od.qpos; qvel[e] = od.qvel; warm[e] = od.qacc_warmstart
+        worst = max(worst, _rel(gq, qpos), _rel(gv, qvel))
+        assert _rel(gq, qpos) <= STEP_RTOL, (name, s, _rel(gq, qpos))
+        assert _rel(gv, qvel) <= STEP_RTOL, (name, s, _rel(gv, qvel))
+        assert _rel(gw, warm) <= 1e-7, (name, s, _rel(gw, warm))
+    assert int(data.flags.max().item()) == 0
+    print(f"{name}: worst per-step rel err {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", ["pendulum", "cartpole", "drone"])
+def test_free_running_trajectory(name):
+    """Independent 200-step rollouts stay within 1e-7 (smooth dynamics, no chaos at this horizon)."""
+    from mujoco_template import _mj as mj
+
+    model = load_model(name)
+    n = 32
+    qpos, qvel, ctrl = random_states(model, name, n, seed=2)
+    if name == "drone":  # near-hover thrust: no tumbling into the floor within 2 s
+        ctrl = np.random.default_rng(7).uniform(2.9, 3.6, ctrl.shape)
+    data = _batch(model, n)
+    _upload(data, qpos, qvel, ctrl)
+    mj.mj_step(model, data, 200)  # fused launch
+    om, od = oracle_for(model)
+    om.batch_rollout(qpos, qvel, ctrl, nsteps=200, nthreads=4)
+    assert np.all(np.isfinite(qpos))
+    assert _rel(data.qpos.cpu().numpy().T, qpos) <= 1e-7
+    assert _rel(data.qvel.cpu().numpy().T, qvel) <= 1e-7
+    assert abs(data.time - 200 * model.opt.timestep) < 1e-9
+
+
+def test_drone_landing_contacts_per_step():
+    """Plane-box and plane-ellipsoid contacts (drone dropped with tilt, motors off)."""
+    from mujoco_template import _mj as mj
+
+    model = load_model("drone")
+    n = 16
+    qpos, qvel, ctrl = random_states(model, "drone", n, seed=8)
+    qpos[:, 2] = np.linspace(0.12, 0.4, n)
+    ctrl[:] = 0.0
+    warm = np.zeros((n, model.nv))
+    data = _batch(model, n)
+    om, od = oracle_for(model)
+    seen = 0
+    for s in range(120):
+        _upload(data, qpos, qvel, ctrl, warm)
+        mj.mj_step(model, data)
+        ncon_gpu = data.ncon.cpu().numpy()[0]
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]; od.qacc_warmstart[:] = warm[e]
+            od.step()
+            assert od.ncon == ncon_gpu[e], (s, e)
+            seen = max(seen, od.ncon)
+            qpos[e] = od.qpos; qvel[e] = od.qvel; warm[e] = od.qacc_warmstart
+        assert _rel(data.qpos.cpu().numpy().T, qpos) <= STEP_RTOL, s
+        assert _rel(data.qvel.cpu().numpy().T, qvel) <= 1e-8, s
+    assert seen >= 4
+
+
+def test_bad_state_is_flagged_not_reset():
+    """Upstream silently resets mjData on NaN/huge values; we flag the env instead."""
+    from mujoco_template import _capi, _mj as mj
+
+    model = load_model("drone")
+    n = 4
+    qpos, qvel, ctrl = random_states(model, "drone", n, seed=9)
+    qvel[1, 0] = 1e12
+    qpos[2, 1] = np.nan
+    data = _batch(model, n)
+    _upload(data, qpos, qvel, ctrl)
+    mj.mj_step(model, data)
+    flags = data.flags.cpu().numpy()[0]
+    assert flags[0] == 0 and flags[3] == 0
+    assert flags[1] & _capi.FLAG_BAD_QVEL and flags[2] & _capi.FLAG_BAD_QPOS
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_linearize_parity(name):
+    model = load_model(name)
+    n = 16 if name != "humanoid" else 4
+    qpos, qvel, ctrl = random_states(model, name, n, seed=3)
+    if name == "drone":
+        ctrl[0, 0] = 0.0   # at the lower ctrlrange bound: forward one-sided difference
+        ctrl[1, 1] = 13.0  # at the upper bound: backward difference
+    if name == "humanoid":
+        ctrl[0, 3] = 1.0
+    data = _batch(model, n)
+    _upload(data, qpos, qvel, ctrl)
+    eps = 1e-6
+    A, B = data.backend.linearize(eps, True)
+    A = A.permute(2, 0, 1).cpu().numpy(); B = B.permute(2, 0, 1).cpu().numpy()
+    # state untouched
+    assert np.array_equal(data.qpos.cpu().numpy().T, qpos)
+    om, od = oracle_for(model)
+    for e in range(n):
+        od.reset()
+        od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+        Ao, Bo = od.transition_fd(eps, True)
+        assert _rel(A[e], Ao) <= AB_RTOL, (name, e, _rel(A[e], Ao))
+        assert _rel(B[e], Bo) <= AB_RTOL, (name, e, _rel(B[e], Bo))
+
+
+@pytest.mark.parametrize("name", MODEL_NAMES)
+def test_forward_derived_and_jacobians(name):
+    from mujoco_template import _capi, _mj as mj
+
+    model = load_model(name)
+    n = 8
+    qpos, qvel, ctrl = random_states(model, name, n, seed=4)
+    data = _batch(model, n)
+    _upload(data, qpos, qvel, ctrl)
+    mj.mj_forward(model, data)
+    om, od = oracle_for(model)
+    body = model.nbody - 1
+    for e in range(n):
+        od.reset()
+        od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+        od.forward()
+        assert _rel(data.xpos[:, e].cpu().numpy().reshape(-1, 3), od.xpos) <= 1e-12
+        assert _rel(data.xipos[:, e].cpu().numpy().reshape(-1, 3), od.xipos) <= 1e-12
+        assert _rel(data.geom_xpos[:, e].cpu().numpy().reshape(-1, 3), od.geom_xpos) <= 1e-12
+        assert _rel(data.subtree_com[:, e].cpu().numpy().reshape(-1, 3), od.subtree_com) <= 1e-12
+        assert _rel(data.qacc[:, e].cpu().numpy(), od.qacc) <= 1e-8
+        assert int(data.ncon[0, e]) == od.ncon and int(data.nefc[0, e]) == od.nefc
+        if model.nsite:
+            assert _rel(data.site_xpos[:, e].cpu().numpy().reshape(-1, 3), od.site_xpos) <= 1e-12
+    kinds = [("body", _capi.JAC_BODY, body), ("bodycom", _capi.JAC_BODYCOM, body), ("subtreecom", _capi.JAC_SUBTREECOM, 1)]
+    if model.nsite:
+        kinds.append(("site", _capi.JAC_SITE, model.nsite - 1))
+    for kname, code, idx in kinds:
+        jp, jr = data.backend.jacobian(code, idx, code in (_capi.JAC_BODY, _capi.JAC_SITE))
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.forward()
+            jpo, jro = od.jac(kname, idx)
+            assert _rel(jp[:, :, e].cpu().numpy(), jpo) <= 1e-12, (name, kname)
+            if jr is not None:
+                assert _rel(jr[:, :, e].cpu().numpy(), jro) <= 1e-12
+
+
+@pytest.mark.parametrize("name", ["drone", "humanoid", "cartpole"])
+def test_integrate_differentiate_pos(name):
+    import torch
+
+    model = load_model(name)
+    n = 8
+    qpos, qvel, _ = random_states(model, name, n, seed=5)
+    rng = np.random.default_rng(6)
+    vel = rng.normal(0, 1.0, (n, model.nv))
+    data = _batch(model, n)
+    dev = data.qpos.device
+    q = torch.as_tensor(qpos.T.copy(), device=dev)
+    v = torch.as_tensor(vel.T.copy(), device=dev)
+    q2 = q.clone()
+    data.backend.batch.integrate_pos(q2.data_ptr(), v.data_ptr(), 0.37)
+    out = torch.zeros_like(v)
+    data.backend.batch.differentiate_pos(out.data_ptr(), 0.37, q.data_ptr(), q2.data_ptr())
+    torch.cuda.synchronize()
+    om, od = oracle_for(model)
+    for e in range(n):
+        qo = od.integrate_pos(qpos[e], vel[e], 0.37)
+        assert _rel(q2[:, e].cpu().numpy(), qo) <= 1e-13
+        assert _rel(out[:, e].cpu().numpy(), od.differentiate_pos(0.37, qpos[e], qo)) <= 1e-12
+    # round trip: differentiate(integrate(q, v, dt)) == v
+    assert _rel(out.cpu().numpy().T, vel) <= 1e-9
+
+
+def test_humanoid_contacts_active_and_reported():
+    from mujoco_template import _mj as mj
+
+    model = load_model("humanoid")
+    data = _batch(model, 8)
+    mj.mj_resetDataKeyframe(model, data, 1)
+    mj.mj_forward(model, data)
+    assert int(data.ncon.min()) == 4 and int(data.nefc.min()) == 16
+    mj.mj_step(model, data, 300)
+    assert int(data.flags.max()) == 0
+    assert float(data.qpos[2].min()) > 0.0  # nobody fell through the floor
+
+
+def test_cartpole_limit_and_floor_contact():
+    """Slider limit (|x| > 2) and pole-floor contact rows match the oracle."""
+    from mujoco_template import _mj as mj
+
+    model = load_model("cartpole")
+    n = 4
+    qpos = np.array([[2.05, 0.1], [-2.1, -0.3], [0.0, 1.75], [1.99, -1.8]])
+    qvel = np.array([[1.0, 0.0], [-0.5, 0.2], [0.0, 1.0], [0.3, -1.0]])
+    ctrl = np.array([[100.0], [-250.0], [0.0], [10.0]])
+    data = _batch(model, n)
+    om, od = oracle_for(model)
+    warm = np.zeros((n, 2))
+    for s in range(60):
+        _upload(data, qpos, qvel, ctrl, warm)
+        mj.mj_step(model, data)
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]; od.qacc_warmstart[:] = warm[e]
+            od.step()
+            qpos[e] = od.qpos; qvel[e] = od.qvel; warm[e] = od.qacc_warmstart
+        assert _rel(data.qpos.cpu().numpy().T, qpos) <= STEP_RTOL, s
+        assert _rel(data.qvel.cpu().numpy().T, qvel) <= STEP_RTOL, s
+
+
+def test_single_env_config1_pendulum_cli():
+    """BASELINE config #1: pendulum, ZeroController, 300 steps from reset (stationary)."""
+    import mujoco_template as mt
+    from conftest import load_model
+
+    model = load_model("pendulum")
+    handle = mt.ModelHandle(model)
+    env = mt.Env(handle, obs_spec=mt.ObservationSpec(include_time=True), controller=mt.ZeroController())
+    env.reset()
+    steps = sum(1 for _ in env.passive(max_steps=300))
+    assert steps == 300
+    assert env.data.qpos[0] == 0.0 and env.data.qvel[0] == 0.0
+    t = 0.0
+    for _ in range(300):
+        t += 0.005
+    assert env.data.time == t
+
+
+def test_single_env_linearize_and_info():
+    import mujoco_template as mt
+
+    class Lin:
+        capabilities = mt.ControllerCapabilities(needs_linearization=True, needs_jacobians=("site:tip", "bodycom:pole"))
+        def prepare(self, model, data): pass
+        def __call__(self, model, data, t): data.ctrl[:] = 0.25
+
+    model = load_model("cartpole")
+    env = mt.Env(mt.ModelHandle(model), obs_spec=mt.ObservationSpec(sites_pos=("tip",), as_dict=False), controller=Lin())
+    env.reset()
+    env.data.qpos[:] = [0.1, 0.05]
+    res = env.step()
+    A, B = res.info["A"], res.info["B"]
+    assert A.shape == (4, 4) and B.shape == (4, 1) and np.all(np.isfinite(A))
+    assert res.info["jacobians"]["site:tip"]["jacp"].shape == (3, 2)
+    assert res.obs.shape == (2 + 2 + 3,)
+    res3 = env.step(3)
+    assert isinstance(res3.info["A"], list) and len(res3.info["A"]) == 3
+    om, od = oracle_for(model)
+    A2, B2 = env.linearize()
+    od.qpos[:] = env.data.qpos; od.qvel[:] = env.data.qvel; od.ctrl[:] = env.data.ctrl
+    od.qacc_warmstart[:] = env.data.qacc_warmstart
+    Ao, Bo = od.transition_fd(1e-6, True)
+    assert _rel(A2, Ao) <= AB_RTOL and _rel(B2, Bo) <= AB_RTOL
+    # python FD fallback path runs and agrees with native in the velocity rows
+    A3, B3 = mt.linearize_discrete(env.model, env.data, use_native=False)
+    assert _rel(A3[2:], A2[2:]) <= 1e-5 and _rel(A3[:2], -A2[:2]) <= 1e-5
