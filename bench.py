@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""Headline benchmark of the batched physics path (contract: see the task brief / DESIGN.md).
+
+A "step" = one pass of the hot path over one batch of synthetic input.  The N=1 workload is
+BASELINE.json configs[1]: cartpole, 65,536 envs per GPU, FP64, every step = batched LQR control
+tick + FD (A, B) linearisation of every env (10 perturbed rollouts per env in one launch) +
+one physics step.  Metric: env-steps/s, whole job (all GPUs).
+
+    python bench.py --gpus 1 --steps 200 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29500 bench.py --gpus 8 --steps 200 --warmup 5
+    python bench.py --impl reference --steps 5 --warmup 1     # CPU arm: oracle on host cores
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "mujoco-template_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+MODEL_FILE = {m: os.path.join(ROOT, "tests", "golden", "models", f"{m}.b2m") for m in ("pendulum", "cartpole", "drone", "humanoid")}
+# algorithmic bytes per env-step / per linearisation (FP64), SURVEY.md section 8(d) / BASELINE.md section 4
+STEP_BYTES = {"pendulum": 40, "cartpole": 72, "drone": 240, "humanoid": 1480}
+LIN_BYTES = {"pendulum": 72, "cartpole": 200, "drone": 1672, "humanoid": 33224}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--model", default="cartpole", choices=list(MODEL_FILE))
+    ap.add_argument("--nenv", type=int, default=None, help="envs per GPU (default: BASELINE config for the model)")
+    ap.add_argument("--no-linearize", action="store_true", help="step only (no per-step FD linearisation)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
+    return ap.parse_args()
+
+
+DEFAULT_NENV = {"pendulum": 65536, "cartpole": 65536, "drone": 262144, "humanoid": 16384}
+
+
+def load_model(name: str):
+    from mujoco_template import _mj as mj
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return mj.MjModel.from_compiled(MODEL_FILE[name])
+
+
+def synth_states(model, name: str, n: int, seed: int):
+    """Synthetic randomized initial states. AoS (n, dim)."""
+    rng = np.random.default_rng(seed)
+    qpos = np.tile(model.qpos0, (n, 1))
+    qvel = np.zeros((n, model.nv))
+    if name == "pendulum":
+        qpos[:, 0] = rng.uniform(-np.pi, np.pi, n)
+    elif name == "cartpole":
+        qpos[:, 0] = rng.uniform(-1, 1, n)
+        qpos[:, 1] = rng.uniform(-0.2, 0.2, n)
+        qvel[:] = rng.uniform(-0.5, 0.5, (n, 2))
+    elif name == "drone":
+        qpos[:] = model.key_qpos[0]
+        qpos[:, 2] = rng.uniform(1, 3, n)
+        rv = rng.normal(0, 0.1, (n, 3))
+        ang = np.linalg.norm(rv, axis=1, keepdims=True)
+        qpos[:, 3] = np.cos(ang[:, 0] / 2)
+        qpos[:, 4:7] = rv / np.maximum(ang, 1e-12) * np.sin(ang / 2)
+        qvel[:] = rng.normal(0, 0.1, (n, model.nv))
+    elif name == "humanoid":
+        qpos[:] = model.key_qpos[1]
+        qpos[:, 7:] += rng.normal(0, 0.02, (n, model.nq - 7))
+        qvel[:] = rng.normal(0, 0.01, (n, model.nv))
+    return qpos, qvel
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.rows: list[list[str]] = []
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self) -> dict:
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_rate(model, name: str, linearize: bool, target_seconds: float, seed: int = 123):
+    """Oracle (CPU restatement of mj_step / mjd_transitionFD) on all host cores over a bounded sample."""
+    from oracle.oracle import OracleModel
+
+    om = OracleModel(model.blob, dict(nq=model.nq, nv=model.nv, nu=model.nu, nbody=model.nbody, njnt=model.njnt,
+                                      ngeom=model.ngeom, nsite=model.nsite, ntendon=model.ntendon))
+    cores = os.cpu_count() or 1
+    n_probe = max(cores * 4, 64)
+    qpos, qvel = synth_states(model, name, n_probe, seed)
+    ctrl = np.zeros((n_probe, model.nu))
+    t0 = time.perf_counter()
+    om.batch_rollout(qpos, qvel, ctrl, nsteps=2, lin=linearize, nthreads=cores)
+    probe_rate = n_probe * 2 / max(time.perf_counter() - t0, 1e-6)
+    nsteps = 10
+    n = int(min(max(probe_rate * target_seconds / nsteps, cores), 1 << 20))
+    qpos, qvel = synth_states(model, name, n, seed + 1)
+    ctrl = np.zeros((n, model.nu))
+    t0 = time.perf_counter()
+    om.batch_rollout(qpos, qvel, ctrl, nsteps=nsteps, lin=linearize, nthreads=cores)
+    dt = time.perf_counter() - t0
+    return dict(value=n * nsteps / dt, unit=UNIT, cores=cores, kind="port",
+                sample=f"{n} envs x {nsteps} steps of the same workload ({'FD linearisation + ' if linearize else ''}step), "
+                       f"{dt:.1f} s wall, pthread shards over {cores} threads; oracle = C restatement of mj_step "
+                       "(mujoco itself is not installable offline)")
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU implementation of the path.  The reference delegates to the
+    `mujoco` wheel, which is not installable offline, so this times the oracle port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    name = args.model
+    model = load_model(name)
+    lin = not args.no_linearize
+    from oracle.oracle import OracleModel
+
+    om = OracleModel(model.blob, dict(nq=model.nq, nv=model.nv, nu=model.nu, nbody=model.nbody, njnt=model.njnt,
+                                      ngeom=model.ngeom, nsite=model.nsite, ntendon=model.ntendon))
+    cores = os.cpu_count() or 1
+    per_step_cost = {"pendulum": 30e-6, "cartpole": 14e-6, "drone": 90e-6, "humanoid": 8e-3}[name] if lin else \
+        {"pendulum": 3e-6, "cartpole": 1e-6, "drone": 2.5e-6, "humanoid": 50e-6}[name]
+    # bounded sample: about 1.5 s of all-core work per step
+    n = int(max(cores, min(1 << 18, 1.5 * cores / per_step_cost)))
+    qpos, qvel = synth_states(model, name, n, 7)
+    ctrl = np.zeros((n, model.nu))
+    warm = np.zeros((n, model.nv))
+    for _ in range(args.warmup):
+        om.batch_rollout(qpos, qvel, ctrl, warm, nsteps=1, lin=lin, nthreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        om.batch_rollout(qpos, qvel, ctrl, warm, nsteps=1, lin=lin, nthreads=cores)
+    dt = time.perf_counter() - t0
+    value = n * args.steps / dt
+    sample = f"{n} envs per step (bounded sample of the {DEFAULT_NENV[name]}-env workload), all {cores} host threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(name, DEFAULT_NENV[name], lin), "sample_envs_per_step": n},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_name(name: str, nenv: int, lin: bool) -> str:
+    return (f"{name} batched rollout, N={nenv} envs/GPU, FP64, " +
+            ("batched LQR + per-step FD (A,B) linearisation + 1 step" if lin else "1 step per launch, zero control"))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_template import BatchedEnv, _capi
+    from mujoco_template.batched_controllers import BatchedLQRController
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    name = args.model
+    lin = not args.no_linearize
+    nenv = args.nenv or DEFAULT_NENV[name]
+    model = load_model(name)
+    controller = None
+    if lin:
+        if name == "cartpole":
+            controller = BatchedLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
+        else:
+            from mujoco_template import ControllerCapabilities
+
+            class HoldLin:
+                capabilities = ControllerCapabilities(needs_linearization=True)
+                def prepare(self, m, d): pass
+                def __call__(self, m, d, t): pass
+            controller = HoldLin()
+    env = BatchedEnv(model, nenv, controller=controller, device=local)
+    env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
+    qpos, qvel = synth_states(model, name, nenv, seed=rank)  # each rank owns its own shard of envs
+    env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev))
+    env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+    env.forward()
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        env.step(return_obs=False)
+    fp64_peak = _capi.fp_peak(64, local)
+    barrier()
+    launches0 = _capi.launch_count()
+    env.data.backend.profile = {}
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.zero_()  # evict state / outputs from L2 between timed iterations (outside the event pair)
+        starts[i].record()
+        env.step(return_obs=False)
+        stops[i].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
+    total_ms = float(sum(step_ms))
+    launches = _capi.launch_count() - launches0
+    kernel_ms = {k: env.data.backend.kernel_ms(k) for k in ("linearize", "step")}
+    env.data.backend.profile = None
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    value = nenv * world * args.steps / (total_ms * 1e-3)
+
+    # untimed: the path's only collective -- gather per-env returns (here: final |x|) across ranks
+    ret = env.data.qpos[0].abs().contiguous()
+    allret = env.gather(ret)
+    flags_bad = int((env.data.flags != 0).sum().item())
+
+    # ---- roofline of the dominant kernel
+    dom = "linearize" if lin else "step"
+    dom_ms = float(np.mean(kernel_ms[dom])) if kernel_ms[dom] else float("nan")
+    alg_bytes = (LIN_BYTES[name] if lin else STEP_BYTES[name]) * nenv
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
+    share = {k: (float(np.sum(v)) / total_ms if v else 0.0) for k, v in kernel_ms.items()}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                "traffic": None, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_share_of_step": share,
+                "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
+    # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
+    evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 600.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
+    roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+                     "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
+                     "flops_source": "a-priori estimate (BASELINE.md section 4)", "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
+
+    # ---- e2e: host buffers through the C-ABI (b2_step_host): H2D state+ctrl, linearise+step, D2H state+(A,B)
+    e2e = None
+    if not args.no_e2e:
+        nq, nv, nu = model.nq, model.nv, model.nu
+        hq = torch.as_tensor(qpos.T.copy()).pin_memory(); hv = torch.as_tensor(qvel.T.copy()).pin_memory()
+        hu = torch.zeros((nu, nenv), dtype=torch.float64).pin_memory(); hw = torch.zeros((nv, nenv), dtype=torch.float64).pin_memory()
+        hA = torch.empty((2 * nv, 2 * nv, nenv), dtype=torch.float64).pin_memory() if lin else None
+        hB = torch.empty((2 * nv, nu, nenv), dtype=torch.float64).pin_memory() if lin else None
+        st = _capi.State(hq.data_ptr(), hv.data_ptr(), hu.data_ptr(), hw.data_ptr(), None)
+        K = getattr(controller, "K", None)
+        batch = env.data.backend.batch
+        e2e_steps = max(3, min(args.steps, 50))
+
+        def host_step():
+            if K is not None:  # host-side LQR tick on the host copy of the state
+                x = np.concatenate([hq.numpy(), hv.numpy()], axis=0)
+                hu.numpy()[:] = np.clip(-(K @ x), -200.0, 200.0)
+            batch.step_host(st, 1, lin, 1e-6, hA.data_ptr() if lin else None, hB.data_ptr() if lin else None, 0)
+
+        for _ in range(3):
+            host_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        h2d = (nq + nv + nu + nv) * nenv * 8
+        d2h = (nq + nv + nv + (2 * nv * (2 * nv + nu) if lin else 0)) * nenv * 8
+        e2e = {"value": nenv * world * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "b2_step_host (C-ABI, pinned host buffers, host LQR tick)"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_oracle_rate(model, name, lin, args.cpu_seconds)
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
+                       "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
+                       "sharding": f"env batch split over {world} rank(s), no inter-step communication"},
+            "linearizations_per_sec": (value if lin else 0.0),
+            "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),
+            "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+            "bad_env_flags": flags_bad, "gathered_returns": int(allret.numel()),
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

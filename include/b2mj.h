@@ -117,11 +117,20 @@ int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void*
 int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int linearize, double eps, void* host_A,
                  void* host_B, void* stream);
 
+/* Measured CUDA-core FMA throughput (TFLOP/s, 2 flops per FMA) of `device` for B2_F64 / B2_F32:
+ * the FP-pipe roofline denominator (MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).
+ * Synchronous. */
+int b2_fp_peak(int precision, int device, double* tflops);
+
 int b2_stream_synchronize(b2_batch* batch, void* stream);
 /* number of kernels launched by this library in the calling process (bench gpu_launches) */
 long long b2_launch_count(void);
 /* size class the model was mapped to: 0 tiny, 1 small, 2 large */
 int b2_batch_size_class(const b2_batch* batch);
+/* "generic" (constant-memory model, any MJCF in the subset) or the name of the compiled-in
+ * model-specialised kernel set the batch runs on (selected by blob hash; env B2_DISABLE_SPEC=1
+ * forces generic) */
+const char* b2_batch_kernel_variant(const b2_batch* batch);
 const char* b2_last_error(void);
 const char* b2_version(void);
 

@@ -5,6 +5,7 @@
 
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -14,6 +15,7 @@
 #include "../../include/b2mj.h"
 #include "b2_kernels.h"
 #include "b2_model_dev.cuh"
+#include "b2_spec_registry.h"
 
 namespace {
 thread_local std::string g_err;
@@ -35,7 +37,25 @@ struct b2_model {
   std::vector<int> disabled;
   int cls;
   unsigned long long serial;
+  const b2::SpecKernels* spec;  // model-specialised FP64 kernels, or nullptr (generic path)
 };
+
+namespace b2 {
+static std::vector<const SpecKernels*>& spec_table() {
+  static std::vector<const SpecKernels*> t;
+  return t;
+}
+void register_spec(const SpecKernels* k) { spec_table().push_back(k); }
+const SpecKernels* find_spec(uint64_t hash, size_t size) {
+  const char* off = getenv("B2_DISABLE_SPEC");
+  if (off && off[0] == '1') return nullptr;
+  for (const SpecKernels* k : spec_table())
+    if (k->blob_hash == hash && k->blob_size == size) return k;
+  return nullptr;
+}
+}  // namespace b2
+
+static inline const b2::SpecKernels* active_spec(const b2_batch* b);
 
 struct b2_batch {
   const b2_model* model;
@@ -65,6 +85,7 @@ int b2_model_create(const void* blob, size_t nbytes, b2_model** out) {
   else { delete m; return fail(B2_ERR_CAPACITY, "b2_model_create: model exceeds the largest compiled size class"); }
   m->disabled.assign(v.actuator_disabled, v.actuator_disabled + v.nu);
   m->serial = g_serial.fetch_add(1);
+  m->spec = b2::find_spec(b2::fnv1a(blob, nbytes), nbytes);
   *out = m;
   return B2_OK;
 }
@@ -74,6 +95,8 @@ int b2_model_set_actuator_disabled(b2_model* m, const int* disabled, int nu) {
   if (!m || (nu && !disabled) || nu != m->v.nu) return fail(B2_ERR_ARG, "b2_model_set_actuator_disabled: bad arguments");
   m->disabled.assign(disabled, disabled + nu);
   m->serial = g_serial.fetch_add(1);  // forces a constant-bank refresh
+  for (int i = 0; i < nu; i++)
+    if (disabled[i] != m->v.actuator_disabled[i]) m->spec = nullptr;  // the specialisation bakes the mask in
   return B2_OK;
 }
 
@@ -97,8 +120,17 @@ void b2_batch_destroy(b2_batch* b) {
   delete b;
 }
 int b2_batch_size_class(const b2_batch* b) { return b ? b->model->cls : -1; }
+const char* b2_batch_kernel_variant(const b2_batch* b) {
+  if (!b) return "";
+  const b2::SpecKernels* k = (b->precision == B2_F64) ? b->model->spec : nullptr;
+  return k ? k->name : "generic";
+}
 
 }  // extern "C"
+
+static inline const b2::SpecKernels* active_spec(const b2_batch* b) {
+  return b->precision == B2_F64 ? b->model->spec : nullptr;
+}
 
 // make sure this batch's model is the image resident in constant memory on its device
 static int ensure_resident(b2_batch* b, void* stream) {
@@ -125,20 +157,34 @@ extern "C" {
 int b2_step(b2_batch* b, const b2_state* st, int nsteps, const b2_derived* derived, void* stream) {
   B2_CHECK_STATE("b2_step");
   if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step: nsteps must be >= 1");
-  int rc = ensure_resident(b, stream);
-  if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
-                              : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
+  int rc;
+  if (const b2::SpecKernels* k = active_spec(b)) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = k->step(st, derived, b->nenv, nsteps, stream);
+  } else {
+    rc = ensure_resident(b, stream);
+    if (rc) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
+                                : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
+  }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_step launch") : B2_OK;
 }
 
 int b2_forward(b2_batch* b, const b2_state* st, const b2_derived* derived, void* stream) {
   B2_CHECK_STATE("b2_forward");
-  int rc = ensure_resident(b, stream);
-  if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, 0, stream)
-                              : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, 0, stream);
+  int rc;
+  if (const b2::SpecKernels* k = active_spec(b)) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = k->step(st, derived, b->nenv, 0, stream);
+  } else {
+    rc = ensure_resident(b, stream);
+    if (rc) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, 0, stream)
+                                : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, 0, stream);
+  }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_forward launch") : B2_OK;
 }
@@ -147,11 +193,18 @@ int b2_linearize(b2_batch* b, const b2_state* st, double eps, int centered, void
   B2_CHECK_STATE("b2_linearize");
   if (!(eps > 0)) return fail(B2_ERR_LINEARIZE, "b2_linearize: eps must be > 0");
   if (!A && !B) return fail(B2_ERR_ARG, "b2_linearize: A and B are both NULL");
-  int rc = ensure_resident(b, stream);
-  if (rc) return rc;
+  int rc;
   const int ncol = 2 * b->model->v.nv + b->model->v.nu;
-  rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream)
-                              : b2::b2k_linearize_f32(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream);
+  if (const b2::SpecKernels* k = active_spec(b)) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = k->linearize(st, b->nenv, eps, centered, A, B, stream);
+  } else {
+    rc = ensure_resident(b, stream);
+    if (rc) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream)
+                                : b2::b2k_linearize_f32(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream);
+  }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_linearize launch") : B2_OK;
 }
@@ -162,10 +215,17 @@ int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp
   const int limit = kind == B2_JAC_SITE ? v.nsite : v.nbody;
   if (kind < B2_JAC_SITE || kind > B2_JAC_SUBTREECOM || objid < 0 || objid >= limit)
     return fail(B2_ERR_ARG, "b2_jacobian: kind/objid out of range");
-  int rc = ensure_resident(b, stream);
-  if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_jacobian_f64(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream)
-                              : b2::b2k_jacobian_f32(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream);
+  int rc;
+  if (const b2::SpecKernels* k = active_spec(b)) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = k->jacobian(st, b->nenv, kind, objid, jacp, jacr, stream);
+  } else {
+    rc = ensure_resident(b, stream);
+    if (rc) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_jacobian_f64(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream)
+                                : b2::b2k_jacobian_f32(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream);
+  }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_jacobian launch") : B2_OK;
 }
@@ -225,6 +285,17 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
     return cuda_fail(e, "b2_step_host: D2H B");
   e = cudaStreamSynchronize(s);
   return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
+}
+
+int b2_fp_peak(int precision, int device, double* tflops) {
+  if (!tflops || (precision != B2_F64 && precision != B2_F32)) return fail(B2_ERR_ARG, "b2_fp_peak: bad arguments");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const double v = precision == B2_F64 ? b2::b2k_fma_peak_f64(nullptr) : b2::b2k_fma_peak_f32(nullptr);
+  g_launches += 6;
+  if (v < 0) return fail(B2_ERR_CUDA, "b2_fp_peak: kernel failed");
+  *tflops = v;
+  return B2_OK;
 }
 
 int b2_stream_synchronize(b2_batch* b, void* stream) {

@@ -4,17 +4,46 @@
 // (reference mujoco_template/model.py:53-57): forward kinematics, composite-rigid-body
 // mass matrix, L'DL factorisation, bias forces (RNE), passive + actuator forces, primitive
 // collisions, limit / contact constraint rows, a warm-started Newton solve, and
-// semi-implicit Euler or RK4 integration.  All model reads are uniform constant-bank
-// loads; all per-env scratch lives in this struct (registers / L1-resident local memory).
+// semi-implicit Euler or RK4 integration.
+//
+// The model is read only through the provider policy `M` (see b2_model_dev.cuh).  With a
+// generated static provider and B2_STATIC_MODEL defined, every loop below has a compile-time
+// trip count and is fully unrolled, all indices fold, and the smooth-dynamics state
+// (poses, inertias, motion axes, M, forces) is register-resident; only the data-dependent
+// contact / constraint-row arrays (touched only when a limit or contact is active) remain in
+// local memory.  With the runtime provider the same code runs out of L1-resident local
+// memory for any model of the size class.
 #pragma once
 #include "b2_math.cuh"
 #include "b2_model_dev.cuh"
 
+#ifdef B2_STATIC_MODEL
+#define B2_UNROLL _Pragma("unroll")
+#else
+#define B2_UNROLL
+#endif
+#define B2_NOUNROLL _Pragma("unroll 1")
+
 namespace b2 {
 
+#define B2_LD3(dst, fn, base) T dst[3] = {M::fn((base)), M::fn((base) + 1), M::fn((base) + 2)}
+#define B2_LD4(dst, fn, base) T dst[4] = {M::fn((base)), M::fn((base) + 1), M::fn((base) + 2), M::fn((base) + 3)}
+
+// Data-dependent contact / constraint-row arrays.  They are indexed with runtime row and
+// contact numbers, so they must live in (L1-resident) local memory; keeping them in their own
+// object lets the compiler promote everything in LaneEnv to registers under a static provider.
 template <typename T, class D>
+struct RowStore {
+  T con_dist[D::NCON], con_pos[3 * D::NCON], con_frame[9 * D::NCON];
+  short con_pair[D::NCON];
+  signed char row_type[D::NEFC];
+  short row_id[D::NEFC];
+  T J[D::NEFC * D::NV], row_pos[D::NEFC], row_margin[D::NEFC], row_D[D::NEFC], row_aref[D::NEFC];
+  T Jaref[D::NEFC], Jv[D::NEFC];
+};
+
+template <typename T, class D, class M>
 struct LaneEnv {
-  const DevModel<T, D>& m;
   // ---- state
   T qpos[D::NQ], qvel[D::NV], ctrl[D::NU], warm[D::NV];
   // ---- position-dependent
@@ -22,62 +51,66 @@ struct LaneEnv {
   T xanchor[3 * D::NJ], xaxis[3 * D::NJ];
   T geom_xpos[3 * D::NG], geom_xmat[9 * D::NG], site_xpos[3 * D::NS], site_xmat[9 * D::NS];
   T com[3 * D::NB], cinert[10 * D::NB], cdof[6 * D::NV];
-  T M[D::NV * D::NV], LD[D::NV * D::NV], dinv[D::NV];
+  T Mm[D::NV * D::NV], LD[D::NV * D::NV], dinv[D::NV];
   T ten_len[D::NT], ten_J[D::NT * D::NV], act_len[D::NU], act_moment[D::NU * D::NV];
   // ---- velocity-dependent
-  T cvel[6 * D::NB], cdof_dot[6 * D::NV], spat[6 * D::NB], spat2[10 * D::NB];  // spat/spat2: cacc, cfrc / crb scratch
+  T cvel[6 * D::NB], cdof_dot[6 * D::NV], spat[6 * D::NB], spat2[10 * D::NB];  // scratch: cacc / crb, cfrc
   T f_bias[D::NV], f_passive[D::NV], f_smooth[D::NV], f_con[D::NV], a_smooth[D::NV], qacc[D::NV];
-  // ---- contacts + constraint rows
+  // ---- contact / constraint-row counters; the rows themselves live in RowStore
   int ncon, nefc, niter, flags;
-  T con_dist[D::NCON], con_pos[3 * D::NCON], con_frame[9 * D::NCON];
-  short con_pair[D::NCON];
-  signed char row_type[D::NEFC];
-  short row_id[D::NEFC];
-  T J[D::NEFC * D::NV], row_pos[D::NEFC], row_margin[D::NEFC], row_D[D::NEFC], row_aref[D::NEFC];
+  RowStore<T, D>& R;
   // ---- solver scratch
-  T Jaref[D::NEFC], Jv[D::NEFC], Ma[D::NV], Mv[D::NV], grad[D::NV], Mgrad[D::NV], search[D::NV];
+  T Ma[D::NV], Mv[D::NV], grad[D::NV], Mgrad[D::NV], search[D::NV];
   T cost, gauss, qg0, qg1, qg2;
   int ls_iter;
 
-  __device__ explicit LaneEnv(const DevModel<T, D>& model) : m(model), ncon(0), nefc(0), niter(0), flags(0) {}
+  __device__ explicit LaneEnv(RowStore<T, D>& rows) : ncon(0), nefc(0), niter(0), flags(0), R(rows) {}
+
+  static B2_DEV bool is_anc(int i, int j) { return (((unsigned)M::dof_anc(i)) >> j) & 1u; }
 
   // ------------------------------------------------------------------ position stage
-  __device__ void kinematics() {
+  B2_DEV void kinematics() {
     xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
     quat_to_mat(xmat, xquat);
     xipos[0] = xipos[1] = xipos[2] = 0; quat_to_mat(ximat, xquat);
-    for (int i = 1; i < m.nbody; i++) {
+    B2_UNROLL
+    for (int i = 1; i < M::nbody(); i++) {
       T p[3], q[4];
-      const int ja = m.body_jntadr[i], jn = m.body_jntnum[i], pid = m.body_parentid[i];
-      if (jn == 1 && m.jnt_type[ja] == JNT_FREE) {
-        const int qa = m.jnt_qposadr[ja];
+      const int ja = M::body_jntadr(i), jn = M::body_jntnum(i), pid = M::body_parentid(i);
+      if (jn == 1 && M::jnt_type(ja) == JNT_FREE) {
+        const int qa = M::jnt_qposadr(ja);
         for (int k = 0; k < 3; k++) p[k] = qpos[qa + k];
         for (int k = 0; k < 4; k++) q[k] = qpos[qa + 3 + k];
         normalize4(q);
-        for (int k = 0; k < 3; k++) { xanchor[3 * ja + k] = p[k]; xaxis[3 * ja + k] = m.jnt_axis[3 * ja + k]; }
+        for (int k = 0; k < 3; k++) { xanchor[3 * ja + k] = p[k]; xaxis[3 * ja + k] = M::jnt_axis(3 * ja + k); }
       } else {
+        B2_LD3(bpos, body_pos, 3 * i);
+        B2_LD4(bquat, body_quat, 4 * i);
         if (pid) {
-          mat_vec(p, xmat + 9 * pid, m.body_pos + 3 * i);
+          mat_vec(p, xmat + 9 * pid, bpos);
           for (int k = 0; k < 3; k++) p[k] += xpos[3 * pid + k];
-          quat_mul(q, xquat + 4 * pid, m.body_quat + 4 * i);
+          quat_mul(q, xquat + 4 * pid, bquat);
         } else {
-          for (int k = 0; k < 3; k++) p[k] = m.body_pos[3 * i + k];
-          for (int k = 0; k < 4; k++) q[k] = m.body_quat[4 * i + k];
+          for (int k = 0; k < 3; k++) p[k] = bpos[k];
+          for (int k = 0; k < 4; k++) q[k] = bquat[k];
         }
+        B2_UNROLL
         for (int j = ja; j < ja + jn; j++) {
           T anchor[3], axis[3];
-          const int qa = m.jnt_qposadr[j];
-          quat_rot(axis, m.jnt_axis + 3 * j, q);
-          quat_rot(anchor, m.jnt_pos + 3 * j, q);
+          const int qa = M::jnt_qposadr(j);
+          B2_LD3(jaxis, jnt_axis, 3 * j);
+          B2_LD3(jpos, jnt_pos, 3 * j);
+          quat_rot(axis, jaxis, q);
+          quat_rot(anchor, jpos, q);
           for (int k = 0; k < 3; k++) anchor[k] += p[k];
-          const T disp = qpos[qa] - m.qpos0[qa];
-          if (m.jnt_type[j] == JNT_SLIDE) {
+          const T disp = qpos[qa] - M::qpos0(qa);
+          if (M::jnt_type(j) == JNT_SLIDE) {
             for (int k = 0; k < 3; k++) p[k] += axis[k] * disp;
           } else {
             T ql[4], off[3];
-            quat_axis_angle(ql, m.jnt_axis + 3 * j, disp);
+            quat_axis_angle(ql, jaxis, disp);
             quat_mul(q, q, ql);
-            quat_rot(off, m.jnt_pos + 3 * j, q);
+            quat_rot(off, jpos, q);
             for (int k = 0; k < 3; k++) p[k] = anchor[k] - off[k];
           }
           for (int k = 0; k < 3; k++) { xanchor[3 * j + k] = anchor[k]; xaxis[3 * j + k] = axis[k]; }
@@ -87,54 +120,66 @@ struct LaneEnv {
       for (int k = 0; k < 3; k++) xpos[3 * i + k] = p[k];
       for (int k = 0; k < 4; k++) xquat[4 * i + k] = q[k];
       quat_to_mat(xmat + 9 * i, q);
-      // inertial frame
       T qi[4];
-      mat_vec(xipos + 3 * i, xmat + 9 * i, m.body_ipos + 3 * i);
+      B2_LD3(ipos, body_ipos, 3 * i);
+      B2_LD4(iquat, body_iquat, 4 * i);
+      mat_vec(xipos + 3 * i, xmat + 9 * i, ipos);
       for (int k = 0; k < 3; k++) xipos[3 * i + k] += p[k];
-      quat_mul(qi, q, m.body_iquat + 4 * i);
+      quat_mul(qi, q, iquat);
       quat_to_mat(ximat + 9 * i, qi);
     }
-    for (int g = 0; g < m.ngeom; g++) {
-      const int b = m.geom_bodyid[g];
+    B2_UNROLL
+    for (int g = 0; g < M::ngeom(); g++) {
+      const int b = M::geom_bodyid(g);
       T q[4];
-      mat_vec(geom_xpos + 3 * g, xmat + 9 * b, m.geom_pos + 3 * g);
+      B2_LD3(gp, geom_pos, 3 * g);
+      B2_LD4(gq, geom_quat, 4 * g);
+      mat_vec(geom_xpos + 3 * g, xmat + 9 * b, gp);
       for (int k = 0; k < 3; k++) geom_xpos[3 * g + k] += xpos[3 * b + k];
-      quat_mul(q, xquat + 4 * b, m.geom_quat + 4 * g);
+      quat_mul(q, xquat + 4 * b, gq);
       quat_to_mat(geom_xmat + 9 * g, q);
     }
-    for (int s = 0; s < m.nsite; s++) {
-      const int b = m.site_bodyid[s];
+    B2_UNROLL
+    for (int s = 0; s < M::nsite(); s++) {
+      const int b = M::site_bodyid(s);
       T q[4];
-      mat_vec(site_xpos + 3 * s, xmat + 9 * b, m.site_pos + 3 * s);
+      B2_LD3(sp, site_pos, 3 * s);
+      B2_LD4(sq, site_quat, 4 * s);
+      mat_vec(site_xpos + 3 * s, xmat + 9 * b, sp);
       for (int k = 0; k < 3; k++) site_xpos[3 * s + k] += xpos[3 * b + k];
-      quat_mul(q, xquat + 4 * b, m.site_quat + 4 * s);
+      quat_mul(q, xquat + 4 * b, sq);
       quat_to_mat(site_xmat + 9 * s, q);
     }
   }
 
   // subtree centres of mass, com-frame inertias, motion axes
-  __device__ void com_frame() {
-    const int nb = m.nbody;
+  B2_DEV void com_frame() {
+    const int nb = M::nbody();
+    B2_UNROLL
     for (int k = 0; k < 3 * nb; k++) com[k] = 0;
+    B2_UNROLL
     for (int i = nb - 1; i >= 0; i--) {
-      for (int k = 0; k < 3; k++) com[3 * i + k] += xipos[3 * i + k] * m.body_mass[i];
-      if (i) { const int p = m.body_parentid[i]; for (int k = 0; k < 3; k++) com[3 * p + k] += com[3 * i + k]; }
-      if (m.body_subtreemass[i] < Num<T>::minval()) { for (int k = 0; k < 3; k++) com[3 * i + k] = xipos[3 * i + k]; }
-      else { const T inv = T(1) / tmax(Num<T>::minval(), m.body_subtreemass[i]); for (int k = 0; k < 3; k++) com[3 * i + k] *= inv; }
+      for (int k = 0; k < 3; k++) com[3 * i + k] += xipos[3 * i + k] * M::body_mass(i);
+      if (i) { const int p = M::body_parentid(i); for (int k = 0; k < 3; k++) com[3 * p + k] += com[3 * i + k]; }
+      if (M::body_subtreemass(i) < Num<T>::minval()) { for (int k = 0; k < 3; k++) com[3 * i + k] = xipos[3 * i + k]; }
+      else { const T inv = T(1) / tmax(Num<T>::minval(), M::body_subtreemass(i)); for (int k = 0; k < 3; k++) com[3 * i + k] *= inv; }
     }
     for (int k = 0; k < 10; k++) cinert[k] = 0;
+    B2_UNROLL
     for (int i = 1; i < nb; i++) {
       T off[3];
-      const int r = m.body_rootid[i];
+      const int r = M::body_rootid(i);
+      B2_LD3(inertia, body_inertia, 3 * i);
       for (int k = 0; k < 3; k++) off[k] = xipos[3 * i + k] - com[3 * r + k];
-      inert_about(cinert + 10 * i, m.body_inertia + 3 * i, ximat + 9 * i, off, m.body_mass[i]);
+      inert_about(cinert + 10 * i, inertia, ximat + 9 * i, off, M::body_mass(i));
     }
-    for (int j = 0; j < m.njnt; j++) {
-      const int b = m.jnt_bodyid[j], r = m.body_rootid[b];
-      T* cd = cdof + 6 * m.jnt_dofadr[j];
+    B2_UNROLL
+    for (int j = 0; j < M::njnt(); j++) {
+      const int b = M::jnt_bodyid(j), r = M::body_rootid(b);
+      T* cd = cdof + 6 * M::jnt_dofadr(j);
       T off[3];
       for (int k = 0; k < 3; k++) off[k] = com[3 * r + k] - xanchor[3 * j + k];
-      const int t = m.jnt_type[j];
+      const int t = M::jnt_type(j);
       if (t == JNT_FREE) {
         for (int k = 0; k < 18; k++) cd[k] = 0;
         cd[3] = 1; cd[10] = 1; cd[17] = 1;
@@ -154,85 +199,113 @@ struct LaneEnv {
     }
   }
 
-  __device__ void tendons() {
-    const int nv = m.nv;
-    for (int t = 0; t < m.ntendon; t++) {
+  B2_DEV void tendons() {
+    const int nv = M::nv();
+    B2_UNROLL
+    for (int t = 0; t < M::ntendon(); t++) {
       T L = 0;
+      B2_UNROLL
       for (int k = 0; k < nv; k++) ten_J[t * nv + k] = 0;
-      for (int w = m.tendon_adr[t]; w < m.tendon_adr[t] + m.tendon_num[t]; w++) {
-        const int j = m.wrap_jntid[w];
-        L += m.wrap_coef[w] * qpos[m.jnt_qposadr[j]];
-        ten_J[t * nv + m.jnt_dofadr[j]] = m.wrap_coef[w];
+      B2_UNROLL
+      for (int w = M::tendon_adr(t); w < M::tendon_adr(t) + M::tendon_num(t); w++) {
+        const int j = M::wrap_jntid(w);
+        L += M::wrap_coef(w) * qpos[M::jnt_qposadr(j)];
+        ten_J[t * nv + M::jnt_dofadr(j)] = M::wrap_coef(w);
       }
       ten_len[t] = L;
     }
   }
 
-  // composite rigid body algorithm -> dense symmetric M
-  __device__ void mass_matrix() {
-    const int nb = m.nbody, nv = m.nv;
+  // composite rigid body algorithm -> dense symmetric mass matrix
+  B2_DEV void mass_matrix() {
+    const int nb = M::nbody(), nv = M::nv();
     T* crb = spat2;
+    B2_UNROLL
     for (int k = 0; k < 10 * nb; k++) crb[k] = cinert[k];
+    B2_UNROLL
     for (int i = nb - 1; i > 0; i--) {
-      const int p = m.body_parentid[i];
+      const int p = M::body_parentid(i);
       if (p > 0) for (int k = 0; k < 10; k++) crb[10 * p + k] += crb[10 * i + k];
     }
-    for (int k = 0; k < nv * nv; k++) M[k] = 0;
+    B2_UNROLL
+    for (int k = 0; k < nv * nv; k++) Mm[k] = 0;
+    B2_UNROLL
     for (int i = 0; i < nv; i++) {
       T buf[6];
-      M[i * nv + i] = m.dof_armature[i];
-      inert_mul(buf, crb + 10 * m.dof_bodyid[i], cdof + 6 * i);
-      for (int j = i; j >= 0; j = m.dof_parentid[j]) {
+      Mm[i * nv + i] = M::dof_armature(i);
+      inert_mul(buf, crb + 10 * M::dof_bodyid(i), cdof + 6 * i);
+      B2_UNROLL
+      for (int j = i; j >= 0; j--) {
+        if (!is_anc(i, j)) continue;
         T s = 0;
         for (int k = 0; k < 6; k++) s += cdof[6 * j + k] * buf[k];
-        M[i * nv + j] += s;
-        if (j != i) M[j * nv + i] = M[i * nv + j];
+        Mm[i * nv + j] += s;
+        if (j != i) Mm[j * nv + i] = Mm[i * nv + j];
       }
     }
   }
 
   // in-place L'DL factorisation of the matrix held in LD (tree sparsity), dinv <- 1/D
-  __device__ void factor_LD() {
-    const int nv = m.nv;
+  B2_DEV void factor_LD() {
+    const int nv = M::nv();
+    B2_UNROLL
     for (int k = nv - 1; k >= 0; k--) {
       const T dkk = LD[k * nv + k];
-      for (int i = m.dof_parentid[k]; i >= 0; i = m.dof_parentid[i]) {
+      B2_UNROLL
+      for (int i = k - 1; i >= 0; i--) {
+        if (!is_anc(k, i)) continue;
         const T t = LD[k * nv + i] / dkk;
-        for (int j = i; j >= 0; j = m.dof_parentid[j]) LD[i * nv + j] -= t * LD[k * nv + j];
+        B2_UNROLL
+        for (int j = i; j >= 0; j--) if (is_anc(i, j)) LD[i * nv + j] -= t * LD[k * nv + j];
         LD[k * nv + i] = t;
       }
       dinv[k] = T(1) / dkk;
     }
   }
-  __device__ void solve(T* x) const {
-    const int nv = m.nv;
-    for (int i = nv - 1; i >= 0; i--)
-      for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) x[j] -= LD[i * nv + j] * x[i];
+  B2_DEV void solve(T* x) const {
+    const int nv = M::nv();
+    B2_UNROLL
+    for (int i = nv - 1; i >= 0; i--) {
+      B2_UNROLL
+      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[j] -= LD[i * nv + j] * x[i];
+    }
+    B2_UNROLL
     for (int i = 0; i < nv; i++) x[i] *= dinv[i];
-    for (int i = 0; i < nv; i++)
-      for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) x[i] -= LD[i * nv + j] * x[j];
-  }
-  __device__ void mul_M(T* r, const T* v) const {
-    const int nv = m.nv;
-    for (int i = 0; i < nv; i++) r[i] = 0;
+    B2_UNROLL
     for (int i = 0; i < nv; i++) {
-      r[i] += M[i * nv + i] * v[i];
-      for (int j = m.dof_parentid[i]; j >= 0; j = m.dof_parentid[j]) {
-        r[i] += M[i * nv + j] * v[j];
-        r[j] += M[i * nv + j] * v[i];
+      B2_UNROLL
+      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[i] -= LD[i * nv + j] * x[j];
+    }
+  }
+  B2_DEV void mul_M(T* r, const T* v) const {
+    const int nv = M::nv();
+    B2_UNROLL
+    for (int i = 0; i < nv; i++) r[i] = 0;
+    B2_UNROLL
+    for (int i = 0; i < nv; i++) {
+      r[i] += Mm[i * nv + i] * v[i];
+      B2_UNROLL
+      for (int j = i - 1; j >= 0; j--) {
+        if (!is_anc(i, j)) continue;
+        r[i] += Mm[i * nv + j] * v[j];
+        r[j] += Mm[i * nv + j] * v[i];
       }
     }
   }
 
   // point Jacobian columns: calls f(dof, jp[3], jr[3]) for every dof that moves `body`
+  // (descending dof order).  `body` may be a runtime value: the dof loop stays static.
   template <class F>
-  __device__ void for_jac(int body, const T* point, F f) const {
+  B2_DEV void for_jac(int body, const T* point, F f) const {
     T off[3];
-    const int r = m.body_rootid[body];
+    const int r = M::body_rootid(body);
     for (int k = 0; k < 3; k++) off[k] = point[k] - com[3 * r + k];
-    while (body && !m.body_dofnum[body]) body = m.body_parentid[body];
+    while (body && !M::body_dofnum(body)) body = M::body_parentid(body);
     if (!body) return;
-    for (int i = m.body_dofadr[body] + m.body_dofnum[body] - 1; i >= 0; i = m.dof_parentid[i]) {
+    const int last = M::body_dofadr(body) + M::body_dofnum(body) - 1;
+    B2_UNROLL
+    for (int i = M::nv() - 1; i >= 0; i--) {
+      if (i > last || !is_anc(last, i)) continue;
       const T* c = cdof + 6 * i;
       T jp[3];
       cross3(jp, c, off);
@@ -241,21 +314,24 @@ struct LaneEnv {
     }
   }
 
-  __device__ void transmission() {
-    const int nv = m.nv;
-    for (int a = 0; a < m.nu; a++) {
+  B2_DEV void transmission() {
+    const int nv = M::nv();
+    B2_UNROLL
+    for (int a = 0; a < M::nu(); a++) {
       T* mom = act_moment + a * nv;
+      B2_UNROLL
       for (int k = 0; k < nv; k++) mom[k] = 0;
-      const int id = m.actuator_trnid[a];
-      const T* gear = m.actuator_gear + 6 * a;
-      if (m.actuator_trntype[a] == TRN_JOINT) {
-        act_len[a] = qpos[m.jnt_qposadr[id]] * gear[0];
-        mom[m.jnt_dofadr[id]] = gear[0];
+      const int id = M::actuator_trnid(a);
+      if (M::actuator_trntype(a) == TRN_JOINT) {
+        act_len[a] = qpos[M::jnt_qposadr(id)] * M::actuator_gear(6 * a);
+        mom[M::jnt_dofadr(id)] = M::actuator_gear(6 * a);
       } else {
         T wf[3], wt[3];
-        mat_vec(wf, site_xmat + 9 * id, gear);
-        mat_vec(wt, site_xmat + 9 * id, gear + 3);
-        for_jac(m.site_bodyid[id], site_xpos + 3 * id, [&](int d, const T* jp, const T* jr) {
+        B2_LD3(gf, actuator_gear, 6 * a);
+        B2_LD3(gt, actuator_gear, 6 * a + 3);
+        mat_vec(wf, site_xmat + 9 * id, gf);
+        mat_vec(wt, site_xmat + 9 * id, gt);
+        for_jac(M::site_bodyid(id), site_xpos + 3 * id, [&](int d, const T* jp, const T* jr) {
           mom[d] = jp[0] * wf[0] + jp[1] * wf[1] + jp[2] * wf[2] + jr[0] * wt[0] + jr[1] * wt[1] + jr[2] * wt[2];
         });
         act_len[a] = 0;
@@ -263,16 +339,84 @@ struct LaneEnv {
     }
   }
 
-  // ------------------------------------------------------------------ collision
-  __device__ bool add_contact(int pair, T dist, const T* pos, const T* normal, const T* tangent_hint) {
+  // ------------------------------------------------------------------ constraint rows
+  B2_DEV int new_row(int type, int id, T pos, T margin) {
+    if (nefc >= D::NEFC) { flags |= 8; return -1; }
+    const int r = nefc++;
+    R.row_type[r] = (signed char)type; R.row_id[r] = (short)id; R.row_pos[r] = pos; R.row_margin[r] = margin;
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) R.J[r * M::nv() + k] = 0;
+    return r;
+  }
+  // joint and tendon limit rows (they precede contact rows, as in mj_makeConstraint)
+  B2_DEV void limit_rows() {
+    const int nv = M::nv();
+    nefc = 0;
+    B2_UNROLL
+    for (int j = 0; j < M::njnt(); j++) {
+      if (!M::jnt_limited(j) || M::jnt_type(j) < JNT_SLIDE) continue;
+      const T value = qpos[M::jnt_qposadr(j)], margin = M::jnt_margin(j);
+      B2_UNROLL
+      for (int side = -1; side <= 1; side += 2) {
+        const T dist = side * (M::jnt_range(2 * j + (side + 1) / 2) - value);
+        if (dist < margin) { const int r = new_row(ROW_LIMIT_JOINT, j, dist, margin); if (r >= 0) R.J[r * nv + M::jnt_dofadr(j)] = T(-side); }
+      }
+    }
+    B2_UNROLL
+    for (int t = 0; t < M::ntendon(); t++) {
+      if (!M::tendon_limited(t)) continue;
+      const T value = ten_len[t], margin = M::tendon_margin(t);
+      B2_UNROLL
+      for (int side = -1; side <= 1; side += 2) {
+        const T dist = side * (M::tendon_range(2 * t + (side + 1) / 2) - value);
+        if (dist < margin) {
+          const int r = new_row(ROW_LIMIT_TENDON, t, dist, margin);
+          if (r >= 0) { B2_UNROLL for (int k = 0; k < nv; k++) R.J[r * nv + k] = -side * ten_J[t * nv + k]; }
+        }
+      }
+    }
+  }
+  // record one contact of candidate pair `pair` and append its rows: frame * (jac(b2) - jac(b1)),
+  // one row for condim 1, four pyramid edges (normal +- mu * tangent) for condim 3
+  B2_DEV bool add_contact(int pair, T dist, const T* pos, const T* normal, const T* tangent_hint) {
     if (ncon >= D::NCON) { flags |= 8; return false; }
     const int c = ncon++;
-    con_dist[c] = dist; con_pair[c] = (short)pair;
-    for (int k = 0; k < 3; k++) { con_pos[3 * c + k] = pos[k]; con_frame[9 * c + k] = normal[k]; con_frame[9 * c + 3 + k] = tangent_hint ? tangent_hint[k] : T(0); }
-    make_frame(con_frame + 9 * c);
+    R.con_dist[c] = dist; R.con_pair[c] = (short)pair;
+    T fr[9];
+    for (int k = 0; k < 3; k++) { fr[k] = normal[k]; fr[3 + k] = tangent_hint ? tangent_hint[k] : T(0); }
+    make_frame(fr);
+    for (int k = 0; k < 3; k++) R.con_pos[3 * c + k] = pos[k];
+    for (int k = 0; k < 9; k++) R.con_frame[9 * c + k] = fr[k];
+    const T incl = M::pair_margin(pair) - M::pair_gap(pair);
+    if (dist >= incl) return true;  // inside the gap: reported but not constrained
+    const int nv = M::nv();
+    const int b1 = M::geom_bodyid(M::pair_geom1(pair)), b2 = M::geom_bodyid(M::pair_geom2(pair));
+    const int dim = M::pair_dim(pair);
+    const T mu = M::pair_friction(2 * pair);
+    int rows[4];
+    const int nrow = dim == 1 ? 1 : 4;
+    for (int k = 0; k < nrow; k++) {
+      rows[k] = new_row(dim == 1 ? ROW_CONTACT_1 : ROW_CONTACT_PYR, c, dist, incl);
+      if (rows[k] < 0) return false;
+    }
+    // body 1 enters with a minus sign, then body 2 with a plus sign (two explicit passes keep
+    // the body index a compile-time constant under a static provider)
+    auto accumulate = [&](int body, T sgn) {
+      for_jac(body, pos, [&](int d, const T* jp, const T*) {
+        const T jn = sgn * dot3(fr, jp);
+        if (dim == 1) { R.J[rows[0] * nv + d] += jn; return; }
+        const T j1 = sgn * dot3(fr + 3, jp), j2 = sgn * dot3(fr + 6, jp);
+        R.J[rows[0] * nv + d] += jn + mu * j1; R.J[rows[1] * nv + d] += jn - mu * j1;
+        R.J[rows[2] * nv + d] += jn + mu * j2; R.J[rows[3] * nv + d] += jn - mu * j2;
+      });
+    };
+    accumulate(b1, T(-1));
+    accumulate(b2, T(1));
     return true;
   }
-  __device__ void plane_sphere(int pair, T margin, const T* ppos, const T* normal, const T* spos, T radius, const T* hint) {
+
+  // ------------------------------------------------------------------ collision
+  B2_DEV void plane_sphere(int pair, T margin, const T* ppos, const T* normal, const T* spos, T radius, const T* hint) {
     T d[3] = {spos[0] - ppos[0], spos[1] - ppos[1], spos[2] - ppos[2]};
     const T cd = dot3(d, normal);
     if (cd > margin + radius) return;
@@ -281,7 +425,7 @@ struct LaneEnv {
     T pos[3] = {spos[0] + normal[0] * s, spos[1] + normal[1] * s, spos[2] + normal[2] * s};
     add_contact(pair, dist, pos, normal, hint);
   }
-  __device__ int sphere_sphere(int pair, T margin, const T* p1, const T* z1, T r1, const T* p2, const T* z2, T r2) {
+  B2_DEV int sphere_sphere(int pair, T margin, const T* p1, const T* z1, T r1, const T* p2, const T* z2, T r2) {
     T n[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
     const T dsq = dot3(n, n), lim = margin + r1 + r2;
     if (dsq > lim * lim) return 0;
@@ -292,7 +436,7 @@ struct LaneEnv {
     T pos[3] = {p1[0] + n[0] * s, p1[1] + n[1] * s, p1[2] + n[2] * s};
     return add_contact(pair, dist, pos, n, nullptr) ? 1 : 0;
   }
-  __device__ void capsule_capsule(int pair, T margin, const T* p1, const T* z1, T r1, T l1, const T* p2, const T* z2, T r2, T l2) {
+  B2_DEV void capsule_capsule(int pair, T margin, const T* p1, const T* z1, T r1, T l1, const T* p2, const T* z2, T r2, T l2) {
     T dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, v1[3], v2[3];
     const T ma = dot3(z1, z1), mb = -dot3(z1, z2), mc = dot3(z2, z2), u = -dot3(z1, dif), w = dot3(z2, dif);
     const T det = ma * mc - mb * mb;
@@ -308,11 +452,13 @@ struct LaneEnv {
     }
     int n = 0;
     T x;
+    B2_NOUNROLL
     for (int side = 1; side >= -1 && n < 2; side -= 2) {
       x = tclip((w - side * mb * l1) / mc, -l2, l2);
       for (int k = 0; k < 3; k++) { v1[k] = p1[k] + z1[k] * (side * l1); v2[k] = p2[k] + z2[k] * x; }
       n += sphere_sphere(pair, margin, v1, z1, r1, v2, z2, r2);
     }
+    B2_NOUNROLL
     for (int side = 1; side >= -1 && n < 2; side -= 2) {
       x = tclip((u - side * mb * l2) / ma, -l1, l1);
       for (int k = 0; k < 3; k++) { v2[k] = p2[k] + z2[k] * (side * l2); v1[k] = p1[k] + z1[k] * x; }
@@ -320,19 +466,22 @@ struct LaneEnv {
     }
   }
 
-  __device__ void collide() {
+  // narrow phase over the statically filtered candidate pairs; contacts append their rows
+  B2_DEV void collide() {
     ncon = 0;
-    for (int p = 0; p < m.npair; p++) {
-      const int g1 = m.pair_geom1[p], g2 = m.pair_geom2[p];
-      const T margin = m.pair_margin[p];
+    B2_UNROLL
+    for (int p = 0; p < M::npair(); p++) {
+      const int g1 = M::pair_geom1(p), g2 = M::pair_geom2(p);
+      const T margin = M::pair_margin(p);
       const T *p1 = geom_xpos + 3 * g1, *R1 = geom_xmat + 9 * g1, *p2 = geom_xpos + 3 * g2, *R2 = geom_xmat + 9 * g2;
-      const T *s1 = m.geom_size + 3 * g1, *s2 = m.geom_size + 3 * g2;
-      const int t1 = m.geom_type[g1], t2 = m.geom_type[g2];
+      B2_LD3(s1, geom_size, 3 * g1);
+      B2_LD3(s2, geom_size, 3 * g2);
+      const int t1 = M::geom_type(g1), t2 = M::geom_type(g2);
       T z1[3] = {R1[2], R1[5], R1[8]}, z2[3] = {R2[2], R2[5], R2[8]};
       T d[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
       if (t1 == GEOM_PLANE) {
         const T h = dot3(d, z1);
-        if (h > margin + m.geom_rbound[g2]) continue;
+        if (h > margin + M::geom_rbound(g2)) continue;
         if (t2 == GEOM_SPHERE) plane_sphere(p, margin, p1, z1, p2, s2[0], nullptr);
         else if (t2 == GEOM_CAPSULE) {
           T e[3];
@@ -342,6 +491,7 @@ struct LaneEnv {
           plane_sphere(p, margin, p1, z1, e, s2[0], z2);
         } else if (t2 == GEOM_BOX) {
           int cnt = 0;
+          B2_NOUNROLL
           for (int c = 0; c < 8 && cnt < 4; c++) {
             T loc[3] = {(c & 1) ? s2[0] : -s2[0], (c & 2) ? s2[1] : -s2[1], (c & 4) ? s2[2] : -s2[2]}, corner[3];
             mat_vec(corner, R2, loc);
@@ -370,7 +520,7 @@ struct LaneEnv {
           add_contact(p, dist, pos, z1, nullptr);
         }
       } else {
-        const T bound = margin + m.geom_rbound[g1] + m.geom_rbound[g2];
+        const T bound = margin + M::geom_rbound(g1) + M::geom_rbound(g2);
         if (dot3(d, d) > bound * bound) continue;
         if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) sphere_sphere(p, margin, p1, z1, s1[0], p2, z2, s2[0]);
         else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
@@ -384,60 +534,7 @@ struct LaneEnv {
     }
   }
 
-  // ------------------------------------------------------------------ constraint rows
-  __device__ int new_row(int type, int id, T pos, T margin) {
-    if (nefc >= D::NEFC) { flags |= 8; return -1; }
-    const int r = nefc++;
-    row_type[r] = (signed char)type; row_id[r] = (short)id; row_pos[r] = pos; row_margin[r] = margin;
-    for (int k = 0; k < m.nv; k++) J[r * m.nv + k] = 0;
-    return r;
-  }
-  __device__ void make_rows() {
-    const int nv = m.nv;
-    nefc = 0;
-    for (int j = 0; j < m.njnt; j++) {
-      if (!m.jnt_limited[j] || m.jnt_type[j] < JNT_SLIDE) continue;
-      const T value = qpos[m.jnt_qposadr[j]], margin = m.jnt_margin[j];
-      for (int side = -1; side <= 1; side += 2) {
-        const T dist = side * (m.jnt_range[2 * j + (side + 1) / 2] - value);
-        if (dist < margin) { const int r = new_row(ROW_LIMIT_JOINT, j, dist, margin); if (r >= 0) J[r * nv + m.jnt_dofadr[j]] = T(-side); }
-      }
-    }
-    for (int t = 0; t < m.ntendon; t++) {
-      if (!m.tendon_limited[t]) continue;
-      const T value = ten_len[t], margin = m.tendon_margin[t];
-      for (int side = -1; side <= 1; side += 2) {
-        const T dist = side * (m.tendon_range[2 * t + (side + 1) / 2] - value);
-        if (dist < margin) { const int r = new_row(ROW_LIMIT_TENDON, t, dist, margin); if (r >= 0) for (int k = 0; k < nv; k++) J[r * nv + k] = -side * ten_J[t * nv + k]; }
-      }
-    }
-    for (int c = 0; c < ncon; c++) {
-      const int p = con_pair[c];
-      const T incl = m.pair_margin[p] - m.pair_gap[p];
-      if (con_dist[c] >= incl) continue;
-      const int b1 = m.geom_bodyid[m.pair_geom1[p]], b2 = m.geom_bodyid[m.pair_geom2[p]];
-      const T* fr = con_frame + 9 * c;
-      const int dim = m.pair_dim[p];
-      const T mu = m.pair_friction[2 * p];
-      int rows[4];
-      const int nrow = dim == 1 ? 1 : 4;
-      bool ok = true;
-      for (int k = 0; k < nrow; k++) { rows[k] = new_row(dim == 1 ? ROW_CONTACT_1 : ROW_CONTACT_PYR, c, con_dist[c], incl); ok = ok && rows[k] >= 0; }
-      if (!ok) break;
-      // rows hold frame * (jac(b2) - jac(b1)); pyramid edges are normal +- mu * tangent
-      for (int sgn = -1; sgn <= 1; sgn += 2) {
-        for_jac(sgn < 0 ? b1 : b2, con_pos + 3 * c, [&](int d, const T* jp, const T*) {
-          const T jn = sgn * dot3(fr, jp);
-          if (dim == 1) { J[rows[0] * nv + d] += jn; return; }
-          const T j1 = sgn * dot3(fr + 3, jp), j2 = sgn * dot3(fr + 6, jp);
-          J[rows[0] * nv + d] += jn + mu * j1; J[rows[1] * nv + d] += jn - mu * j1;
-          J[rows[2] * nv + d] += jn + mu * j2; J[rows[3] * nv + d] += jn - mu * j2;
-        });
-      }
-    }
-  }
-
-  static __device__ T impedance(const T* si, T pos, T margin) {
+  static B2_DEV T impedance(const T* si, T pos, T margin) {
     const T lo = T(0.0001), hi = T(0.9999);
     const T dmin = tclip(si[0], lo, hi), dmax = tclip(si[1], lo, hi), width = tmax(Num<T>::minval(), si[2]);
     const T mid = tclip(si[3], lo, hi), power = tmax(T(1), si[4]);
@@ -453,91 +550,98 @@ struct LaneEnv {
     return dmin + y * (dmax - dmin);
   }
 
-  // impedance, regulariser D = 1/R and reference acceleration of every row
-  __device__ void row_params() {
-    const int nv = m.nv;
+  // impedance, regulariser D = 1/R and reference acceleration of every row (runtime row loop)
+  B2_DEV void row_params() {
+    const int nv = M::nv();
     int within = 0;  // row index inside the current pyramidal contact
     T Rpy = 0;
+    B2_NOUNROLL
     for (int i = 0; i < nefc; i++) {
-      const T *sr, *si;
-      T diag;
-      const int id = row_id[i], type = row_type[i];
-      if (type == ROW_LIMIT_JOINT) { sr = m.jnt_solref + 2 * id; si = m.jnt_solimp + 5 * id; diag = m.dof_invweight0[m.jnt_dofadr[id]]; }
-      else if (type == ROW_LIMIT_TENDON) { sr = m.tendon_solref + 2 * id; si = m.tendon_solimp + 5 * id; diag = m.tendon_invweight0[id]; }
-      else {
-        const int p = con_pair[id];
-        sr = m.pair_solref + 2 * p; si = m.pair_solimp + 5 * p;
-        const T tran = m.body_invweight0[2 * m.geom_bodyid[m.pair_geom1[p]]] + m.body_invweight0[2 * m.geom_bodyid[m.pair_geom2[p]]];
-        const T mu = m.pair_friction[2 * p];
+      T sr[2], si[5], diag;
+      const int id = R.row_id[i], type = R.row_type[i];
+      if (type == ROW_LIMIT_JOINT) {
+        for (int k = 0; k < 2; k++) sr[k] = M::jnt_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = M::jnt_solimp(5 * id + k);
+        diag = M::dof_invweight0(M::jnt_dofadr(id));
+      } else if (type == ROW_LIMIT_TENDON) {
+        for (int k = 0; k < 2; k++) sr[k] = M::tendon_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = M::tendon_solimp(5 * id + k);
+        diag = M::tendon_invweight0(id);
+      } else {
+        const int p = R.con_pair[id];
+        for (int k = 0; k < 2; k++) sr[k] = M::pair_solref(2 * p + k);
+        for (int k = 0; k < 5; k++) si[k] = M::pair_solimp(5 * p + k);
+        const T tran = M::body_invweight0(2 * M::geom_bodyid(M::pair_geom1(p))) + M::body_invweight0(2 * M::geom_bodyid(M::pair_geom2(p)));
+        const T mu = M::pair_friction(2 * p);
         diag = (type == ROW_CONTACT_1) ? tran : tran + mu * mu * tran;
       }
-      const T pos = row_pos[i], margin = row_margin[i];
+      const T pos = R.row_pos[i], margin = R.row_margin[i];
       const T imp = impedance(si, pos, margin);
       const T dmax = tclip(si[1], T(0.0001), T(0.9999));
       T K, B;
       if (sr[0] > 0) {
-        const T tc = tmax(sr[0], 2 * m.timestep), dr = sr[1];
+        const T tc = tmax(sr[0], 2 * M::timestep()), dr = sr[1];
         K = T(1) / tmax(Num<T>::minval(), dmax * dmax * tc * tc * dr * dr);
         B = T(2) / tmax(Num<T>::minval(), dmax * tc);
       } else {
         K = -sr[0] / tmax(Num<T>::minval(), dmax * dmax);
         B = -sr[1] / tmax(Num<T>::minval(), dmax);
       }
-      T R = tmax(Num<T>::minval(), (T(1) - imp) * diag / imp);
+      T reg = tmax(Num<T>::minval(), (T(1) - imp) * diag / imp);
       if (type == ROW_CONTACT_PYR) {
-        if (within == 0) { const T mu = m.pair_friction[2 * con_pair[id]]; Rpy = 2 * mu * mu * R; }
-        R = Rpy;
+        if (within == 0) { const T mu = M::pair_friction(2 * R.con_pair[id]); Rpy = 2 * mu * mu * reg; }
+        reg = Rpy;
         within = (within + 1) & 3;
       }
-      row_D[i] = T(1) / R;
+      R.row_D[i] = T(1) / reg;
       T vel = 0;
-      for (int k = 0; k < nv; k++) vel += J[i * nv + k] * qvel[k];
-      row_aref[i] = -B * vel - K * imp * (pos - margin);
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) vel += R.J[i * nv + k] * qvel[k];
+      R.row_aref[i] = -B * vel - K * imp * (pos - margin);
     }
   }
 
   // ------------------------------------------------------------------ velocity stage
-  __device__ void velocities() {
+  B2_DEV void velocities() {
     for (int k = 0; k < 6; k++) cvel[k] = 0;
-    for (int i = 1; i < m.nbody; i++) {
+    B2_UNROLL
+    for (int i = 1; i < M::nbody(); i++) {
       T v[6];
-      const int da = m.body_dofadr[i], dn = m.body_dofnum[i], p = m.body_parentid[i];
+      const int da = M::body_dofadr(i), dn = M::body_dofnum(i), p = M::body_parentid(i);
       for (int k = 0; k < 6; k++) v[k] = cvel[6 * p + k];
-      int j = 0;
-      while (j < dn) {
-        if (m.jnt_type[m.dof_jntid[da + j]] == JNT_FREE) {
-          for (int k = 0; k < 18; k++) cdof_dot[6 * da + k] = 0;
-          for (int k = 0; k < 6; k++) {
-            T t = 0;
-            for (int q = 0; q < 3; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
-            v[k] += t;
-          }
-          for (int q = 3; q < 6; q++) cross_motion(cdof_dot + 6 * (da + q), v, cdof + 6 * (da + q));
-          for (int k = 0; k < 6; k++) {
-            T t = 0;
-            for (int q = 3; q < 6; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
-            v[k] += t;
-          }
-          j += 6;
-        } else {
+      if (dn == 6 && M::jnt_type(M::dof_jntid(da)) == JNT_FREE) {
+        for (int k = 0; k < 18; k++) cdof_dot[6 * da + k] = 0;
+        for (int k = 0; k < 6; k++) {
+          T t = 0;
+          for (int q = 0; q < 3; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
+          v[k] += t;
+        }
+        for (int q = 3; q < 6; q++) cross_motion(cdof_dot + 6 * (da + q), v, cdof + 6 * (da + q));
+        for (int k = 0; k < 6; k++) {
+          T t = 0;
+          for (int q = 3; q < 6; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
+          v[k] += t;
+        }
+      } else {
+        B2_UNROLL
+        for (int j = 0; j < dn; j++) {
           cross_motion(cdof_dot + 6 * (da + j), v, cdof + 6 * (da + j));
           for (int k = 0; k < 6; k++) v[k] += cdof[6 * (da + j) + k] * qvel[da + j];
-          j += 1;
         }
       }
       for (int k = 0; k < 6; k++) cvel[6 * i + k] = v[k];
     }
   }
 
-  __device__ void fluid_body(int i) {
-    const T* I = m.body_inertia + 3 * i;
-    const T mass = m.body_mass[i];
+  B2_DEV void fluid_body(int i) {
+    B2_LD3(I, body_inertia, 3 * i);
+    const T mass = M::body_mass(i);
     T box[3], lv[6], lf[6] = {0, 0, 0, 0, 0, 0}, wf[6];
     box[0] = sqrt(tmax(Num<T>::minval(), I[1] + I[2] - I[0]) / mass * T(6));
     box[1] = sqrt(tmax(Num<T>::minval(), I[0] + I[2] - I[1]) / mass * T(6));
     box[2] = sqrt(tmax(Num<T>::minval(), I[0] + I[1] - I[2]) / mass * T(6));
     // com-frame velocity -> local velocity at the inertial frame, minus wind
-    const int r = m.body_rootid[i];
+    const int r = M::body_rootid(i);
     T dif[3], tmp[3], lin[3];
     for (int k = 0; k < 3; k++) dif[k] = xipos[3 * i + k] - com[3 * r + k];
     cross3(tmp, dif, cvel + 6 * i);
@@ -545,21 +649,23 @@ struct LaneEnv {
     matT_vec(lv, ximat + 9 * i, cvel + 6 * i);
     matT_vec(lv + 3, ximat + 9 * i, lin);
     T lw[3];
-    matT_vec(lw, ximat + 9 * i, m.wind);
+    B2_LD3(wind, wind, 0);
+    matT_vec(lw, ximat + 9 * i, wind);
     for (int k = 0; k < 3; k++) lv[3 + k] -= lw[k];
-    if (m.viscosity > 0) {
+    if (M::viscosity() > 0) {
       const T diam = (box[0] + box[1] + box[2]) / T(3);
-      const T ca = -Num<T>::pi() * diam * diam * diam * m.viscosity, cl = T(-3) * Num<T>::pi() * diam * m.viscosity;
+      const T ca = -Num<T>::pi() * diam * diam * diam * M::viscosity(), cl = T(-3) * Num<T>::pi() * diam * M::viscosity();
       for (int k = 0; k < 3; k++) { lf[k] = lv[k] * ca; lf[3 + k] = lv[3 + k] * cl; }
     }
-    if (m.density > 0) {
-      lf[3] -= T(0.5) * m.density * box[1] * box[2] * fabs(lv[3]) * lv[3];
-      lf[4] -= T(0.5) * m.density * box[0] * box[2] * fabs(lv[4]) * lv[4];
-      lf[5] -= T(0.5) * m.density * box[0] * box[1] * fabs(lv[5]) * lv[5];
+    if (M::density() > 0) {
+      const T rho = M::density();
+      lf[3] -= T(0.5) * rho * box[1] * box[2] * fabs(lv[3]) * lv[3];
+      lf[4] -= T(0.5) * rho * box[0] * box[2] * fabs(lv[4]) * lv[4];
+      lf[5] -= T(0.5) * rho * box[0] * box[1] * fabs(lv[5]) * lv[5];
       const T b0 = box[0] * box[0], b1 = box[1] * box[1], b2 = box[2] * box[2];
-      lf[0] -= m.density * box[0] * (b1 * b1 + b2 * b2) * fabs(lv[0]) * lv[0] / T(64);
-      lf[1] -= m.density * box[1] * (b0 * b0 + b2 * b2) * fabs(lv[1]) * lv[1] / T(64);
-      lf[2] -= m.density * box[2] * (b0 * b0 + b1 * b1) * fabs(lv[2]) * lv[2] / T(64);
+      lf[0] -= rho * box[0] * (b1 * b1 + b2 * b2) * fabs(lv[0]) * lv[0] / T(64);
+      lf[1] -= rho * box[1] * (b0 * b0 + b2 * b2) * fabs(lv[1]) * lv[1] / T(64);
+      lf[2] -= rho * box[2] * (b0 * b0 + b1 * b1) * fabs(lv[2]) * lv[2] / T(64);
     }
     mat_vec(wf, ximat + 9 * i, lf);
     mat_vec(wf + 3, ximat + 9 * i, lf + 3);
@@ -568,17 +674,19 @@ struct LaneEnv {
     });
   }
 
-  __device__ void passive_forces() {
-    const int nv = m.nv;
+  B2_DEV void passive_forces() {
+    const int nv = M::nv();
+    B2_UNROLL
     for (int k = 0; k < nv; k++) f_passive[k] = 0;
-    for (int j = 0; j < m.njnt; j++) {
-      const T st = m.jnt_stiffness[j];
+    B2_UNROLL
+    for (int j = 0; j < M::njnt(); j++) {
+      const T st = M::jnt_stiffness(j);
       if (st == 0) continue;
-      const int pa = m.jnt_qposadr[j], da = m.jnt_dofadr[j];
-      if (m.jnt_type[j] >= JNT_SLIDE) f_passive[da] -= st * (qpos[pa] - m.qpos_spring[pa]);
-      else if (m.jnt_type[j] == JNT_FREE) {
-        T q[4], qs[4] = {m.qpos_spring[pa + 3], -m.qpos_spring[pa + 4], -m.qpos_spring[pa + 5], -m.qpos_spring[pa + 6]}, qd[4], dv[3];
-        for (int k = 0; k < 3; k++) f_passive[da + k] -= st * (qpos[pa + k] - m.qpos_spring[pa + k]);
+      const int pa = M::jnt_qposadr(j), da = M::jnt_dofadr(j);
+      if (M::jnt_type(j) >= JNT_SLIDE) f_passive[da] -= st * (qpos[pa] - M::qpos_spring(pa));
+      else if (M::jnt_type(j) == JNT_FREE) {
+        T q[4], qs[4] = {M::qpos_spring(pa + 3), -M::qpos_spring(pa + 4), -M::qpos_spring(pa + 5), -M::qpos_spring(pa + 6)}, qd[4], dv[3];
+        for (int k = 0; k < 3; k++) f_passive[da + k] -= st * (qpos[pa + k] - M::qpos_spring(pa + k));
         for (int k = 0; k < 4; k++) q[k] = qpos[pa + 3 + k];
         normalize4(q);
         quat_mul(qd, qs, q);
@@ -586,34 +694,42 @@ struct LaneEnv {
         for (int k = 0; k < 3; k++) f_passive[da + 3 + k] -= st * dv[k];
       }
     }
-    for (int k = 0; k < nv; k++) f_passive[k] -= m.dof_damping[k] * qvel[k];
-    for (int t = 0; t < m.ntendon; t++) {
-      const T st = m.tendon_stiffness[t], dm = m.tendon_damping[t];
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) f_passive[k] -= M::dof_damping(k) * qvel[k];
+    B2_UNROLL
+    for (int t = 0; t < M::ntendon(); t++) {
+      const T st = M::tendon_stiffness(t), dm = M::tendon_damping(t);
       if (st == 0 && dm == 0) continue;
       T frc = 0, vel = 0;
-      const T lo = m.tendon_lengthspring[2 * t], hi = m.tendon_lengthspring[2 * t + 1], L = ten_len[t];
+      const T lo = M::tendon_lengthspring(2 * t), hi = M::tendon_lengthspring(2 * t + 1), L = ten_len[t];
       if (L > hi) frc = st * (hi - L); else if (L < lo) frc = st * (lo - L);
+      B2_UNROLL
       for (int k = 0; k < nv; k++) vel += ten_J[t * nv + k] * qvel[k];
       frc -= dm * vel;
+      B2_UNROLL
       for (int k = 0; k < nv; k++) f_passive[k] += ten_J[t * nv + k] * frc;
     }
-    if (m.has_fluid)
-      for (int i = 1; i < m.nbody; i++)
-        if (m.body_mass[i] >= Num<T>::minval()) fluid_body(i);
+    if (M::has_fluid()) {
+      B2_UNROLL
+      for (int i = 1; i < M::nbody(); i++)
+        if (M::body_mass(i) >= Num<T>::minval()) fluid_body(i);
+    }
   }
 
   // recursive Newton-Euler without accelerations: Coriolis, centrifugal, gravity
-  __device__ void bias_forces() {
-    const int nb = m.nbody, nv = m.nv;
-    T* cacc = spat;      // 6 per body, overwritten by cfrc as we go
-    T* cfrc = spat2;     // 6 per body (spat2 holds 10 per body)
+  B2_DEV void bias_forces() {
+    const int nb = M::nbody(), nv = M::nv();
+    T* cacc = spat;
+    T* cfrc = spat2;
     cacc[0] = cacc[1] = cacc[2] = 0;
-    cacc[3] = -m.gravity[0]; cacc[4] = -m.gravity[1]; cacc[5] = -m.gravity[2];
+    cacc[3] = -M::gravity(0); cacc[4] = -M::gravity(1); cacc[5] = -M::gravity(2);
     for (int k = 0; k < 6; k++) cfrc[k] = 0;
+    B2_UNROLL
     for (int i = 1; i < nb; i++) {
-      const int da = m.body_dofadr[i], p = m.body_parentid[i];
+      const int da = M::body_dofadr(i), p = M::body_parentid(i);
       T t[6] = {0, 0, 0, 0, 0, 0}, t1[6];
-      for (int j = 0; j < m.body_dofnum[i]; j++)
+      B2_UNROLL
+      for (int j = 0; j < M::body_dofnum(i); j++)
         for (int k = 0; k < 6; k++) t[k] += cdof_dot[6 * (da + j) + k] * qvel[da + j];
       for (int k = 0; k < 6; k++) cacc[6 * i + k] = cacc[6 * p + k] + t[k];
       inert_mul(cfrc + 6 * i, cinert + 10 * i, cacc + 6 * i);
@@ -621,34 +737,41 @@ struct LaneEnv {
       cross_force(t1, cvel + 6 * i, t);
       for (int k = 0; k < 6; k++) cfrc[6 * i + k] += t1[k];
     }
+    B2_UNROLL
     for (int i = nb - 1; i > 0; i--) {
-      const int p = m.body_parentid[i];
+      const int p = M::body_parentid(i);
       if (p) for (int k = 0; k < 6; k++) cfrc[6 * p + k] += cfrc[6 * i + k];
     }
+    B2_UNROLL
     for (int d = 0; d < nv; d++) {
       T s = 0;
-      const int b = m.dof_bodyid[d];
+      const int b = M::dof_bodyid(d);
       for (int k = 0; k < 6; k++) s += cdof[6 * d + k] * cfrc[6 * b + k];
       f_bias[d] = s;
     }
   }
 
   // ------------------------------------------------------------------ smooth acceleration
-  __device__ void smooth_dynamics() {
-    const int nv = m.nv;
+  B2_DEV void smooth_dynamics() {
+    const int nv = M::nv();
     T* f_act = grad;  // scratch: generalized actuator force
+    B2_UNROLL
     for (int k = 0; k < nv; k++) f_act[k] = 0;
-    for (int a = 0; a < m.nu; a++) {
+    B2_UNROLL
+    for (int a = 0; a < M::nu(); a++) {
       T u = ctrl[a];
-      if (m.actuator_ctrllimited[a]) u = tclip(u, m.actuator_ctrlrange[2 * a], m.actuator_ctrlrange[2 * a + 1]);
-      const T* bp = m.actuator_biasprm + 3 * a;
+      if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
       T vel = 0;
+      B2_UNROLL
       for (int k = 0; k < nv; k++) vel += act_moment[a * nv + k] * qvel[k];
-      T force = m.actuator_gainprm[a] * u + bp[0] + bp[1] * act_len[a] + bp[2] * vel;
-      if (m.actuator_forcelimited[a]) force = tclip(force, m.actuator_forcerange[2 * a], m.actuator_forcerange[2 * a + 1]);
-      if (m.actuator_disabled[a]) force = 0;
+      T force = M::actuator_gainprm(a) * u + M::actuator_biasprm(3 * a) + M::actuator_biasprm(3 * a + 1) * act_len[a] +
+                M::actuator_biasprm(3 * a + 2) * vel;
+      if (M::actuator_forcelimited(a)) force = tclip(force, M::actuator_forcerange(2 * a), M::actuator_forcerange(2 * a + 1));
+      if (M::actuator_disabled(a)) force = 0;
+      B2_UNROLL
       for (int k = 0; k < nv; k++) f_act[k] += act_moment[a * nv + k] * force;
     }
+    B2_UNROLL
     for (int k = 0; k < nv; k++) {
       f_smooth[k] = f_passive[k] - f_bias[k];
       f_smooth[k] += f_act[k];
@@ -658,32 +781,34 @@ struct LaneEnv {
   }
 
   // ------------------------------------------------------------------ Newton solver
-  // constraint cost at Jaref; optionally refresh f_con = J' * force
-  __device__ T row_cost(const T* jar, bool write_force) {
-    const int nv = m.nv;
+  // constraint cost at jar; optionally refresh f_con = R.J' * force
+  B2_DEV T row_cost(const T* jar, bool write_force) {
+    const int nv = M::nv();
     T c = 0;
-    if (write_force) for (int k = 0; k < nv; k++) f_con[k] = 0;
+    if (write_force) { B2_UNROLL for (int k = 0; k < nv; k++) f_con[k] = 0; }
+    B2_NOUNROLL
     for (int i = 0; i < nefc; i++) {
       if (jar[i] >= 0) continue;
-      c += T(0.5) * row_D[i] * jar[i] * jar[i];
-      if (write_force) { const T f = -row_D[i] * jar[i]; for (int k = 0; k < nv; k++) f_con[k] += J[i * nv + k] * f; }
+      c += T(0.5) * R.row_D[i] * jar[i] * jar[i];
+      if (write_force) { const T f = -R.row_D[i] * jar[i]; B2_UNROLL for (int k = 0; k < nv; k++) f_con[k] += R.J[i * nv + k] * f; }
     }
     return c;
   }
   struct LsPoint { T alpha, cost, d1, d2; };
-  __device__ void ls_eval(T alpha, LsPoint& p) {
+  B2_DEV void ls_eval(T alpha, LsPoint& p) {
     ls_iter++;
     T q0 = qg0, q1 = qg1, q2 = qg2;
+    B2_NOUNROLL
     for (int i = 0; i < nefc; i++) {
-      if (Jaref[i] + alpha * Jv[i] < 0) {
-        const T dj = row_D[i] * Jaref[i];
-        q0 += T(0.5) * Jaref[i] * dj; q1 += Jv[i] * dj; q2 += T(0.5) * Jv[i] * row_D[i] * Jv[i];
+      if (R.Jaref[i] + alpha * R.Jv[i] < 0) {
+        const T dj = R.row_D[i] * R.Jaref[i];
+        q0 += T(0.5) * R.Jaref[i] * dj; q1 += R.Jv[i] * dj; q2 += T(0.5) * R.Jv[i] * R.row_D[i] * R.Jv[i];
       }
     }
     p.alpha = alpha; p.cost = alpha * alpha * q2 + alpha * q1 + q0; p.d1 = 2 * alpha * q2 + q1; p.d2 = 2 * q2;
     if (p.d2 <= 0) p.d2 = Num<T>::minval();
   }
-  __device__ int ls_bracket(LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
+  B2_DEV int ls_bracket(LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
     int flag = 0;
     for (int i = 0; i < 3; i++) {
       if (p.d1 < 0 && cand[i].d1 < 0 && p.d1 < cand[i].d1) { p = cand[i]; flag = 1; }
@@ -693,19 +818,22 @@ struct LaneEnv {
     return flag;
   }
   // exact 1-D minimisation of the piecewise-quadratic cost along `search`
-  __device__ T line_search() {
-    const int nv = m.nv;
+  B2_DEV T line_search() {
+    const int nv = M::nv();
     LsPoint p0, p1, p2, pmid, p1n, p2n;
     ls_iter = 0;
     T sn = 0;
+    B2_UNROLL
     for (int k = 0; k < nv; k++) sn += search[k] * search[k];
     sn = sqrt(sn);
     if (sn < Num<T>::minval()) return 0;
-    const T scale = T(1) / (m.meaninertia * T(nv > 1 ? nv : 1));
-    const T gtol = m.tolerance * m.ls_tolerance * sn / scale;
+    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
+    const T gtol = M::tolerance() * M::ls_tolerance() * sn / scale;
     mul_M(Mv, search);
-    for (int i = 0; i < nefc; i++) { T s = 0; for (int k = 0; k < nv; k++) s += J[i * nv + k] * search[k]; Jv[i] = s; }
+    B2_NOUNROLL
+    for (int i = 0; i < nefc; i++) { T s = 0; B2_UNROLL for (int k = 0; k < nv; k++) s += R.J[i * nv + k] * search[k]; R.Jv[i] = s; }
     T a = 0, b = 0, e = 0;
+    B2_UNROLL
     for (int k = 0; k < nv; k++) { a += search[k] * Ma[k]; b += f_smooth[k] * search[k]; e += search[k] * Mv[k]; }
     qg0 = gauss; qg1 = a - b; qg2 = T(0.5) * e;
     ls_eval(0, p0);
@@ -714,7 +842,8 @@ struct LaneEnv {
     if (fabs(p1.d1) < gtol) return p1.alpha;
     const int dir = p1.d1 < 0 ? 1 : -1;
     bool p2up = false;
-    const int maxls = m.ls_iterations;
+    const int maxls = M::ls_iterations();
+    B2_NOUNROLL
     while (p1.d1 * dir <= -gtol && ls_iter < maxls) {
       p2 = p1; p2up = true;
       ls_eval(p1.alpha - p1.d1 / p1.d2, p1);
@@ -723,6 +852,7 @@ struct LaneEnv {
     if (ls_iter >= maxls || !p2up) return p1.alpha;
     p2n = p1;
     ls_eval(p1.alpha - p1.d1 / p1.d2, p1n);
+    B2_NOUNROLL
     while (ls_iter < maxls) {
       ls_eval(T(0.5) * (p1.alpha + p2.alpha), pmid);
       LsPoint cand[3] = {p1n, p2n, pmid};
@@ -737,120 +867,161 @@ struct LaneEnv {
     if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
     return 0;
   }
-  __device__ void newton_refresh() {  // cost, forces, gradient, Newton direction at the current qacc
-    const int nv = m.nv;
-    cost = row_cost(Jaref, true);
+  // cost, forces, gradient and Newton direction at the current qacc
+  B2_DEV void newton_refresh() {
+    const int nv = M::nv();
+    cost = row_cost(R.Jaref, true);
     T g = 0;
+    B2_UNROLL
     for (int k = 0; k < nv; k++) g += (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]);
     gauss = T(0.5) * g;
     cost += gauss;
+    B2_UNROLL
     for (int k = 0; k < nv; k++) grad[k] = Ma[k] - f_smooth[k] - f_con[k];
-    // H = M + J' D_active J  (lower triangle in LD), dense Cholesky, Mgrad = H^-1 grad
+    // H = M + R.J' D_active R.J  (lower triangle, held in LD), dense Cholesky, Mgrad = H^-1 grad
     T* H = LD;
-    for (int k = 0; k < nv * nv; k++) H[k] = M[k];
+    B2_UNROLL
+    for (int k = 0; k < nv * nv; k++) H[k] = Mm[k];
+    B2_NOUNROLL
     for (int i = 0; i < nefc; i++) {
-      if (Jaref[i] >= 0) continue;
-      const T* Ji = J + i * nv;
+      if (R.Jaref[i] >= 0) continue;
+      const T* Ji = R.J + i * nv;
+      B2_UNROLL
       for (int r = 0; r < nv; r++) {
         if (Ji[r] == 0) continue;
-        const T s = row_D[i] * Ji[r];
+        const T s = R.row_D[i] * Ji[r];
+        B2_UNROLL
         for (int q = 0; q <= r; q++) H[r * nv + q] += s * Ji[q];
       }
     }
+    B2_UNROLL
     for (int j = 0; j < nv; j++) {
       T t = H[j * nv + j];
+      B2_UNROLL
       for (int k = 0; k < j; k++) t -= H[j * nv + k] * H[j * nv + k];
       if (t < Num<T>::minval()) t = Num<T>::minval();
       const T djj = sqrt(t);
       H[j * nv + j] = djj;
       const T inv = T(1) / djj;
+      B2_UNROLL
       for (int i = j + 1; i < nv; i++) {
         T s = H[i * nv + j];
+        B2_UNROLL
         for (int k = 0; k < j; k++) s -= H[i * nv + k] * H[j * nv + k];
         H[i * nv + j] = s * inv;
       }
     }
+    B2_UNROLL
     for (int i = 0; i < nv; i++) {
       T s = grad[i];
+      B2_UNROLL
       for (int k = 0; k < i; k++) s -= H[i * nv + k] * Mgrad[k];
       Mgrad[i] = s / H[i * nv + i];
     }
+    B2_UNROLL
     for (int i = nv - 1; i >= 0; i--) {
       T s = Mgrad[i];
+      B2_UNROLL
       for (int k = i + 1; k < nv; k++) s -= H[k * nv + i] * Mgrad[k];
       Mgrad[i] = s / H[i * nv + i];
     }
   }
-  __device__ void constrained_acceleration() {
-    const int nv = m.nv;
+  // warm-started Newton solve (only entered when at least one row exists)
+  B2_DEV void newton_solve() {
+    const int nv = M::nv();
+    // warm start: keep qacc_warmstart only if it is cheaper than the unconstrained acceleration
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) qacc[k] = warm[k];
+    B2_NOUNROLL
+    for (int i = 0; i < nefc; i++) { T s = 0; B2_UNROLL for (int k = 0; k < nv; k++) s += R.J[i * nv + k] * qacc[k]; R.Jaref[i] = s - R.row_aref[i]; }
+    T cw = row_cost(R.Jaref, false);
+    mul_M(Ma, qacc);
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) cw += T(0.5) * (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]);
+    B2_NOUNROLL
+    for (int i = 0; i < nefc; i++) { T s = 0; B2_UNROLL for (int k = 0; k < nv; k++) s += R.J[i * nv + k] * a_smooth[k]; R.Jv[i] = s - R.row_aref[i]; }
+    const T cs = row_cost(R.Jv, false);
+    if (cw > cs) {
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) qacc[k] = a_smooth[k];
+      B2_NOUNROLL
+      for (int i = 0; i < nefc; i++) R.Jaref[i] = R.Jv[i];
+      mul_M(Ma, qacc);
+    }
+    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
+    T old = 0;
+    bool first = true;
+    // one refresh / one line-search call site: the loop is the upstream iteration unrolled by half a turn
+    B2_NOUNROLL
+    while (true) {
+      newton_refresh();
+      if (!first) {
+        T gn = 0;
+        B2_UNROLL
+        for (int k = 0; k < nv; k++) gn += grad[k] * grad[k];
+        niter++;
+        if (scale * (old - cost) < M::tolerance() || scale * sqrt(gn) < M::tolerance()) break;
+      }
+      first = false;
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) search[k] = -Mgrad[k];
+      if (niter >= M::iterations()) break;
+      const T alpha = line_search();
+      if (alpha == 0) break;
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
+      B2_NOUNROLL
+      for (int i = 0; i < nefc; i++) R.Jaref[i] += alpha * R.Jv[i];
+      old = cost;
+    }
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) warm[k] = qacc[k];
+  }
+  B2_DEV void constrained_acceleration() {
+    const int nv = M::nv();
     niter = 0;
     if (!nefc) {
+      B2_UNROLL
       for (int k = 0; k < nv; k++) { qacc[k] = a_smooth[k]; warm[k] = a_smooth[k]; f_con[k] = 0; }
       return;
     }
-    // warm start: keep qacc_warmstart only if it is cheaper than the unconstrained acceleration
-    for (int k = 0; k < nv; k++) qacc[k] = warm[k];
-    for (int i = 0; i < nefc; i++) { T s = 0; for (int k = 0; k < nv; k++) s += J[i * nv + k] * qacc[k]; Jaref[i] = s - row_aref[i]; }
-    T cw = row_cost(Jaref, false);
-    mul_M(Ma, qacc);
-    for (int k = 0; k < nv; k++) cw += T(0.5) * (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]);
-    for (int i = 0; i < nefc; i++) { T s = 0; for (int k = 0; k < nv; k++) s += J[i * nv + k] * a_smooth[k]; Jv[i] = s - row_aref[i]; }
-    const T cs = row_cost(Jv, false);
-    if (cw > cs) {
-      for (int k = 0; k < nv; k++) qacc[k] = a_smooth[k];
-      for (int i = 0; i < nefc; i++) Jaref[i] = Jv[i];
-      mul_M(Ma, qacc);
-    }
-    newton_refresh();
-    for (int k = 0; k < nv; k++) search[k] = -Mgrad[k];
-    const T scale = T(1) / (m.meaninertia * T(nv > 1 ? nv : 1));
-    while (niter < m.iterations) {
-      const T alpha = line_search();
-      if (alpha == 0) break;
-      for (int k = 0; k < nv; k++) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
-      for (int i = 0; i < nefc; i++) Jaref[i] += alpha * Jv[i];
-      const T old = cost;
-      newton_refresh();
-      T gn = 0;
-      for (int k = 0; k < nv; k++) gn += grad[k] * grad[k];
-      niter++;
-      if (scale * (old - cost) < m.tolerance || scale * sqrt(gn) < m.tolerance) break;
-      for (int k = 0; k < nv; k++) search[k] = -Mgrad[k];
-    }
-    for (int k = 0; k < nv; k++) warm[k] = qacc[k];
+    row_params();
+    newton_solve();
   }
 
   // ------------------------------------------------------------------ forward + integrators
-  __device__ void forward() {
+  B2_DEV void forward() {
     kinematics();
     com_frame();
     tendons();
     mass_matrix();
-    for (int k = 0; k < m.nv * m.nv; k++) LD[k] = M[k];
+    B2_UNROLL
+    for (int k = 0; k < M::nv() * M::nv(); k++) LD[k] = Mm[k];
     factor_LD();
+    limit_rows();
     collide();
-    make_rows();
     transmission();
     velocities();
     passive_forces();
-    row_params();
     bias_forces();
     smooth_dynamics();
     constrained_acceleration();
   }
-  __device__ void integrate_pos(T* q, const T* v, T dt) const {
-    for (int j = 0; j < m.njnt; j++) {
-      const int pa = m.jnt_qposadr[j], va = m.jnt_dofadr[j];
-      if (m.jnt_type[j] == JNT_FREE) {
+  B2_DEV void integrate_pos(T* q, const T* v, T dt) const {
+    B2_UNROLL
+    for (int j = 0; j < M::njnt(); j++) {
+      const int pa = M::jnt_qposadr(j), va = M::jnt_dofadr(j);
+      if (M::jnt_type(j) == JNT_FREE) {
         for (int k = 0; k < 3; k++) q[pa + k] += dt * v[va + k];
         quat_integrate(q + pa + 3, v + va + 3, dt);
       } else q[pa] += dt * v[va];
     }
   }
-  __device__ void differentiate_pos(T* out, T dt, const T* q1, const T* q2) const {
-    for (int j = 0; j < m.njnt; j++) {
-      const int pa = m.jnt_qposadr[j], va = m.jnt_dofadr[j];
-      if (m.jnt_type[j] == JNT_FREE) {
+  B2_DEV void differentiate_pos(T* out, T dt, const T* q1, const T* q2) const {
+    B2_UNROLL
+    for (int j = 0; j < M::njnt(); j++) {
+      const int pa = M::jnt_qposadr(j), va = M::jnt_dofadr(j);
+      if (M::jnt_type(j) == JNT_FREE) {
         for (int k = 0; k < 3; k++) out[va + k] = (q2[pa + k] - q1[pa + k]) / dt;
         T neg[4] = {q1[pa + 3], -q1[pa + 4], -q1[pa + 5], -q1[pa + 6]}, dq[4];
         quat_mul(dq, neg, q2 + pa + 3);
@@ -858,64 +1029,88 @@ struct LaneEnv {
       } else out[va] = (q2[pa] - q1[pa]) / dt;
     }
   }
-  __device__ void check_state() {
-    for (int k = 0; k < m.nq; k++) if (!(fabs(qpos[k]) <= T(1e10))) flags |= 1;
-    for (int k = 0; k < m.nv; k++) if (!(fabs(qvel[k]) <= T(1e10))) flags |= 2;
+  B2_DEV void check_state() {
+    B2_UNROLL
+    for (int k = 0; k < M::nq(); k++) if (!(fabs(qpos[k]) <= T(1e10))) flags |= 1;
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) if (!(fabs(qvel[k]) <= T(1e10))) flags |= 2;
   }
-  __device__ void euler() {
-    const int nv = m.nv;
-    const T h = m.timestep;
+  B2_DEV void euler() {
+    const int nv = M::nv();
+    const T h = M::timestep();
     T* acc = grad;
-    if (!m.has_dofdamping) { for (int k = 0; k < nv; k++) acc[k] = qacc[k]; }
+    if (!M::has_dofdamping()) { B2_UNROLL for (int k = 0; k < nv; k++) acc[k] = qacc[k]; }
     else {
       // (M + h*diag(damping)) acc = f_smooth + f_con   (implicit in joint damping)
-      for (int k = 0; k < nv * nv; k++) LD[k] = M[k];
-      for (int k = 0; k < nv; k++) LD[k * nv + k] += h * m.dof_damping[k];
+      B2_UNROLL
+      for (int k = 0; k < nv * nv; k++) LD[k] = Mm[k];
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) LD[k * nv + k] += h * M::dof_damping(k);
       factor_LD();
+      B2_UNROLL
       for (int k = 0; k < nv; k++) acc[k] = f_smooth[k] + f_con[k];
       solve(acc);
     }
+    B2_UNROLL
     for (int k = 0; k < nv; k++) qvel[k] += acc[k] * h;
     integrate_pos(qpos, qvel, h);
   }
-  __device__ void rk4() {
-    const int nq = m.nq, nv = m.nv;
-    const T h = m.timestep;
+  // classical RK4 over (qpos, qvel) with tangent-space position updates; the stage loop is
+  // kept rolled so forward() is instantiated once here
+  B2_DEV void rk4() {
+    const int nq = M::nq(), nv = M::nv();
+    const T h = M::timestep();
     const T A[9] = {T(0.5), 0, 0, 0, T(0.5), 0, 0, 0, 1}, B[4] = {T(1) / 6, T(1) / 3, T(1) / 3, T(1) / 6};
     T X[4][D::NQ + D::NV], F[4][D::NV], dX[2 * D::NV];
+    B2_UNROLL
     for (int k = 0; k < nq; k++) X[0][k] = qpos[k];
+    B2_UNROLL
     for (int k = 0; k < nv; k++) { X[0][nq + k] = qvel[k]; F[0][k] = qacc[k]; }
+    B2_NOUNROLL
     for (int i = 1; i < 4; i++) {
+      B2_UNROLL
       for (int k = 0; k < 2 * nv; k++) dX[k] = 0;
       for (int j = 0; j < i; j++) {
         const T a = A[(i - 1) * 3 + j];
+        B2_UNROLL
         for (int k = 0; k < nv; k++) { dX[k] += a * X[j][nq + k]; dX[nv + k] += a * F[j][k]; }
       }
-      for (int k = 0; k < nq + nv; k++) X[i][k] = X[0][k];
-      integrate_pos(X[i], dX, h);
-      for (int k = 0; k < nv; k++) X[i][nq + k] += h * dX[nv + k];
-      for (int k = 0; k < nq; k++) qpos[k] = X[i][k];
-      for (int k = 0; k < nv; k++) qvel[k] = X[i][nq + k];
+      B2_UNROLL
+      for (int k = 0; k < nq; k++) qpos[k] = X[0][k];
+      integrate_pos(qpos, dX, h);
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) qvel[k] = X[0][nq + k] + h * dX[nv + k];
+      B2_UNROLL
+      for (int k = 0; k < nq; k++) X[i][k] = qpos[k];
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) X[i][nq + k] = qvel[k];
       forward();
+      B2_UNROLL
       for (int k = 0; k < nv; k++) F[i][k] = qacc[k];
     }
+    B2_UNROLL
     for (int k = 0; k < 2 * nv; k++) dX[k] = 0;
-    for (int j = 0; j < 4; j++)
+    for (int j = 0; j < 4; j++) {
+      B2_UNROLL
       for (int k = 0; k < nv; k++) { dX[k] += B[j] * X[j][nq + k]; dX[nv + k] += B[j] * F[j][k]; }
+    }
+    B2_UNROLL
     for (int k = 0; k < nq; k++) qpos[k] = X[0][k];
+    B2_UNROLL
     for (int k = 0; k < nv; k++) qvel[k] = X[0][nq + k] + dX[nv + k] * h;
     integrate_pos(qpos, dX, h);
   }
-  // one mj_step; when `snapshot` is set it is invoked after the pre-integration forward pass
+  // one mj_step; `snapshot` is invoked after the pre-integration forward pass
   template <class Snap>
-  __device__ void step(Snap snapshot) {
+  B2_DEV void step(Snap snapshot) {
     check_state();
     forward();
-    for (int k = 0; k < m.nv; k++) if (!(fabs(qacc[k]) <= T(1e10))) flags |= 4;
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) if (!(fabs(qacc[k]) <= T(1e10))) flags |= 4;
     snapshot();
-    if (m.integrator == 1) rk4(); else euler();
+    if (M::integrator() == 1) rk4(); else euler();
   }
-  __device__ void step() { step([] {}); }
+  B2_DEV void step() { step([] {}); }
 };
 
 }  // namespace b2

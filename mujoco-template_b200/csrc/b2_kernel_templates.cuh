@@ -1,0 +1,230 @@
+// Kernel templates of the lane engine, parameterised on <arithmetic type T, capacities D,
+// model provider M>.  Instantiated by the generic translation units (runtime provider, one per
+// precision) and by the generated per-model translation units (static providers).
+//
+// SoA layout: element (k, e) of a (dim, nenv) array is base[k * nenv + e]; a warp reads 32
+// consecutive envs of one component -> fully coalesced 256 B (FP64) transactions.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/b2mj.h"
+#include "b2_engine.cuh"
+
+namespace b2 {
+
+template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
+template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias; int *ncon, *nefc, *solver_iter; };
+
+template <typename T>
+static inline StateDev<T> to_dev(const b2_state* s) {
+  StateDev<T> d;
+  d.qpos = (T*)s->qpos; d.qvel = (T*)s->qvel; d.ctrl = (T*)s->ctrl; d.warm = (T*)s->qacc_warmstart; d.flags = s->flags;
+  return d;
+}
+template <typename T>
+static inline DerivedDev<T> to_dev(const b2_derived* o) {
+  DerivedDev<T> d;
+  memset(&d, 0, sizeof(d));
+  if (o) {
+    d.xpos = (T*)o->xpos; d.xquat = (T*)o->xquat; d.xipos = (T*)o->xipos; d.geom_xpos = (T*)o->geom_xpos;
+    d.site_xpos = (T*)o->site_xpos; d.subtree_com = (T*)o->subtree_com; d.qacc = (T*)o->qacc;
+    d.qfrc_bias = (T*)o->qfrc_bias; d.ncon = o->ncon; d.nefc = o->nefc; d.solver_iter = o->solver_iter;
+  }
+  return d;
+}
+
+template <typename T, class D, class M>
+B2_DEV void load_state(LaneEnv<T, D, M>& env, const StateDev<T>& st, int N, int e) {
+  B2_UNROLL
+  for (int k = 0; k < M::nq(); k++) env.qpos[k] = st.qpos[(size_t)k * N + e];
+  B2_UNROLL
+  for (int k = 0; k < M::nv(); k++) env.qvel[k] = st.qvel[(size_t)k * N + e];
+  B2_UNROLL
+  for (int k = 0; k < M::nu(); k++) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
+  B2_UNROLL
+  for (int k = 0; k < M::nv(); k++) env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0);
+}
+template <typename T, class D, class M>
+B2_DEV void store_derived(const LaneEnv<T, D, M>& env, const DerivedDev<T>& o, int N, int e) {
+  if (o.xpos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xpos[(size_t)k * N + e] = env.xpos[k]; }
+  if (o.xquat) { B2_UNROLL for (int k = 0; k < 4 * M::nbody(); k++) o.xquat[(size_t)k * N + e] = env.xquat[k]; }
+  if (o.xipos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xipos[(size_t)k * N + e] = env.xipos[k]; }
+  if (o.geom_xpos) { B2_UNROLL for (int k = 0; k < 3 * M::ngeom(); k++) o.geom_xpos[(size_t)k * N + e] = env.geom_xpos[k]; }
+  if (o.site_xpos) { B2_UNROLL for (int k = 0; k < 3 * M::nsite(); k++) o.site_xpos[(size_t)k * N + e] = env.site_xpos[k]; }
+  if (o.subtree_com) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.subtree_com[(size_t)k * N + e] = env.com[k]; }
+  if (o.qacc) { B2_UNROLL for (int k = 0; k < M::nv(); k++) o.qacc[(size_t)k * N + e] = env.qacc[k]; }
+  if (o.qfrc_bias) { B2_UNROLL for (int k = 0; k < M::nv(); k++) o.qfrc_bias[(size_t)k * N + e] = env.f_bias[k]; }
+  if (o.ncon) o.ncon[e] = env.ncon;
+  if (o.nefc) o.nefc[e] = env.nefc;
+  if (o.solver_iter) o.solver_iter[e] = env.niter;
+}
+
+// nsteps x mj_step with ctrl held; nsteps == 0 means mj_forward (no integration).
+// The step loop is rolled: one inlined copy of the physics per kernel.
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  load_state(env, st, N, e);
+  const int total = nsteps > 0 ? nsteps : 1;
+  B2_NOUNROLL
+  for (int s = 0; s < total; s++) {
+    env.check_state();
+    env.forward();
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
+    if (want_derived && s == total - 1) store_derived(env, out, N, e);
+    if (nsteps > 0) { if (M::integrator() == 1) env.rk4(); else env.euler(); }
+  }
+  if (nsteps > 0) {
+    B2_UNROLL
+    for (int k = 0; k < M::nq(); k++) st.qpos[(size_t)k * N + e] = env.qpos[k];
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) st.qvel[(size_t)k * N + e] = env.qvel[k];
+  }
+  if (st.warm) { B2_UNROLL for (int k = 0; k < M::nv(); k++) st.warm[(size_t)k * N + e] = env.warm[k]; }
+  if (st.flags && env.flags) st.flags[e] |= env.flags;
+}
+
+// Centred / one-sided finite differences of one step: one thread per (env, input column).
+// Columns 0..nv-1 perturb tangent-space position, nv..2nv-1 velocity, 2nv..2nv+nu-1 control.
+// Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state and
+// qacc_warmstart of every rollout start from the saved nominal values; control columns fall
+// back to one-sided differences at the ctrlrange bounds.
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_linearize(StateDev<T> st, int N, T eps, int centered, T* A, T* B) {
+  constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * (ndx + nu)) return;
+  const int e = (int)(idx % N), c = (int)(idx / N);
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  T q0[NQ], v0[NV], u0[NU], w0[NV], yp[NQ + NV], ym[NQ + NV], yn[NQ + NV], col[2 * NV];
+  B2_UNROLL
+  for (int k = 0; k < nq; k++) q0[k] = st.qpos[(size_t)k * N + e];
+  B2_UNROLL
+  for (int k = 0; k < nv; k++) { v0[k] = st.qvel[(size_t)k * N + e]; w0[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
+  B2_UNROLL
+  for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
+  int kind, i;
+  bool fwd = true, back = centered != 0;
+  if (c < nv) { kind = 1; i = c; }
+  else if (c < ndx) { kind = 2; i = c - nv; }
+  else {
+    kind = 3; i = c - ndx;
+    int lim = 0;
+    T lo = 0, hi = 0, u = 0;
+    B2_UNROLL
+    for (int a = 0; a < nu; a++)
+      if (a == i) { lim = M::actuator_ctrllimited(a); lo = M::actuator_ctrlrange(2 * a); hi = M::actuator_ctrlrange(2 * a + 1); u = u0[a]; }
+    fwd = !lim || (u >= lo && u <= hi && u + eps >= lo && u + eps <= hi);
+    back = (centered || !fwd) && (!lim || (u - eps >= lo && u - eps <= hi && u >= lo && u <= hi));
+  }
+  const int need = (fwd ? 1 : 0) | (back ? 2 : 0) | ((fwd != back) ? 4 : 0);  // plus, minus, nominal rollouts
+  // rolled phase loop: the physics is instantiated once; all array indices stay static
+  B2_NOUNROLL
+  for (int phase = 0; phase < 3; phase++) {
+    if (!((need >> phase) & 1)) continue;
+    const T delta = phase == 0 ? eps : (phase == 1 ? -eps : T(0));
+    B2_UNROLL
+    for (int k = 0; k < nq; k++) env.qpos[k] = q0[k];
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) { env.qvel[k] = v0[k] + ((kind == 2 && k == i) ? delta : T(0)); env.warm[k] = w0[k]; }
+    B2_UNROLL
+    for (int k = 0; k < nu; k++) env.ctrl[k] = u0[k] + ((kind == 3 && k == i) ? delta : T(0));
+    if (kind == 1 && phase < 2) {
+      T dp[NV];
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) dp[k] = (k == i) ? T(1) : T(0);
+      env.integrate_pos(env.qpos, dp, delta);
+    }
+    env.step();
+    B2_UNROLL
+    for (int k = 0; k < nq + nv; k++) {
+      const T val = k < nq ? env.qpos[k < nq ? k : 0] : env.qvel[k >= nq ? k - nq : 0];
+      if (phase == 0) yp[k] = val; else if (phase == 1) ym[k] = val; else yn[k] = val;
+    }
+  }
+  if (fwd || back) {
+    const T h = (fwd && back) ? 2 * eps : eps;
+    T s1[NQ + NV], s2[NQ + NV];
+    B2_UNROLL
+    for (int k = 0; k < nq + nv; k++) { s1[k] = back ? ym[k] : yn[k]; s2[k] = fwd ? yp[k] : yn[k]; }
+    env.differentiate_pos(col, h, s1, s2);
+    const T ih = T(1) / h;
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) col[nv + k] = (s2[nq + k] - s1[nq + k]) * ih;
+  } else {
+    B2_UNROLL
+    for (int k = 0; k < ndx; k++) col[k] = 0;
+  }
+  if (c < ndx) { if (A) { B2_UNROLL for (int r = 0; r < ndx; r++) A[((size_t)r * ndx + c) * N + e] = col[r]; } }
+  else if (B) { B2_UNROLL for (int r = 0; r < ndx; r++) B[((size_t)r * nu + (c - ndx)) * N + e] = col[r]; }
+  if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
+}
+
+// point Jacobians from the current qpos (mj_jacSite/Body/BodyCom/SubtreeCom)
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kind, int objid, T* jacp, T* jacr) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  const int nv = M::nv();
+  B2_UNROLL
+  for (int k = 0; k < M::nq(); k++) env.qpos[k] = st.qpos[(size_t)k * N + e];
+  env.kinematics();
+  env.com_frame();
+  T jp[3 * D::NV], jr[3 * D::NV];
+  B2_UNROLL
+  for (int k = 0; k < 3 * nv; k++) { jp[k] = 0; jr[k] = 0; }
+  auto put = [&](int d, const T* p, const T* r) {
+    for (int a = 0; a < 3; a++) { jp[a * nv + d] = p[a]; jr[a * nv + d] = r[a]; }
+  };
+  if (kind == B2_JAC_SITE) env.for_jac(M::site_bodyid(objid), env.site_xpos + 3 * objid, put);
+  else if (kind == B2_JAC_BODY) env.for_jac(objid, env.xpos + 3 * objid, put);
+  else if (kind == B2_JAC_BODYCOM) env.for_jac(objid, env.xipos + 3 * objid, put);
+  else {
+    B2_NOUNROLL
+    for (int b = objid; b < M::nbody(); b++) {
+      if (b > objid && M::body_parentid(b) < objid) break;
+      const T mass = M::body_mass(b);
+      env.for_jac(b, env.xipos + 3 * b, [&](int d, const T* p, const T*) {
+        for (int a = 0; a < 3; a++) jp[a * nv + d] += p[a] * mass;
+      });
+    }
+    const T inv = T(1) / M::body_subtreemass(objid);
+    B2_UNROLL
+    for (int k = 0; k < 3 * nv; k++) jp[k] *= inv;
+  }
+  if (jacp) { B2_UNROLL for (int k = 0; k < 3 * nv; k++) jacp[(size_t)k * N + e] = jp[k]; }
+  if (jacr) { B2_UNROLL for (int k = 0; k < 3 * nv; k++) jacr[(size_t)k * N + e] = jr[k]; }
+}
+
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T dt, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  for (int k = 0; k < M::nq(); k++) env.qpos[k] = qpos[(size_t)k * N + e];
+  for (int k = 0; k < M::nv(); k++) env.qvel[k] = qvel[(size_t)k * N + e];
+  env.integrate_pos(env.qpos, env.qvel, dt);
+  for (int k = 0; k < M::nq(); k++) qpos[(size_t)k * N + e] = env.qpos[k];
+}
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_differentiate_pos(T* out, T dt, const T* q1, const T* q2, int N) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  T a[D::NQ], b[D::NQ];
+  for (int k = 0; k < M::nq(); k++) { a[k] = q1[(size_t)k * N + e]; b[k] = q2[(size_t)k * N + e]; }
+  env.differentiate_pos(env.qvel, dt, a, b);
+  for (int k = 0; k < M::nv(); k++) out[(size_t)k * N + e] = env.qvel[k];
+}
+
+}  // namespace b2

@@ -5,6 +5,7 @@
 
 namespace b2 {
 #define B2_DECL(SUF)                                                                                                       \
+  double b2k_fma_peak##SUF(void* stream);                                                                                  \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
   int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);                  \
   int b2k_linearize##SUF(int cls, const b2_state* st, int N, int ncol, double eps, int centered, void* A, void* B,         \

@@ -1,24 +1,32 @@
-// Device-side model constants: one POD struct per (precision, size class) living in
-// __constant__ memory, so every model read is a uniform constant-bank operand.
-// Filled on the host from the compiled-model blob (include/b2_model_layout.h), which
-// replaces the reference's mj.MjModel (reference mujoco_template/model.py:14-25).
+// Device-side model constants.
+//
+// The engine never touches a model struct directly; it reads the model through a *provider*
+// policy class with one static accessor per field (`M::nbody()`, `M::body_parentid(i)`, ...):
+//
+//  * RuntimeModel<T, D>  (b2_kernels_impl.cuh) returns fields of a POD image in __constant__
+//    memory -- uniform constant-bank operands, any model that fits size class D;
+//  * generated static providers (csrc/generated/spec_<model>.cuh, emitted by
+//    mujoco_template/_specialize.py) return compile-time constants from function-local
+//    constexpr tables, so that after unrolling every index, branch and model constant folds
+//    and the whole per-env state lives in registers.
+//
+// The image is filled on the host from the compiled-model blob (include/b2_model_layout.h),
+// which replaces the reference's mj.MjModel (reference mujoco_template/model.py:14-25).
 #pragma once
 #include "../../include/b2_model_layout.h"
 
 namespace b2 {
 
-// Compile-time capacities.  A model is mapped to the smallest class that holds it.
+// Compile-time capacities of the generic size classes.  A model is mapped to the smallest
+// class that holds it.
 struct DimsTiny {   // pendulum, cartpole, the reference test fixture
   static constexpr int NB = 4, NJ = 4, NQ = 4, NV = 4, NU = 2, NG = 4, NS = 2, NT = 1, NW = 2, NPAIR = 4, NCON = 8, NEFC = 36;
-  static constexpr int ID = 0;
 };
 struct DimsSmall {  // drone: one free body with many geoms
   static constexpr int NB = 4, NJ = 4, NQ = 10, NV = 8, NU = 8, NG = 12, NS = 8, NT = 1, NW = 2, NPAIR = 12, NCON = 24, NEFC = 100;
-  static constexpr int ID = 1;
 };
 struct DimsLarge {  // humanoid
   static constexpr int NB = 20, NJ = 24, NQ = 32, NV = 32, NU = 24, NG = 24, NS = 4, NT = 4, NW = 8, NPAIR = 176, NCON = 48, NEFC = 160;
-  static constexpr int ID = 2;
 };
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
@@ -26,47 +34,66 @@ enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4, GE
 enum { TRN_JOINT = 0, TRN_SITE = 4 };
 enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT_PYR = 3 };
 
+// Field lists (X-macros): X(name) for scalars, X(name, capacity) for arrays.
+#define B2_MODEL_INT_SCALARS(X) \
+  X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(npair) X(integrator) X(iterations) X(ls_iterations) \
+  X(has_fluid) X(has_dofdamping)
+#define B2_MODEL_REAL_SCALARS(X) X(timestep) X(density) X(viscosity) X(tolerance) X(ls_tolerance) X(meaninertia)
+#define B2_MODEL_INT_ARRAYS(X)                                                                                        \
+  X(body_parentid, D::NB) X(body_rootid, D::NB) X(body_jntnum, D::NB) X(body_jntadr, D::NB) X(body_dofnum, D::NB)    \
+  X(body_dofadr, D::NB) X(jnt_type, D::NJ) X(jnt_qposadr, D::NJ) X(jnt_dofadr, D::NJ) X(jnt_bodyid, D::NJ)           \
+  X(jnt_limited, D::NJ) X(dof_bodyid, D::NV) X(dof_jntid, D::NV) X(dof_parentid, D::NV) X(dof_anc, D::NV)            \
+  X(geom_type, D::NG) X(geom_bodyid, D::NG) X(site_bodyid, D::NS) X(tendon_adr, D::NT) X(tendon_num, D::NT)          \
+  X(tendon_limited, D::NT) X(wrap_jntid, D::NW) X(actuator_trntype, D::NU) X(actuator_trnid, D::NU)                  \
+  X(actuator_ctrllimited, D::NU) X(actuator_forcelimited, D::NU) X(actuator_disabled, D::NU) X(pair_geom1, D::NPAIR) \
+  X(pair_geom2, D::NPAIR) X(pair_dim, D::NPAIR)
+#define B2_MODEL_REAL_ARRAYS(X)                                                                                       \
+  X(gravity, 3) X(wind, 3) X(body_pos, 3 * D::NB) X(body_quat, 4 * D::NB) X(body_ipos, 3 * D::NB)                     \
+  X(body_iquat, 4 * D::NB) X(body_mass, D::NB) X(body_subtreemass, D::NB) X(body_inertia, 3 * D::NB)                  \
+  X(body_invweight0, 2 * D::NB) X(jnt_pos, 3 * D::NJ) X(jnt_axis, 3 * D::NJ) X(jnt_stiffness, D::NJ)                  \
+  X(jnt_range, 2 * D::NJ) X(jnt_margin, D::NJ) X(jnt_solref, 2 * D::NJ) X(jnt_solimp, 5 * D::NJ) X(qpos0, D::NQ)      \
+  X(qpos_spring, D::NQ) X(dof_armature, D::NV) X(dof_damping, D::NV) X(dof_invweight0, D::NV) X(geom_size, 3 * D::NG) \
+  X(geom_rbound, D::NG) X(geom_pos, 3 * D::NG) X(geom_quat, 4 * D::NG) X(site_pos, 3 * D::NS) X(site_quat, 4 * D::NS) \
+  X(tendon_range, 2 * D::NT) X(tendon_margin, D::NT) X(tendon_solref, 2 * D::NT) X(tendon_solimp, 5 * D::NT)          \
+  X(tendon_invweight0, D::NT) X(tendon_stiffness, D::NT) X(tendon_damping, D::NT) X(tendon_lengthspring, 2 * D::NT)   \
+  X(wrap_coef, D::NW) X(actuator_gear, 6 * D::NU) X(actuator_ctrlrange, 2 * D::NU) X(actuator_forcerange, 2 * D::NU)  \
+  X(actuator_gainprm, D::NU) X(actuator_biasprm, 3 * D::NU) X(pair_margin, D::NPAIR) X(pair_gap, D::NPAIR)            \
+  X(pair_friction, 2 * D::NPAIR) X(pair_solref, 2 * D::NPAIR) X(pair_solimp, 5 * D::NPAIR)
+
 template <typename T, class D>
 struct DevModel {
-  int nq, nv, nu, nbody, njnt, ngeom, nsite, ntendon, npair, integrator, iterations, ls_iterations, has_fluid, has_dofdamping;
-  T timestep, gravity[3], wind[3], density, viscosity, tolerance, ls_tolerance, meaninertia;
-  // bodies
-  int body_parentid[D::NB], body_rootid[D::NB], body_jntnum[D::NB], body_jntadr[D::NB], body_dofnum[D::NB], body_dofadr[D::NB];
-  T body_pos[3 * D::NB], body_quat[4 * D::NB], body_ipos[3 * D::NB], body_iquat[4 * D::NB], body_mass[D::NB];
-  T body_subtreemass[D::NB], body_inertia[3 * D::NB], body_invweight0[2 * D::NB];
-  // joints
-  int jnt_type[D::NJ], jnt_qposadr[D::NJ], jnt_dofadr[D::NJ], jnt_bodyid[D::NJ], jnt_limited[D::NJ];
-  T jnt_pos[3 * D::NJ], jnt_axis[3 * D::NJ], jnt_stiffness[D::NJ], jnt_range[2 * D::NJ], jnt_margin[D::NJ];
-  T jnt_solref[2 * D::NJ], jnt_solimp[5 * D::NJ], qpos0[D::NQ], qpos_spring[D::NQ];
-  // dofs
-  int dof_bodyid[D::NV], dof_jntid[D::NV], dof_parentid[D::NV];
-  T dof_armature[D::NV], dof_damping[D::NV], dof_invweight0[D::NV];
-  // geoms / sites
-  int geom_type[D::NG], geom_bodyid[D::NG];
-  T geom_size[3 * D::NG], geom_rbound[D::NG], geom_pos[3 * D::NG], geom_quat[4 * D::NG];
-  int site_bodyid[D::NS];
-  T site_pos[3 * D::NS], site_quat[4 * D::NS];
-  // fixed tendons
-  int tendon_adr[D::NT], tendon_num[D::NT], tendon_limited[D::NT], wrap_jntid[D::NW];
-  T tendon_range[2 * D::NT], tendon_margin[D::NT], tendon_solref[2 * D::NT], tendon_solimp[5 * D::NT], tendon_invweight0[D::NT];
-  T tendon_stiffness[D::NT], tendon_damping[D::NT], tendon_lengthspring[2 * D::NT], wrap_coef[D::NW];
-  // actuators
-  int actuator_trntype[D::NU], actuator_trnid[D::NU], actuator_ctrllimited[D::NU], actuator_forcelimited[D::NU], actuator_disabled[D::NU];
-  T actuator_gear[6 * D::NU], actuator_ctrlrange[2 * D::NU], actuator_forcerange[2 * D::NU], actuator_gainprm[D::NU], actuator_biasprm[3 * D::NU];
-  // collision candidates with pre-mixed contact parameters
-  int pair_geom1[D::NPAIR], pair_geom2[D::NPAIR], pair_dim[D::NPAIR];
-  T pair_margin[D::NPAIR], pair_gap[D::NPAIR], pair_friction[2 * D::NPAIR], pair_solref[2 * D::NPAIR], pair_solimp[5 * D::NPAIR];
+#define X(name) int name;
+  B2_MODEL_INT_SCALARS(X)
+#undef X
+#define X(name) T name;
+  B2_MODEL_REAL_SCALARS(X)
+#undef X
+#define X(name, cap) int name[cap];
+  B2_MODEL_INT_ARRAYS(X)
+#undef X
+#define X(name, cap) T name[cap];
+  B2_MODEL_REAL_ARRAYS(X)
+#undef X
 };
 
 template <class D>
 inline bool model_fits(const b2m_view& v) {
   return v.nbody <= D::NB && v.njnt <= D::NJ && v.nq <= D::NQ && v.nv <= D::NV && v.nu <= D::NU && v.ngeom <= D::NG &&
-         v.nsite <= D::NS && v.ntendon <= D::NT && v.nwrap <= D::NW && v.npair <= D::NPAIR;
+         v.nsite <= D::NS && v.ntendon <= D::NT && v.nwrap <= D::NW && v.npair <= D::NPAIR && v.nv <= 32;
 }
 
 template <typename T, typename S>
 inline void fill(T* dst, const S* src, int n) {
   for (int i = 0; i < n; i++) dst[i] = (T)src[i];
+}
+
+// bit j of dof_anc[i] is set iff dof j is i itself or an ancestor of i in the kinematic tree
+inline void dof_ancestor_masks(const b2m_view& v, int* out) {
+  for (int i = 0; i < v.nv; i++) {
+    unsigned mask = 0;
+    for (int j = i; j >= 0; j = v.dof_parentid[j]) mask |= 1u << j;
+    out[i] = (int)mask;
+  }
 }
 
 template <typename T, class D>
@@ -90,6 +117,7 @@ inline void fill_dev_model(DevModel<T, D>& m, const b2m_view& v, const int* actu
   fill(m.jnt_range, v.jnt_range, 2 * nj); fill(m.jnt_margin, v.jnt_margin, nj); fill(m.jnt_solref, v.jnt_solref, 2 * nj);
   fill(m.jnt_solimp, v.jnt_solimp, 5 * nj); fill(m.qpos0, v.qpos0, v.nq); fill(m.qpos_spring, v.qpos_spring, v.nq);
   fill(m.dof_bodyid, v.dof_bodyid, nv); fill(m.dof_jntid, v.dof_jntid, nv); fill(m.dof_parentid, v.dof_parentid, nv);
+  dof_ancestor_masks(v, m.dof_anc);
   fill(m.dof_armature, v.dof_armature, nv); fill(m.dof_damping, v.dof_damping, nv); fill(m.dof_invweight0, v.dof_invweight0, nv);
   fill(m.geom_type, v.geom_type, ng); fill(m.geom_bodyid, v.geom_bodyid, ng); fill(m.geom_size, v.geom_size, 3 * ng);
   fill(m.geom_rbound, v.geom_rbound, ng); fill(m.geom_pos, v.geom_pos, 3 * ng); fill(m.geom_quat, v.geom_quat, 4 * ng);
@@ -109,7 +137,7 @@ inline void fill_dev_model(DevModel<T, D>& m, const b2m_view& v, const int* actu
   fill(m.pair_geom1, v.pair_geom1, np); fill(m.pair_geom2, v.pair_geom2, np); fill(m.pair_dim, v.pair_dim, np);
   fill(m.pair_margin, v.pair_margin, np); fill(m.pair_gap, v.pair_gap, np); fill(m.pair_solref, v.pair_solref, 2 * np);
   fill(m.pair_solimp, v.pair_solimp, 5 * np);
-  // only friction[0] (tangential) and friction[2] are distinct for condim<=3; keep the two used values
+  // condim <= 3 uses only the tangential friction coefficient; keep friction[0..1]
   for (int p = 0; p < np; p++) { m.pair_friction[2 * p] = (T)v.pair_friction[5 * p]; m.pair_friction[2 * p + 1] = (T)v.pair_friction[5 * p + 1]; }
 }
 

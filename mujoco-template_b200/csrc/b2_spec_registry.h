@@ -1,0 +1,30 @@
+// Registry of model-specialised kernel sets (generated translation units register themselves
+// at load time; b2_model_create looks a model up by the FNV-1a hash of its blob).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "../../include/b2mj.h"
+
+namespace b2 {
+
+struct SpecKernels {
+  const char* name;
+  uint64_t blob_hash;
+  size_t blob_size;
+  int (*step)(const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);
+  int (*linearize)(const b2_state* st, int N, double eps, int centered, void* A, void* B, void* stream);
+  int (*jacobian)(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
+};
+
+void register_spec(const SpecKernels* k);
+const SpecKernels* find_spec(uint64_t hash, size_t size);
+
+inline uint64_t fnv1a(const void* data, size_t n) {
+  const unsigned char* p = (const unsigned char*)data;
+  uint64_t h = 1469598103934665603ull;
+  for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+
+}  // namespace b2

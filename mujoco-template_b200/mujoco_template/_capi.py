@@ -25,7 +25,7 @@ EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
     "b2_differentiate_pos", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
-    "b2_batch_size_class", "b2_last_error", "b2_version",
+    "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
 )
 
 
@@ -66,6 +66,8 @@ def lib() -> C.CDLL:
     L.b2_batch_destroy.argtypes = [vp]
     L.b2_batch_destroy.restype = None
     L.b2_batch_size_class.argtypes = [vp]
+    L.b2_batch_kernel_variant.argtypes = [vp]
+    L.b2_batch_kernel_variant.restype = C.c_char_p
     L.b2_step.argtypes = [vp, C.POINTER(State), i, C.POINTER(Derived), vp]
     L.b2_forward.argtypes = [vp, C.POINTER(State), C.POINTER(Derived), vp]
     L.b2_linearize.argtypes = [vp, C.POINTER(State), d, i, vp, vp, vp]
@@ -74,6 +76,7 @@ def lib() -> C.CDLL:
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
     L.b2_stream_synchronize.argtypes = [vp, vp]
+    L.b2_fp_peak.argtypes = [i, i, C.POINTER(d)]
     _lib = L
     return L
 
@@ -88,6 +91,13 @@ def check(rc: int) -> None:
     if rc == -5:
         raise LinearizationError(msg)
     raise TemplateError(msg)
+
+
+def fp_peak(precision: int = B2_F64, device: int = 0) -> float:
+    """Measured CUDA-core FMA peak in TFLOP/s (roofline denominator for the FP-bound kernels)."""
+    out = C.c_double()
+    check(lib().b2_fp_peak(int(precision), int(device), C.byref(out)))
+    return float(out.value)
 
 
 def launch_count() -> int:
@@ -128,6 +138,10 @@ class NativeBatch:
     @property
     def size_class(self) -> int:
         return int(self._L.b2_batch_size_class(self.handle))
+
+    @property
+    def kernel_variant(self) -> str:
+        return self._L.b2_batch_kernel_variant(self.handle).decode()
 
     def step(self, state: State, nsteps: int, derived: Derived | None, stream: int = 0) -> None:
         check(self._L.b2_step(self.handle, C.byref(state), int(nsteps), C.byref(derived) if derived is not None else None, stream))

@@ -210,7 +210,8 @@ class NativeBackend:
         for name in _INT_FIELDS:
             self.buffers[name] = self._alloc(1, torch.int32)
         self._scratch: dict[str, Any] = {}
-        self.stream = 0  # legacy default stream; torch's current stream is used for ordering via sync below
+        self.stream = 0  # legacy default stream; device batches launch on torch's current stream (see _pre)
+        self.profile: dict[str, list] | None = None  # name -> [(start_event, end_event)], filled when enabled
 
     def _alloc(self, dim: int, dtype):
         torch = self.torch
@@ -248,30 +249,48 @@ class NativeBackend:
         if self.host_mapped:
             self.batch.synchronize(self.stream)
 
-    def step(self, nsteps: int = 1, derived: bool = True) -> None:
+    def _launch(self, name: str, fn, *args) -> None:
+        """Run one C-ABI launch; when profiling, bracket it with CUDA events on the launch stream."""
         self._pre()
-        self.batch.step(self.state_struct(), nsteps, self.derived_struct() if derived else None, self.stream)
+        if self.profile is None or self.host_mapped:
+            fn(*args, self.stream)
+        else:
+            torch = self.torch
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(torch.cuda.current_stream(self.device))
+            fn(*args, self.stream)
+            e1.record(torch.cuda.current_stream(self.device))
+            self.profile.setdefault(name, []).append((e0, e1))
         self._post()
+
+    def kernel_ms(self, name: str) -> list[float]:
+        """Per-launch device times (ms) collected while ``profile`` was enabled."""
+        return [a.elapsed_time(b) for a, b in (self.profile or {}).get(name, [])]
+
+    def step(self, nsteps: int = 1, derived: bool = True) -> None:
+        self._launch("step", self.batch.step, self.state_struct(), nsteps, self.derived_struct() if derived else None)
 
     def forward(self) -> None:
-        self._pre()
-        self.batch.forward(self.state_struct(), self.derived_struct(), self.stream)
-        self._post()
+        self._launch("forward", self.batch.forward, self.state_struct(), self.derived_struct())
 
-    def linearize(self, eps: float, centered: bool):
-        """Returns (A, B) as fresh SoA buffers of shape (2nv, 2nv, nenv) and (2nv, nu, nenv)."""
+    def linearize(self, eps: float, centered: bool, out=None):
+        """Returns (A, B) as SoA buffers of shape (2nv, 2nv, nenv) and (2nv, nu, nenv).
+
+        Fresh buffers by default (the reference returns fresh arrays, linearization.py:24-27);
+        pass ``out=(A, B)`` to overwrite existing ones."""
         torch, m = self.torch, self.model
         nx = 2 * m.nv
         kw = dict(dtype=self.dtype)
-        if self.host_mapped:
+        if out is not None:
+            A, B = out
+        elif self.host_mapped:
             A = torch.zeros((nx, nx, self.nenv), **kw).pin_memory()
             B = torch.zeros((nx, m.nu, self.nenv), **kw).pin_memory()
         else:
-            A = torch.zeros((nx, nx, self.nenv), device=f"cuda:{self.device}", **kw)
-            B = torch.zeros((nx, m.nu, self.nenv), device=f"cuda:{self.device}", **kw)
-        self._pre()
-        self.batch.linearize(self.state_struct(), eps, centered, A.data_ptr(), B.data_ptr() if m.nu else None, self.stream)
-        self._post()
+            A = torch.empty((nx, nx, self.nenv), device=f"cuda:{self.device}", **kw)  # every entry is written
+            B = torch.empty((nx, m.nu, self.nenv), device=f"cuda:{self.device}", **kw)
+        self._launch("linearize", self.batch.linearize, self.state_struct(), eps, centered, A.data_ptr(),
+                     B.data_ptr() if m.nu else None)
         return A, B
 
     def jacobian(self, kind: int, objid: int, want_rot: bool):
@@ -280,9 +299,8 @@ class NativeBackend:
             lambda: torch.zeros((3, m.nv, self.nenv), dtype=self.dtype, device=f"cuda:{self.device}"))
         jp = mk()
         jr = mk() if want_rot else None
-        self._pre()
-        self.batch.jacobian(self.state_struct(), kind, objid, jp.data_ptr(), jr.data_ptr() if jr is not None else None, self.stream)
-        self._post()
+        self._launch("jacobian", self.batch.jacobian, self.state_struct(), kind, objid, jp.data_ptr(),
+                     jr.data_ptr() if jr is not None else None)
         return jp, jr
 
     def _tmp(self, key: str, dim: int):

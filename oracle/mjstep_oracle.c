@@ -62,10 +62,24 @@ typedef struct orc_data {
   double *efc_J, *efc_pos, *efc_margin, *efc_D, *efc_R, *efc_aref, *efc_vel, *efc_force, *efc_diagApprox;
   /* solver stats / flags */
   int solver_iter, warn_bad_qpos, warn_bad_qvel, warn_bad_qacc, warn_overflow;
-  long long flop_count; /* unused placeholder kept for ABI stability */
+  /* bump-allocated scratch for per-call temporaries (no malloc on the hot path) */
+  double* arena; size_t arena_top, arena_cap;
 } orc_data;
 
 #define ALLOC(n) ((double*)calloc((size_t)((n) > 0 ? (n) : 1), sizeof(double)))
+/* scratch from the per-data arena: zero-filled, released by restoring the saved top */
+static double* orc_scratch(struct orc_data* d, size_t n);
+#define SCRATCH(n) orc_scratch(d, (size_t)((n) > 0 ? (n) : 1))
+#define ARENA_MARK size_t arena_mark__ = d->arena_top
+#define ARENA_RELEASE d->arena_top = arena_mark__
+
+static double* orc_scratch(struct orc_data* d, size_t n) {
+  if (d->arena_top + n > d->arena_cap) { fprintf(stderr, "oracle scratch arena exhausted\n"); abort(); }
+  double* p = d->arena + d->arena_top;
+  d->arena_top += n;
+  memset(p, 0, n * sizeof(double));
+  return p;
+}
 
 /* ------------------------------------------------------------------ lifecycle */
 orc_model* orc_model_create(const void* blob, size_t nbytes) {
@@ -101,6 +115,8 @@ orc_data* orc_data_create(const orc_model* m) {
   d->efc_type = (int*)calloc((size_t)me, sizeof(int)); d->efc_id = (int*)calloc((size_t)me, sizeof(int));
   d->efc_J = ALLOC(me * nv); d->efc_pos = ALLOC(me); d->efc_margin = ALLOC(me); d->efc_D = ALLOC(me); d->efc_R = ALLOC(me);
   d->efc_aref = ALLOC(me); d->efc_vel = ALLOC(me); d->efc_force = ALLOC(me); d->efc_diagApprox = ALLOC(me);
+  d->arena_cap = (size_t)(64 * (nq + nv + nu + 8) + 40 * nb + 8 * nv * nv + 12 * me + 16 * nv * 6 + 4096);
+  d->arena = ALLOC(d->arena_cap); d->arena_top = 0;
   return d;
 }
 void orc_data_free(orc_data* d) {
@@ -113,7 +129,7 @@ void orc_data_free(orc_data* d) {
                   &d->qfrc_actuator, &d->qfrc_smooth, &d->qacc_smooth, &d->qfrc_constraint, &d->efc_J, &d->efc_pos,
                   &d->efc_margin, &d->efc_D, &d->efc_R, &d->efc_aref, &d->efc_vel, &d->efc_force, &d->efc_diagApprox};
   for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(*p[i]);
-  free(d->contact); free(d->efc_type); free(d->efc_id); free(d);
+  free(d->arena); free(d->contact); free(d->efc_type); free(d->efc_id); free(d);
 }
 
 /* mj_resetData / mj_resetDataKeyframe */
@@ -357,7 +373,7 @@ void orc_jac_subtreecom(const orc_model* m, const orc_data* d, double* jacp, int
 static void orc_transmission(const orc_model* m, orc_data* d) {
   const b2m_view* v = &m->v;
   int nv = v->nv;
-  double* jac = ALLOC(6 * nv);
+  double* jac = SCRATCH(6 * nv);
   for (int i = 0; i < v->nu; i++) {
     double* moment = d->actuator_moment + i * nv;
     const double* gear = v->actuator_gear + 6 * i;
@@ -379,7 +395,6 @@ static void orc_transmission(const orc_model* m, orc_data* d) {
       d->actuator_length[i] = 0;
     }
   }
-  free(jac);
 }
 
 /* ------------------------------------------------------------------ collision */
@@ -594,9 +609,9 @@ static void orc_make_constraint(const orc_model* m, orc_data* d) {
       }
     }
   }
-  double* j1 = ALLOC(3 * nv);
-  double* j2 = ALLOC(3 * nv);
-  double* jc = ALLOC(3 * nv);
+  double* j1 = SCRATCH(3 * nv);
+  double* j2 = SCRATCH(3 * nv);
+  double* jc = SCRATCH(3 * nv);
   for (int c = 0; c < d->ncon; c++) {
     orc_contact* con = d->contact + c;
     if (con->exclude) continue;
@@ -622,7 +637,6 @@ static void orc_make_constraint(const orc_model* m, orc_data* d) {
       }
     }
   }
-  free(j1); free(j2); free(jc);
 }
 
 /* getimpedance (engine_core_constraint.c) */
@@ -800,19 +814,18 @@ static void orc_passive(const orc_model* m, orc_data* d) {
     for (int k = 0; k < nv; k++) d->qfrc_passive[k] += d->ten_J[t * nv + k] * frc;
   }
   if (v->density > 0 || v->viscosity > 0) {
-    double* jacp = ALLOC(3 * nv);
-    double* jacr = ALLOC(3 * nv);
+    double* jacp = SCRATCH(3 * nv);
+    double* jacr = SCRATCH(3 * nv);
     for (int i = 1; i < v->nbody; i++)
       if (v->body_mass[i] >= ORC_MINVAL) orc_fluid_body(m, d, i, jacp, jacr);
-    free(jacp); free(jacr);
   }
 }
 
 /* mj_rne with flg_acc = 0: bias forces */
 static void orc_rne(const b2m_view* v, orc_data* d) {
   int nb = v->nbody, nv = v->nv;
-  double* cacc = ALLOC(6 * nb);
-  double* cfrc = ALLOC(6 * nb);
+  double* cacc = SCRATCH(6 * nb);
+  double* cfrc = SCRATCH(6 * nb);
   cacc[3] = -v->gravity[0]; cacc[4] = -v->gravity[1]; cacc[5] = -v->gravity[2];
   for (int i = 1; i < nb; i++) {
     int bda = v->body_dofadr[i];
@@ -833,7 +846,6 @@ static void orc_rne(const b2m_view* v, orc_data* d) {
     for (int k = 0; k < 6; k++) s += d->cdof[6 * i + k] * cfrc[6 * v->dof_bodyid[i] + k];
     d->qfrc_bias[i] = s;
   }
-  free(cacc); free(cfrc);
 }
 
 /* ------------------------------------------------------------------ acceleration stage */
@@ -1029,8 +1041,8 @@ static void orc_sol_newton(const orc_model* m, orc_data* d) {
   newton_ctx c;
   memset(&c, 0, sizeof(c));
   c.m = m; c.d = d;
-  c.Jaref = ALLOC(nefc); c.Jv = ALLOC(nefc); c.Ma = ALLOC(nv); c.Mv = ALLOC(nv); c.grad = ALLOC(nv);
-  c.Mgrad = ALLOC(nv); c.search = ALLOC(nv); c.quad = ALLOC(3 * nefc); c.H = ALLOC(nv * nv);
+  c.Jaref = SCRATCH(nefc); c.Jv = SCRATCH(nefc); c.Ma = SCRATCH(nv); c.Mv = SCRATCH(nv); c.grad = SCRATCH(nv);
+  c.Mgrad = SCRATCH(nv); c.search = SCRATCH(nv); c.quad = SCRATCH(3 * nefc); c.H = SCRATCH(nv * nv);
   for (int i = 0; i < nefc; i++) {
     double s = 0;
     for (int k = 0; k < nv; k++) s += d->efc_J[(size_t)i * nv + k] * d->qacc[k];
@@ -1058,7 +1070,6 @@ static void orc_sol_newton(const orc_model* m, orc_data* d) {
     for (int k = 0; k < nv; k++) c.search[k] = -c.Mgrad[k];
   }
   d->solver_iter = iter;
-  free(c.Jaref); free(c.Jv); free(c.Ma); free(c.Mv); free(c.grad); free(c.Mgrad); free(c.search); free(c.quad); free(c.H);
 }
 
 /* mj_fwdConstraint */
@@ -1070,8 +1081,8 @@ static void orc_fwd_constraint(const orc_model* m, orc_data* d) {
     for (int k = 0; k < nv; k++) { d->qacc[k] = d->qacc_smooth[k]; d->qacc_warmstart[k] = d->qacc_smooth[k]; d->qfrc_constraint[k] = 0; }
     return;
   }
-  double* jar = ALLOC(nefc);
-  double* Ma = ALLOC(nv);
+  double* jar = SCRATCH(nefc);
+  double* Ma = SCRATCH(nv);
   /* warmstart(): pick the cheaper of qacc_warmstart and qacc_smooth */
   for (int k = 0; k < nv; k++) d->qacc[k] = d->qacc_warmstart[k];
   for (int i = 0; i < nefc; i++) {
@@ -1089,7 +1100,6 @@ static void orc_fwd_constraint(const orc_model* m, orc_data* d) {
   }
   double cost_smooth = orc_constraint_update(m, d, jar, 0);
   if (cost_warm > cost_smooth) for (int k = 0; k < nv; k++) d->qacc[k] = d->qacc_smooth[k];
-  free(jar); free(Ma);
   orc_sol_newton(m, d);
   for (int k = 0; k < nv; k++) d->qacc_warmstart[k] = d->qacc[k];
 }
@@ -1135,11 +1145,13 @@ static void orc_fwd_acceleration(const orc_model* m, orc_data* d) {
 }
 /* mj_forward (sensors are outside the hot path) */
 void orc_forward(const orc_model* m, orc_data* d) {
+  ARENA_MARK;
   orc_fwd_position(m, d);
   orc_fwd_velocity(m, d);
   orc_actuation(&m->v, d);
   orc_fwd_acceleration(m, d);
   orc_fwd_constraint(m, d);
+  ARENA_RELEASE;
 }
 
 /* mj_integratePos */
@@ -1179,21 +1191,19 @@ static void orc_euler(const orc_model* m, orc_data* d) {
   const b2m_view* v = &m->v;
   int nv = v->nv;
   double h = v->timestep;
-  double* qacc = ALLOC(nv);
+  double* qacc = SCRATCH(nv);
   if (!v->has_dofdamping) memcpy(qacc, d->qacc, sizeof(double) * nv);
   else {
-    double* MhB = ALLOC(nv * nv);
+    double* MhB = SCRATCH(nv * nv);
     memcpy(MhB, d->qM, sizeof(double) * nv * nv);
     for (int i = 0; i < nv; i++) MhB[i * nv + i] += h * v->dof_damping[i];
     orc_factor(v, MhB, d->qH, d->qHDiagInv);
     for (int k = 0; k < nv; k++) qacc[k] = d->qfrc_smooth[k] + d->qfrc_constraint[k];
     orc_solve_ld(v, d->qH, d->qHDiagInv, qacc);
-    free(MhB);
   }
   for (int k = 0; k < nv; k++) d->qvel[k] += qacc[k] * h;
   orc_integrate_pos(m, d->qpos, d->qvel, h);
   d->time += h;
-  free(qacc);
 }
 
 /* mj_RungeKutta(N=4) */
@@ -1204,8 +1214,8 @@ static void orc_rk4(const orc_model* m, orc_data* d) {
   static const double A[9] = {0.5, 0, 0, 0, 0.5, 0, 0, 0, 1}, B[4] = {1.0 / 6, 1.0 / 3, 1.0 / 3, 1.0 / 6};
   double C[3], T[3];
   for (int i = 1; i < 4; i++) { C[i - 1] = 0; for (int j = 0; j < i; j++) C[i - 1] += A[(i - 1) * 3 + j]; T[i - 1] = time + C[i - 1] * h; }
-  double *X[4], *F[4], *dX = ALLOC(2 * nv);
-  for (int i = 0; i < 4; i++) { X[i] = ALLOC(nq + nv); F[i] = ALLOC(nv); }
+  double *X[4], *F[4], *dX = SCRATCH(2 * nv);
+  for (int i = 0; i < 4; i++) { X[i] = SCRATCH(nq + nv); F[i] = SCRATCH(nv); }
   memcpy(X[0], d->qpos, sizeof(double) * nq); memcpy(X[0] + nq, d->qvel, sizeof(double) * nv);
   memcpy(F[0], d->qacc, sizeof(double) * nv);
   for (int i = 1; i < 4; i++) {
@@ -1230,23 +1240,23 @@ static void orc_rk4(const orc_model* m, orc_data* d) {
   for (int k = 0; k < nv; k++) d->qvel[k] += dX[nv + k] * h;
   orc_integrate_pos(m, d->qpos, dX, h);
   d->time += h;
-  for (int i = 0; i < 4; i++) { free(X[i]); free(F[i]); }
-  free(dX);
 }
 
 /* mj_step */
 void orc_step(const orc_model* m, orc_data* d) {
+  ARENA_MARK;
   orc_check(m, d);
   orc_forward(m, d);
   for (int i = 0; i < m->v.nv; i++) if (!(fabs(d->qacc[i]) <= 1e10)) d->warn_bad_qacc = 1;
   if (m->v.integrator == 1) orc_rk4(m, d); else orc_euler(m, d);
+  ARENA_RELEASE;
 }
 
 /* ------------------------------------------------------------------ mjd_transitionFD */
 typedef struct { double time, *qpos, *qvel, *ctrl, *warm; } orc_state;
-static void state_save(const b2m_view* v, const orc_data* d, orc_state* s) {
+static void state_save(const b2m_view* v, orc_data* d, orc_state* s) {
   s->time = d->time;
-  s->qpos = ALLOC(v->nq); s->qvel = ALLOC(v->nv); s->ctrl = ALLOC(v->nu); s->warm = ALLOC(v->nv);
+  s->qpos = SCRATCH(v->nq); s->qvel = SCRATCH(v->nv); s->ctrl = SCRATCH(v->nu); s->warm = SCRATCH(v->nv);
   memcpy(s->qpos, d->qpos, sizeof(double) * v->nq); memcpy(s->qvel, d->qvel, sizeof(double) * v->nv);
   memcpy(s->ctrl, d->ctrl, sizeof(double) * v->nu); memcpy(s->warm, d->qacc_warmstart, sizeof(double) * v->nv);
 }
@@ -1255,7 +1265,6 @@ static void state_restore(const b2m_view* v, orc_data* d, const orc_state* s) {
   memcpy(d->qpos, s->qpos, sizeof(double) * v->nq); memcpy(d->qvel, s->qvel, sizeof(double) * v->nv);
   memcpy(d->ctrl, s->ctrl, sizeof(double) * v->nu); memcpy(d->qacc_warmstart, s->warm, sizeof(double) * v->nv);
 }
-static void state_free(orc_state* s) { free(s->qpos); free(s->qvel); free(s->ctrl); free(s->warm); }
 static void get_next(const b2m_view* v, const orc_data* d, double* y) {
   memcpy(y, d->qpos, sizeof(double) * v->nq); memcpy(y + v->nq, d->qvel, sizeof(double) * v->nv);
 }
@@ -1271,9 +1280,10 @@ static int in_range(double x1, double x2, const double* r) { return x1 >= r[0] &
 void orc_transition_fd(const orc_model* m, orc_data* d, double eps, int centered, double* A, double* B) {
   const b2m_view* v = &m->v;
   int nq = v->nq, nv = v->nv, nu = v->nu, ndx = 2 * nv;
+  ARENA_MARK;
   orc_state s;
   state_save(v, d, &s);
-  double *next = ALLOC(nq + nv), *plus = ALLOC(nq + nv), *minus = ALLOC(nq + nv), *col = ALLOC(ndx), *dpos = ALLOC(nv);
+  double *next = SCRATCH(nq + nv), *plus = SCRATCH(nq + nv), *minus = SCRATCH(nq + nv), *col = SCRATCH(ndx), *dpos = SCRATCH(nv);
   orc_step(m, d);
   get_next(v, d, next);
   state_restore(v, d, &s);
@@ -1303,8 +1313,7 @@ void orc_transition_fd(const orc_model* m, orc_data* d, double eps, int centered
     state_diff(m, col, centered ? minus : next, plus, centered ? 2 * eps : eps);
     if (A) for (int r2 = 0; r2 < ndx; r2++) A[r2 * ndx + i] = col[r2];
   }
-  free(next); free(plus); free(minus); free(col); free(dpos);
-  state_free(&s);
+  ARENA_RELEASE;
 }
 
 /* ------------------------------------------------------------------ ctypes accessors */
