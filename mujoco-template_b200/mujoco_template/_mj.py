@@ -384,6 +384,8 @@ class MjData(_DataBase):
         self.act = np.zeros(0)
         self.sensordata = np.zeros(0)
         self.time = 0.0
+        # data-less calls (mj_integratePos / mj_differentiatePos) reuse this env's backend scratch
+        _HELPERS.setdefault(id(model), self.backend)
         mj_resetData(model, self)
 
     @property

@@ -1,0 +1,75 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/b2mj.h declares.
+No compute entry point is called here (that needs a GPU)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT, load_model
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b2mj.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from mujoco_template import _capi
+
+    lib = _capi.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 15
+    for sym in declared:
+        assert hasattr(lib, sym), f"{sym} declared in include/b2mj.h but not exported"
+    assert sorted(_capi.EXPORTED_SYMBOLS) == declared
+    assert b"b2mj" in lib.b2_version()
+
+
+def test_model_create_is_host_only_and_picks_size_class_and_specialisation():
+    from mujoco_template import _capi
+    import torch
+
+    for name, cls in (("pendulum", 0), ("cartpole", 0), ("drone", 1), ("humanoid", 2)):
+        nm = _capi.NativeModel(load_model(name).blob)
+        assert nm.handle
+    with pytest.raises(_capi.ConfigError):
+        _capi.NativeModel(b"not a model blob at all")
+    if not torch.cuda.is_available():
+        nm = _capi.NativeModel(load_model("cartpole").blob)
+        with pytest.raises(_capi.TemplateError, match="no CUDA device"):
+            _capi.NativeBatch(nm, 4)
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+
+    import mujoco_template as mt
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mt.TemplateError, match="no CPU fallback"):
+        mt.BatchedEnv(load_model("cartpole"), 8)
+    with pytest.raises(mt.TemplateError):
+        mt.Env(mt.ModelHandle(load_model("pendulum")))
+
+
+def test_product_package_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under the product package may import, load or link it."""
+    pkg = os.path.join(ROOT, "mujoco-template_b200")
+    pat = re.compile(r"^\s*(from|import)\s+oracle\b|liborc|oracle/|orc_[a-z_]+\(", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not pat.search(text), f"{os.path.join(dirpath, f)} references the oracle"
+
+
+def test_generated_headers_are_current():
+    from mujoco_template import _layout, _specialize
+
+    assert open(os.path.join(ROOT, "include", "b2_model_layout.h")).read() == _layout.emit_c_header()
+    for name in ("pendulum", "cartpole", "drone"):
+        path = os.path.join(ROOT, "mujoco-template_b200", "csrc", "generated", f"spec_{name}.cu")
+        assert open(path).read() == _specialize.emit_spec(load_model(name)._c, name)
