@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--model", default="cartpole", choices=list(MODEL_FILE))
     ap.add_argument("--nenv", type=int, default=None, help="envs per GPU (default: BASELINE config for the model)")
     ap.add_argument("--no-linearize", action="store_true", help="step only (no per-step FD linearisation)")
+    ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
@@ -142,11 +143,15 @@ def cpu_oracle_rate(model, name: str, linearize: bool, target_seconds: float, se
     probe_rate = n_probe * 2 / max(time.perf_counter() - t0, 1e-6)
     nsteps = 10
     n = int(min(max(probe_rate * target_seconds / nsteps, cores), 1 << 20))
-    qpos, qvel = synth_states(model, name, n, seed + 1)
-    ctrl = np.zeros((n, model.nu))
-    t0 = time.perf_counter()
-    om.batch_rollout(qpos, qvel, ctrl, nsteps=nsteps, lin=linearize, nthreads=cores)
-    dt = time.perf_counter() - t0
+    for _ in range(3):  # the short probe under-estimates the rate (thread start-up): grow the sample if needed
+        qpos, qvel = synth_states(model, name, n, seed + 1)
+        ctrl = np.zeros((n, model.nu))
+        t0 = time.perf_counter()
+        om.batch_rollout(qpos, qvel, ctrl, nsteps=nsteps, lin=linearize, nthreads=cores)
+        dt = time.perf_counter() - t0
+        if dt >= 0.5 * target_seconds or n >= (1 << 20):
+            break
+        n = int(min(n * target_seconds / max(dt, 1e-3), 1 << 20))
     return dict(value=n * nsteps / dt, unit=UNIT, cores=cores, kind="port",
                 sample=f"{n} envs x {nsteps} steps of the same workload ({'FD linearisation + ' if linearize else ''}step), "
                        f"{dt:.1f} s wall, pthread shards over {cores} threads; oracle = C restatement of mj_step "
@@ -246,12 +251,24 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # per-kernel device times for the roofline: a short eager pass with CUDA events around each launch
+    env.data.backend.profile = {}
     for _ in range(max(args.warmup, 3)):
         env.step(return_obs=False)
+    for _ in range(10):
+        flush.zero_()
+        env.step(return_obs=False)
+    torch.cuda.synchronize()
+    kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("linearize", "step")}
+    env.data.backend.profile = None
+    use_graph = controller is not None and not args.no_graph
+    if use_graph:
+        env.enable_cuda_graph(True)
+        for _ in range(3):  # eager call, capture + replay, replay
+            env.step(return_obs=False)
     fp64_peak = _capi.fp_peak(64, local)
     barrier()
     launches0 = _capi.launch_count()
-    env.data.backend.profile = {}
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.25)
@@ -269,9 +286,9 @@ def main():
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     total_ms = float(sum(step_ms))
-    launches = _capi.launch_count() - launches0
-    kernel_ms = {k: env.data.backend.kernel_ms(k) for k in ("linearize", "step")}
-    env.data.backend.profile = None
+    # graph replays re-launch the captured kernels without passing through the C-ABI counter
+    per_step_launches = (1 if lin else 0) + 1
+    launches = (_capi.launch_count() - launches0) if not use_graph else per_step_launches * args.steps
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -293,7 +310,7 @@ def main():
     else:
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    share = {k: (float(np.sum(v)) / total_ms if v else 0.0) for k, v in kernel_ms.items()}
+    share = {k: (float(np.mean(v)) * args.steps / total_ms if v else 0.0) for k, v in kernel_ms.items()}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                 "traffic": None, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
@@ -301,11 +318,13 @@ def main():
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 600.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul): cartpole from the ncu capture in
+    # profiles/ncu_k_linearize_cartpole_spec_r01.txt; the others are the a-priori estimates of BASELINE.md
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 989.0, "drone": 1500.0, "humanoid": 100000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
-                     "flops_source": "a-priori estimate (BASELINE.md section 4)", "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
+                     "flops_source": ("ncu-counted executed flops (profiles/)" if name == "cartpole" else "a-priori estimate (BASELINE.md section 4)"), "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
 
     # ---- e2e: host buffers through the C-ABI (b2_step_host): H2D state+ctrl, linearise+step, D2H state+(A,B)
     e2e = None
@@ -353,6 +372,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
                        "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
+                       "launch": "CUDA graph replay of one env.step()" if use_graph else "eager launches",
                        "sharding": f"env batch split over {world} rank(s), no inter-step communication"},
             "linearizations_per_sec": (value if lin else 0.0),
             "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),

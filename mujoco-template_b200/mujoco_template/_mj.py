@@ -252,7 +252,7 @@ class NativeBackend:
     def _launch(self, name: str, fn, *args) -> None:
         """Run one C-ABI launch; when profiling, bracket it with CUDA events on the launch stream."""
         self._pre()
-        if self.profile is None or self.host_mapped:
+        if self.profile is None or self.host_mapped or self.torch.cuda.is_current_stream_capturing():
             fn(*args, self.stream)
         else:
             torch = self.torch

@@ -183,16 +183,15 @@ class BatchedEnv:
             out[token] = entry
         return out
 
-    def step(self, n: int = 1, *, return_obs: bool = True) -> StepResult:
-        if n < 1:
-            raise ConfigError("BatchedEnv.step(n): n must be >= 1")
-        info: InfoDict = {}
+    def _device_work(self, n: int):
+        """Controller ticks, (A, B), Jacobians and n physics steps: device work only (no host sync)."""
         lin_A, lin_B, jacs = [], [], []
+        backend = self.data.backend
         pending = 0  # consecutive steps with no controller tick are fused into one launch
         for _ in range(n):
             if self.controller is not None and self._substep % self.control_decimation == 0:
                 if pending:
-                    mj.mj_step(self.model, self.data, pending)
+                    backend.step(pending)
                     pending = 0
                 self.controller(self.model, self.data, float(self.data.time))
                 caps = self.controller.capabilities
@@ -205,7 +204,54 @@ class BatchedEnv:
             pending += 1
             self._substep += 1
         if pending:
-            mj.mj_step(self.model, self.data, pending)
+            backend.step(pending)
+        return lin_A, lin_B, jacs
+
+    def _advance_time(self, n: int) -> None:
+        h = float(self.model.opt.timestep)
+        for _ in range(n):
+            self.data.time += h  # repeated addition, as upstream accumulates mjData.time
+
+    def enable_cuda_graph(self, enabled: bool = True) -> None:
+        """Replay ``step()`` (controller tick + (A, B) + Jacobians + physics step) as one CUDA graph.
+
+        Valid when the controller is pure tensor code that does not depend on ``t`` and
+        ``control_decimation == 1``.  The first graphed call runs eagerly, the second captures.
+        ``info['A']`` / ``info['B']`` / Jacobians then alias graph-owned buffers that the next
+        ``step()`` overwrites (clone them to keep a history)."""
+        if enabled and self.control_decimation != 1:
+            raise ConfigError("CUDA-graph stepping requires control_decimation == 1")
+        self._graph_enabled = bool(enabled)
+        self._graph = None
+        self._graph_warm = False
+        self._graph_out = None
+
+    def _graphed_work(self):
+        import torch
+
+        if not self._graph_warm:  # eager first call: loads the kernels, makes the model image resident
+            self._graph_warm = True
+            return self._device_work(1)
+        if self._graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self._device_work(1)
+            self._graph = g
+        else:
+            self._substep += 1
+        self._graph.replay()
+        return self._graph_out
+
+    def step(self, n: int = 1, *, return_obs: bool = True) -> StepResult:
+        if n < 1:
+            raise ConfigError("BatchedEnv.step(n): n must be >= 1")
+        info: InfoDict = {}
+        if getattr(self, "_graph_enabled", False) and n == 1 and self.controller is not None:
+            lin_A, lin_B, jacs = self._graphed_work()
+        else:
+            lin_A, lin_B, jacs = self._device_work(n)
+        self._advance_time(n)
         if lin_A:
             info["A"], info["B"] = _one_or_many(lin_A), _one_or_many(lin_B)
         if jacs:
@@ -224,7 +270,8 @@ class BatchedEnv:
         """``nsteps`` steps with the current controls held, fused in one kernel launch."""
         if nsteps < 1:
             raise ConfigError("nsteps must be >= 1")
-        mj.mj_step(self.model, self.data, int(nsteps))
+        self.data.backend.step(int(nsteps))
+        self._advance_time(int(nsteps))
         self._substep += int(nsteps)
 
     def passive(self, *, duration: float | None = None, max_steps: int | None = None, hooks=None,

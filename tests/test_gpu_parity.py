@@ -309,3 +309,64 @@ def test_single_env_linearize_and_info():
     # python FD fallback path runs and agrees with native in the velocity rows
     A3, B3 = mt.linearize_discrete(env.model, env.data, use_native=False)
     assert _rel(A3[2:], A2[2:]) <= 1e-5 and _rel(A3[:2], -A2[:2]) <= 1e-5
+
+
+def test_batched_env_lqr_graph_equals_eager_and_stabilises():
+    """BatchedEnv + batched LQR: CUDA-graph replay is bit-identical to eager stepping; the pole stays up."""
+    import torch
+    import mujoco_template as mt
+    from mujoco_template.batched_controllers import BatchedLQRController
+
+    model = load_model("cartpole")
+    n = 512
+    qpos, qvel, _ = random_states(model, "cartpole", n, seed=12)
+    outs = []
+    for graph in (False, True):
+        ctrl = BatchedLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
+        env = mt.BatchedEnv(model, n, controller=ctrl)
+        env.reset()
+        env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=env.data.qpos.device))
+        env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=env.data.qpos.device))
+        if graph:
+            env.enable_cuda_graph(True)
+        last = None
+        for _ in range(300):
+            last = env.step(return_obs=False)
+        torch.cuda.synchronize()
+        assert last.info["A"].shape == (n, 4, 4) and last.info["B"].shape == (n, 4, 1)
+        outs.append((env.data.qpos.cpu().numpy(), env.data.qvel.cpu().numpy(), last.info["A"].cpu().numpy(), env.data.time))
+        assert int(env.data.flags.max()) == 0
+        assert float(env.data.qpos[1].abs().max()) < 0.05      # every pole is upright after 3 s
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+    # (A, B) of env 0 at the final state agree with the oracle's mjd_transitionFD
+    om, od = oracle_for(model)
+    env2 = mt.BatchedEnv(model, n)
+    A, B = env.linearize()
+    od.qpos[:] = env.data.qpos[:, 0].cpu().numpy(); od.qvel[:] = env.data.qvel[:, 0].cpu().numpy()
+    od.ctrl[:] = env.data.ctrl[:, 0].cpu().numpy(); od.qacc_warmstart[:] = env.data.qacc_warmstart[:, 0].cpu().numpy()
+    Ao, Bo = od.transition_fd(1e-6, True)
+    assert _rel(A[0].cpu().numpy(), Ao) <= AB_RTOL and _rel(B[0].cpu().numpy(), Bo) <= AB_RTOL
+    assert env.data.backend.batch.kernel_variant == "cartpole" and env2.data.backend.batch.kernel_variant == "cartpole"
+
+
+def test_batched_observations_and_jacobians():
+    import torch
+    import mujoco_template as mt
+
+    model = load_model("drone")
+    n = 16
+
+    class Hold:
+        capabilities = mt.ControllerCapabilities(needs_jacobians=("site:imu", "subtreecom:x2"))
+        def prepare(self, m, d): pass
+        def __call__(self, m, d, t): d.ctrl[:] = 3.2495625
+
+    env = mt.BatchedEnv(model, n, controller=Hold(), obs_spec=mt.ObservationSpec(include_time=True, sites_pos=("imu",), as_dict=False))
+    obs0 = env.reset("hover")
+    assert obs0.shape == (7 + 6 + 3 + 1, n)
+    res = env.step(2)
+    assert isinstance(res.info["jacobians"], list) and res.info["jacobians"][0]["site:imu"]["jacp"].shape == (n, 3, 6)
+    assert "jacr" not in res.info["jacobians"][0]["subtreecom:x2"]
+    assert torch.allclose(env.data.qpos[2], torch.full((n,), 0.3, dtype=torch.float64, device=env.data.qpos.device), atol=1e-9)
+    assert env.data.time == 0.01 + 0.01
