@@ -63,7 +63,28 @@ struct b2_batch {
   size_t esz;
   // device staging for b2_step_host
   void *d_qpos = nullptr, *d_qvel = nullptr, *d_ctrl = nullptr, *d_warm = nullptr, *d_A = nullptr, *d_B = nullptr;
+  // warp engine (large models): -1 not yet decided, 0 lane engine, 1 warp engine
+  int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
+  void* d_jscratch = nullptr;
 };
+
+// The warp engine covers the feature set of large articulated models (humanoid); everything else
+// in the large size class runs on the lane engine.
+static bool warp_engine_supports(const b2m_view& v) {
+  const char* off = getenv("B2_DISABLE_WARP");
+  if (off && off[0] == '1') return false;
+  if (v.integrator != 0 || v.has_fluid || v.nbody > 32 || v.nv > 32 || v.nsite != 0) return false;
+  for (int a = 0; a < v.nu; a++) if (v.actuator_trntype[a] != b2::TRN_JOINT) return false;
+  for (int g = 0; g < v.ngeom; g++) {
+    const int t = v.geom_type[g];
+    if (t != b2::GEOM_PLANE && t != b2::GEOM_SPHERE && t != b2::GEOM_CAPSULE) {
+      bool collides = false;
+      for (int p = 0; p < v.npair; p++) collides = collides || v.pair_geom1[p] == g || v.pair_geom2[p] == g;
+      if (collides) return false;
+    }
+  }
+  return true;
+}
 
 extern "C" {
 
@@ -115,7 +136,7 @@ int b2_batch_create(const b2_model* model, int nenv, int device, int precision, 
 }
 void b2_batch_destroy(b2_batch* b) {
   if (!b) return;
-  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B};
+  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch};
   for (void* q : p) if (q) cudaFree(q);
   delete b;
 }
@@ -123,13 +144,45 @@ int b2_batch_size_class(const b2_batch* b) { return b ? b->model->cls : -1; }
 const char* b2_batch_kernel_variant(const b2_batch* b) {
   if (!b) return "";
   const b2::SpecKernels* k = (b->precision == B2_F64) ? b->model->spec : nullptr;
-  return k ? k->name : "generic";
+  if (k) return k->name;
+  if (b->warp_mode == 1 || (b->warp_mode < 0 && b->model->cls == 2 && warp_engine_supports(b->model->v))) return "generic-warp";
+  return "generic";
 }
 
 }  // extern "C"
 
 static inline const b2::SpecKernels* active_spec(const b2_batch* b) {
   return b->precision == B2_F64 ? b->model->spec : nullptr;
+}
+
+static int ensure_resident(b2_batch* b, void* stream);
+
+// decide once per batch whether the large-model warp engine is used; plan its launch and scratch
+static int prepare_warp(b2_batch* b) {
+  if (b->warp_mode >= 0) return B2_OK;
+  b->warp_mode = 0;
+  if (b->model->cls != 2 || !warp_engine_supports(b->model->v)) return B2_OK;
+  const bool f64 = b->precision == B2_F64;
+  int wpb = 0, blocks = 0;
+  const int slots = f64 ? b2::b2k_warp_plan_f64(&b->model->v, b->nenv, &wpb, &blocks)
+                        : b2::b2k_warp_plan_f32(&b->model->v, b->nenv, &wpb, &blocks);
+  if (slots <= 0) return B2_OK;  // not enough shared memory: stay on the lane engine
+  const size_t bytes = f64 ? b2::b2k_warp_scratch_bytes_f64(&b->model->v, slots) : b2::b2k_warp_scratch_bytes_f32(&b->model->v, slots);
+  cudaError_t e = cudaMalloc(&b->d_jscratch, bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "warp-engine scratch cudaMalloc");
+  b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
+  return B2_OK;
+}
+static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int nsteps, void* stream) {
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  if ((rc = prepare_warp(b))) return rc;
+  const bool f64 = b->precision == B2_F64;
+  if (b->warp_mode == 1)
+    return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream);
+  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
+             : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
 }
 
 // make sure this batch's model is the image resident in constant memory on its device
@@ -163,10 +216,8 @@ int b2_step(b2_batch* b, const b2_state* st, int nsteps, const b2_derived* deriv
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     rc = k->step(st, derived, b->nenv, nsteps, stream);
   } else {
-    rc = ensure_resident(b, stream);
-    if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
-                                : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
+    rc = launch_generic_step(b, st, derived, nsteps, stream);
+    if (rc < 0) return rc;
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_step launch") : B2_OK;
@@ -180,10 +231,8 @@ int b2_forward(b2_batch* b, const b2_state* st, const b2_derived* derived, void*
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     rc = k->step(st, derived, b->nenv, 0, stream);
   } else {
-    rc = ensure_resident(b, stream);
-    if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, 0, stream)
-                                : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, 0, stream);
+    rc = launch_generic_step(b, st, derived, 0, stream);
+    if (rc < 0) return rc;
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_forward launch") : B2_OK;

@@ -23,6 +23,13 @@
 #define B2_UNROLL
 #endif
 #define B2_NOUNROLL _Pragma("unroll 1")
+// stage-sized member functions: inlined under a static provider (registers), real calls in the
+// generic build (the env lives in local memory there anyway; keeps compile time and code size down)
+#ifdef B2_STATIC_MODEL
+#define B2_STAGE __device__ __forceinline__
+#else
+#define B2_STAGE __device__ __noinline__
+#endif
 
 namespace b2 {
 
@@ -69,7 +76,7 @@ struct LaneEnv {
   static B2_DEV bool is_anc(int i, int j) { return (((unsigned)M::dof_anc(i)) >> j) & 1u; }
 
   // ------------------------------------------------------------------ position stage
-  B2_DEV void kinematics() {
+  B2_STAGE void kinematics() {
     xpos[0] = xpos[1] = xpos[2] = 0; xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
     quat_to_mat(xmat, xquat);
     xipos[0] = xipos[1] = xipos[2] = 0; quat_to_mat(ximat, xquat);
@@ -153,7 +160,7 @@ struct LaneEnv {
   }
 
   // subtree centres of mass, com-frame inertias, motion axes
-  B2_DEV void com_frame() {
+  B2_STAGE void com_frame() {
     const int nb = M::nbody();
     B2_UNROLL
     for (int k = 0; k < 3 * nb; k++) com[k] = 0;
@@ -199,7 +206,7 @@ struct LaneEnv {
     }
   }
 
-  B2_DEV void tendons() {
+  B2_STAGE void tendons() {
     const int nv = M::nv();
     B2_UNROLL
     for (int t = 0; t < M::ntendon(); t++) {
@@ -217,7 +224,7 @@ struct LaneEnv {
   }
 
   // composite rigid body algorithm -> dense symmetric mass matrix
-  B2_DEV void mass_matrix() {
+  B2_STAGE void mass_matrix() {
     const int nb = M::nbody(), nv = M::nv();
     T* crb = spat2;
     B2_UNROLL
@@ -246,7 +253,7 @@ struct LaneEnv {
   }
 
   // in-place L'DL factorisation of the matrix held in LD (tree sparsity), dinv <- 1/D
-  B2_DEV void factor_LD() {
+  B2_STAGE void factor_LD() {
     const int nv = M::nv();
     B2_UNROLL
     for (int k = nv - 1; k >= 0; k--) {
@@ -314,7 +321,7 @@ struct LaneEnv {
     }
   }
 
-  B2_DEV void transmission() {
+  B2_STAGE void transmission() {
     const int nv = M::nv();
     B2_UNROLL
     for (int a = 0; a < M::nu(); a++) {
@@ -349,7 +356,7 @@ struct LaneEnv {
     return r;
   }
   // joint and tendon limit rows (they precede contact rows, as in mj_makeConstraint)
-  B2_DEV void limit_rows() {
+  B2_STAGE void limit_rows() {
     const int nv = M::nv();
     nefc = 0;
     B2_UNROLL
@@ -378,7 +385,7 @@ struct LaneEnv {
   }
   // record one contact of candidate pair `pair` and append its rows: frame * (jac(b2) - jac(b1)),
   // one row for condim 1, four pyramid edges (normal +- mu * tangent) for condim 3
-  B2_DEV bool add_contact(int pair, T dist, const T* pos, const T* normal, const T* tangent_hint) {
+  B2_STAGE bool add_contact(int pair, T dist, const T* pos, const T* normal, const T* tangent_hint) {
     if (ncon >= D::NCON) { flags |= 8; return false; }
     const int c = ncon++;
     R.con_dist[c] = dist; R.con_pair[c] = (short)pair;
@@ -467,7 +474,7 @@ struct LaneEnv {
   }
 
   // narrow phase over the statically filtered candidate pairs; contacts append their rows
-  B2_DEV void collide() {
+  B2_STAGE void collide() {
     ncon = 0;
     B2_UNROLL
     for (int p = 0; p < M::npair(); p++) {
@@ -551,7 +558,7 @@ struct LaneEnv {
   }
 
   // impedance, regulariser D = 1/R and reference acceleration of every row (runtime row loop)
-  B2_DEV void row_params() {
+  B2_STAGE void row_params() {
     const int nv = M::nv();
     int within = 0;  // row index inside the current pyramidal contact
     T Rpy = 0;
@@ -602,7 +609,7 @@ struct LaneEnv {
   }
 
   // ------------------------------------------------------------------ velocity stage
-  B2_DEV void velocities() {
+  B2_STAGE void velocities() {
     for (int k = 0; k < 6; k++) cvel[k] = 0;
     B2_UNROLL
     for (int i = 1; i < M::nbody(); i++) {
@@ -674,7 +681,7 @@ struct LaneEnv {
     });
   }
 
-  B2_DEV void passive_forces() {
+  B2_STAGE void passive_forces() {
     const int nv = M::nv();
     B2_UNROLL
     for (int k = 0; k < nv; k++) f_passive[k] = 0;
@@ -717,7 +724,7 @@ struct LaneEnv {
   }
 
   // recursive Newton-Euler without accelerations: Coriolis, centrifugal, gravity
-  B2_DEV void bias_forces() {
+  B2_STAGE void bias_forces() {
     const int nb = M::nbody(), nv = M::nv();
     T* cacc = spat;
     T* cfrc = spat2;
@@ -752,7 +759,7 @@ struct LaneEnv {
   }
 
   // ------------------------------------------------------------------ smooth acceleration
-  B2_DEV void smooth_dynamics() {
+  B2_STAGE void smooth_dynamics() {
     const int nv = M::nv();
     T* f_act = grad;  // scratch: generalized actuator force
     B2_UNROLL
@@ -818,7 +825,7 @@ struct LaneEnv {
     return flag;
   }
   // exact 1-D minimisation of the piecewise-quadratic cost along `search`
-  B2_DEV T line_search() {
+  B2_STAGE T line_search() {
     const int nv = M::nv();
     LsPoint p0, p1, p2, pmid, p1n, p2n;
     ls_iter = 0;
@@ -868,7 +875,7 @@ struct LaneEnv {
     return 0;
   }
   // cost, forces, gradient and Newton direction at the current qacc
-  B2_DEV void newton_refresh() {
+  B2_STAGE void newton_refresh() {
     const int nv = M::nv();
     cost = row_cost(R.Jaref, true);
     T g = 0;
@@ -927,7 +934,7 @@ struct LaneEnv {
     }
   }
   // warm-started Newton solve (only entered when at least one row exists)
-  B2_DEV void newton_solve() {
+  B2_STAGE void newton_solve() {
     const int nv = M::nv();
     // warm start: keep qacc_warmstart only if it is cheaper than the unconstrained acceleration
     B2_UNROLL
@@ -990,7 +997,7 @@ struct LaneEnv {
   }
 
   // ------------------------------------------------------------------ forward + integrators
-  B2_DEV void forward() {
+  B2_STAGE void forward() {
     kinematics();
     com_frame();
     tendons();
@@ -1035,7 +1042,7 @@ struct LaneEnv {
     B2_UNROLL
     for (int k = 0; k < M::nv(); k++) if (!(fabs(qvel[k]) <= T(1e10))) flags |= 2;
   }
-  B2_DEV void euler() {
+  B2_STAGE void euler() {
     const int nv = M::nv();
     const T h = M::timestep();
     T* acc = grad;
@@ -1057,7 +1064,7 @@ struct LaneEnv {
   }
   // classical RK4 over (qpos, qvel) with tangent-space position updates; the stage loop is
   // kept rolled so forward() is instantiated once here
-  B2_DEV void rk4() {
+  B2_STAGE void rk4() {
     const int nq = M::nq(), nv = M::nv();
     const T h = M::timestep();
     const T A[9] = {T(0.5), 0, 0, 0, T(0.5), 0, 0, 0, 1}, B[4] = {T(1) / 6, T(1) / 3, T(1) / 3, T(1) / 6};

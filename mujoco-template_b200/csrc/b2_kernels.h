@@ -6,6 +6,10 @@
 namespace b2 {
 #define B2_DECL(SUF)                                                                                                       \
   double b2k_fma_peak##SUF(void* stream);                                                                                  \
+  int b2k_warp_plan##SUF(const b2m_view* v, int N, int* out_wpb, int* out_blocks);                                        \
+  size_t b2k_warp_scratch_bytes##SUF(const b2m_view* v, int slots);                                                        \
+  int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,  \
+                         int wpb, int blocks, void* stream);                                                                                  \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
   int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);                  \
   int b2k_linearize##SUF(int cls, const b2_state* st, int N, int ncol, double eps, int centered, void* A, void* B,         \

@@ -6,6 +6,7 @@
 
 #include "b2_kernel_templates.cuh"
 #include "b2_kernels.h"
+#include "b2_warp_kernels.cuh"
 
 namespace b2 {
 
@@ -21,8 +22,9 @@ template <> struct ConstImage<DimsSmall> { static B2_DEV const DevModel<real, Di
 template <> struct ConstImage<DimsLarge> { static B2_DEV const DevModel<real, DimsLarge>& get() { return c_model_large; } };
 
 // provider that reads the constant-bank image: uniform operands, any model of the size class
-template <class D>
+template <class DD>
 struct RuntimeModel {
+  typedef DD D;
 #define X(name) static B2_DEV int name() { return ConstImage<D>::get().name; }
   B2_MODEL_INT_SCALARS(X)
 #undef X
@@ -33,6 +35,26 @@ struct RuntimeModel {
   B2_MODEL_INT_ARRAYS(X)
 #undef X
 #define X(name, cap) static B2_DEV real name(int i) { return ConstImage<D>::get().name[i]; }
+  B2_MODEL_REAL_ARRAYS(X)
+#undef X
+};
+
+// Global-memory copy of the large image for the warp engine: its lanes read the model with
+// lane-dependent indices, which the constant cache would serialise (one address per cycle);
+// read-only global loads are gathered by L1 instead.
+__device__ DevModel<real, DimsLarge> g_model_large;
+struct GlobalModelLarge {
+  typedef DimsLarge D;
+#define X(name) static B2_DEV int name() { return __ldg(&g_model_large.name); }
+  B2_MODEL_INT_SCALARS(X)
+#undef X
+#define X(name) static B2_DEV real name() { return __ldg(&g_model_large.name); }
+  B2_MODEL_REAL_SCALARS(X)
+#undef X
+#define X(name, cap) static B2_DEV int name(int i) { return __ldg(&g_model_large.name[i]); }
+  B2_MODEL_INT_ARRAYS(X)
+#undef X
+#define X(name, cap) static B2_DEV real name(int i) { return __ldg(&g_model_large.name[i]); }
   B2_MODEL_REAL_ARRAYS(X)
 #undef X
 };
@@ -66,6 +88,9 @@ template <> cudaError_t upload_t<DimsSmall>(const b2m_view& v, const int* disabl
 }
 template <> cudaError_t upload_t<DimsLarge>(const b2m_view& v, const int* disabled, cudaStream_t s) {
   static DevModel<real, DimsLarge> h; fill_dev_model(h, v, disabled);
+  cudaError_t e = cudaMemcpyToSymbolAsync(g_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  if ((e = upload_tri_tables(s)) != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
@@ -111,6 +136,40 @@ int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int N, i
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_step<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
                        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps)));
+  return (int)cudaGetLastError();
+}
+// ---- warp engine (large models): launch geometry and per-warp scratch are sized by the host
+static int warp_ws_reals_of(const b2m_view* v) {
+  return warp_ws_reals<void>(v->nq, v->nv, v->nu, v->nbody, v->njnt, v->ngeom, v->ntendon);
+}
+static size_t warp_block_smem(const b2m_view* v, int wpb) {
+  return (size_t)wpb * ((size_t)warp_ws_reals_of(v) * sizeof(real) + (size_t)kWarpIntsAsReals * sizeof(double));
+}
+// chooses warps-per-block / grid so that every SM is filled; returns the number of warp slots
+int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int wpb = 2;
+  const size_t smem = warp_block_smem(v, wpb);
+  auto kern = k_warp_step<real, GlobalModelLarge>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return -1;
+  int blocks = sms * per_sm;
+  const int need = (N + wpb - 1) / wpb;
+  if (blocks > need) blocks = need;
+  *out_wpb = wpb; *out_blocks = blocks;
+  return blocks * wpb;
+}
+size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
+  return (size_t)slots * WarpCaps::NEFC * (v->nv + 6) * sizeof(real);
+}
+int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
+                         int wpb, int blocks, void* stream) {
+  const size_t smem = warp_block_smem(v, wpb);
+  k_warp_step<real, GlobalModelLarge><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+      to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, warp_ws_reals_of(v));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int N, int ncol, double eps, int centered, void* A, void* B, void* stream) {

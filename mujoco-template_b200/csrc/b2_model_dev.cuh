@@ -37,12 +37,12 @@ enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT
 // Field lists (X-macros): X(name) for scalars, X(name, capacity) for arrays.
 #define B2_MODEL_INT_SCALARS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(npair) X(integrator) X(iterations) X(ls_iterations) \
-  X(has_fluid) X(has_dofdamping)
+  X(has_fluid) X(has_dofdamping) X(maxdepth)
 #define B2_MODEL_REAL_SCALARS(X) X(timestep) X(density) X(viscosity) X(tolerance) X(ls_tolerance) X(meaninertia)
 #define B2_MODEL_INT_ARRAYS(X)                                                                                        \
   X(body_parentid, D::NB) X(body_rootid, D::NB) X(body_jntnum, D::NB) X(body_jntadr, D::NB) X(body_dofnum, D::NB)    \
-  X(body_dofadr, D::NB) X(jnt_type, D::NJ) X(jnt_qposadr, D::NJ) X(jnt_dofadr, D::NJ) X(jnt_bodyid, D::NJ)           \
-  X(jnt_limited, D::NJ) X(dof_bodyid, D::NV) X(dof_jntid, D::NV) X(dof_parentid, D::NV) X(dof_anc, D::NV)            \
+  X(body_dofadr, D::NB) X(body_anc, D::NB) X(body_depth, D::NB) X(jnt_type, D::NJ) X(jnt_qposadr, D::NJ) X(jnt_dofadr, D::NJ) X(jnt_bodyid, D::NJ)           \
+  X(jnt_limited, D::NJ) X(dof_bodyid, D::NV) X(dof_jntid, D::NV) X(dof_parentid, D::NV) X(dof_anc, D::NV) X(dof_nanc, D::NV) X(dof_anclist, D::NV * D::NV)            \
   X(geom_type, D::NG) X(geom_bodyid, D::NG) X(site_bodyid, D::NS) X(tendon_adr, D::NT) X(tendon_num, D::NT)          \
   X(tendon_limited, D::NT) X(wrap_jntid, D::NW) X(actuator_trntype, D::NU) X(actuator_trnid, D::NU)                  \
   X(actuator_ctrllimited, D::NU) X(actuator_forcelimited, D::NU) X(actuator_disabled, D::NU) X(pair_geom1, D::NPAIR) \
@@ -118,6 +118,21 @@ inline void fill_dev_model(DevModel<T, D>& m, const b2m_view& v, const int* actu
   fill(m.jnt_solimp, v.jnt_solimp, 5 * nj); fill(m.qpos0, v.qpos0, v.nq); fill(m.qpos_spring, v.qpos_spring, v.nq);
   fill(m.dof_bodyid, v.dof_bodyid, nv); fill(m.dof_jntid, v.dof_jntid, nv); fill(m.dof_parentid, v.dof_parentid, nv);
   dof_ancestor_masks(v, m.dof_anc);
+  // proper-ancestor lists (nearest first) with stride D::NV, for the warp engine's pivot updates
+  for (int i = 0; i < nv; i++) {
+    int n = 0;
+    for (int j = v.dof_parentid[i]; j >= 0; j = v.dof_parentid[j]) m.dof_anclist[i * D::NV + n++] = j;
+    m.dof_nanc[i] = n;
+  }
+  // body_anc[i]: bit j set iff body j is i or an ancestor of i (needs nbody <= 32); depth of world = 0
+  m.maxdepth = 0;
+  for (int i = 0; i < nb && i < 32; i++) {
+    unsigned mask = 1u << i;
+    int depth = 0;
+    for (int j = i; j > 0; j = v.body_parentid[j]) { mask |= 1u << v.body_parentid[j]; depth++; }
+    m.body_anc[i] = (int)mask; m.body_depth[i] = depth;
+    if (depth > m.maxdepth) m.maxdepth = depth;
+  }
   fill(m.dof_armature, v.dof_armature, nv); fill(m.dof_damping, v.dof_damping, nv); fill(m.dof_invweight0, v.dof_invweight0, nv);
   fill(m.geom_type, v.geom_type, ng); fill(m.geom_bodyid, v.geom_bodyid, ng); fill(m.geom_size, v.geom_size, 3 * ng);
   fill(m.geom_rbound, v.geom_rbound, ng); fill(m.geom_pos, v.geom_pos, 3 * ng); fill(m.geom_quat, v.geom_quat, 4 * ng);

@@ -1,0 +1,994 @@
+// Warp-cooperative rigid-body engine ("warp engine": one env per warp) for large models.
+//
+// Same physics as the lane engine (b2_engine.cuh) -- what the reference reaches through
+// mj.mj_step (reference mujoco_template/model.py:56-57) -- but one env is spread over the 32
+// lanes of a warp: tree passes run level by level with one body per lane, the packed mass matrix
+// and the Newton Hessian are updated with one entry group per lane, constraint rows and contact
+// candidates are distributed over lanes, reductions use warp shuffles.  The per-env workspace
+// (poses, inertias, motion axes, packed M / L'DL / H, force vectors, contact and row metadata)
+// lives in shared memory; only the dense constraint Jacobian J (nefc x nv) sits in an
+// L2-resident global scratch slot owned by the warp (together with the per-row vectors).
+//
+// Supported model features: free / hinge / slide joints, joint-transmission actuators, fixed
+// tendons, plane / sphere / capsule geoms, semi-implicit Euler.  Anything else (fluid forces, site
+// transmissions, box / ellipsoid geoms, RK4) is routed to the lane engine by the host.
+#pragma once
+#include "b2_math.cuh"
+#include "b2_model_dev.cuh"
+
+namespace b2 {
+
+#define WFOR(i, n) for (int i = lane; i < (n); i += 32)
+
+template <typename T> B2_DEV T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+B2_DEV int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower triangle, j <= i
+// inverse of tri(): (row, col) of packed entry e, for matrices up to 32 x 32 (filled at load time)
+static __device__ unsigned char g_tri_row[528], g_tri_col[528];
+B2_DEV void untri(int e, int& i, int& j) { i = __ldg(&g_tri_row[e]); j = __ldg(&g_tri_col[e]); }
+inline cudaError_t upload_tri_tables(cudaStream_t s) {
+  static unsigned char row[528], col[528];
+  int e = 0;
+  for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) { row[e] = (unsigned char)i; col[e] = (unsigned char)j; e++; }
+  cudaError_t err = cudaMemcpyToSymbolAsync(g_tri_row, row, sizeof(row), 0, cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return err;
+  return cudaMemcpyToSymbolAsync(g_tri_col, col, sizeof(col), 0, cudaMemcpyHostToDevice, s);
+}
+
+struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
+
+// number of T elements of shared memory one env needs
+template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int nj, int ng, int nt) {
+  const int np = nv * (nv + 1) / 2;
+  int overlayA = 9 * nb + 6 * nj;          // ximat + xanchor + xaxis   | cdof_dot + cvel
+  const int overlayB = 6 * nv + 6 * nb;
+  if (overlayB > overlayA) overlayA = overlayB;
+  return (nq + 2 * nv + nu) + (3 + 4 + 9 + 3) * nb + overlayA + 6 * ng + 3 * nb + 10 * nb + 10 * nb + 6 * nv + 6 * nb +
+         2 * np + nv + nt + nt * nv + 11 * nv + 6 * (nv > nb ? nv : nb) + 13 * WarpCaps::NCON;
+}
+
+template <typename T, class M>
+struct WarpEnv {
+  int lane, ncon, nefc, niter, flags;
+  T *qpos, *qvel, *ctrl, *warm;
+  T *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *cdof_dot, *cvel;
+  T *geom_xpos, *geom_z, *com, *cinert, *crb, *cdof, *cacc;
+  T *Mp, *LDp, *dinv, *ten_len, *ten_J;
+  T *f_bias, *f_passive, *f_smooth, *f_con, *a_smooth, *qacc, *Ma, *Mv, *grad, *Mgrad, *search, *buf6;
+  T *con_dist, *con_pos, *con_frame, *row_pos, *row_margin, *row_D, *row_aref, *Jaref, *Jv;
+  int *con_pair, *row_meta;  // row_meta = type | id << 8
+  T* J;                      // global scratch, NEFC * nv
+  T cost, gauss, qg0, qg1, qg2;
+  int ls_iter;
+  unsigned active_sig[(WarpCaps::NEFC + 31) / 32];  // active-row bit set the factor in LDp was built for
+  bool hess_valid;
+
+  B2_DEV void bind(T* base, int* ibase, T* jscratch) {
+    const int nq = M::nq(), nv = M::nv(), nu = M::nu(), nb = M::nbody(), nj = M::njnt(), ng = M::ngeom(), nt = M::ntendon();
+    const int np = nv * (nv + 1) / 2;
+    T* p = base;
+    auto take = [&](int n) { T* r = p; p += n; return r; };
+    qpos = take(nq); qvel = take(nv); ctrl = take(nu); warm = take(nv);
+    xpos = take(3 * nb); xquat = take(4 * nb); xmat = take(9 * nb); xipos = take(3 * nb);
+    T* ov = p;
+    ximat = take(9 * nb); xanchor = take(3 * nj); xaxis = take(3 * nj);
+    cdof_dot = ov; cvel = ov + 6 * nv;
+    const int ovA = 9 * nb + 6 * nj, ovB = 6 * nv + 6 * nb;
+    p = ov + (ovA > ovB ? ovA : ovB);
+    geom_xpos = take(3 * ng); geom_z = take(3 * ng); com = take(3 * nb); cinert = take(10 * nb); crb = take(10 * nb);
+    cdof = take(6 * nv); cacc = take(6 * nb);
+    Mp = take(np); LDp = take(np); dinv = take(nv); ten_len = take(nt); ten_J = take(nt * nv);
+    f_bias = take(nv); f_passive = take(nv); f_smooth = take(nv); f_con = take(nv); a_smooth = take(nv); qacc = take(nv);
+    Ma = take(nv); Mv = take(nv); grad = take(nv); Mgrad = take(nv); search = take(nv); buf6 = take(6 * (nv > nb ? nv : nb));
+    con_dist = take(WarpCaps::NCON); con_pos = take(3 * WarpCaps::NCON); con_frame = take(9 * WarpCaps::NCON);
+    con_pair = ibase; row_meta = ibase + WarpCaps::NCON;
+    // per-row data lives in the warp's global scratch slot (L1/L2 resident): J, then six row vectors
+    J = jscratch;
+    T* rv = jscratch + WarpCaps::NEFC * nv;
+    row_pos = rv; row_margin = rv + WarpCaps::NEFC; row_D = rv + 2 * WarpCaps::NEFC; row_aref = rv + 3 * WarpCaps::NEFC;
+    Jaref = rv + 4 * WarpCaps::NEFC; Jv = rv + 5 * WarpCaps::NEFC;
+    lane = threadIdx.x & 31;
+    ncon = nefc = niter = flags = 0;
+  }
+  static B2_DEV bool dof_is_anc(int i, int j) { return (((unsigned)M::dof_anc(i)) >> j) & 1u; }
+  static B2_DEV bool in_subtree(int root, int b) { return (((unsigned)M::body_anc(b)) >> root) & 1u; }
+
+  // ------------------------------------------------------------------ position stage
+  B2_DEV void kinematics() {
+    const int nb = M::nbody();
+    if (lane == 0) {
+      for (int k = 0; k < 3; k++) { xpos[k] = 0; xipos[k] = 0; }
+      xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
+      quat_to_mat(xmat, xquat); quat_to_mat(ximat, xquat);
+    }
+    __syncwarp();
+    for (int level = 1; level <= M::maxdepth(); level++) {
+      const int i = lane;
+      if (i < nb && M::body_depth(i) == level) {
+        T p[3], q[4];
+        const int ja = M::body_jntadr(i), jn = M::body_jntnum(i), pid = M::body_parentid(i);
+        if (jn == 1 && M::jnt_type(ja) == JNT_FREE) {
+          const int qa = M::jnt_qposadr(ja);
+          for (int k = 0; k < 3; k++) p[k] = qpos[qa + k];
+          for (int k = 0; k < 4; k++) q[k] = qpos[qa + 3 + k];
+          normalize4(q);
+          for (int k = 0; k < 3; k++) { xanchor[3 * ja + k] = p[k]; xaxis[3 * ja + k] = M::jnt_axis(3 * ja + k); }
+        } else {
+          T bpos[3] = {M::body_pos(3 * i), M::body_pos(3 * i + 1), M::body_pos(3 * i + 2)};
+          T bquat[4] = {M::body_quat(4 * i), M::body_quat(4 * i + 1), M::body_quat(4 * i + 2), M::body_quat(4 * i + 3)};
+          if (pid) {
+            T pm[9], pq[4];
+            for (int k = 0; k < 9; k++) pm[k] = xmat[9 * pid + k];
+            for (int k = 0; k < 4; k++) pq[k] = xquat[4 * pid + k];
+            mat_vec(p, pm, bpos);
+            for (int k = 0; k < 3; k++) p[k] += xpos[3 * pid + k];
+            quat_mul(q, pq, bquat);
+          } else {
+            for (int k = 0; k < 3; k++) p[k] = bpos[k];
+            for (int k = 0; k < 4; k++) q[k] = bquat[k];
+          }
+          for (int j = ja; j < ja + jn; j++) {
+            T anchor[3], axis[3];
+            const int qa = M::jnt_qposadr(j);
+            T jaxis[3] = {M::jnt_axis(3 * j), M::jnt_axis(3 * j + 1), M::jnt_axis(3 * j + 2)};
+            T jpos[3] = {M::jnt_pos(3 * j), M::jnt_pos(3 * j + 1), M::jnt_pos(3 * j + 2)};
+            quat_rot(axis, jaxis, q);
+            quat_rot(anchor, jpos, q);
+            for (int k = 0; k < 3; k++) anchor[k] += p[k];
+            const T disp = qpos[qa] - M::qpos0(qa);
+            if (M::jnt_type(j) == JNT_SLIDE) {
+              for (int k = 0; k < 3; k++) p[k] += axis[k] * disp;
+            } else {
+              T ql[4], off[3];
+              quat_axis_angle(ql, jaxis, disp);
+              quat_mul(q, q, ql);
+              quat_rot(off, jpos, q);
+              for (int k = 0; k < 3; k++) p[k] = anchor[k] - off[k];
+            }
+            for (int k = 0; k < 3; k++) { xanchor[3 * j + k] = anchor[k]; xaxis[3 * j + k] = axis[k]; }
+          }
+        }
+        normalize4(q);
+        T m9[9], qi[4], ip[3];
+        quat_to_mat(m9, q);
+        for (int k = 0; k < 3; k++) xpos[3 * i + k] = p[k];
+        for (int k = 0; k < 4; k++) xquat[4 * i + k] = q[k];
+        for (int k = 0; k < 9; k++) xmat[9 * i + k] = m9[k];
+        T ipos[3] = {M::body_ipos(3 * i), M::body_ipos(3 * i + 1), M::body_ipos(3 * i + 2)};
+        T iquat[4] = {M::body_iquat(4 * i), M::body_iquat(4 * i + 1), M::body_iquat(4 * i + 2), M::body_iquat(4 * i + 3)};
+        mat_vec(ip, m9, ipos);
+        for (int k = 0; k < 3; k++) xipos[3 * i + k] = ip[k] + p[k];
+        quat_mul(qi, q, iquat);
+        quat_to_mat(m9, qi);
+        for (int k = 0; k < 9; k++) ximat[9 * i + k] = m9[k];
+      }
+      __syncwarp();
+    }
+    WFOR(g, M::ngeom()) {
+      const int b = M::geom_bodyid(g);
+      T gp[3] = {M::geom_pos(3 * g), M::geom_pos(3 * g + 1), M::geom_pos(3 * g + 2)};
+      T gq[4] = {M::geom_quat(4 * g), M::geom_quat(4 * g + 1), M::geom_quat(4 * g + 2), M::geom_quat(4 * g + 3)};
+      T bm[9], bq[4], r[3], q[4], m9[9];
+      for (int k = 0; k < 9; k++) bm[k] = xmat[9 * b + k];
+      for (int k = 0; k < 4; k++) bq[k] = xquat[4 * b + k];
+      mat_vec(r, bm, gp);
+      for (int k = 0; k < 3; k++) geom_xpos[3 * g + k] = r[k] + xpos[3 * b + k];
+      quat_mul(q, bq, gq);
+      quat_to_mat(m9, q);
+      geom_z[3 * g] = m9[2]; geom_z[3 * g + 1] = m9[5]; geom_z[3 * g + 2] = m9[8];
+    }
+    __syncwarp();
+  }
+
+  // subtree centres of mass, com-frame inertias, motion axes
+  B2_DEV void com_frame() {
+    const int nb = M::nbody();
+    WFOR(i, nb) {
+      T s[3] = {0, 0, 0};
+      for (int j = i; j < nb; j++)
+        if (in_subtree(i, j)) { const T mj = M::body_mass(j); for (int k = 0; k < 3; k++) s[k] += xipos[3 * j + k] * mj; }
+      if (M::body_subtreemass(i) < Num<T>::minval()) { for (int k = 0; k < 3; k++) s[k] = xipos[3 * i + k]; }
+      else { const T inv = T(1) / tmax(Num<T>::minval(), M::body_subtreemass(i)); for (int k = 0; k < 3; k++) s[k] *= inv; }
+      for (int k = 0; k < 3; k++) com[3 * i + k] = s[k];
+    }
+    __syncwarp();
+    WFOR(i, nb) {
+      T ci[10];
+      if (i == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; }
+      else {
+        const int r = M::body_rootid(i);
+        T off[3], inertia[3] = {M::body_inertia(3 * i), M::body_inertia(3 * i + 1), M::body_inertia(3 * i + 2)}, im[9];
+        for (int k = 0; k < 3; k++) off[k] = xipos[3 * i + k] - com[3 * r + k];
+        for (int k = 0; k < 9; k++) im[k] = ximat[9 * i + k];
+        inert_about(ci, inertia, im, off, M::body_mass(i));
+      }
+      for (int k = 0; k < 10; k++) cinert[10 * i + k] = ci[k];
+    }
+    WFOR(j, M::njnt()) {
+      const int b = M::jnt_bodyid(j), r = M::body_rootid(b);
+      T* cd = cdof + 6 * M::jnt_dofadr(j);
+      T off[3], ax[3];
+      for (int k = 0; k < 3; k++) off[k] = com[3 * r + k] - xanchor[3 * j + k];
+      const int t = M::jnt_type(j);
+      if (t == JNT_FREE) {
+        for (int k = 0; k < 18; k++) cd[k] = 0;
+        cd[3] = 1; cd[10] = 1; cd[17] = 1;
+        for (int a = 0; a < 3; a++) {
+          T c3[3];
+          ax[0] = xmat[9 * b + a]; ax[1] = xmat[9 * b + a + 3]; ax[2] = xmat[9 * b + a + 6];
+          cross3(c3, ax, off);
+          T* c = cd + 18 + 6 * a;
+          c[0] = ax[0]; c[1] = ax[1]; c[2] = ax[2]; c[3] = c3[0]; c[4] = c3[1]; c[5] = c3[2];
+        }
+      } else if (t == JNT_SLIDE) {
+        cd[0] = cd[1] = cd[2] = 0;
+        for (int k = 0; k < 3; k++) cd[3 + k] = xaxis[3 * j + k];
+      } else {
+        T c3[3];
+        for (int k = 0; k < 3; k++) ax[k] = xaxis[3 * j + k];
+        cross3(c3, ax, off);
+        for (int k = 0; k < 3; k++) { cd[k] = ax[k]; cd[3 + k] = c3[k]; }
+      }
+    }
+    WFOR(t, M::ntendon()) {
+      T L = 0;
+      for (int k = 0; k < M::nv(); k++) ten_J[t * M::nv() + k] = 0;
+      for (int w = M::tendon_adr(t); w < M::tendon_adr(t) + M::tendon_num(t); w++) {
+        const int j = M::wrap_jntid(w);
+        L += M::wrap_coef(w) * qpos[M::jnt_qposadr(j)];
+        ten_J[t * M::nv() + M::jnt_dofadr(j)] = M::wrap_coef(w);
+      }
+      ten_len[t] = L;
+    }
+    __syncwarp();
+  }
+
+  // composite inertias (subtree sums) and the packed lower-triangular mass matrix
+  B2_DEV void mass_matrix() {
+    const int nb = M::nbody(), nv = M::nv();
+    WFOR(i, nb) {
+      T s[10];
+      for (int k = 0; k < 10; k++) s[k] = cinert[10 * i + k];
+      if (i > 0)
+        for (int j = nb - 1; j > i; j--)   // children accumulate from the last body backwards, as upstream's reverse pass
+          if (in_subtree(i, j)) for (int k = 0; k < 10; k++) s[k] += cinert[10 * j + k];
+      for (int k = 0; k < 10; k++) crb[10 * i + k] = s[k];
+    }
+    __syncwarp();
+    WFOR(d, nv) {
+      T b6[6], c[10], cd[6];
+      const int b = M::dof_bodyid(d);
+      for (int k = 0; k < 10; k++) c[k] = crb[10 * b + k];
+      for (int k = 0; k < 6; k++) cd[k] = cdof[6 * d + k];
+      inert_mul(b6, c, cd);
+      for (int k = 0; k < 6; k++) buf6[6 * d + k] = b6[k];
+    }
+    __syncwarp();
+    const int np = nv * (nv + 1) / 2;
+    WFOR(e, np) {
+      int i, j;
+      untri(e, i, j);
+      T v = 0;
+      if (dof_is_anc(i, j)) { for (int k = 0; k < 6; k++) v += cdof[6 * j + k] * buf6[6 * i + k]; }
+      if (i == j) v = M::dof_armature(i) + v;
+      Mp[e] = v;
+    }
+    __syncwarp();
+  }
+
+  // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
+  B2_DEV void factor_LD() {
+    const int nv = M::nv();
+    T* tk = Mv;  // scratch: scaled pivot row (Mv is only live inside the line search)
+    constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
+    for (int k = nv - 1; k >= 0; k--) {
+      const int m = M::dof_nanc(k);  // proper ancestors of k, nearest first
+      const T dkk = LDp[tri(k, k)];
+      if (m) {
+        // t_i = L[k,i] / d_k once per ancestor i, then all ancestor pairs (i, j), j <= i, at once:
+        // L[i,j] -= t_i * L[k,j]   (the unscaled row k, exactly the scalar algorithm's operands)
+        if (lane < m) { const int i = M::dof_anclist(k * LS + lane); tk[i] = LDp[tri(k, i)] / dkk; }
+        __syncwarp();
+        for (int e = lane; e < m * m; e += 32) {
+          const int a = e / m, b = e - a * m;
+          if (b < a) continue;  // the list is descending: position b >= a  <=>  dof j <= dof i
+          const int i = M::dof_anclist(k * LS + a), j = M::dof_anclist(k * LS + b);
+          LDp[tri(i, j)] -= tk[i] * LDp[tri(k, j)];
+        }
+        __syncwarp();
+        if (lane < m) { const int i = M::dof_anclist(k * LS + lane); LDp[tri(k, i)] = tk[i]; }
+      }
+      if (lane == 0) dinv[k] = T(1) / dkk;
+      __syncwarp();
+    }
+  }
+  // x <- (L'DL)^-1 x, column-oriented sweeps (no reductions)
+  B2_DEV void solve_LD(T* x) {
+    const int nv = M::nv();
+    for (int i = nv - 1; i > 0; i--) {
+      const unsigned anc = ((unsigned)M::dof_anc(i)) & ~(1u << i);
+      const T xi = x[i];
+      WFOR(j, i) if ((anc >> j) & 1u) x[j] -= LDp[tri(i, j)] * xi;
+      __syncwarp();
+    }
+    WFOR(i, nv) x[i] *= dinv[i];
+    __syncwarp();
+    for (int j = 0; j < nv - 1; j++) {
+      const T xj = x[j];
+      for (int i = j + 1 + lane; i < nv; i += 32) if (dof_is_anc(i, j)) x[i] -= LDp[tri(i, j)] * xj;
+      __syncwarp();
+    }
+  }
+  B2_DEV void mul_M(T* r, const T* v) {
+    const int nv = M::nv();
+    WFOR(i, nv) {
+      T s = 0;
+      for (int j = 0; j < nv; j++) s += (j <= i ? Mp[tri(i, j)] : Mp[tri(j, i)]) * v[j];
+      r[i] = s;
+    }
+    __syncwarp();
+  }
+
+  // Jacobian column of dof d for a point on `body` at offset `off` from the root's subtree CoM; false if d does not move body
+  B2_DEV bool jac_col(int last, int d, const T* off, T* jp) const {
+    if (last < 0 || d > last || !dof_is_anc(last, d)) return false;
+    T c[6];
+    for (int k = 0; k < 6; k++) c[k] = cdof[6 * d + k];
+    cross3(jp, c, off);
+    jp[0] += c[3]; jp[1] += c[4]; jp[2] += c[5];
+    return true;
+  }
+  static B2_DEV int last_dof(int body) {
+    while (body && !M::body_dofnum(body)) body = M::body_parentid(body);
+    return body ? M::body_dofadr(body) + M::body_dofnum(body) - 1 : -1;
+  }
+
+  // ------------------------------------------------------------------ collision + rows
+  // candidate pairs are tested 32 at a time; contacts are appended in pair order (ballot prefix)
+  B2_DEV void collide() {
+    ncon = 0;
+    const int np = M::npair();
+    for (int base = 0; base < np; base += 32) {
+      const int p = base + lane;
+      int cnt = 0;
+      T cd[2], cpos[6], cfr[12];
+      if (p < np) {
+        const int g1 = M::pair_geom1(p), g2 = M::pair_geom2(p);
+        const T margin = M::pair_margin(p);
+        T p1[3], p2[3], z1[3], z2[3], d[3];
+        for (int k = 0; k < 3; k++) { p1[k] = geom_xpos[3 * g1 + k]; p2[k] = geom_xpos[3 * g2 + k]; z1[k] = geom_z[3 * g1 + k]; z2[k] = geom_z[3 * g2 + k]; d[k] = p2[k] - p1[k]; }
+        const int t1 = M::geom_type(g1), t2 = M::geom_type(g2);
+        const T r1 = M::geom_size(3 * g1), l1 = M::geom_size(3 * g1 + 1), r2 = M::geom_size(3 * g2), l2 = M::geom_size(3 * g2 + 1);
+        auto emit = [&](T dist, const T* pos, const T* n, const T* hint) {
+          cd[cnt] = dist;
+          for (int k = 0; k < 3; k++) { cpos[3 * cnt + k] = pos[k]; cfr[6 * cnt + k] = n[k]; cfr[6 * cnt + 3 + k] = hint ? hint[k] : T(0); }
+          cnt++;
+        };
+        auto plane_sphere = [&](const T* sp, T radius, const T* hint) {
+          T dd[3] = {sp[0] - p1[0], sp[1] - p1[1], sp[2] - p1[2]};
+          const T c = dot3(dd, z1);
+          if (c > margin + radius) return;
+          const T dist = c - radius, s = -dist / 2 - radius;
+          T pos[3] = {sp[0] + z1[0] * s, sp[1] + z1[1] * s, sp[2] + z1[2] * s};
+          emit(dist, pos, z1, hint);
+        };
+        auto sphere_sphere = [&](const T* a, T ra, const T* b, T rb) -> int {
+          T n[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+          const T dsq = dot3(n, n), lim = margin + ra + rb;
+          if (dsq > lim * lim) return 0;
+          const T c = normalize3(n);
+          const T dist = c - ra - rb;
+          if (c < Num<T>::minval()) { cross3(n, z1, z2); normalize3(n); }
+          const T s = ra + T(0.5) * dist;
+          T pos[3] = {a[0] + n[0] * s, a[1] + n[1] * s, a[2] + n[2] * s};
+          emit(dist, pos, n, nullptr);
+          return 1;
+        };
+        if (t1 == GEOM_PLANE) {
+          if (dot3(d, z1) <= margin + M::geom_rbound(g2)) {
+            if (t2 == GEOM_SPHERE) plane_sphere(p2, r2, nullptr);
+            else if (t2 == GEOM_CAPSULE) {
+              T e[3];
+              for (int k = 0; k < 3; k++) e[k] = p2[k] + z2[k] * l2;
+              plane_sphere(e, r2, z2);
+              for (int k = 0; k < 3; k++) e[k] = p2[k] - z2[k] * l2;
+              plane_sphere(e, r2, z2);
+            }
+          }
+        } else {
+          const T bound = margin + M::geom_rbound(g1) + M::geom_rbound(g2);
+          if (dot3(d, d) <= bound * bound) {
+            if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) sphere_sphere(p1, r1, p2, r2);
+            else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
+              T v[3] = {-d[0], -d[1], -d[2]};
+              const T x = tclip(dot3(z2, v), -l2, l2);
+              for (int k = 0; k < 3; k++) v[k] = p2[k] + z2[k] * x;
+              sphere_sphere(p1, r1, v, r2);
+            } else if (t1 == GEOM_CAPSULE && t2 == GEOM_CAPSULE) {
+              T dif[3] = {-d[0], -d[1], -d[2]}, v1[3], v2[3];
+              const T ma = dot3(z1, z1), mb = -dot3(z1, z2), mc = dot3(z2, z2), u = -dot3(z1, dif), w = dot3(z2, dif);
+              const T det = ma * mc - mb * mb;
+              if (fabs(det) >= Num<T>::minval()) {
+                T x1 = (mc * u - mb * w) / det, x2 = (ma * w - mb * u) / det;
+                if (x1 > l1) { x1 = l1; x2 = (w - mb * l1) / mc; }
+                else if (x1 < -l1) { x1 = -l1; x2 = (w + mb * l1) / mc; }
+                if (x2 > l2) { x2 = l2; x1 = tclip((u - mb * l2) / ma, -l1, l1); }
+                else if (x2 < -l2) { x2 = -l2; x1 = tclip((u + mb * l2) / ma, -l1, l1); }
+                for (int k = 0; k < 3; k++) { v1[k] = p1[k] + z1[k] * x1; v2[k] = p2[k] + z2[k] * x2; }
+                sphere_sphere(v1, r1, v2, r2);
+              } else {
+                int n = 0;
+                for (int side = 1; side >= -1 && n < 2; side -= 2) {
+                  const T x = tclip((w - side * mb * l1) / mc, -l2, l2);
+                  for (int k = 0; k < 3; k++) { v1[k] = p1[k] + z1[k] * (side * l1); v2[k] = p2[k] + z2[k] * x; }
+                  n += sphere_sphere(v1, r1, v2, r2);
+                }
+                for (int side = 1; side >= -1 && n < 2; side -= 2) {
+                  const T x = tclip((u - side * mb * l2) / ma, -l1, l1);
+                  for (int k = 0; k < 3; k++) { v2[k] = p2[k] + z2[k] * (side * l2); v1[k] = p1[k] + z1[k] * x; }
+                  n += sphere_sphere(v1, r1, v2, r2);
+                }
+              }
+            }
+          }
+        }
+      }
+      // exclusive prefix of per-lane contact counts (0..2) keeps pair order
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+      const int total = __shfl_sync(0xffffffffu, incl, 31);
+      const int start = ncon + incl - cnt;
+      for (int c = 0; c < cnt; c++) {
+        const int slot = start + c;
+        if (slot < WarpCaps::NCON) {
+          T fr[9];
+          for (int k = 0; k < 6; k++) fr[k] = cfr[6 * c + k];
+          make_frame(fr);
+          con_dist[slot] = cd[c]; con_pair[slot] = p;
+          for (int k = 0; k < 3; k++) con_pos[3 * slot + k] = cpos[3 * c + k];
+          for (int k = 0; k < 9; k++) con_frame[9 * slot + k] = fr[k];
+        }
+      }
+      ncon += total;
+      if (ncon > WarpCaps::NCON) { ncon = WarpCaps::NCON; flags |= 8; }
+    }
+    __syncwarp();
+  }
+
+  // limit rows (joints, then tendons) followed by contact rows; J rows are written one dof per lane
+  B2_DEV void make_rows() {
+    const int nv = M::nv();
+    nefc = 0;
+    auto zero_row = [&](int r) { WFOR(k, nv) J[r * nv + k] = 0; };
+    // joint limits: sequential over joints keeps upstream row order; the test itself is uniform
+    for (int j = 0; j < M::njnt(); j++) {
+      if (!M::jnt_limited(j) || M::jnt_type(j) < JNT_SLIDE) continue;
+      const T value = qpos[M::jnt_qposadr(j)], margin = M::jnt_margin(j);
+      for (int side = -1; side <= 1; side += 2) {
+        const T dist = side * (M::jnt_range(2 * j + (side + 1) / 2) - value);
+        if (dist < margin) {
+          if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
+          const int r = nefc++;
+          zero_row(r);
+          __syncwarp();
+          if (lane == 0) { row_meta[r] = ROW_LIMIT_JOINT | (j << 8); row_pos[r] = dist; row_margin[r] = margin; J[r * nv + M::jnt_dofadr(j)] = T(-side); }
+        }
+      }
+    }
+    for (int t = 0; t < M::ntendon(); t++) {
+      if (!M::tendon_limited(t)) continue;
+      const T value = ten_len[t], margin = M::tendon_margin(t);
+      for (int side = -1; side <= 1; side += 2) {
+        const T dist = side * (M::tendon_range(2 * t + (side + 1) / 2) - value);
+        if (dist < margin) {
+          if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
+          const int r = nefc++;
+          WFOR(k, nv) J[r * nv + k] = -side * ten_J[t * nv + k];
+          if (lane == 0) { row_meta[r] = ROW_LIMIT_TENDON | (t << 8); row_pos[r] = dist; row_margin[r] = margin; }
+        }
+      }
+    }
+    for (int c = 0; c < ncon; c++) {
+      const int p = con_pair[c];
+      const T incl = M::pair_margin(p) - M::pair_gap(p), dist = con_dist[c];
+      if (dist >= incl) continue;
+      const int dim = M::pair_dim(p), nrow = dim == 1 ? 1 : 4;
+      if (nefc + nrow > WarpCaps::NEFC) { flags |= 8; break; }
+      const int r0 = nefc;
+      nefc += nrow;
+      const int b1 = M::geom_bodyid(M::pair_geom1(p)), b2 = M::geom_bodyid(M::pair_geom2(p));
+      const int last1 = last_dof(b1), last2 = last_dof(b2);
+      const T mu = M::pair_friction(2 * p);
+      T fr[9], pos[3], off1[3], off2[3];
+      for (int k = 0; k < 9; k++) fr[k] = con_frame[9 * c + k];
+      for (int k = 0; k < 3; k++) { pos[k] = con_pos[3 * c + k]; off1[k] = pos[k] - com[3 * M::body_rootid(b1) + k]; off2[k] = pos[k] - com[3 * M::body_rootid(b2) + k]; }
+      WFOR(d, nv) {
+        T acc[4] = {0, 0, 0, 0}, jp[3];
+        // body 1 enters with a minus sign, then body 2 with a plus sign (same accumulation order as the lane engine)
+        for (int pass = 0; pass < 2; pass++) {
+          const T sgn = pass ? T(1) : T(-1);
+          if (!jac_col(pass ? last2 : last1, d, pass ? off2 : off1, jp)) continue;
+          const T jn = sgn * dot3(fr, jp);
+          if (dim == 1) { acc[0] += jn; continue; }
+          const T j1 = sgn * dot3(fr + 3, jp), j2 = sgn * dot3(fr + 6, jp);
+          acc[0] += jn + mu * j1; acc[1] += jn - mu * j1; acc[2] += jn + mu * j2; acc[3] += jn - mu * j2;
+        }
+        for (int k = 0; k < nrow; k++) J[(r0 + k) * nv + d] = acc[k];
+      }
+      if (lane < nrow) { row_meta[r0 + lane] = (dim == 1 ? ROW_CONTACT_1 : ROW_CONTACT_PYR) | (c << 8); row_pos[r0 + lane] = dist; row_margin[r0 + lane] = incl; }
+    }
+    __syncwarp();
+  }
+
+  static B2_DEV T impedance(const T* si, T pos, T margin) {
+    const T lo = T(0.0001), hi = T(0.9999);
+    const T dmin = tclip(si[0], lo, hi), dmax = tclip(si[1], lo, hi), width = tmax(Num<T>::minval(), si[2]);
+    const T mid = tclip(si[3], lo, hi), power = tmax(T(1), si[4]);
+    if (dmin == dmax || width <= Num<T>::minval()) return T(0.5) * (dmin + dmax);
+    T x = (pos - margin) / width;
+    if (x < 0) x = -x;
+    if (x >= 1) return dmax;
+    if (x == 0) return dmin;
+    T y;
+    if (power == 1) y = x;
+    else if (x <= mid) y = (T(1) / pow(mid, power - 1)) * pow(x, power);
+    else y = T(1) - (T(1) / pow(T(1) - mid, power - 1)) * pow(T(1) - x, power);
+    return dmin + y * (dmax - dmin);
+  }
+  B2_DEV void row_params() {
+    const int nv = M::nv();
+    WFOR(i, nefc) {
+      T sr[2], si[5], diag;
+      const int type = row_meta[i] & 255, id = row_meta[i] >> 8;
+      T mu = 0;
+      if (type == ROW_LIMIT_JOINT) {
+        for (int k = 0; k < 2; k++) sr[k] = M::jnt_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = M::jnt_solimp(5 * id + k);
+        diag = M::dof_invweight0(M::jnt_dofadr(id));
+      } else if (type == ROW_LIMIT_TENDON) {
+        for (int k = 0; k < 2; k++) sr[k] = M::tendon_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = M::tendon_solimp(5 * id + k);
+        diag = M::tendon_invweight0(id);
+      } else {
+        const int p = con_pair[id];
+        for (int k = 0; k < 2; k++) sr[k] = M::pair_solref(2 * p + k);
+        for (int k = 0; k < 5; k++) si[k] = M::pair_solimp(5 * p + k);
+        const T tran = M::body_invweight0(2 * M::geom_bodyid(M::pair_geom1(p))) + M::body_invweight0(2 * M::geom_bodyid(M::pair_geom2(p)));
+        mu = M::pair_friction(2 * p);
+        diag = (type == ROW_CONTACT_1) ? tran : tran + mu * mu * tran;
+      }
+      const T pos = row_pos[i], margin = row_margin[i];
+      const T imp = impedance(si, pos, margin);
+      const T dmax = tclip(si[1], T(0.0001), T(0.9999));
+      T K, B;
+      if (sr[0] > 0) {
+        const T tc = tmax(sr[0], 2 * M::timestep()), dr = sr[1];
+        K = T(1) / tmax(Num<T>::minval(), dmax * dmax * tc * tc * dr * dr);
+        B = T(2) / tmax(Num<T>::minval(), dmax * tc);
+      } else {
+        K = -sr[0] / tmax(Num<T>::minval(), dmax * dmax);
+        B = -sr[1] / tmax(Num<T>::minval(), dmax);
+      }
+      T reg = tmax(Num<T>::minval(), (T(1) - imp) * diag / imp);
+      if (type == ROW_CONTACT_PYR) reg = 2 * mu * mu * reg;  // all four edges share pos/margin, hence the same value
+      row_D[i] = T(1) / reg;
+      T vel = 0;
+      for (int k = 0; k < nv; k++) vel += J[i * nv + k] * qvel[k];
+      row_aref[i] = -B * vel - K * imp * (pos - margin);
+    }
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ velocity stage
+  B2_DEV void velocities() {
+    const int nb = M::nbody();
+    if (lane < 6) cvel[lane] = 0;
+    __syncwarp();
+    for (int level = 1; level <= M::maxdepth(); level++) {
+      const int i = lane;
+      if (i < nb && M::body_depth(i) == level) {
+        T v[6], cd[6], cdd[6];
+        const int da = M::body_dofadr(i), dn = M::body_dofnum(i), p = M::body_parentid(i);
+        for (int k = 0; k < 6; k++) v[k] = cvel[6 * p + k];
+        if (dn == 6 && M::jnt_type(M::dof_jntid(da)) == JNT_FREE) {
+          for (int k = 0; k < 18; k++) cdof_dot[6 * da + k] = 0;
+          for (int k = 0; k < 6; k++) {
+            T t = 0;
+            for (int q = 0; q < 3; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
+            v[k] += t;
+          }
+          for (int q = 3; q < 6; q++) {
+            for (int k = 0; k < 6; k++) cd[k] = cdof[6 * (da + q) + k];
+            cross_motion(cdd, v, cd);
+            for (int k = 0; k < 6; k++) cdof_dot[6 * (da + q) + k] = cdd[k];
+          }
+          for (int k = 0; k < 6; k++) {
+            T t = 0;
+            for (int q = 3; q < 6; q++) t += cdof[6 * (da + q) + k] * qvel[da + q];
+            v[k] += t;
+          }
+        } else {
+          for (int j = 0; j < dn; j++) {
+            for (int k = 0; k < 6; k++) cd[k] = cdof[6 * (da + j) + k];
+            cross_motion(cdd, v, cd);
+            for (int k = 0; k < 6; k++) { cdof_dot[6 * (da + j) + k] = cdd[k]; v[k] += cd[k] * qvel[da + j]; }
+          }
+        }
+        for (int k = 0; k < 6; k++) cvel[6 * i + k] = v[k];
+      }
+      __syncwarp();
+    }
+  }
+
+  B2_DEV void passive_forces() {
+    const int nv = M::nv();
+    WFOR(d, nv) {
+      const int j = M::dof_jntid(d);
+      T f = 0;
+      const T st = M::jnt_stiffness(j);
+      if (st != 0 && M::jnt_type(j) >= JNT_SLIDE) { const int pa = M::jnt_qposadr(j); f -= st * (qpos[pa] - M::qpos_spring(pa)); }
+      f -= M::dof_damping(d) * qvel[d];
+      f_passive[d] = f;
+    }
+    __syncwarp();
+    for (int t = 0; t < M::ntendon(); t++) {
+      const T st = M::tendon_stiffness(t), dm = M::tendon_damping(t);
+      if (st == 0 && dm == 0) continue;
+      T frc = 0, vel = 0;
+      const T lo = M::tendon_lengthspring(2 * t), hi = M::tendon_lengthspring(2 * t + 1), L = ten_len[t];
+      if (L > hi) frc = st * (hi - L); else if (L < lo) frc = st * (lo - L);
+      for (int k = 0; k < nv; k++) vel += ten_J[t * nv + k] * qvel[k];
+      frc -= dm * vel;
+      WFOR(k, nv) f_passive[k] += ten_J[t * nv + k] * frc;
+      __syncwarp();
+    }
+  }
+
+  // recursive Newton-Euler without accelerations
+  B2_DEV void bias_forces() {
+    const int nb = M::nbody(), nv = M::nv();
+    if (lane < 6) cacc[lane] = lane < 3 ? T(0) : -M::gravity(lane - 3);
+    __syncwarp();
+    for (int level = 1; level <= M::maxdepth(); level++) {
+      const int i = lane;
+      if (i < nb && M::body_depth(i) == level) {
+        const int da = M::body_dofadr(i), p = M::body_parentid(i);
+        T t[6] = {0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < M::body_dofnum(i); j++)
+          for (int k = 0; k < 6; k++) t[k] += cdof_dot[6 * (da + j) + k] * qvel[da + j];
+        for (int k = 0; k < 6; k++) cacc[6 * i + k] = cacc[6 * p + k] + t[k];
+      }
+      __syncwarp();
+    }
+    T* cfrc_body = buf6;  // 6 per body (nb <= nv + 1 is not guaranteed; buf6 holds 6*nv >= 6*(nb-1); world slot unused)
+    WFOR(i, nb) {
+      if (i == 0) continue;
+      T ci[10], a[6], v[6], f[6], t[6], t1[6];
+      for (int k = 0; k < 10; k++) ci[k] = cinert[10 * i + k];
+      for (int k = 0; k < 6; k++) { a[k] = cacc[6 * i + k]; v[k] = cvel[6 * i + k]; }
+      inert_mul(f, ci, a);
+      inert_mul(t, ci, v);
+      cross_force(t1, v, t);
+      for (int k = 0; k < 6; k++) cfrc_body[6 * (i - 1) + k] = f[k] + t1[k];
+    }
+    __syncwarp();
+    // subtree force sums land in crb's storage (dead after the mass matrix): 6 per body
+    T* cfrc = crb;
+    WFOR(i, nb) {
+      if (i == 0) continue;
+      T s[6];
+      for (int k = 0; k < 6; k++) s[k] = cfrc_body[6 * (i - 1) + k];
+      for (int j = nb - 1; j > i; j--)
+        if (in_subtree(i, j)) for (int k = 0; k < 6; k++) s[k] += cfrc_body[6 * (j - 1) + k];
+      for (int k = 0; k < 6; k++) cfrc[6 * i + k] = s[k];
+    }
+    __syncwarp();
+    WFOR(d, nv) {
+      T s = 0;
+      const int b = M::dof_bodyid(d);
+      for (int k = 0; k < 6; k++) s += cdof[6 * d + k] * cfrc[6 * b + k];
+      f_bias[d] = s;
+    }
+    __syncwarp();
+  }
+
+  B2_DEV void smooth_dynamics() {
+    const int nv = M::nv();
+    WFOR(d, nv) {
+      T fa = 0;
+      for (int a = 0; a < M::nu(); a++) {
+        const int jid = M::actuator_trnid(a);
+        if (M::jnt_dofadr(jid) != d) continue;
+        T u = ctrl[a];
+        if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
+        const T gear = M::actuator_gear(6 * a);
+        const T len = qpos[M::jnt_qposadr(jid)] * gear, vel = gear * qvel[d];
+        T force = M::actuator_gainprm(a) * u + M::actuator_biasprm(3 * a) + M::actuator_biasprm(3 * a + 1) * len + M::actuator_biasprm(3 * a + 2) * vel;
+        if (M::actuator_forcelimited(a)) force = tclip(force, M::actuator_forcerange(2 * a), M::actuator_forcerange(2 * a + 1));
+        if (M::actuator_disabled(a)) force = 0;
+        fa += gear * force;
+      }
+      T fs = f_passive[d] - f_bias[d];
+      fs += fa;
+      f_smooth[d] = fs; a_smooth[d] = fs;
+    }
+    __syncwarp();
+    solve_LD(a_smooth);
+  }
+
+  // ------------------------------------------------------------------ Newton solver
+  // J v for all rows: one row per lane
+  B2_DEV void mul_J(T* out, const T* v, const T* sub) {
+    const int nv = M::nv();
+    WFOR(i, nefc) {
+      T s = 0;
+      for (int k = 0; k < nv; k++) s += J[i * nv + k] * v[k];
+      out[i] = sub ? s - sub[i] : s;
+    }
+    __syncwarp();
+  }
+  B2_DEV T row_cost(const T* jar) {
+    T c = 0;
+    WFOR(i, nefc) if (jar[i] < 0) c += T(0.5) * row_D[i] * jar[i] * jar[i];
+    return warp_sum(c);
+  }
+  B2_DEV T dotv(const T* a, const T* b) {
+    T s = 0;
+    WFOR(k, M::nv()) s += a[k] * b[k];
+    return warp_sum(s);
+  }
+  struct LsPoint { T alpha, cost, d1, d2; };
+  B2_DEV void ls_eval(T alpha, LsPoint& p) {
+    ls_iter++;
+    T q0 = 0, q1 = 0, q2 = 0;
+    WFOR(i, nefc) {
+      if (Jaref[i] + alpha * Jv[i] < 0) {
+        const T dj = row_D[i] * Jaref[i];
+        q0 += T(0.5) * Jaref[i] * dj; q1 += Jv[i] * dj; q2 += T(0.5) * Jv[i] * row_D[i] * Jv[i];
+      }
+    }
+    q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
+    p.alpha = alpha; p.cost = alpha * alpha * q2 + alpha * q1 + q0; p.d1 = 2 * alpha * q2 + q1; p.d2 = 2 * q2;
+    if (p.d2 <= 0) p.d2 = Num<T>::minval();
+  }
+  B2_DEV int ls_bracket(LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
+    int flag = 0;
+    for (int i = 0; i < 3; i++) {
+      if (p.d1 < 0 && cand[i].d1 < 0 && p.d1 < cand[i].d1) { p = cand[i]; flag = 1; }
+      else if (p.d1 > 0 && cand[i].d1 > 0 && p.d1 > cand[i].d1) { p = cand[i]; flag = 2; }
+    }
+    if (flag) ls_eval(p.alpha - p.d1 / p.d2, pnext);
+    return flag;
+  }
+  B2_DEV T line_search() {
+    const int nv = M::nv();
+    LsPoint p0, p1, p2, pmid, p1n, p2n;
+    ls_iter = 0;
+    const T sn = sqrt(dotv(search, search));
+    if (sn < Num<T>::minval()) return 0;
+    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
+    const T gtol = M::tolerance() * M::ls_tolerance() * sn / scale;
+    mul_M(Mv, search);
+    mul_J(Jv, search, nullptr);
+    qg0 = gauss; qg1 = dotv(search, Ma) - dotv(f_smooth, search); qg2 = T(0.5) * dotv(search, Mv);
+    ls_eval(0, p0);
+    ls_eval(p0.alpha - p0.d1 / p0.d2, p1);
+    if (p0.cost < p1.cost) p1 = p0;
+    if (fabs(p1.d1) < gtol) return p1.alpha;
+    const int dir = p1.d1 < 0 ? 1 : -1;
+    bool p2up = false;
+    const int maxls = M::ls_iterations();
+    while (p1.d1 * dir <= -gtol && ls_iter < maxls) {
+      p2 = p1; p2up = true;
+      ls_eval(p1.alpha - p1.d1 / p1.d2, p1);
+      if (fabs(p1.d1) < gtol) return p1.alpha;
+    }
+    if (ls_iter >= maxls || !p2up) return p1.alpha;
+    p2n = p1;
+    ls_eval(p1.alpha - p1.d1 / p1.d2, p1n);
+    while (ls_iter < maxls) {
+      ls_eval(T(0.5) * (p1.alpha + p2.alpha), pmid);
+      LsPoint cand[3] = {p1n, p2n, pmid};
+      T best = 0; int bi = -1;
+      for (int i = 0; i < 3; i++)
+        if (fabs(cand[i].d1) < gtol && (bi == -1 || cand[i].cost < best)) { best = cand[i].cost; bi = i; }
+      if (bi >= 0) return cand[bi].alpha;
+      const int b1 = ls_bracket(p1, cand, p1n), b2 = ls_bracket(p2, cand, p2n);
+      if (!b1 && !b2) return pmid.alpha;
+    }
+    if (p1.cost <= p2.cost && p1.cost < p0.cost) return p1.alpha;
+    if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
+    return 0;
+  }
+  // cost, constraint force, gradient, and the Newton direction H^-1 grad (H = M + J' D_active J)
+  B2_DEV void newton_refresh() {
+    const int nv = M::nv(), np = nv * (nv + 1) / 2;
+    cost = row_cost(Jaref);
+    WFOR(k, nv) {
+      T f = 0;
+      for (int i = 0; i < nefc; i++) if (Jaref[i] < 0) f += J[i * nv + k] * (-row_D[i] * Jaref[i]);
+      f_con[k] = f;
+    }
+    __syncwarp();
+    T g = 0;
+    WFOR(k, nv) { g += (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]); grad[k] = Ma[k] - f_smooth[k] - f_con[k]; }
+    gauss = T(0.5) * warp_sum(g);
+    cost += gauss;
+    // Hessian, packed lower triangle in LDp: each lane owns entries e = lane, lane + 32, ...
+    // It only depends on the active set: when no row changed state since the last refresh the
+    // factor in LDp is still valid (bit-identical to refactoring) and is reused.
+    T* H = LDp;
+    unsigned sig[(WarpCaps::NEFC + 31) / 32];
+    bool same = hess_valid;
+#pragma unroll
+    for (int w = 0; w < (WarpCaps::NEFC + 31) / 32; w++) {
+      const int r = w * 32 + lane;
+      sig[w] = __ballot_sync(0xffffffffu, r < nefc && Jaref[r] < 0);
+      same = same && sig[w] == active_sig[w];
+      active_sig[w] = sig[w];
+    }
+    hess_valid = true;
+    if (!same) {
+    for (int e = lane; e < np; e += 32) {
+      int i, j;
+      untri(e, i, j);
+      T h = Mp[e];
+      for (int r = 0; r < nefc; r++) {
+        if (Jaref[r] >= 0) continue;
+        const T ji = J[r * nv + i];
+        if (ji == 0) continue;
+        h += (row_D[r] * ji) * J[r * nv + j];
+      }
+      H[e] = h;
+    }
+    __syncwarp();
+    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop
+    for (int j = 0; j < nv; j++) {
+      T t = H[tri(j, j)];
+      if (t < Num<T>::minval()) t = Num<T>::minval();
+      const T djj = sqrt(t), inv = T(1) / djj;
+      __syncwarp();
+      for (int i = j + lane; i < nv; i += 32) H[tri(i, j)] = (i == j) ? djj : H[tri(i, j)] * inv;
+      __syncwarp();
+      const int m = nv - j - 1;  // trailing block: entries (j+1+a, j+1+b), b <= a
+      for (int e = lane; e < m * (m + 1) / 2; e += 32) {
+        int a, b;
+        untri(e, a, b);
+        H[tri(j + 1 + a, j + 1 + b)] -= H[tri(j + 1 + a, j)] * H[tri(j + 1 + b, j)];
+      }
+      __syncwarp();
+    }
+    }  // !same
+    WFOR(k, nv) Mgrad[k] = grad[k];
+    __syncwarp();
+    for (int j = 0; j < nv; j++) {
+      const T xj = Mgrad[j] / H[tri(j, j)];
+      __syncwarp();
+      if (lane == 0) Mgrad[j] = xj;
+      for (int i = j + 1 + lane; i < nv; i += 32) Mgrad[i] -= H[tri(i, j)] * xj;
+      __syncwarp();
+    }
+    for (int j = nv - 1; j >= 0; j--) {
+      const T xj = Mgrad[j] / H[tri(j, j)];
+      __syncwarp();
+      if (lane == 0) Mgrad[j] = xj;
+      WFOR(i, j) Mgrad[i] -= H[tri(j, i)] * xj;
+      __syncwarp();
+    }
+  }
+  B2_DEV void constrained_acceleration() {
+    const int nv = M::nv();
+    niter = 0;
+    if (!nefc) {
+      WFOR(k, nv) { qacc[k] = a_smooth[k]; warm[k] = a_smooth[k]; f_con[k] = 0; }
+      __syncwarp();
+      return;
+    }
+    row_params();
+    hess_valid = false;
+    WFOR(k, nv) qacc[k] = warm[k];
+    __syncwarp();
+    mul_J(Jaref, qacc, row_aref);
+    T cw = row_cost(Jaref);
+    mul_M(Ma, qacc);
+    T g = 0;
+    WFOR(k, nv) g += T(0.5) * (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]);
+    cw += warp_sum(g);
+    mul_J(Jv, a_smooth, row_aref);
+    const T cs = row_cost(Jv);
+    if (cw > cs) {
+      WFOR(k, nv) qacc[k] = a_smooth[k];
+      WFOR(i, nefc) Jaref[i] = Jv[i];
+      __syncwarp();
+      mul_M(Ma, qacc);
+    }
+    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
+    T old = 0;
+    bool first = true;
+    while (true) {
+      newton_refresh();
+      if (!first) {
+        const T gn = dotv(grad, grad);
+        niter++;
+        if (scale * (old - cost) < M::tolerance() || scale * sqrt(gn) < M::tolerance()) break;
+      }
+      first = false;
+      WFOR(k, nv) search[k] = -Mgrad[k];
+      __syncwarp();
+      if (niter >= M::iterations()) break;
+      const T alpha = line_search();
+      if (alpha == 0) break;
+      WFOR(k, nv) { qacc[k] += alpha * search[k]; Ma[k] += alpha * Mv[k]; }
+      WFOR(i, nefc) Jaref[i] += alpha * Jv[i];
+      __syncwarp();
+      old = cost;
+    }
+    WFOR(k, nv) warm[k] = qacc[k];
+    __syncwarp();
+  }
+
+  // ------------------------------------------------------------------ forward + Euler
+  B2_DEV void forward() {
+    const int nv = M::nv(), np = nv * (nv + 1) / 2;
+    kinematics();
+    com_frame();
+    mass_matrix();
+    WFOR(e, np) LDp[e] = Mp[e];
+    __syncwarp();
+    factor_LD();
+    collide();
+    make_rows();
+    velocities();
+    passive_forces();
+    bias_forces();
+    smooth_dynamics();
+    constrained_acceleration();
+  }
+  B2_DEV void check_state() {
+    int bad = 0;
+    WFOR(k, M::nq()) if (!(fabs(qpos[k]) <= T(1e10))) bad |= 1;
+    WFOR(k, M::nv()) if (!(fabs(qvel[k]) <= T(1e10))) bad |= 2;
+    flags |= __reduce_or_sync(0xffffffffu, bad);
+  }
+  B2_DEV void check_acc() {
+    int bad = 0;
+    WFOR(k, M::nv()) if (!(fabs(qacc[k]) <= T(1e10))) bad |= 4;
+    flags |= __reduce_or_sync(0xffffffffu, bad);
+  }
+  B2_DEV void euler() {
+    const int nv = M::nv(), np = nv * (nv + 1) / 2;
+    const T h = M::timestep();
+    T* acc = grad;
+    if (!M::has_dofdamping()) { WFOR(k, nv) acc[k] = qacc[k]; __syncwarp(); }
+    else {
+      WFOR(e, np) LDp[e] = Mp[e];
+      __syncwarp();
+      WFOR(k, nv) LDp[tri(k, k)] += h * M::dof_damping(k);
+      __syncwarp();
+      factor_LD();
+      WFOR(k, nv) acc[k] = f_smooth[k] + f_con[k];
+      __syncwarp();
+      solve_LD(acc);
+    }
+    WFOR(k, nv) qvel[k] += acc[k] * h;
+    __syncwarp();
+    WFOR(j, M::njnt()) {
+      const int pa = M::jnt_qposadr(j), va = M::jnt_dofadr(j);
+      if (M::jnt_type(j) == JNT_FREE) {
+        T q[4], w[3];
+        for (int k = 0; k < 3; k++) qpos[pa + k] += h * qvel[va + k];
+        for (int k = 0; k < 4; k++) q[k] = qpos[pa + 3 + k];
+        for (int k = 0; k < 3; k++) w[k] = qvel[va + 3 + k];
+        quat_integrate(q, w, h);
+        for (int k = 0; k < 4; k++) qpos[pa + 3 + k] = q[k];
+      } else qpos[pa] += h * qvel[va];
+    }
+    __syncwarp();
+  }
+};
+
+}  // namespace b2

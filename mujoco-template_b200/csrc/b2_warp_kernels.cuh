@@ -1,0 +1,61 @@
+// Kernels of the warp engine (one env per warp, workspace in shared memory).
+#pragma once
+#include "b2_kernel_templates.cuh"
+#include "b2_warp_engine.cuh"
+
+namespace b2 {
+
+constexpr int kWarpIntsAsReals = (WarpCaps::NCON + WarpCaps::NEFC + 1) / 2;  // int metadata, counted in 8-byte units
+
+template <typename T, class M>
+B2_DEV void warp_store_derived(const WarpEnv<T, M>& env, const DerivedDev<T>& o, int N, int e) {
+  const int lane = env.lane;
+  if (o.xpos) WFOR(k, 3 * M::nbody()) o.xpos[(size_t)k * N + e] = env.xpos[k];
+  if (o.xquat) WFOR(k, 4 * M::nbody()) o.xquat[(size_t)k * N + e] = env.xquat[k];
+  if (o.xipos) WFOR(k, 3 * M::nbody()) o.xipos[(size_t)k * N + e] = env.xipos[k];
+  if (o.geom_xpos) WFOR(k, 3 * M::ngeom()) o.geom_xpos[(size_t)k * N + e] = env.geom_xpos[k];
+  if (o.subtree_com) WFOR(k, 3 * M::nbody()) o.subtree_com[(size_t)k * N + e] = env.com[k];
+  if (o.qacc) WFOR(k, M::nv()) o.qacc[(size_t)k * N + e] = env.qacc[k];
+  if (o.qfrc_bias) WFOR(k, M::nv()) o.qfrc_bias[(size_t)k * N + e] = env.f_bias[k];
+  if (lane == 0) {
+    if (o.ncon) o.ncon[e] = env.ncon;
+    if (o.nefc) o.nefc[e] = env.nefc;
+    if (o.solver_iter) o.solver_iter[e] = env.niter;
+  }
+}
+
+// nsteps x mj_step (nsteps == 0: mj_forward) for envs gw, gw + nwarps, ...; one env per warp
+template <typename T, class M>
+__global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps,
+                                                  T* jscratch, int ws_reals) {
+  extern __shared__ double b2_smem[];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+  T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T)));
+  WarpEnv<T, M> env;
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  const int total = nsteps > 0 ? nsteps : 1;
+  for (int e = gw; e < N; e += nw) {
+    WFOR(k, M::nq()) env.qpos[k] = st.qpos[(size_t)k * N + e];
+    WFOR(k, M::nv()) { env.qvel[k] = st.qvel[(size_t)k * N + e]; env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
+    WFOR(k, M::nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
+    env.flags = 0;
+    __syncwarp();
+    for (int s = 0; s < total; s++) {
+      env.check_state();
+      env.forward();
+      env.check_acc();
+      if (want_derived && s == total - 1) warp_store_derived(env, out, N, e);
+      if (nsteps > 0) env.euler();
+    }
+    if (nsteps > 0) {
+      WFOR(k, M::nq()) st.qpos[(size_t)k * N + e] = env.qpos[k];
+      WFOR(k, M::nv()) st.qvel[(size_t)k * N + e] = env.qvel[k];
+    }
+    if (st.warm) WFOR(k, M::nv()) st.warm[(size_t)k * N + e] = env.warm[k];
+    if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
+    __syncwarp();
+  }
+}
+
+}  // namespace b2

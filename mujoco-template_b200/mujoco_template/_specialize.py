@@ -20,10 +20,12 @@ from . import _layout
 
 # (field, kind) in the order of the X-macro lists in csrc/b2_model_dev.cuh
 INT_SCALARS = ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon", "npair", "integrator", "iterations",
-               "ls_iterations", "has_fluid", "has_dofdamping")
+               "ls_iterations", "has_fluid", "has_dofdamping", "maxdepth")
 REAL_SCALARS = ("timestep", "density", "viscosity", "tolerance", "ls_tolerance", "meaninertia")
-INT_ARRAYS = ("body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "jnt_type",
+INT_ARRAYS = ("body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_anc",
+              "body_depth", "jnt_type",
               "jnt_qposadr", "jnt_dofadr", "jnt_bodyid", "jnt_limited", "dof_bodyid", "dof_jntid", "dof_parentid", "dof_anc",
+              "dof_nanc", "dof_anclist",
               "geom_type", "geom_bodyid", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "wrap_jntid",
               "actuator_trntype", "actuator_trnid", "actuator_ctrllimited", "actuator_forcelimited", "actuator_disabled",
               "pair_geom1", "pair_geom2", "pair_dim")
@@ -56,6 +58,29 @@ def _values(c: dict, name: str) -> np.ndarray:
                 j = int(c["dof_parentid"][j])
             out.append(mask - (1 << 32) if mask >= (1 << 31) else mask)
         return np.array(out, dtype=np.int64)
+    if name in ("dof_nanc", "dof_anclist"):
+        nv = int(c["nv"])
+        stride = max(1, nv)  # generated Dims use exact sizes: NV == nv
+        counts, flat = [], [0] * (stride * stride)
+        for i in range(nv):
+            n, j = 0, int(c["dof_parentid"][i])
+            while j >= 0:
+                flat[i * stride + n] = j
+                n += 1
+                j = int(c["dof_parentid"][j])
+            counts.append(n)
+        return np.array(counts if name == "dof_nanc" else flat, dtype=np.int64)
+    if name in ("body_anc", "body_depth"):
+        masks, depths = [], []
+        for i in range(int(c["nbody"])):
+            mask, depth, j = 1 << i, 0, i
+            while j > 0:
+                j = int(c["body_parentid"][j])
+                mask |= 1 << j
+                depth += 1
+            masks.append(mask - (1 << 32) if mask >= (1 << 31) else mask)
+            depths.append(depth)
+        return np.array(masks if name == "body_anc" else depths, dtype=np.int64)
     if name == "pair_friction":
         return np.asarray(c["pair_friction"], dtype=float).reshape(-1, 5)[:, :2].ravel()
     return np.asarray(c[name]).ravel()
@@ -95,7 +120,8 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("};")
     A("struct SModel {")
     for k in INT_SCALARS:
-        A(f"  static B2_DEV constexpr int {k}() {{ return {int(c[k])}; }}")
+        val = int(max(_values(c, "body_depth"))) if k == "maxdepth" else int(c[k])
+        A(f"  static B2_DEV constexpr int {k}() {{ return {val}; }}")
     for k in REAL_SCALARS:
         A(f"  static B2_DEV constexpr double {k}() {{ return {_lit(c[k])}; }}")
     for k in INT_ARRAYS:
