@@ -339,10 +339,19 @@ def main():
         batch = env.data.backend.batch
         e2e_steps = max(3, min(args.steps, 50))
 
+        qn, vn, un = hq.numpy(), hv.numpy(), hu.numpy()
+        tmp = np.empty(nenv)
+        lo = float(model.actuator_ctrlrange[0, 0]) if model.nu else 0.0
+        hi = float(model.actuator_ctrlrange[0, 1]) if model.nu else 0.0
+
         def host_step():
-            if K is not None:  # host-side LQR tick on the host copy of the state
-                x = np.concatenate([hq.numpy(), hv.numpy()], axis=0)
-                hu.numpy()[:] = np.clip(-(K @ x), -200.0, 200.0)
+            if K is not None:  # host-side LQR tick on the host copy of the state: u = clip(-K [q; v]), no temporaries
+                rows = (qn[0], qn[1], vn[0], vn[1])
+                np.multiply(rows[0], -K[0, 0], out=un[0])
+                for k in range(1, 4):
+                    np.multiply(rows[k], -K[0, k], out=tmp)
+                    np.add(un[0], tmp, out=un[0])
+                np.clip(un[0], lo, hi, out=un[0])
             batch.step_host(st, 1, lin, 1e-6, hA.data_ptr() if lin else None, hB.data_ptr() if lin else None, 0)
 
         for _ in range(3):

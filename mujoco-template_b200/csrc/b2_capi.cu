@@ -57,6 +57,13 @@ const SpecKernels* find_spec(uint64_t hash, size_t size) {
 
 static inline const b2::SpecKernels* active_spec(const b2_batch* b);
 
+struct HostStepKey {
+  void *qpos, *qvel, *ctrl, *warm, *A, *B;
+  int nsteps, linearize;
+  double eps;
+  unsigned long long model_serial;
+};
+
 struct b2_batch {
   const b2_model* model;
   int nenv, device, precision;
@@ -66,6 +73,12 @@ struct b2_batch {
   // warp engine (large models): -1 not yet decided, 0 lane engine, 1 warp engine
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
+  cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
+  bool pipe_ready = false;
+  cudaGraphExec_t host_graph = nullptr;  // captured pipeline, valid for host_key
+  HostStepKey host_key;
+  int host_graph_launches = 0;
 };
 
 // The warp engine covers the feature set of large articulated models (humanoid); everything else
@@ -138,6 +151,8 @@ void b2_batch_destroy(b2_batch* b) {
   if (!b) return;
   void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch};
   for (void* q : p) if (q) cudaFree(q);
+  if (b->host_graph) cudaGraphExecDestroy(b->host_graph);
+  if (b->pipe_ready) { for (cudaStream_t st : b->pipe) cudaStreamDestroy(st); for (cudaEvent_t ev : b->pipe_ev) cudaEventDestroy(ev); }
   delete b;
 }
 int b2_batch_size_class(const b2_batch* b) { return b ? b->model->cls : -1; }
@@ -173,16 +188,16 @@ static int prepare_warp(b2_batch* b) {
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
-static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int nsteps, void* stream) {
+static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, void* stream) {
   int rc = ensure_resident(b, stream);
   if (rc) return rc;
   if ((rc = prepare_warp(b))) return rc;
   const bool f64 = b->precision == B2_F64;
-  if (b->warp_mode == 1)
+  if (b->warp_mode == 1 && count == b->nenv)
     return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream)
                : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream);
-  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, b->nenv, nsteps, stream)
-             : b2::b2k_step_f32(b->model->cls, st, derived, b->nenv, nsteps, stream);
+  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, stream)
+             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, stream);
 }
 
 // make sure this batch's model is the image resident in constant memory on its device
@@ -207,55 +222,53 @@ static int ensure_resident(b2_batch* b, void* stream) {
 
 extern "C" {
 
-int b2_step(b2_batch* b, const b2_state* st, int nsteps, const b2_derived* derived, void* stream) {
-  B2_CHECK_STATE("b2_step");
-  if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step: nsteps must be >= 1");
+// count envs (a leading chunk of the arrays `st` points at; the env stride is always b->nenv)
+static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const b2_derived* derived, void* stream) {
   int rc;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->step(st, derived, b->nenv, nsteps, stream);
+    rc = k->step(st, derived, count, b->nenv, nsteps, stream);
   } else {
-    rc = launch_generic_step(b, st, derived, nsteps, stream);
+    rc = launch_generic_step(b, st, derived, count, nsteps, stream);
     if (rc < 0) return rc;
   }
   g_launches++;
-  return rc ? cuda_fail((cudaError_t)rc, "b2_step launch") : B2_OK;
+  return rc ? cuda_fail((cudaError_t)rc, "step launch") : B2_OK;
+}
+static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, int centered, void* A, void* B, void* stream) {
+  int rc;
+  const int ncol = 2 * b->model->v.nv + b->model->v.nu;
+  if (const b2::SpecKernels* k = active_spec(b)) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    rc = k->linearize(st, count, b->nenv, eps, centered, A, B, stream);
+  } else {
+    rc = ensure_resident(b, stream);
+    if (rc) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, stream)
+                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, stream);
+  }
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "linearize launch") : B2_OK;
+}
+
+int b2_step(b2_batch* b, const b2_state* st, int nsteps, const b2_derived* derived, void* stream) {
+  B2_CHECK_STATE("b2_step");
+  if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step: nsteps must be >= 1");
+  return do_step(b, st, b->nenv, nsteps, derived, stream);
 }
 
 int b2_forward(b2_batch* b, const b2_state* st, const b2_derived* derived, void* stream) {
   B2_CHECK_STATE("b2_forward");
-  int rc;
-  if (const b2::SpecKernels* k = active_spec(b)) {
-    cudaError_t e = cudaSetDevice(b->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->step(st, derived, b->nenv, 0, stream);
-  } else {
-    rc = launch_generic_step(b, st, derived, 0, stream);
-    if (rc < 0) return rc;
-  }
-  g_launches++;
-  return rc ? cuda_fail((cudaError_t)rc, "b2_forward launch") : B2_OK;
+  return do_step(b, st, b->nenv, 0, derived, stream);
 }
 
 int b2_linearize(b2_batch* b, const b2_state* st, double eps, int centered, void* A, void* B, void* stream) {
   B2_CHECK_STATE("b2_linearize");
   if (!(eps > 0)) return fail(B2_ERR_LINEARIZE, "b2_linearize: eps must be > 0");
   if (!A && !B) return fail(B2_ERR_ARG, "b2_linearize: A and B are both NULL");
-  int rc;
-  const int ncol = 2 * b->model->v.nv + b->model->v.nu;
-  if (const b2::SpecKernels* k = active_spec(b)) {
-    cudaError_t e = cudaSetDevice(b->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->linearize(st, b->nenv, eps, centered, A, B, stream);
-  } else {
-    rc = ensure_resident(b, stream);
-    if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream)
-                                : b2::b2k_linearize_f32(b->model->cls, st, b->nenv, ncol, eps, centered, A, B, stream);
-  }
-  g_launches++;
-  return rc ? cuda_fail((cudaError_t)rc, "b2_linearize launch") : B2_OK;
+  return do_linearize(b, st, b->nenv, eps, centered, A, B, stream);
 }
 
 int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp, void* jacr, void* stream) {
@@ -300,39 +313,97 @@ int b2_differentiate_pos(b2_batch* b, void* out, double dt, const void* q1, cons
   return rc ? cuda_fail((cudaError_t)rc, "b2_differentiate_pos launch") : B2_OK;
 }
 
+// Host-buffer step.  The env range is cut into chunks that flow through a small pool of streams:
+// H2D of chunk c+1 and D2H of chunk c-1 overlap the kernels of chunk c (both copy engines busy).
 int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, double eps, void* host_A, void* host_B, void* stream) {
   if (!b || !hs || !hs->qpos || !hs->qvel || (b->model->v.nu && !hs->ctrl)) return fail(B2_ERR_ARG, "b2_step_host: null pointer");
   if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step_host: nsteps must be >= 1");
   cudaError_t e = cudaSetDevice(b->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const b2m_view& v = b->model->v;
-  const size_t N = (size_t)b->nenv, es = b->esz, nx = 2 * (size_t)v.nv;
-  const size_t bq = v.nq * N * es, bv = v.nv * N * es, bu = (v.nu ? v.nu : 1) * N * es, bA = nx * nx * N * es, bB = nx * (v.nu ? v.nu : 1) * N * es;
+  const size_t N = (size_t)b->nenv, es = b->esz, nx = 2 * (size_t)v.nv, nu1 = v.nu ? v.nu : 1;
   auto need = [&](void** p, size_t bytes) -> cudaError_t { return *p ? cudaSuccess : cudaMalloc(p, bytes); };
-  if ((e = need(&b->d_qpos, bq)) || (e = need(&b->d_qvel, bv)) || (e = need(&b->d_ctrl, bu)) || (e = need(&b->d_warm, bv)))
+  if ((e = need(&b->d_qpos, v.nq * N * es)) || (e = need(&b->d_qvel, v.nv * N * es)) || (e = need(&b->d_ctrl, nu1 * N * es)) ||
+      (e = need(&b->d_warm, v.nv * N * es)))
     return cuda_fail(e, "b2_step_host: cudaMalloc");
-  if (linearize && ((e = need(&b->d_A, bA)) || (e = need(&b->d_B, bB)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
-  cudaStream_t s = (cudaStream_t)stream;
-  if ((e = cudaMemcpyAsync(b->d_qpos, hs->qpos, bq, cudaMemcpyHostToDevice, s)) ||
-      (e = cudaMemcpyAsync(b->d_qvel, hs->qvel, bv, cudaMemcpyHostToDevice, s)) ||
-      (v.nu && (e = cudaMemcpyAsync(b->d_ctrl, hs->ctrl, v.nu * N * es, cudaMemcpyHostToDevice, s))))
-    return cuda_fail(e, "b2_step_host: H2D copy");
-  if (hs->qacc_warmstart) e = cudaMemcpyAsync(b->d_warm, hs->qacc_warmstart, bv, cudaMemcpyHostToDevice, s);
-  else e = cudaMemsetAsync(b->d_warm, 0, bv, s);
-  if (e) return cuda_fail(e, "b2_step_host: warm-start copy");
-  b2_state ds = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, nullptr};
-  int rc;
-  if (linearize && (rc = b2_linearize(b, &ds, eps, 1, b->d_A, b->d_B, stream))) return rc;
-  if ((rc = b2_step(b, &ds, nsteps, nullptr, stream))) return rc;
-  if ((e = cudaMemcpyAsync(hs->qpos, b->d_qpos, bq, cudaMemcpyDeviceToHost, s)) ||
-      (e = cudaMemcpyAsync(hs->qvel, b->d_qvel, bv, cudaMemcpyDeviceToHost, s)))
-    return cuda_fail(e, "b2_step_host: D2H copy");
-  if (hs->qacc_warmstart && (e = cudaMemcpyAsync(hs->qacc_warmstart, b->d_warm, bv, cudaMemcpyDeviceToHost, s)))
-    return cuda_fail(e, "b2_step_host: D2H copy");
-  if (linearize && host_A && (e = cudaMemcpyAsync(host_A, b->d_A, bA, cudaMemcpyDeviceToHost, s))) return cuda_fail(e, "b2_step_host: D2H A");
-  if (linearize && host_B && v.nu && (e = cudaMemcpyAsync(host_B, b->d_B, nx * v.nu * N * es, cudaMemcpyDeviceToHost, s)))
-    return cuda_fail(e, "b2_step_host: D2H B");
-  e = cudaStreamSynchronize(s);
+  if (linearize && ((e = need(&b->d_A, nx * nx * N * es)) || (e = need(&b->d_B, nx * nu1 * N * es)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
+  int rc = prepare_warp(b);
+  if (rc) return rc;
+  if (!active_spec(b) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
+  // chunking: warp-engine batches and small batches go through in one piece
+  const int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 4;
+  if (!b->pipe_ready) {
+    for (int i = 0; i < 3; i++) if ((e = cudaStreamCreateWithFlags(&b->pipe[i], cudaStreamNonBlocking))) return cuda_fail(e, "cudaStreamCreate");
+    for (int i = 0; i < 3; i++) if ((e = cudaEventCreateWithFlags(&b->pipe_ev[i], cudaEventDisableTiming))) return cuda_fail(e, "cudaEventCreate");
+    b->pipe_ready = true;
+  }
+  // The whole copy/compute pipeline is captured once into a CUDA graph (the host buffers of a
+  // rollout loop are the same every step) and replayed with a single launch afterwards.
+  HostStepKey key;
+  memset(&key, 0, sizeof(key));
+  key.qpos = hs->qpos; key.qvel = hs->qvel; key.ctrl = hs->ctrl; key.warm = hs->qacc_warmstart; key.A = host_A; key.B = host_B;
+  key.nsteps = nsteps; key.linearize = linearize; key.eps = eps; key.model_serial = b->model->serial;
+  if (b->host_graph && memcmp(&key, &b->host_key, sizeof(key)) != 0) {
+    cudaGraphExecDestroy(b->host_graph);
+    b->host_graph = nullptr;
+  }
+  cudaStream_t s0 = b->pipe[0];
+  if (!b->host_graph) {
+    const size_t pitch = N * es;
+    auto copy_rows = [&](void* dst, const void* src, size_t e0, size_t cnt, size_t rows, cudaMemcpyKind kind, cudaStream_t s) {
+      return cudaMemcpy2DAsync((char*)dst + e0 * es, pitch, (const char*)src + e0 * es, pitch, cnt * es, rows, kind, s);
+    };
+    const long long launches_before = g_launches.load();
+    if ((e = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal))) return cuda_fail(e, "cudaStreamBeginCapture");
+    int err = B2_OK;
+    // fork the side streams off the capturing stream
+    if (!(e = cudaEventRecord(b->pipe_ev[0], s0)))
+      for (int i = 1; i < 3 && !e; i++) e = cudaStreamWaitEvent(b->pipe[i], b->pipe_ev[0], 0);
+    const size_t per = (N + nchunk - 1) / nchunk;
+    for (int c = 0; c < nchunk && !e && !err; c++) {
+      const size_t e0 = (size_t)c * per;
+      if (e0 >= N) break;
+      const size_t cnt = (e0 + per <= N) ? per : N - e0;
+      cudaStream_t s = b->pipe[c % 3];
+      if ((e = copy_rows(b->d_qpos, hs->qpos, e0, cnt, v.nq, cudaMemcpyHostToDevice, s)) ||
+          (e = copy_rows(b->d_qvel, hs->qvel, e0, cnt, v.nv, cudaMemcpyHostToDevice, s)) ||
+          (v.nu && (e = copy_rows(b->d_ctrl, hs->ctrl, e0, cnt, v.nu, cudaMemcpyHostToDevice, s))))
+        break;
+      if (hs->qacc_warmstart) e = copy_rows(b->d_warm, hs->qacc_warmstart, e0, cnt, v.nv, cudaMemcpyHostToDevice, s);
+      else e = cudaMemset2DAsync((char*)b->d_warm + e0 * es, pitch, 0, cnt * es, v.nv, s);
+      if (e) break;
+      b2_state ds = {(char*)b->d_qpos + e0 * es, (char*)b->d_qvel + e0 * es, (char*)b->d_ctrl + e0 * es, (char*)b->d_warm + e0 * es, nullptr};
+      if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, (char*)b->d_A + e0 * es, (char*)b->d_B + e0 * es, s))) break;
+      if ((err = do_step(b, &ds, (int)cnt, nsteps, nullptr, s))) break;
+      if ((e = copy_rows(hs->qpos, b->d_qpos, e0, cnt, v.nq, cudaMemcpyDeviceToHost, s)) ||
+          (e = copy_rows(hs->qvel, b->d_qvel, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s)))
+        break;
+      if (hs->qacc_warmstart && (e = copy_rows(hs->qacc_warmstart, b->d_warm, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s))) break;
+      if (linearize && host_A && (e = copy_rows(host_A, b->d_A, e0, cnt, nx * nx, cudaMemcpyDeviceToHost, s))) break;
+      if (linearize && host_B && v.nu && (e = copy_rows(host_B, b->d_B, e0, cnt, nx * v.nu, cudaMemcpyDeviceToHost, s))) break;
+    }
+    // join the side streams back
+    for (int i = 1; i < 3; i++) {
+      cudaError_t e2 = cudaEventRecord(b->pipe_ev[i], b->pipe[i]);
+      if (!e2) e2 = cudaStreamWaitEvent(s0, b->pipe_ev[i], 0);
+      if (!e) e = e2;
+    }
+    cudaGraph_t graph = nullptr;
+    cudaError_t ec = cudaStreamEndCapture(s0, &graph);
+    if (err) { if (graph) cudaGraphDestroy(graph); return err; }
+    if (e || ec) { if (graph) cudaGraphDestroy(graph); return cuda_fail(e ? e : ec, "b2_step_host: pipeline capture"); }
+    e = cudaGraphInstantiate(&b->host_graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e) { b->host_graph = nullptr; return cuda_fail(e, "cudaGraphInstantiate"); }
+    b->host_key = key;
+    b->host_graph_launches = (int)(g_launches.load() - launches_before);
+    g_launches -= b->host_graph_launches;  // counted per replay below
+  }
+  // order after work the caller queued on `stream`, then replay
+  if ((e = cudaStreamSynchronize((cudaStream_t)stream))) return cuda_fail(e, "b2_step_host: synchronize");
+  if ((e = cudaGraphLaunch(b->host_graph, s0))) return cuda_fail(e, "cudaGraphLaunch");
+  g_launches += b->host_graph_launches;
+  e = cudaStreamSynchronize(s0);
   return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
 }
 

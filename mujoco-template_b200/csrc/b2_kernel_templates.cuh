@@ -34,7 +34,7 @@ static inline DerivedDev<T> to_dev(const b2_derived* o) {
 }
 
 template <typename T, class D, class M>
-B2_DEV void load_state(LaneEnv<T, D, M>& env, const StateDev<T>& st, int N, int e) {
+B2_DEV void load_state(LaneEnv<T, D, M>& env, const StateDev<T>& st, int N, int e) {  // N: env stride (leading dimension)
   B2_UNROLL
   for (int k = 0; k < M::nq(); k++) env.qpos[k] = st.qpos[(size_t)k * N + e];
   B2_UNROLL
@@ -62,9 +62,10 @@ B2_DEV void store_derived(const LaneEnv<T, D, M>& env, const DerivedDev<T>& o, i
 // nsteps x mj_step with ctrl held; nsteps == 0 means mj_forward (no integration).
 // The step loop is rolled: one inlined copy of the physics per kernel.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps) {
+__global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps) {
+  // count envs are processed; N is the env stride of the SoA arrays (count < N for a chunk of a larger batch)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N) return;
+  if (e >= count) return;
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
   load_state(env, st, N, e);
@@ -94,12 +95,12 @@ __global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out,
 // qacc_warmstart of every rollout start from the saved nominal values; control columns fall
 // back to one-sided differences at the ctrlrange bounds.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_linearize(StateDev<T> st, int N, T eps, int centered, T* A, T* B) {
+__global__ void __launch_bounds__(128) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
   constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)N * (ndx + nu)) return;
-  const int e = (int)(idx % N), c = (int)(idx / N);
+  if (idx >= (long long)count * (ndx + nu)) return;
+  const int e = (int)(idx % count), c = (int)(idx / count);  // count envs, env stride N
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
   T q0[NQ], v0[NV], u0[NU], w0[NV], yp[NQ + NV], ym[NQ + NV], yn[NQ + NV], col[2 * NV];

@@ -11,8 +11,8 @@ namespace b2 {
   int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,  \
                          int wpb, int blocks, void* stream);                                                                                  \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
-  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);                  \
-  int b2k_linearize##SUF(int cls, const b2_state* st, int N, int ncol, double eps, int centered, void* A, void* B,         \
+  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);                  \
+  int b2k_linearize##SUF(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
                          void* stream);                                                                                    \
   int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
   int b2k_integrate_pos##SUF(int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \

@@ -12,8 +12,8 @@ struct SpecKernels {
   const char* name;
   uint64_t blob_hash;
   size_t blob_size;
-  int (*step)(const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream);
-  int (*linearize)(const b2_state* st, int N, double eps, int centered, void* A, void* B, void* stream);
+  int (*step)(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);  // count envs, env stride N
+  int (*linearize)(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream);
   int (*jacobian)(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
 };
 

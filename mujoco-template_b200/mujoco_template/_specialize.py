@@ -134,15 +134,15 @@ def emit_spec(compiled: dict, name: str) -> str:
         A(f"  static B2_DEV double {k}(int i) {{ static constexpr double t[{one(v.size)}] = {{{body}}}; return t[i]; }}")
     A("};")
     A("")
-    A("int spec_step(const b2_state* st, const b2_derived* out, int N, int nsteps, void* stream) {")
-    A("  const int threads = 128, blocks = (N + threads - 1) / threads;")
-    A("  k_step<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), to_dev<double>(out), out != nullptr, N, nsteps);")
+    A("int spec_step(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream) {")
+    A("  const int threads = 128, blocks = (count + threads - 1) / threads;")
+    A("  k_step<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), to_dev<double>(out), out != nullptr, count, N, nsteps);")
     A("  return (int)cudaGetLastError();")
     A("}")
-    A("int spec_linearize(const b2_state* st, int N, double eps, int centered, void* A, void* B, void* stream) {")
-    A(f"  const int threads = 128; const long long total = (long long)N * {2 * nv + nu};")
+    A("int spec_linearize(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream) {")
+    A(f"  const int threads = 128; const long long total = (long long)count * {2 * nv + nu};")
     A("  const int blocks = (int)((total + threads - 1) / threads);")
-    A("  k_linearize<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), N, eps, centered, (double*)A, (double*)B);")
+    A("  k_linearize<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), count, N, eps, centered, (double*)A, (double*)B);")
     A("  return (int)cudaGetLastError();")
     A("}")
     A("int spec_jacobian(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {")
