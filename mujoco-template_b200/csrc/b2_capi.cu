@@ -158,7 +158,7 @@ void b2_batch_destroy(b2_batch* b) {
 int b2_batch_size_class(const b2_batch* b) { return b ? b->model->cls : -1; }
 const char* b2_batch_kernel_variant(const b2_batch* b) {
   if (!b) return "";
-  const b2::SpecKernels* k = (b->precision == B2_F64) ? b->model->spec : nullptr;
+  const b2::SpecKernels* k = b->model->spec;
   if (k) return k->name;
   if (b->warp_mode == 1 || (b->warp_mode < 0 && b->model->cls == 2 && warp_engine_supports(b->model->v))) return "generic-warp";
   return "generic";
@@ -166,9 +166,8 @@ const char* b2_batch_kernel_variant(const b2_batch* b) {
 
 }  // extern "C"
 
-static inline const b2::SpecKernels* active_spec(const b2_batch* b) {
-  return b->precision == B2_F64 ? b->model->spec : nullptr;
-}
+static inline const b2::SpecKernels* active_spec(const b2_batch* b) { return b->model->spec; }
+static inline int prec_index(const b2_batch* b) { return b->precision == B2_F64 ? 0 : 1; }
 
 static int ensure_resident(b2_batch* b, void* stream);
 
@@ -228,7 +227,7 @@ static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->step(st, derived, count, b->nenv, nsteps, stream);
+    rc = k->step[prec_index(b)](st, derived, count, b->nenv, nsteps, stream);
   } else {
     rc = launch_generic_step(b, st, derived, count, nsteps, stream);
     if (rc < 0) return rc;
@@ -242,7 +241,7 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->linearize(st, count, b->nenv, eps, centered, A, B, stream);
+    rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, stream);
   } else {
     rc = ensure_resident(b, stream);
     if (rc) return rc;
@@ -281,7 +280,7 @@ int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->jacobian(st, b->nenv, kind, objid, jacp, jacr, stream);
+    rc = k->jacobian[prec_index(b)](st, b->nenv, kind, objid, jacp, jacr, stream);
   } else {
     rc = ensure_resident(b, stream);
     if (rc) return rc;

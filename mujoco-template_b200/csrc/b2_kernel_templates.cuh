@@ -10,6 +10,11 @@
 #include "../../include/b2mj.h"
 #include "b2_engine.cuh"
 
+// minimum resident blocks per SM requested for the FD kernel (caps registers per thread)
+#ifndef B2_LIN_MIN_BLOCKS
+#define B2_LIN_MIN_BLOCKS 1
+#endif
+
 namespace b2 {
 
 template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
@@ -95,7 +100,7 @@ __global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out,
 // qacc_warmstart of every rollout start from the saved nominal values; control columns fall
 // back to one-sided differences at the ctrlrange bounds.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
+__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
   constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;

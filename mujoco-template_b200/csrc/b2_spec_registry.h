@@ -12,9 +12,10 @@ struct SpecKernels {
   const char* name;
   uint64_t blob_hash;
   size_t blob_size;
-  int (*step)(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);  // count envs, env stride N
-  int (*linearize)(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream);
-  int (*jacobian)(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
+  // [0] FP64, [1] FP32; count envs, env stride N
+  int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);
+  int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream);
+  int (*jacobian[2])(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
 };
 
 void register_spec(const SpecKernels* k);

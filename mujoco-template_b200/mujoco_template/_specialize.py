@@ -109,6 +109,8 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"// GENERATED by mujoco_template/_specialize.py for model '{name}' -- do not edit.")
     A("// Static model provider: every accessor folds to a compile-time constant after unrolling.")
     A("#define B2_STATIC_MODEL 1")
+    # small models: ask for >= 3 resident blocks/SM in the FD kernel (<= 168 registers, measured best on B200)
+    A(f"#define B2_LIN_MIN_BLOCKS {3 if nv <= 2 else 1}")
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
     A("")
@@ -118,12 +120,13 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"  static constexpr int NB = {one(nb)}, NJ = {one(nj)}, NQ = {one(nq)}, NV = {one(nv)}, NU = {one(nu)}, NG = {one(ng)}, "
       f"NS = {one(ns)}, NT = {one(nt)}, NW = {one(nw)}, NPAIR = {one(npair)}, NCON = {one(ncon)}, NEFC = {one(nefc)};")
     A("};")
+    A("template <typename T>")
     A("struct SModel {")
     for k in INT_SCALARS:
         val = int(max(_values(c, "body_depth"))) if k == "maxdepth" else int(c[k])
         A(f"  static B2_DEV constexpr int {k}() {{ return {val}; }}")
     for k in REAL_SCALARS:
-        A(f"  static B2_DEV constexpr double {k}() {{ return {_lit(c[k])}; }}")
+        A(f"  static B2_DEV constexpr T {k}() {{ return T({_lit(c[k])}); }}")
     for k in INT_ARRAYS:
         v = _values(c, k)
         body = ", ".join(str(int(x)) for x in v) if v.size else "0"
@@ -131,26 +134,28 @@ def emit_spec(compiled: dict, name: str) -> str:
     for k in REAL_ARRAYS:
         v = _values(c, k)
         body = ", ".join(_lit(x) for x in v) if v.size else "0.0"
-        A(f"  static B2_DEV double {k}(int i) {{ static constexpr double t[{one(v.size)}] = {{{body}}}; return t[i]; }}")
+        A(f"  static B2_DEV T {k}(int i) {{ static constexpr T t[{one(v.size)}] = {{{body}}}; return t[i]; }}")
     A("};")
     A("")
-    A("int spec_step(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream) {")
-    A("  const int threads = 128, blocks = (count + threads - 1) / threads;")
-    A("  k_step<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), to_dev<double>(out), out != nullptr, count, N, nsteps);")
-    A("  return (int)cudaGetLastError();")
-    A("}")
-    A("int spec_linearize(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream) {")
-    A(f"  const int threads = 128; const long long total = (long long)count * {2 * nv + nu};")
-    A("  const int blocks = (int)((total + threads - 1) / threads);")
-    A("  k_linearize<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), count, N, eps, centered, (double*)A, (double*)B);")
-    A("  return (int)cudaGetLastError();")
-    A("}")
-    A("int spec_jacobian(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {")
-    A("  const int threads = 128, blocks = (N + threads - 1) / threads;")
-    A("  k_jacobian<double, SDims, SModel><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<double>(st), N, kind, objid, (double*)jacp, (double*)jacr);")
-    A("  return (int)cudaGetLastError();")
-    A("}")
-    A(f'const SpecKernels kSpec = {{"{name}", 0x{fnv1a(blob):016x}ull, {len(blob)}, spec_step, spec_linearize, spec_jacobian}};')
+    for T, suf in (("double", ""), ("float", "32")):
+        A(f"int spec_step{suf}(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream) {{")
+        A("  const int threads = 128, blocks = (count + threads - 1) / threads;")
+        A(f"  k_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, nsteps);")
+        A("  return (int)cudaGetLastError();")
+        A("}")
+        A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream) {{")
+        A(f"  const int threads = 128; const long long total = (long long)count * {2 * nv + nu};")
+        A("  const int blocks = (int)((total + threads - 1) / threads);")
+        A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B);")
+        A("  return (int)cudaGetLastError();")
+        A("}")
+        A(f"int spec_jacobian{suf}(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {{")
+        A("  const int threads = 128, blocks = (N + threads - 1) / threads;")
+        A(f"  k_jacobian<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), N, kind, objid, ({T}*)jacp, ({T}*)jacr);")
+        A("  return (int)cudaGetLastError();")
+        A("}")
+    A(f'const SpecKernels kSpec = {{"{name}", 0x{fnv1a(blob):016x}ull, {len(blob)}, {{spec_step, spec_step32}}, '
+      '{spec_linearize, spec_linearize32}, {spec_jacobian, spec_jacobian32}};')
     A("struct Registrar { Registrar() { register_spec(&kSpec); } } registrar;")
     A("}  // namespace")
     A("}  // namespace b2")
