@@ -135,28 +135,50 @@ struct LaneEnv {
       quat_mul(qi, q, iquat);
       quat_to_mat(ximat + 9 * i, qi);
     }
-    B2_UNROLL
-    for (int g = 0; g < M::ngeom(); g++) {
-      const int b = M::geom_bodyid(g);
-      T q[4];
-      B2_LD3(gp, geom_pos, 3 * g);
-      B2_LD4(gq, geom_quat, 4 * g);
-      mat_vec(geom_xpos + 3 * g, xmat + 9 * b, gp);
-      for (int k = 0; k < 3; k++) geom_xpos[3 * g + k] += xpos[3 * b + k];
-      quat_mul(q, xquat + 4 * b, gq);
-      quat_to_mat(geom_xmat + 9 * g, q);
-    }
-    B2_UNROLL
-    for (int s = 0; s < M::nsite(); s++) {
-      const int b = M::site_bodyid(s);
-      T q[4];
-      B2_LD3(sp, site_pos, 3 * s);
-      B2_LD4(sq, site_quat, 4 * s);
-      mat_vec(site_xpos + 3 * s, xmat + 9 * b, sp);
-      for (int k = 0; k < 3; k++) site_xpos[3 * s + k] += xpos[3 * b + k];
-      quat_mul(q, xquat + 4 * b, sq);
-      quat_to_mat(site_xmat + 9 * s, q);
-    }
+#ifndef B2_STATIC_MODEL
+    // generic build: geom / site poses are materialised once per forward pass
+    for (int g = 0; g < M::ngeom(); g++) compute_geom_pose(g, geom_xpos + 3 * g, geom_xmat + 9 * g);
+    for (int s = 0; s < M::nsite(); s++) compute_site_pose(s, site_xpos + 3 * s, site_xmat + 9 * s);
+#endif
+  }
+  B2_DEV void compute_geom_pose(int g, T* p, T* R) const {
+    const int b = M::geom_bodyid(g);
+    T q[4];
+    B2_LD3(gp, geom_pos, 3 * g);
+    B2_LD4(gq, geom_quat, 4 * g);
+    mat_vec(p, xmat + 9 * b, gp);
+    for (int k = 0; k < 3; k++) p[k] += xpos[3 * b + k];
+    quat_mul(q, xquat + 4 * b, gq);
+    quat_to_mat(R, q);
+  }
+  B2_DEV void compute_site_pose(int s, T* p, T* R) const {
+    const int b = M::site_bodyid(s);
+    T q[4];
+    B2_LD3(sp, site_pos, 3 * s);
+    B2_LD4(sq, site_quat, 4 * s);
+    mat_vec(p, xmat + 9 * b, sp);
+    for (int k = 0; k < 3; k++) p[k] += xpos[3 * b + k];
+    quat_mul(q, xquat + 4 * b, sq);
+    quat_to_mat(R, q);
+  }
+  // Pose of a geom / site.  Under a static provider poses are recomputed from the body pose where
+  // they are consumed (a handful of FMAs) instead of staying live in registers across the stages
+  // in between; the generic build reads the arrays filled by kinematics().  Same arithmetic.
+  B2_DEV void geom_pose(int g, T* p, T* R) const {
+#ifdef B2_STATIC_MODEL
+    compute_geom_pose(g, p, R);
+#else
+    for (int k = 0; k < 3; k++) p[k] = geom_xpos[3 * g + k];
+    for (int k = 0; k < 9; k++) R[k] = geom_xmat[9 * g + k];
+#endif
+  }
+  B2_DEV void site_pose(int s, T* p, T* R) const {
+#ifdef B2_STATIC_MODEL
+    compute_site_pose(s, p, R);
+#else
+    for (int k = 0; k < 3; k++) p[k] = site_xpos[3 * s + k];
+    for (int k = 0; k < 9; k++) R[k] = site_xmat[9 * s + k];
+#endif
   }
 
   // subtree centres of mass, com-frame inertias, motion axes
@@ -336,9 +358,11 @@ struct LaneEnv {
         T wf[3], wt[3];
         B2_LD3(gf, actuator_gear, 6 * a);
         B2_LD3(gt, actuator_gear, 6 * a + 3);
-        mat_vec(wf, site_xmat + 9 * id, gf);
-        mat_vec(wt, site_xmat + 9 * id, gt);
-        for_jac(M::site_bodyid(id), site_xpos + 3 * id, [&](int d, const T* jp, const T* jr) {
+        T sp[3], sR[9];
+        site_pose(id, sp, sR);
+        mat_vec(wf, sR, gf);
+        mat_vec(wt, sR, gt);
+        for_jac(M::site_bodyid(id), sp, [&](int d, const T* jp, const T* jr) {
           mom[d] = jp[0] * wf[0] + jp[1] * wf[1] + jp[2] * wf[2] + jr[0] * wt[0] + jr[1] * wt[1] + jr[2] * wt[2];
         });
         act_len[a] = 0;
@@ -480,7 +504,9 @@ struct LaneEnv {
     for (int p = 0; p < M::npair(); p++) {
       const int g1 = M::pair_geom1(p), g2 = M::pair_geom2(p);
       const T margin = M::pair_margin(p);
-      const T *p1 = geom_xpos + 3 * g1, *R1 = geom_xmat + 9 * g1, *p2 = geom_xpos + 3 * g2, *R2 = geom_xmat + 9 * g2;
+      T p1[3], R1[9], p2[3], R2[9];
+      geom_pose(g1, p1, R1);
+      geom_pose(g2, p2, R2);
       B2_LD3(s1, geom_size, 3 * g1);
       B2_LD3(s2, geom_size, 3 * g2);
       const int t1 = M::geom_type(g1), t2 = M::geom_type(g2);
@@ -997,22 +1023,31 @@ struct LaneEnv {
   }
 
   // ------------------------------------------------------------------ forward + integrators
-  B2_STAGE void forward() {
+  // position-dependent part of mj_forward: poses, inertias, mass matrix, limit and contact rows,
+  // actuator moments.  Depends on qpos only, so the FD kernel reuses it across rollouts that
+  // perturb velocities or controls (upstream's mjSTAGE_POS skip, bit-identical by construction).
+  B2_STAGE void forward_position() {
     kinematics();
     com_frame();
     tendons();
     mass_matrix();
-    B2_UNROLL
-    for (int k = 0; k < M::nv() * M::nv(); k++) LD[k] = Mm[k];
-    factor_LD();
     limit_rows();
     collide();
     transmission();
+  }
+  B2_STAGE void forward_rest() {
+    B2_UNROLL
+    for (int k = 0; k < M::nv() * M::nv(); k++) LD[k] = Mm[k];
+    factor_LD();
     velocities();
     passive_forces();
     bias_forces();
     smooth_dynamics();
     constrained_acceleration();
+  }
+  B2_DEV void forward() {
+    forward_position();
+    forward_rest();
   }
   B2_DEV void integrate_pos(T* q, const T* v, T dt) const {
     B2_UNROLL

@@ -54,8 +54,14 @@ B2_DEV void store_derived(const LaneEnv<T, D, M>& env, const DerivedDev<T>& o, i
   if (o.xpos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xpos[(size_t)k * N + e] = env.xpos[k]; }
   if (o.xquat) { B2_UNROLL for (int k = 0; k < 4 * M::nbody(); k++) o.xquat[(size_t)k * N + e] = env.xquat[k]; }
   if (o.xipos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xipos[(size_t)k * N + e] = env.xipos[k]; }
-  if (o.geom_xpos) { B2_UNROLL for (int k = 0; k < 3 * M::ngeom(); k++) o.geom_xpos[(size_t)k * N + e] = env.geom_xpos[k]; }
-  if (o.site_xpos) { B2_UNROLL for (int k = 0; k < 3 * M::nsite(); k++) o.site_xpos[(size_t)k * N + e] = env.site_xpos[k]; }
+  if (o.geom_xpos) {
+    B2_UNROLL
+    for (int g = 0; g < M::ngeom(); g++) { T p[3], R[9]; env.geom_pose(g, p, R); for (int k = 0; k < 3; k++) o.geom_xpos[(size_t)(3 * g + k) * N + e] = p[k]; }
+  }
+  if (o.site_xpos) {
+    B2_UNROLL
+    for (int s = 0; s < M::nsite(); s++) { T p[3], R[9]; env.site_pose(s, p, R); for (int k = 0; k < 3; k++) o.site_xpos[(size_t)(3 * s + k) * N + e] = p[k]; }
+  }
   if (o.subtree_com) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.subtree_com[(size_t)k * N + e] = env.com[k]; }
   if (o.qacc) { B2_UNROLL for (int k = 0; k < M::nv(); k++) o.qacc[(size_t)k * N + e] = env.qacc[k]; }
   if (o.qfrc_bias) { B2_UNROLL for (int k = 0; k < M::nv(); k++) o.qfrc_bias[(size_t)k * N + e] = env.f_bias[k]; }
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
   }
   const int need = (fwd ? 1 : 0) | (back ? 2 : 0) | ((fwd != back) ? 4 : 0);  // plus, minus, nominal rollouts
   // rolled phase loop: the physics is instantiated once; all array indices stay static
+  bool pos_valid = false;
   B2_NOUNROLL
   for (int phase = 0; phase < 3; phase++) {
     if (!((need >> phase) & 1)) continue;
@@ -147,7 +154,15 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
       for (int k = 0; k < nv; k++) dp[k] = (k == i) ? T(1) : T(0);
       env.integrate_pos(env.qpos, dp, delta);
     }
-    env.step();
+    // one mj_step; the position stage is skipped when an earlier rollout of this thread already ran
+    // it at the same qpos (velocity / control columns under Euler)
+    env.check_state();
+    if (!pos_valid) env.forward_position();
+    env.forward_rest();
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
+    if (M::integrator() == 1) env.rk4(); else env.euler();
+    pos_valid = kind != 1 && M::integrator() == 0;
     B2_UNROLL
     for (int k = 0; k < nq + nv; k++) {
       const T val = k < nq ? env.qpos[k < nq ? k : 0] : env.qvel[k >= nq ? k - nq : 0];
@@ -190,7 +205,7 @@ __global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kin
   auto put = [&](int d, const T* p, const T* r) {
     for (int a = 0; a < 3; a++) { jp[a * nv + d] = p[a]; jr[a * nv + d] = r[a]; }
   };
-  if (kind == B2_JAC_SITE) env.for_jac(M::site_bodyid(objid), env.site_xpos + 3 * objid, put);
+  if (kind == B2_JAC_SITE) { T sp[3], sR[9]; env.compute_site_pose(objid, sp, sR); env.for_jac(M::site_bodyid(objid), sp, put); }
   else if (kind == B2_JAC_BODY) env.for_jac(objid, env.xpos + 3 * objid, put);
   else if (kind == B2_JAC_BODYCOM) env.for_jac(objid, env.xipos + 3 * objid, put);
   else {
