@@ -299,6 +299,9 @@ def main():
     ret = env.data.qpos[0].abs().contiguous()
     allret = env.gather(ret)
     flags_bad = int((env.data.flags != 0).sum().item())
+    env.forward()  # refresh derived outputs (contact / solver statistics are reported beside the throughput)
+    contact_stats = {"mean_ncon": float(env.data.ncon.float().mean().item()), "mean_nefc": float(env.data.nefc.float().mean().item()),
+                     "mean_newton_iter": float(env.data.solver_iter.float().mean().item())}
 
     # ---- roofline of the dominant kernel
     dom = "linearize" if lin else "step"
@@ -309,10 +312,14 @@ def main():
         peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
+    if os.path.exists(tfile):
+        traffic = json.load(open(tfile)).get(f"{name}:{dom}:{nenv}")
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     share = {k: (float(np.mean(v)) * args.steps / total_ms if v else 0.0) for k, v in kernel_ms.items()}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": None, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
+                "traffic": traffic, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": share,
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
@@ -387,7 +394,8 @@ def main():
             "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),
             "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
-            "bad_env_flags": flags_bad, "gathered_returns": int(allret.numel()),
+            "bad_env_flags": flags_bad, "gathered_returns": int(allret.numel()), "contact_stats": contact_stats,
+            "kernel_variant": env.data.backend.batch.kernel_variant,
         }
         print(json.dumps(out))
     if world > 1:

@@ -14,6 +14,9 @@
 #ifndef B2_LIN_MIN_BLOCKS
 #define B2_LIN_MIN_BLOCKS 1
 #endif
+#ifndef B2_STEP_MIN_BLOCKS
+#define B2_STEP_MIN_BLOCKS 1
+#endif
 
 namespace b2 {
 
@@ -73,7 +76,7 @@ B2_DEV void store_derived(const LaneEnv<T, D, M>& env, const DerivedDev<T>& o, i
 // nsteps x mj_step with ctrl held; nsteps == 0 means mj_forward (no integration).
 // The step loop is rolled: one inlined copy of the physics per kernel.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps) {
+__global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps) {
   // count envs are processed; N is the env stride of the SoA arrays (count < N for a chunk of a larger batch)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
