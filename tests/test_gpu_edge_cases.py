@@ -1,0 +1,152 @@
+"""GPU edge cases: ragged / tiny batches, models outside the compiled-in specialisations (generic kernels),
+no-actuator models, joint limits, RK4 with springs and servo actuators, capacity errors."""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_model, oracle_for
+from test_mjcf_compiler import ARM_XML
+from test_host_logic import BASE_XML
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b))))) if a.size else 0.0
+
+
+def _compile(xml):
+    from mujoco_template import _mj as mj
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return mj.MjModel.from_xml_string(xml)
+
+
+def _parity_rollout(model, qpos, qvel, ctrl, nsteps, tol=1e-9, check_lin=True):
+    import torch
+    from mujoco_template import _mj as mj
+
+    n = qpos.shape[0]
+    data = mj.BatchData(model, n)
+    dev = data.qpos.device
+    om, od = oracle_for(model)
+    warm = np.zeros((n, model.nv))
+    for s in range(nsteps):
+        data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev)); data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+        if model.nu:
+            data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev))
+        data.qacc_warmstart.copy_(torch.as_tensor(warm.T.copy(), device=dev))
+        if check_lin and s % 10 == 0:
+            A, B = data.backend.linearize(1e-6, True)
+            od.reset(); od.qpos[:] = qpos[0]; od.qvel[:] = qvel[0]; od.qacc_warmstart[:] = warm[0]
+            if model.nu:
+                od.ctrl[:] = ctrl[0]
+            Ao, Bo = od.transition_fd(1e-6, True)
+            assert _rel(A[:, :, 0].cpu().numpy(), Ao) <= 1e-6
+            if model.nu:
+                assert _rel(B[:, :, 0].cpu().numpy(), Bo) <= 1e-6
+            assert tuple(B.shape) == (2 * model.nv, model.nu, n)
+        mj.mj_step(model, data)
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.qacc_warmstart[:] = warm[e]
+            if model.nu:
+                od.ctrl[:] = ctrl[e]
+            od.step()
+            qpos[e] = od.qpos; qvel[e] = od.qvel; warm[e] = od.qacc_warmstart
+        assert _rel(data.qpos.cpu().numpy().T, qpos) <= tol, s
+        assert _rel(data.qvel.cpu().numpy().T, qvel) <= tol, s
+    return data
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 129, 1000])
+def test_ragged_batch_sizes(n):
+    model = load_model("cartpole")
+    rng = np.random.default_rng(n)
+    qpos = rng.uniform(-0.3, 0.3, (n, 2)); qvel = rng.uniform(-1, 1, (n, 2)); ctrl = rng.uniform(-2, 2, (n, 1))
+    _parity_rollout(model, qpos, qvel, ctrl, 5)
+
+
+def test_reference_fixture_model_limits_and_servo():
+    """The reference's own test fixture (hinge limited to +-1 degree, motor + position servo): generic kernels."""
+    model = _compile(BASE_XML)
+    n = 8
+    rng = np.random.default_rng(0)
+    qpos = rng.uniform(-0.03, 0.03, (n, 1))          # beyond the +-0.01745 rad limit for several envs
+    qvel = rng.uniform(-0.5, 0.5, (n, 1)); ctrl = rng.uniform(-1, 1, (n, 2))
+    data = _parity_rollout(model, qpos, qvel, ctrl, 30)
+    assert data.backend.batch.kernel_variant == "generic"
+    assert int(data.nefc.max()) >= 1                   # the joint limit was active somewhere
+
+
+def test_two_link_arm_rk4_springs_generic():
+    model = _compile(ARM_XML)
+    n = 16
+    rng = np.random.default_rng(1)
+    qpos = rng.uniform(-1.2, 1.2, (n, 2)); qvel = rng.uniform(-2, 2, (n, 2)); ctrl = rng.uniform(-1.5, 1.5, (n, 2))
+    qpos[0, 0] = 1.7                                   # past the +-90 degree shoulder limit
+    _parity_rollout(model, qpos, qvel, ctrl, 25)
+
+
+def test_model_without_actuators():
+    xml = BASE_XML[: BASE_XML.index("<actuator>")] + "</mujoco>"
+    model = _compile(xml)
+    assert model.nu == 0
+    n = 4
+    qpos = np.array([[0.0], [0.005], [-0.01], [0.012]]); qvel = np.array([[0.1], [0.0], [-0.2], [0.3]])
+    _parity_rollout(model, qpos, qvel, np.zeros((n, 0)), 10)
+
+
+def test_capacity_and_argument_errors():
+    import mujoco_template as mt
+    from mujoco_template import _capi, _mj as mj
+
+    bodies = "".join(f'<body pos="{i} 0 1"><joint type="slide"/><geom size=".1"/></body>' for i in range(40))
+    big = _compile(f"<mujoco><worldbody>{bodies}</worldbody></mujoco>")
+    with pytest.raises(mt.ConfigError, match="size class"):
+        mj.BatchData(big, 4)
+    model = load_model("cartpole")
+    with pytest.raises(mt.ConfigError):
+        mj.BatchData(model, 0)
+    data = mj.BatchData(model, 4)
+    with pytest.raises(mt.ConfigError):
+        data.backend.batch.jacobian(data.backend.state_struct(), _capi.JAC_SITE, 7, data.qpos.data_ptr(), None)
+    with pytest.raises(mt.LinearizationError):
+        data.backend.linearize(0.0, True)
+    with pytest.raises(mt.ConfigError):
+        data.backend.step(0)
+
+
+def test_actuator_group_mask_reaches_the_kernels():
+    import mujoco_template as mt
+
+    model = _compile(BASE_XML)
+    env = mt.Env(mt.ModelHandle(model))
+    env.reset()
+    env.data.ctrl[:] = [5.0, 0.0]
+    env.step()
+    moved = float(env.data.qvel[0])
+    assert moved > 0
+    env.reset()
+    env.handle.set_enabled_actuator_groups([1])      # disables the torque motor (group 0)
+    env.data.ctrl[:] = [5.0, 0.0]
+    env.step()
+    assert abs(float(env.data.qvel[0])) < 1e-12
+    assert env.data.backend.batch.kernel_variant == "generic"
+
+
+def test_humanoid_lying_down_many_contacts_warp_vs_lane(monkeypatch):
+    """Prone keyframe: ~10+ contacts, 40+ rows.  Warp engine and lane engine agree with the oracle step by step."""
+    import torch
+    from mujoco_template import _mj as mj
+
+    model = load_model("humanoid")
+    n = 6
+    qpos = np.tile(model.key_qpos[2], (n, 1)); qpos[:, 2] += np.linspace(0.0, 0.05, n)
+    qvel = np.zeros((n, model.nv)); ctrl = np.zeros((n, model.nu))
+    data = _parity_rollout(model, qpos.copy(), qvel.copy(), ctrl, 40, tol=1e-8, check_lin=False)
+    assert data.backend.batch.kernel_variant == "generic-warp" and int(data.ncon.max()) >= 8 and int(data.flags.max()) == 0
+    monkeypatch.setenv("B2_DISABLE_WARP", "1")
+    data2 = _parity_rollout(model, qpos.copy(), qvel.copy(), ctrl, 40, tol=1e-8, check_lin=False)
+    assert data2.backend.batch.kernel_variant == "generic"
