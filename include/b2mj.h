@@ -106,6 +106,11 @@ int b2_linearize(b2_batch* batch, const b2_state* state, double eps, int centere
  * (reference mujoco_template/jacobians.py:44,55,67,79).  jacp/jacr: (3, nv, nenv); jacr may be NULL. */
 int b2_jacobian(b2_batch* batch, const b2_state* state, int kind, int objid, void* jacp, void* jacr, void* stream);
 
+/* Replaces mj.mj_inverse + the dense actuator moment (reference mujoco_template/setpoints.py:23-48, steady_ctrl0):
+ * qfrc_inverse (nv, nenv) = M qacc + bias - passive - constraint for the prescribed qacc (nv, nenv; NULL = zeros);
+ * actuator_moment (nu*nv, nenv), row-major nu x nv per env, may be NULL.  State is not modified. */
+int b2_inverse(b2_batch* batch, const b2_state* state, const void* qacc, void* qfrc_inverse, void* actuator_moment, void* stream);
+
 /* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */
 int b2_integrate_pos(b2_batch* batch, void* qpos, const void* qvel, double dt, void* stream);
 int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void* qpos1, const void* qpos2, void* stream);

@@ -291,6 +291,17 @@ int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp
   return rc ? cuda_fail((cudaError_t)rc, "b2_jacobian launch") : B2_OK;
 }
 
+int b2_inverse(b2_batch* b, const b2_state* st, const void* qacc, void* qfrc_inverse, void* actuator_moment, void* stream) {
+  B2_CHECK_STATE("b2_inverse");
+  if (!qfrc_inverse) return fail(B2_ERR_ARG, "b2_inverse: qfrc_inverse is NULL");
+  int rc = ensure_resident(b, stream);  // one-shot setup call: always the generic kernels
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_inverse_f64(b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream)
+                              : b2::b2k_inverse_f32(b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_inverse launch") : B2_OK;
+}
+
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {
   if (!b || !qpos || !qvel) return fail(B2_ERR_ARG, "b2_integrate_pos: null pointer");
   int rc = ensure_resident(b, stream);

@@ -1049,6 +1049,33 @@ struct LaneEnv {
     forward_position();
     forward_rest();
   }
+  // inverse dynamics (mj_inverse, continuous time) at (qpos, qvel) for a prescribed acceleration:
+  // out = M acc + bias - passive - J' f, with the row forces the prescribed acceleration implies
+  B2_DEV void inverse(const T* acc, T* out) {
+    const int nv = M::nv();
+    forward_position();
+    velocities();
+    passive_forces();
+    bias_forces();
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) f_con[k] = 0;
+    if (nefc) {
+      row_params();
+      B2_NOUNROLL
+      for (int i = 0; i < nefc; i++) {
+        T jar = -R.row_aref[i];
+        B2_UNROLL
+        for (int k = 0; k < nv; k++) jar += R.J[i * nv + k] * acc[k];
+        if (jar >= 0) continue;
+        const T f = -R.row_D[i] * jar;
+        B2_UNROLL
+        for (int k = 0; k < nv; k++) f_con[k] += R.J[i * nv + k] * f;
+      }
+    }
+    mul_M(Ma, acc);
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) out[k] = Ma[k] + f_bias[k] - f_passive[k] - f_con[k];
+  }
   B2_DEV void integrate_pos(T* q, const T* v, T dt) const {
     B2_UNROLL
     for (int j = 0; j < M::njnt(); j++) {

@@ -228,6 +228,22 @@ __global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kin
   if (jacr) { B2_UNROLL for (int k = 0; k < 3 * nv; k++) jacr[(size_t)k * N + e] = jr[k]; }
 }
 
+// mj_inverse for a prescribed acceleration (steady_ctrl0: reference mujoco_template/setpoints.py:23-30);
+// optionally exports the dense actuator moment matrix (nu x nv) of every env
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T* qacc, T* qfrc, T* moment) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  load_state(env, st, N, e);
+  T acc[D::NV], out[D::NV];
+  for (int k = 0; k < M::nv(); k++) acc[k] = qacc ? qacc[(size_t)k * N + e] : T(0);
+  env.inverse(acc, out);
+  for (int k = 0; k < M::nv(); k++) qfrc[(size_t)k * N + e] = out[k];
+  if (moment) for (int k = 0; k < M::nu() * M::nv(); k++) moment[(size_t)k * N + e] = env.act_moment[k];
+}
+
 template <typename T, class D, class M>
 __global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T dt, int N) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

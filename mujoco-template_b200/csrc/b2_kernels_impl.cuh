@@ -186,6 +186,12 @@ int B2_FN(b2k_jacobian)(int cls, const b2_state* st, int N, int kind, int objid,
                        to_dev<real>(st), N, kind, objid, (real*)jacp, (real*)jacr)));
   return (int)cudaGetLastError();
 }
+int B2_FN(b2k_inverse)(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream) {
+  const int threads = 128, blocks = (N + threads - 1) / threads;
+  B2_DISPATCH(cls, (k_inverse<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
+                       to_dev<real>(st), N, (const real*)qacc, (real*)qfrc, (real*)moment)));
+  return (int)cudaGetLastError();
+}
 int B2_FN(b2k_integrate_pos)(int cls, void* qpos, const void* qvel, double dt, int N, void* stream) {
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_integrate_pos<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(

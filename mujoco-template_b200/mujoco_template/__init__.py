@@ -4,7 +4,7 @@ Same public names as the reference package for everything on the path
 (reference ``mujoco_template/__init__.py:81-135``), plus ``BatchedEnv``.  ``mj`` is the
 MuJoCo-shaped facade over ``libb2mj.so`` (``_mj.py``), since the real ``mujoco`` module is
 neither required nor used.  Out-of-scope reference components (viewer, video, adaptive
-camera, run harness, setpoints) are intentionally absent; see DESIGN.md.
+camera, run harness) are intentionally absent; see DESIGN.md.
 """
 
 from __future__ import annotations
@@ -23,6 +23,7 @@ from .logging import DataProbe, StateControlRecorder
 from .model import ModelHandle
 from .observations import ObservationExtractor, ObservationProducer, ObservationSpec
 from .runtime import StepHook, TrajectoryLogger, iterate_passive, run_passive_headless
+from .setpoints import batched_steady_ctrl0, steady_ctrl0
 
 __version__ = "0.1.0"
 
@@ -31,7 +32,8 @@ __all__ = [
     "ControlSpace", "Controller", "ControllerCapabilities", "ObservationSpec", "ObservationExtractor",
     "ObservationProducer", "ModelHandle", "CompatibilityReport", "StepResult", "Env", "BatchedEnv",
     "BatchedObservationExtractor", "shard_range", "ZeroController", "PositionTargetDemo",
-    "check_controller_compat", "linearize_discrete", "compute_requested_jacobians", "TrajectoryLogger",
+    "check_controller_compat", "linearize_discrete", "compute_requested_jacobians", "steady_ctrl0",
+    "batched_steady_ctrl0", "TrajectoryLogger",
     "DataProbe", "StateControlRecorder", "StepHook", "iterate_passive", "run_passive_headless",
     "ObservationDict", "ObservationArray", "Observation", "JacobianDict", "JacobiansDict", "InfoDict",
     "StateSnapshot", "mj", "__version__",

@@ -24,7 +24,7 @@ _lib: C.CDLL | None = None
 EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
-    "b2_differentiate_pos", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_differentiate_pos", "b2_inverse", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
 )
 
@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
     L.b2_forward.argtypes = [vp, C.POINTER(State), C.POINTER(Derived), vp]
     L.b2_linearize.argtypes = [vp, C.POINTER(State), d, i, vp, vp, vp]
     L.b2_jacobian.argtypes = [vp, C.POINTER(State), i, i, vp, vp, vp]
+    L.b2_inverse.argtypes = [vp, C.POINTER(State), vp, vp, vp, vp]
     L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
@@ -154,6 +155,9 @@ class NativeBatch:
 
     def jacobian(self, state: State, kind: int, objid: int, jacp: int, jacr: int | None, stream: int = 0) -> None:
         check(self._L.b2_jacobian(self.handle, C.byref(state), int(kind), int(objid), jacp, jacr, stream))
+
+    def inverse(self, state: State, qacc: int | None, qfrc: int, moment: int | None, stream: int = 0) -> None:
+        check(self._L.b2_inverse(self.handle, C.byref(state), qacc, qfrc, moment, stream))
 
     def integrate_pos(self, qpos: int, qvel: int, dt: float, stream: int = 0) -> None:
         check(self._L.b2_integrate_pos(self.handle, qpos, qvel, float(dt), stream))

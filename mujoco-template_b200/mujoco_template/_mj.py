@@ -181,7 +181,7 @@ _STATE_FIELDS = ("qpos", "qvel", "ctrl", "qacc_warmstart")
 def _field_dims(m: MjModel) -> dict[str, int]:
     return dict(qpos=m.nq, qvel=m.nv, ctrl=m.nu, qacc_warmstart=m.nv, xpos=3 * m.nbody, xquat=4 * m.nbody,
                 xipos=3 * m.nbody, geom_xpos=3 * m.ngeom, site_xpos=3 * m.nsite, subtree_com=3 * m.nbody,
-                qacc=m.nv, qfrc_bias=m.nv)
+                qacc=m.nv, qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv)
 
 
 _INT_FIELDS = ("flags", "ncon", "nefc", "solver_iter")
@@ -303,6 +303,11 @@ class NativeBackend:
                      jr.data_ptr() if jr is not None else None)
         return jp, jr
 
+    def inverse(self) -> None:
+        """mj_inverse for the acceleration in the ``qacc`` buffer -> ``qfrc_inverse``, ``actuator_moment`` buffers."""
+        self._launch("inverse", self.batch.inverse, self.state_struct(), self._ptr("qacc"), self._ptr("qfrc_inverse"),
+                     self._ptr("actuator_moment"))
+
     def _tmp(self, key: str, dim: int):
         t = self._scratch.get(key)
         if t is None:
@@ -381,6 +386,8 @@ class MjData(_DataBase):
         self.geom_xpos = b.array("geom_xpos")[:, 0].reshape(m.ngeom, 3)
         self.site_xpos = b.array("site_xpos")[:, 0].reshape(m.nsite, 3)
         self.subtree_com = b.array("subtree_com")[:, 0].reshape(m.nbody, 3)
+        self.qfrc_inverse = b.array("qfrc_inverse")[:, 0]
+        self.actuator_moment = b.array("actuator_moment")[:, 0].reshape(m.nu, m.nv)  # dense nu x nv
         self.act = np.zeros(0)
         self.sensordata = np.zeros(0)
         self.time = 0.0
@@ -458,6 +465,12 @@ def mj_step(model: MjModel, data: _DataBase, nstep: int = 1) -> None:
         data.time += h  # repeated addition, exactly as upstream accumulates mjData.time
 
 
+def mj_inverse(model: MjModel, data: _DataBase) -> None:
+    """Inverse dynamics for ``data.qacc`` at the current state: fills ``data.qfrc_inverse`` and the dense
+    ``data.actuator_moment`` (reference ``mujoco_template/setpoints.py:28-48``)."""
+    data.backend.inverse()
+
+
 def _to_host_matrix(t, nenv: int) -> np.ndarray:
     a = t.numpy() if t.device.type == "cpu" else t.cpu().numpy()
     return a
@@ -515,6 +528,6 @@ def mj_subtreeCoM(model: MjModel, data: _DataBase) -> None:
 
 __all__ = [
     "MjModel", "MjData", "BatchData", "NativeBackend", "mjtObj", "mjtJoint", "mj_name2id", "mj_id2name", "mj_resetData",
-    "mj_resetDataKeyframe", "mj_forward", "mj_step", "mjd_transitionFD", "mj_integratePos", "mj_differentiatePos",
+    "mj_resetDataKeyframe", "mj_forward", "mj_step", "mj_inverse", "mjd_transitionFD", "mj_integratePos", "mj_differentiatePos",
     "mj_jacSite", "mj_jacBody", "mj_jacBodyCom", "mj_jacSubtreeCom", "mj_subtreeCoM",
 ]

@@ -1154,6 +1154,28 @@ void orc_forward(const orc_model* m, orc_data* d) {
   ARENA_RELEASE;
 }
 
+/* mj_inverse (continuous-time): qfrc_inverse = M*qacc + qfrc_bias - qfrc_passive - qfrc_constraint, with the
+ * constraint forces of mj_invConstraint (the given qacc fixes every row's residual: f = -D * min(0, J qacc - aref)).
+ * Used by steady_ctrl0 (reference mujoco_template/setpoints.py:23-30).  Also refreshes actuator_moment. */
+void orc_inverse(const orc_model* m, orc_data* d, const double* qacc, double* qfrc_inverse) {
+  const b2m_view* v = &m->v;
+  int nv = v->nv;
+  ARENA_MARK;
+  orc_fwd_position(m, d);
+  orc_fwd_velocity(m, d);
+  double* jar = SCRATCH(d->nefc);
+  double* Ma = SCRATCH(nv);
+  for (int i = 0; i < d->nefc; i++) {
+    double s = 0;
+    for (int k = 0; k < nv; k++) s += d->efc_J[(size_t)i * nv + k] * qacc[k];
+    jar[i] = s - d->efc_aref[i];
+  }
+  orc_constraint_update(m, d, jar, 1);
+  orc_mul_m(v, d, Ma, qacc);
+  for (int k = 0; k < nv; k++) qfrc_inverse[k] = Ma[k] + d->qfrc_bias[k] - d->qfrc_passive[k] - d->qfrc_constraint[k];
+  ARENA_RELEASE;
+}
+
 /* mj_integratePos */
 void orc_integrate_pos(const orc_model* m, double* qpos, const double* qvel, double dt) {
   const b2m_view* v = &m->v;

@@ -43,6 +43,7 @@ def lib() -> C.CDLL:
         L.orc_forward.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_transition_fd.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, _dp, _dp]
+        L.orc_inverse.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp]
         L.orc_integrate_pos.argtypes = [C.c_void_p, _dp, _dp, C.c_double]
         L.orc_differentiate_pos.argtypes = [C.c_void_p, _dp, C.c_double, _dp, _dp]
         L.orc_jac.argtypes = [C.c_void_p, C.c_void_p, _dp, _dp, _dp, C.c_int]
@@ -195,6 +196,13 @@ class OracleData:
         A = np.zeros((2 * d["nv"], 2 * d["nv"])); B = np.zeros((2 * d["nv"], d["nu"]))
         self._L.orc_transition_fd(self.model.h, self.h, float(eps), int(centered), _p(A), _p(B) if d["nu"] else None)
         return A, B
+
+    def inverse(self, qacc: np.ndarray) -> np.ndarray:
+        """mj_inverse at the current (qpos, qvel) for the given qacc; also refreshes ``actuator_moment``."""
+        out = np.zeros(self.model.dims["nv"])
+        a = np.ascontiguousarray(qacc, dtype=float)
+        self._L.orc_inverse(self.model.h, self.h, _p(a), _p(out))
+        return out
 
     def integrate_pos(self, qpos: np.ndarray, qvel: np.ndarray, dt: float) -> np.ndarray:
         q = np.array(qpos, dtype=float); v = np.ascontiguousarray(qvel, dtype=float)

@@ -19,7 +19,7 @@ class OracleBackend:
         m = model
         dims = dict(qpos=m.nq, qvel=m.nv, ctrl=m.nu, qacc_warmstart=m.nv, xpos=3 * m.nbody, xquat=4 * m.nbody,
                     xipos=3 * m.nbody, geom_xpos=3 * m.ngeom, site_xpos=3 * m.nsite, subtree_com=3 * m.nbody, qacc=m.nv,
-                    qfrc_bias=m.nv)
+                    qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv)
         self.buf = {k: np.zeros((v, 1)) for k, v in dims.items()}
         for k in ("flags", "ncon", "nefc", "solver_iter"):
             self.buf[k] = np.zeros((1, 1), dtype=np.int32)
@@ -81,6 +81,11 @@ class OracleBackend:
         jp, jr = self.od.jac(name, objid)
         t = lambda a: torch.as_tensor(a[:, :, None].copy())  # noqa: E731
         return t(jp), (t(jr) if (want_rot and jr is not None) else None)
+
+    def inverse(self):
+        self._push()
+        self.buf["qfrc_inverse"][:, 0] = self.od.inverse(self.buf["qacc"][:, 0])
+        self.buf["actuator_moment"][:, 0] = self.od.actuator_moment.ravel()
 
     def integrate_pos_host(self, qpos, qvel, dt):
         qpos[:] = self.od.integrate_pos(qpos, qvel, dt)

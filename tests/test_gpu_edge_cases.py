@@ -150,3 +150,39 @@ def test_humanoid_lying_down_many_contacts_warp_vs_lane(monkeypatch):
     monkeypatch.setenv("B2_DISABLE_WARP", "1")
     data2 = _parity_rollout(model, qpos.copy(), qvel.copy(), ctrl, 40, tol=1e-8, check_lin=False)
     assert data2.backend.batch.kernel_variant == "generic"
+
+
+@pytest.mark.parametrize("name", ["pendulum", "drone", "humanoid"])
+def test_inverse_dynamics_and_steady_ctrl0(name):
+    """b2_inverse vs the oracle's mj_inverse; forward/inverse consistency; batched steady-state controls."""
+    import torch
+    import mujoco_template as mt
+    from mujoco_template import _mj as mj
+    from conftest import random_states
+
+    model = load_model(name)
+    n = 16
+    qpos, qvel, ctrl = random_states(model, name, n, seed=41)
+    env = mt.BatchedEnv(model, n)
+    dev = env.data.qpos.device
+    env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev)); env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+    env.data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev))
+    env.forward()                                     # qacc of the forward dynamics
+    qacc = env.data.qacc.cpu().numpy().T.copy()
+    mj.mj_inverse(model, env.data)                    # inverse dynamics for that qacc
+    qfrc = env.data.qfrc_inverse.cpu().numpy().T
+    moment = env.data.actuator_moment.cpu().numpy().reshape(model.nu, model.nv, n)
+    om, od = oracle_for(model)
+    for e in range(n):
+        od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+        ref = od.inverse(qacc[e])
+        assert _rel(qfrc[e], ref) <= 1e-9, (name, e)
+        assert _rel(moment[:, :, e], od.actuator_moment) <= 1e-12
+        od.forward()
+        assert _rel(qfrc[e], np.array(od.qfrc_actuator)) <= 1e-6   # inverse(forward(u)) recovers the actuator force
+    u = mt.batched_steady_ctrl0(env)
+    assert tuple(u.shape) == (model.nu, n) and bool(torch.isfinite(u).all())
+    if name == "pendulum":
+        expect = float(model.body_mass[1]) * 9.81 * 0.25 * np.sin(qpos[:, 0]) 
+        # qvel != 0 adds no bias for a single hinge about a fixed axis; damping is zero
+        assert np.allclose(u.cpu().numpy()[0], expect, atol=1e-10)

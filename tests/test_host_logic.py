@@ -276,3 +276,26 @@ def test_shard_range_partitions_exactly():
         assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
     with pytest.raises(mt.ConfigError):
         mt.shard_range(8, 2, 2)
+
+
+def test_steady_ctrl0_preserves_state_and_holds_the_pose(handle):
+    model, data = handle.model, handle.data
+    data.qpos[:] = 0.1
+    data.qvel[:] = -0.05
+    q0, v0 = np.copy(data.qpos), np.copy(data.qvel)
+    u = mt.steady_ctrl0(model, data, qpos0=np.zeros(model.nq), qvel0=np.zeros(model.nv))
+    assert u.shape == (model.nu,)
+    np.testing.assert_allclose(data.qpos, q0)
+    np.testing.assert_allclose(data.qvel, v0)
+    with pytest.raises(mt.ConfigError):
+        mt.steady_ctrl0(model, data, qpos0=np.zeros(model.nq + 1))
+    # pendulum: the holding control equals the gravity torque m g l sin(theta) (gear 1)
+    pend = load_model("pendulum")
+    env = make_env(pend)
+    u = mt.steady_ctrl0(env.model, env.data, qpos0=np.array([0.7]))
+    assert abs(u[0] - float(pend.body_mass[1]) * 9.81 * 0.25 * np.sin(0.7)) < 1e-12
+    # drone hover: four equal thrusts m g / 4 (site transmissions: state-dependent moment matrix)
+    drone = load_model("drone")
+    env = make_env(drone)
+    u = mt.steady_ctrl0(env.model, env.data, qpos0=drone.key_qpos[0])
+    assert np.allclose(u, 1.325 * 9.81 / 4, atol=1e-9)
