@@ -261,6 +261,9 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("linearize", "step")}
     env.data.backend.profile = None
+    c0 = _capi.launch_count()
+    env.step(return_obs=False)
+    per_step_launches = _capi.launch_count() - c0  # library kernels per step (controller tick, FD, step)
     use_graph = controller is not None and not args.no_graph
     if use_graph:
         env.enable_cuda_graph(True)
@@ -287,7 +290,6 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     total_ms = float(sum(step_ms))
     # graph replays re-launch the captured kernels without passing through the C-ABI counter
-    per_step_launches = (1 if lin else 0) + 1
     launches = (_capi.launch_count() - launches0) if not use_graph else per_step_launches * args.steps
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:

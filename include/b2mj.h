@@ -111,6 +111,13 @@ int b2_jacobian(b2_batch* batch, const b2_state* state, int kind, int objid, voi
  * actuator_moment (nu*nv, nenv), row-major nu x nv per env, may be NULL.  State is not modified. */
 int b2_inverse(b2_batch* batch, const b2_state* state, const void* qacc, void* qfrc_inverse, void* actuator_moment, void* stream);
 
+/* On-device LQR control tick.  Replaces the per-step arithmetic of the reference's LQR
+ * controllers (reference examples/drone/controllers/lqr.py:227-278, examples/humanoid/controllers/lqr.py:153-170):
+ * ctrl = clip(ctrl_ref - K [mj_differentiatePos(qpos_ref -> qpos); qvel], ctrlrange) for every env in one launch.
+ * b2_lqr_set_gain (synchronous) uploads K (nu x 2nv, row-major), qpos_ref (nq), ctrl_ref (nu), given in double. */
+int b2_lqr_set_gain(b2_batch* batch, const double* K, const double* qpos_ref, const double* ctrl_ref);
+int b2_lqr_control(b2_batch* batch, const b2_state* state, void* stream);
+
 /* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */
 int b2_integrate_pos(b2_batch* batch, void* qpos, const void* qvel, double dt, void* stream);
 int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void* qpos1, const void* qpos2, void* stream);

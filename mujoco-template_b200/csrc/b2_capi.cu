@@ -73,6 +73,7 @@ struct b2_batch {
   // warp engine (large models): -1 not yet decided, 0 lane engine, 1 warp engine
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
+  void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
   cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
   bool pipe_ready = false;
@@ -149,7 +150,7 @@ int b2_batch_create(const b2_model* model, int nenv, int device, int precision, 
 }
 void b2_batch_destroy(b2_batch* b) {
   if (!b) return;
-  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch};
+  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch, b->d_gain};
   for (void* q : p) if (q) cudaFree(q);
   if (b->host_graph) cudaGraphExecDestroy(b->host_graph);
   if (b->pipe_ready) { for (cudaStream_t st : b->pipe) cudaStreamDestroy(st); for (cudaEvent_t ev : b->pipe_ev) cudaEventDestroy(ev); }
@@ -300,6 +301,34 @@ int b2_inverse(b2_batch* b, const b2_state* st, const void* qacc, void* qfrc_inv
                               : b2::b2k_inverse_f32(b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream);
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_inverse launch") : B2_OK;
+}
+
+int b2_lqr_set_gain(b2_batch* b, const double* K, const double* qpos_ref, const double* ctrl_ref) {
+  if (!b || !K || !qpos_ref || !ctrl_ref) return fail(B2_ERR_ARG, "b2_lqr_set_gain: null pointer");
+  const b2m_view& v = b->model->v;
+  if (v.nu == 0) return fail(B2_ERR_ARG, "b2_lqr_set_gain: model has no actuators");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const size_t n = (size_t)v.nu * 2 * v.nv + v.nq + v.nu;
+  std::vector<unsigned char> host(n * b->esz);
+  for (size_t i = 0; i < n; i++) {
+    const double x = i < (size_t)v.nu * 2 * v.nv ? K[i] : (i < (size_t)v.nu * 2 * v.nv + v.nq ? qpos_ref[i - (size_t)v.nu * 2 * v.nv] : ctrl_ref[i - (size_t)v.nu * 2 * v.nv - v.nq]);
+    if (b->precision == B2_F64) ((double*)host.data())[i] = x; else ((float*)host.data())[i] = (float)x;
+  }
+  if (!b->d_gain && (e = cudaMalloc(&b->d_gain, n * b->esz))) return cuda_fail(e, "b2_lqr_set_gain: cudaMalloc");
+  if ((e = cudaMemcpy(b->d_gain, host.data(), n * b->esz, cudaMemcpyHostToDevice))) return cuda_fail(e, "b2_lqr_set_gain: copy");
+  return B2_OK;
+}
+
+int b2_lqr_control(b2_batch* b, const b2_state* st, void* stream) {
+  B2_CHECK_STATE("b2_lqr_control");
+  if (!b->d_gain) return fail(B2_ERR_ARG, "b2_lqr_control: call b2_lqr_set_gain first");
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_f64(b->model->cls, st, b->nenv, b->d_gain, stream)
+                              : b2::b2k_lqr_control_f32(b->model->cls, st, b->nenv, b->d_gain, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_lqr_control launch") : B2_OK;
 }
 
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {

@@ -244,6 +244,30 @@ __global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T*
   if (moment) for (int k = 0; k < M::nu() * M::nv(); k++) moment[(size_t)k * N + e] = env.act_moment[k];
 }
 
+// Fused LQR control tick for every env: u = clip(u_ref - K [qpos (-) qpos_ref ; qvel], ctrlrange), where (-) is the
+// tangent-space difference (mj_differentiatePos, so free-joint quaternions are handled).  One launch replaces
+// the per-step controller arithmetic of the reference's LQR controllers
+// (reference examples/drone/controllers/lqr.py:227-278, examples/humanoid/controllers/lqr.py:153-170).
+// gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int N, const T* __restrict__ gain) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  T q[D::NQ], qr[D::NQ], x[2 * D::NV];
+  for (int k = 0; k < nq; k++) { q[k] = st.qpos[(size_t)k * N + e]; qr[k] = gain[nu * 2 * nv + k]; }
+  env.differentiate_pos(x, T(1), qr, q);
+  for (int k = 0; k < nv; k++) x[nv + k] = st.qvel[(size_t)k * N + e];
+  for (int a = 0; a < nu; a++) {
+    T u = gain[nu * 2 * nv + nq + a];
+    for (int k = 0; k < 2 * nv; k++) u -= gain[a * 2 * nv + k] * x[k];
+    if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
+    st.ctrl[(size_t)a * N + e] = u;
+  }
+}
+
 template <typename T, class D, class M>
 __global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T dt, int N) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;

@@ -24,7 +24,7 @@ _lib: C.CDLL | None = None
 EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
-    "b2_differentiate_pos", "b2_inverse", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
 )
 
@@ -73,6 +73,8 @@ def lib() -> C.CDLL:
     L.b2_linearize.argtypes = [vp, C.POINTER(State), d, i, vp, vp, vp]
     L.b2_jacobian.argtypes = [vp, C.POINTER(State), i, i, vp, vp, vp]
     L.b2_inverse.argtypes = [vp, C.POINTER(State), vp, vp, vp, vp]
+    L.b2_lqr_set_gain.argtypes = [vp, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
+    L.b2_lqr_control.argtypes = [vp, C.POINTER(State), vp]
     L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
@@ -158,6 +160,17 @@ class NativeBatch:
 
     def inverse(self, state: State, qacc: int | None, qfrc: int, moment: int | None, stream: int = 0) -> None:
         check(self._L.b2_inverse(self.handle, C.byref(state), qacc, qfrc, moment, stream))
+
+    def lqr_set_gain(self, K, qpos_ref, ctrl_ref) -> None:
+        import numpy as np
+
+        K = np.ascontiguousarray(K, dtype=np.float64); q = np.ascontiguousarray(qpos_ref, dtype=np.float64)
+        u = np.ascontiguousarray(ctrl_ref, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        check(self._L.b2_lqr_set_gain(self.handle, K.ctypes.data_as(dp), q.ctypes.data_as(dp), u.ctypes.data_as(dp)))
+
+    def lqr_control(self, state: State, stream: int = 0) -> None:
+        check(self._L.b2_lqr_control(self.handle, C.byref(state), stream))
 
     def integrate_pos(self, qpos: int, qvel: int, dt: float, stream: int = 0) -> None:
         check(self._L.b2_integrate_pos(self.handle, qpos, qvel, float(dt), stream))

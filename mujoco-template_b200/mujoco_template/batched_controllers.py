@@ -30,12 +30,14 @@ def dlqr_gain(A: np.ndarray, B: np.ndarray, Q: np.ndarray, R: np.ndarray) -> np.
 class BatchedLQRController:
     def __init__(self, qpos_ref: np.ndarray | None = None, ctrl_ref: np.ndarray | None = None,
                  Q: np.ndarray | None = None, R: np.ndarray | None = None, eps: float = 1e-6,
-                 needs_linearization: bool = True):
+                 needs_linearization: bool = True, fused: bool = True):
         self.qpos_ref = None if qpos_ref is None else np.asarray(qpos_ref, dtype=float)
         self.ctrl_ref = None if ctrl_ref is None else np.asarray(ctrl_ref, dtype=float)
         self.Q, self.R, self.eps = Q, R, float(eps)
         self.capabilities = ControllerCapabilities(control_space=ControlSpace.TORQUE,
                                                    needs_linearization=bool(needs_linearization))
+        self.fused = bool(fused)  # False: the same tick as a handful of torch ops (reference-style arithmetic)
+        self._gain_uploaded = False
         self.K: np.ndarray | None = None
         self._dev: dict[str, Any] = {}
 
@@ -70,17 +72,25 @@ class BatchedLQRController:
                 hi=torch.as_tensor(model.actuator_ctrlrange[:, 1], device=dev, dtype=dt)[:, None],
                 limited=torch.as_tensor(np.asarray(model.actuator_ctrllimited, dtype=bool), device=dev)[:, None],
                 qref_full=None, dq=torch.zeros((nv, data.qpos.shape[1]), device=dev, dtype=dt))
+        self._gain_uploaded = False
         self._free = bool(np.any(model.jnt_type == 0))
         self._qref_np, self._uref_np = qref, uref
 
     def __call__(self, model: Any, data: Any, t: float) -> None:
+        b = data.backend
+        if self.fused and hasattr(b, "batch") and hasattr(data.qpos, "device"):
+            # one kernel: tangent-space state error, gain product, ctrlrange clamp (b2_lqr_control)
+            if not self._gain_uploaded:
+                b.batch.lqr_set_gain(self.K, self._qref_np, self._uref_np)
+                self._gain_uploaded = True
+            b._launch("lqr_control", b.batch.lqr_control, b.state_struct())
+            return
         import torch
 
         d = self._dev
         if self._free:
             if d["qref_full"] is None:
                 d["qref_full"] = d["qref"].expand_as(data.qpos).contiguous()
-            b = data.backend
             b._pre()
             b.batch.differentiate_pos(d["dq"].data_ptr(), 1.0, d["qref_full"].data_ptr(), data.qpos.data_ptr(), b.stream)
             dq = d["dq"]

@@ -48,6 +48,34 @@ def _labels(table: dict, joint_type: int, count: int) -> Sequence[str]:
     return known
 
 
+def build_schema(model: Any, probe_names: Sequence[str] = ()):
+    """Reference CSV schema: (columns, qpos indices, qvel indices, ctrl column names)."""
+    m = model
+    columns = ["time_s"]
+    qpos_idx: list[int] = []
+    qvel_idx: list[int] = []
+    for j in range(m.njnt):
+        name = mj.mj_id2name(m, mj.mjtObj.mjOBJ_JOINT, j) or f"joint_{j}"
+        jtype = int(m.jnt_type[j])
+        q0 = int(m.jnt_qposadr[j])
+        q1 = int(m.jnt_qposadr[j + 1]) if j + 1 < m.njnt else int(m.nq)
+        v0 = int(m.jnt_dofadr[j])
+        v1 = int(m.jnt_dofadr[j + 1]) if j + 1 < m.njnt else int(m.nv)
+        for idx, comp in zip(range(q0, q1), _labels(_QPOS_LABELS, jtype, q1 - q0)):
+            columns.append(f"qpos[{name}].{comp}" if comp else f"qpos[{name}]")
+            qpos_idx.append(idx)
+        for idx, comp in zip(range(v0, v1), _labels(_QVEL_LABELS, jtype, v1 - v0)):
+            columns.append(f"qvel[{name}].{comp}" if comp else f"qvel[{name}]")
+            qvel_idx.append(idx)
+    if m.nu > 0:
+        ctrl_cols = tuple(f"ctrl[{mj.mj_id2name(m, mj.mjtObj.mjOBJ_ACTUATOR, a) or f'actuator_{a}'}]" for a in range(m.nu))
+    else:
+        ctrl_cols = ("ctrl[none]",)
+    columns.extend(ctrl_cols)
+    columns.extend(probe_names)
+    return tuple(columns), qpos_idx, qvel_idx, ctrl_cols
+
+
 class StateControlRecorder:
     """StepHook that logs time, generalized coordinates, velocities, controls and probes."""
 
@@ -79,30 +107,7 @@ class StateControlRecorder:
         return tuple(probes)
 
     def _schema(self):
-        m = self._model
-        columns = ["time_s"]
-        qpos_idx: list[int] = []
-        qvel_idx: list[int] = []
-        for j in range(m.njnt):
-            name = mj.mj_id2name(m, mj.mjtObj.mjOBJ_JOINT, j) or f"joint_{j}"
-            jtype = int(m.jnt_type[j])
-            q0 = int(m.jnt_qposadr[j])
-            q1 = int(m.jnt_qposadr[j + 1]) if j + 1 < m.njnt else int(m.nq)
-            v0 = int(m.jnt_dofadr[j])
-            v1 = int(m.jnt_dofadr[j + 1]) if j + 1 < m.njnt else int(m.nv)
-            for idx, comp in zip(range(q0, q1), _labels(_QPOS_LABELS, jtype, q1 - q0)):
-                columns.append(f"qpos[{name}].{comp}" if comp else f"qpos[{name}]")
-                qpos_idx.append(idx)
-            for idx, comp in zip(range(v0, v1), _labels(_QVEL_LABELS, jtype, v1 - v0)):
-                columns.append(f"qvel[{name}].{comp}" if comp else f"qvel[{name}]")
-                qvel_idx.append(idx)
-        if m.nu > 0:
-            ctrl_cols = tuple(f"ctrl[{mj.mj_id2name(m, mj.mjtObj.mjOBJ_ACTUATOR, a) or f'actuator_{a}'}]" for a in range(m.nu))
-        else:
-            ctrl_cols = ("ctrl[none]",)
-        columns.extend(ctrl_cols)
-        columns.extend(p.name for p in self._probes)
-        return tuple(columns), qpos_idx, qvel_idx, ctrl_cols
+        return build_schema(self._model, [p.name for p in self._probes])
 
     @property
     def columns(self) -> tuple[str, ...]:
@@ -162,4 +167,114 @@ class StateControlRecorder:
             yield {name: row[i] for name, i in self._column_index_map.items()}
 
 
-__all__ = ["DataProbe", "StateControlRecorder"]
+class BatchedStateControlRecorder:
+    """StepHook for ``BatchedEnv``: the reference's CSV rows for a selection of envs.
+
+    Every step appends ``[time, qpos.., qvel.., ctrl..]`` of the selected envs to a device-side ring buffer
+    with one gather (no host synchronisation in the step loop); full chunks are copied to pinned host memory
+    asynchronously and written out as CSV with the reference schema plus a leading ``env`` column.  Probes are
+    vectorised: ``extractor(env, result)`` must return one value per selected env (tensor or array)."""
+
+    def __init__(self, env: Any, *, log_path: str | Path | None = None, env_indices: Sequence[int] | None = None,
+                 chunk_steps: int = 256, store_rows: bool = False, probes: Sequence[DataProbe] = ()) -> None:
+        import torch
+
+        self._env, self._model = env, env.model
+        m = env.model
+        self._probes = StateControlRecorder._validate_probes(probes)
+        cols, self._qi, self._vi, _ = build_schema(m, [p.name for p in self._probes])
+        self.columns = ("env",) + cols
+        n = env.data.qpos.shape[1]
+        sel = list(range(n)) if env_indices is None else [int(i) for i in env_indices]
+        if not sel or min(sel) < 0 or max(sel) >= n:
+            raise ConfigError("env_indices must be a non-empty list of valid env indices")
+        dev, dt = env.data.qpos.device, env.data.qpos.dtype
+        self._sel = torch.as_tensor(sel, device=dev, dtype=torch.long)
+        self._sel_host = sel
+        self._qi_t = torch.as_tensor(self._qi, device=dev, dtype=torch.long)
+        self._vi_t = torch.as_tensor(self._vi, device=dev, dtype=torch.long)
+        self._nrow = 1 + m.nq + m.nv + max(m.nu, 1) + len(self._probes)
+        self._chunk = int(chunk_steps)
+        if self._chunk < 1:
+            raise ConfigError("chunk_steps must be >= 1")
+        self._ring = torch.zeros((self._chunk, self._nrow, len(sel)), device=dev, dtype=dt)
+        self._host = torch.zeros((self._chunk, self._nrow, len(sel)), dtype=dt).pin_memory() if dev.type == "cuda" else None
+        self._fill = 0
+        self._store_rows = bool(store_rows)
+        self.rows: list[tuple[object, ...]] = []
+        self._path = None if log_path is None else Path(log_path)
+        self._file = None
+        self._writer = None
+        self.steps = 0
+
+    def __enter__(self) -> "BatchedStateControlRecorder":
+        if self._path is not None:
+            import csv
+
+            self._path.parent.mkdir(parents=True, exist_ok=True)
+            self._file = self._path.open("w", newline="", encoding="utf-8")
+            self._writer = csv.writer(self._file)
+            self._writer.writerow(self.columns)
+        return self
+
+    def __exit__(self, exc_type, exc, exc_tb) -> None:
+        self.close()
+
+    def __call__(self, result: Any) -> None:
+        import torch
+
+        data, m = self._env.data, self._model
+        slot = self._ring[self._fill]
+        slot[0] = float(data.time)
+        slot[1: 1 + m.nq] = data.qpos[self._qi_t][:, self._sel]
+        slot[1 + m.nq: 1 + m.nq + m.nv] = data.qvel[self._vi_t][:, self._sel]
+        base = 1 + m.nq + m.nv
+        if m.nu:
+            slot[base: base + m.nu] = data.ctrl[:, self._sel]
+        else:
+            slot[base] = float("nan")
+        base += max(m.nu, 1)
+        for k, probe in enumerate(self._probes):
+            slot[base + k] = torch.as_tensor(probe.extractor(self._env, result), device=slot.device, dtype=slot.dtype)
+        self._fill += 1
+        self.steps += 1
+        if self._fill == self._chunk:
+            self.flush()
+
+    def flush(self) -> None:
+        """Copy the filled part of the ring to the host and emit its rows (env-major within each step)."""
+        if self._fill == 0:
+            return
+        k = self._fill
+        self._fill = 0
+        if self._host is not None:
+            self._host[:k].copy_(self._ring[:k], non_blocking=True)
+            import torch
+
+            torch.cuda.current_stream(self._ring.device).synchronize()
+            block = self._host[:k].numpy()
+        else:
+            block = self._ring[:k].numpy()
+        m = self._model
+        nu1 = max(m.nu, 1)
+        for t in range(k):
+            for c, e in enumerate(self._sel_host):
+                vals = block[t, :, c]
+                row: list[object] = [e] + [float(x) for x in vals[: 1 + m.nq + m.nv]]
+                row += [float(x) for x in vals[1 + m.nq + m.nv: 1 + m.nq + m.nv + nu1]] if m.nu else [""]
+                row += [float(x) for x in vals[1 + m.nq + m.nv + nu1:]]
+                tup = tuple(row)
+                if self._writer is not None:
+                    self._writer.writerow(tup)
+                if self._store_rows:
+                    self.rows.append(tup)
+
+    def close(self) -> None:
+        self.flush()
+        if self._file is not None:
+            self._file.close()
+        self._file = None
+        self._writer = None
+
+
+__all__ = ["DataProbe", "StateControlRecorder", "BatchedStateControlRecorder", "build_schema"]

@@ -435,3 +435,68 @@ def test_step_host_pipeline_matches_device_path(name, n):
         assert np.array_equal(hw.numpy(), data.qacc_warmstart.cpu().numpy()), rep
         if lin:
             assert np.array_equal(hA.numpy(), A.cpu().numpy()) and np.array_equal(hB.numpy(), B.cpu().numpy()), rep
+
+
+@pytest.mark.parametrize("name", ["cartpole", "drone"])
+def test_fused_lqr_control_kernel_matches_torch_reference(name):
+    """b2_lqr_control (one launch) == the same tick written with torch ops, incl. quaternion error and ctrl clamp."""
+    import torch
+    import mujoco_template as mt
+    from mujoco_template.batched_controllers import BatchedLQRController
+
+    model = load_model(name)
+    n = 200
+    qpos, qvel, _ = random_states(model, name, n, seed=51)
+    kw = dict(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]])) if name == "cartpole" else \
+        dict(qpos_ref=model.key_qpos[0], ctrl_ref=model.key_ctrl[0], R=np.eye(4) * 0.1)
+    out = []
+    for fused in (True, False):
+        ctrl = BatchedLQRController(needs_linearization=False, fused=fused, **kw)
+        env = mt.BatchedEnv(model, n, controller=ctrl)
+        env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=env.data.qpos.device))
+        env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=env.data.qpos.device))
+        if name == "cartpole":
+            env.data.qpos[0, :4] = 50.0    # far away: the +-200 ctrlrange clamp is hit
+        ctrl(model, env.data, 0.0)
+        torch.cuda.synchronize()
+        out.append(env.data.ctrl.cpu().numpy().copy())
+    assert np.allclose(out[0], out[1], rtol=1e-12, atol=1e-12)
+    if name == "cartpole":
+        assert np.all(np.abs(out[0][0, :4]) == 200.0)
+
+
+def test_batched_recorder_matches_single_env_csv(tmp_path):
+    """BatchedStateControlRecorder rows of env k == StateControlRecorder rows of a single Env started from the same state."""
+    import csv
+    import torch
+    import mujoco_template as mt
+
+    model = load_model("cartpole")
+    n, T = 8, 13
+    qpos, qvel, _ = random_states(model, "cartpole", n, seed=61)
+
+    class Push:
+        capabilities = mt.ControllerCapabilities()
+        def prepare(self, m, d): pass
+        def __call__(self, m, d, t): d.ctrl[:] = 0.5
+
+    benv = mt.BatchedEnv(model, n, controller=Push())
+    benv.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=benv.data.qpos.device))
+    benv.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=benv.data.qpos.device))
+    path = tmp_path / "batched.csv"
+    with mt.BatchedStateControlRecorder(benv, log_path=path, env_indices=[1, 5], chunk_steps=4, store_rows=True) as rec:
+        steps = mt.run_passive_headless(benv, max_steps=T, hooks=rec, return_obs=False)
+    assert steps == T and rec.steps == T and len(rec.rows) == 2 * T
+    rows = list(csv.reader(open(path)))
+    assert rows[0] == ["env", "time_s", "qpos[slider]", "qvel[slider]", "qpos[hinge]", "qvel[hinge]", "ctrl[cart_force]"]
+    assert len(rows) == 1 + 2 * T
+    for k in (1, 5):
+        env = mt.Env(mt.ModelHandle(model), controller=Push())
+        env.reset()
+        env.data.qpos[:] = qpos[k]; env.data.qvel[:] = qvel[k]
+        single = mt.StateControlRecorder(env)
+        mt.run_passive_headless(env, max_steps=T, hooks=single, return_obs=False)
+        mine = [r[1:] for r in rec.rows if r[0] == k]
+        assert len(mine) == T
+        for a, b in zip(mine, single.rows):
+            assert np.allclose(np.array(a, dtype=float), np.array(b, dtype=float), rtol=0, atol=1e-13)
