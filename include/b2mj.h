@@ -77,6 +77,7 @@ typedef struct b2_derived {
   int* ncon;         /* (nenv) active contacts */
   int* nefc;         /* (nenv) constraint rows */
   int* solver_iter;  /* (nenv) Newton iterations */
+  void* sensordata;  /* (nsensordata, nenv) mjData.sensordata (reference observations.py:117-127) */
 } b2_derived;
 
 /* Replaces mj.MjModel.from_xml_path/from_xml_string (reference mujoco_template/model.py:22-31):

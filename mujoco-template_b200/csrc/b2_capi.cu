@@ -87,7 +87,7 @@ struct b2_batch {
 static bool warp_engine_supports(const b2m_view& v) {
   const char* off = getenv("B2_DISABLE_WARP");
   if (off && off[0] == '1') return false;
-  if (v.integrator != 0 || v.has_fluid || v.nbody > 32 || v.nv > 32 || v.nsite != 0) return false;
+  if (v.integrator != 0 || v.has_fluid || v.nbody > 32 || v.nv > 32 || v.nsite != 0 || v.nsensor != 0) return false;
   for (int a = 0; a < v.nu; a++) if (v.actuator_trntype[a] != b2::TRN_JOINT) return false;
   for (int g = 0; g < v.ngeom; g++) {
     const int t = v.geom_type[g];

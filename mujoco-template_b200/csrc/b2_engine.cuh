@@ -784,6 +784,80 @@ struct LaneEnv {
     }
   }
 
+  // ------------------------------------------------------------------ sensors
+  // mj_sensorPos / mj_sensorVel / mj_sensorAcc for the compiled subset (type codes SENS_*); call after forward().
+  // Feeds data.sensordata (reference mujoco_template/observations.py:117-127, examples/drone/x2.xml:83-87).
+  B2_DEV void site_motion(int s, const T* vec6, T* res) const {  // com-based spatial vector -> site-local frame
+    T p[3], R[9];
+    site_pose(s, p, R);
+    const int b = M::site_bodyid(s), root = M::body_rootid(b);
+    const T dif[3] = {p[0] - com[3 * root], p[1] - com[3 * root + 1], p[2] - com[3 * root + 2]};
+    T cr[3], lin[3];
+    cross3(cr, dif, vec6);
+    for (int k = 0; k < 3; k++) lin[k] = vec6[3 + k] - cr[k];
+    matT_vec(res, R, vec6);
+    matT_vec(res + 3, R, lin);
+  }
+  B2_DEV void sensors(T* out) {
+    bool need_acc = false;
+    B2_UNROLL
+    for (int s = 0; s < M::nsensor(); s++) need_acc |= M::sensor_type(s) == SENS_ACCELEROMETER;
+    T* cacc = spat;
+    if (need_acc) {  // acceleration pass of mj_rnePostConstraint: cacc = cacc_parent + cdof_dot*qvel + cdof*qacc
+      cacc[0] = cacc[1] = cacc[2] = 0;
+      cacc[3] = -M::gravity(0); cacc[4] = -M::gravity(1); cacc[5] = -M::gravity(2);
+      B2_UNROLL
+      for (int i = 1; i < M::nbody(); i++) {
+        const int da = M::body_dofadr(i), p = M::body_parentid(i);
+        T a[6];
+        for (int k = 0; k < 6; k++) a[k] = cacc[6 * p + k];
+        B2_UNROLL
+        for (int j = 0; j < M::body_dofnum(i); j++)
+          for (int k = 0; k < 6; k++) a[k] += cdof_dot[6 * (da + j) + k] * qvel[da + j] + cdof[6 * (da + j) + k] * qacc[da + j];
+        for (int k = 0; k < 6; k++) cacc[6 * i + k] = a[k];
+      }
+    }
+    B2_UNROLL
+    for (int s = 0; s < M::nsensor(); s++) {
+      const int type = M::sensor_type(s), id = M::sensor_objid(s), ot = M::sensor_objtype(s), adr = M::sensor_adr(s);
+      T v[6] = {0, 0, 0, 0, 0, 0};
+      int dim = 3;
+      if (type == SENS_JOINTPOS) { v[0] = qpos[M::jnt_qposadr(id)]; dim = 1; }
+      else if (type == SENS_JOINTVEL) { v[0] = qvel[M::jnt_dofadr(id)]; dim = 1; }
+      else if (type == SENS_FRAMEPOS) {
+        if (ot == 1) { for (int k = 0; k < 3; k++) v[k] = xipos[3 * id + k]; }
+        else if (ot == 2) { for (int k = 0; k < 3; k++) v[k] = xpos[3 * id + k]; }
+        else { T R[9]; if (ot == 5) geom_pose(id, v, R); else site_pose(id, v, R); }
+      } else if (type == SENS_FRAMEQUAT) {
+        dim = 4;
+        if (ot == 2) { for (int k = 0; k < 4; k++) v[k] = xquat[4 * id + k]; }
+        else {
+          T lq[4];
+          int b = id;
+          if (ot == 1) { for (int k = 0; k < 4; k++) lq[k] = M::body_iquat(4 * id + k); }
+          else if (ot == 5) { b = M::geom_bodyid(id); for (int k = 0; k < 4; k++) lq[k] = M::geom_quat(4 * id + k); }
+          else { b = M::site_bodyid(id); for (int k = 0; k < 4; k++) lq[k] = M::site_quat(4 * id + k); }
+          quat_mul(v, xquat + 4 * b, lq);
+        }
+        normalize4(v);
+      } else if (type == SENS_GYRO || type == SENS_VELOCIMETER) {
+        T loc[6];
+        site_motion(id, cvel + 6 * M::site_bodyid(id), loc);
+        for (int k = 0; k < 3; k++) v[k] = loc[(type == SENS_GYRO ? 0 : 3) + k];
+      } else if (type == SENS_ACCELEROMETER) {
+        T vel[6], acc[6], corr[3];
+        site_motion(id, cvel + 6 * M::site_bodyid(id), vel);
+        site_motion(id, cacc + 6 * M::site_bodyid(id), acc);
+        cross3(corr, vel, vel + 3);
+        for (int k = 0; k < 3; k++) v[k] = acc[3 + k] + corr[k];
+      }
+      const T cut = M::sensor_cutoff(s);
+      B2_UNROLL
+      for (int k = 0; k < 4; k++)
+        if (k < dim) out[adr + k] = (cut > 0 && type != SENS_FRAMEQUAT) ? tclip(v[k], -cut, cut) : v[k];
+    }
+  }
+
   // ------------------------------------------------------------------ smooth acceleration
   B2_STAGE void smooth_dynamics() {
     const int nv = M::nv();

@@ -21,7 +21,7 @@
 namespace b2 {
 
 template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
-template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias; int *ncon, *nefc, *solver_iter; };
+template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias, *sensordata; int *ncon, *nefc, *solver_iter; };
 
 template <typename T>
 static inline StateDev<T> to_dev(const b2_state* s) {
@@ -36,7 +36,7 @@ static inline DerivedDev<T> to_dev(const b2_derived* o) {
   if (o) {
     d.xpos = (T*)o->xpos; d.xquat = (T*)o->xquat; d.xipos = (T*)o->xipos; d.geom_xpos = (T*)o->geom_xpos;
     d.site_xpos = (T*)o->site_xpos; d.subtree_com = (T*)o->subtree_com; d.qacc = (T*)o->qacc;
-    d.qfrc_bias = (T*)o->qfrc_bias; d.ncon = o->ncon; d.nefc = o->nefc; d.solver_iter = o->solver_iter;
+    d.qfrc_bias = (T*)o->qfrc_bias; d.sensordata = (T*)o->sensordata; d.ncon = o->ncon; d.nefc = o->nefc; d.solver_iter = o->solver_iter;
   }
   return d;
 }
@@ -53,7 +53,13 @@ B2_DEV void load_state(LaneEnv<T, D, M>& env, const StateDev<T>& st, int N, int 
   for (int k = 0; k < M::nv(); k++) env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0);
 }
 template <typename T, class D, class M>
-B2_DEV void store_derived(const LaneEnv<T, D, M>& env, const DerivedDev<T>& o, int N, int e) {
+B2_DEV void store_derived(LaneEnv<T, D, M>& env, const DerivedDev<T>& o, int N, int e) {
+  if (o.sensordata && M::nsensor() > 0) {
+    T sd[D::NSD];
+    env.sensors(sd);
+    B2_UNROLL
+    for (int k = 0; k < M::nsensordata(); k++) o.sensordata[(size_t)k * N + e] = sd[k];
+  }
   if (o.xpos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xpos[(size_t)k * N + e] = env.xpos[k]; }
   if (o.xquat) { B2_UNROLL for (int k = 0; k < 4 * M::nbody(); k++) o.xquat[(size_t)k * N + e] = env.xquat[k]; }
   if (o.xipos) { B2_UNROLL for (int k = 0; k < 3 * M::nbody(); k++) o.xipos[(size_t)k * N + e] = env.xipos[k]; }

@@ -20,24 +20,25 @@ namespace b2 {
 // Compile-time capacities of the generic size classes.  A model is mapped to the smallest
 // class that holds it.
 struct DimsTiny {   // pendulum, cartpole, the reference test fixture
-  static constexpr int NB = 4, NJ = 4, NQ = 4, NV = 4, NU = 2, NG = 4, NS = 2, NT = 1, NW = 2, NPAIR = 4, NCON = 8, NEFC = 36;
+  static constexpr int NB = 4, NJ = 4, NQ = 4, NV = 4, NU = 2, NG = 4, NS = 2, NT = 1, NW = 2, NPAIR = 4, NCON = 8, NEFC = 36, NSEN = 4, NSD = 16;
 };
 struct DimsSmall {  // drone: one free body with many geoms
-  static constexpr int NB = 4, NJ = 4, NQ = 10, NV = 8, NU = 8, NG = 12, NS = 8, NT = 1, NW = 2, NPAIR = 12, NCON = 24, NEFC = 100;
+  static constexpr int NB = 4, NJ = 4, NQ = 10, NV = 8, NU = 8, NG = 12, NS = 8, NT = 1, NW = 2, NPAIR = 12, NCON = 24, NEFC = 100, NSEN = 8, NSD = 32;
 };
 struct DimsLarge {  // humanoid
-  static constexpr int NB = 20, NJ = 24, NQ = 32, NV = 32, NU = 24, NG = 24, NS = 4, NT = 4, NW = 8, NPAIR = 176, NCON = 48, NEFC = 160;
+  static constexpr int NB = 20, NJ = 24, NQ = 32, NV = 32, NU = 24, NG = 24, NS = 4, NT = 4, NW = 8, NPAIR = 176, NCON = 48, NEFC = 160, NSEN = 16, NSD = 48;
 };
 
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4, GEOM_BOX = 6 };
 enum { TRN_JOINT = 0, TRN_SITE = 4 };
+enum { SENS_JOINTPOS = 0, SENS_JOINTVEL, SENS_FRAMEPOS, SENS_FRAMEQUAT, SENS_GYRO, SENS_VELOCIMETER, SENS_ACCELEROMETER };
 enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT_PYR = 3 };
 
 // Field lists (X-macros): X(name) for scalars, X(name, capacity) for arrays.
 #define B2_MODEL_INT_SCALARS(X) \
   X(nq) X(nv) X(nu) X(nbody) X(njnt) X(ngeom) X(nsite) X(ntendon) X(npair) X(integrator) X(iterations) X(ls_iterations) \
-  X(has_fluid) X(has_dofdamping) X(maxdepth)
+  X(has_fluid) X(has_dofdamping) X(maxdepth) X(nsensor) X(nsensordata)
 #define B2_MODEL_REAL_SCALARS(X) X(timestep) X(density) X(viscosity) X(tolerance) X(ls_tolerance) X(meaninertia)
 #define B2_MODEL_INT_ARRAYS(X)                                                                                        \
   X(body_parentid, D::NB) X(body_rootid, D::NB) X(body_jntnum, D::NB) X(body_jntadr, D::NB) X(body_dofnum, D::NB)    \
@@ -46,7 +47,8 @@ enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT
   X(geom_type, D::NG) X(geom_bodyid, D::NG) X(site_bodyid, D::NS) X(tendon_adr, D::NT) X(tendon_num, D::NT)          \
   X(tendon_limited, D::NT) X(wrap_jntid, D::NW) X(actuator_trntype, D::NU) X(actuator_trnid, D::NU)                  \
   X(actuator_ctrllimited, D::NU) X(actuator_forcelimited, D::NU) X(actuator_disabled, D::NU) X(pair_geom1, D::NPAIR) \
-  X(pair_geom2, D::NPAIR) X(pair_dim, D::NPAIR)
+  X(pair_geom2, D::NPAIR) X(pair_dim, D::NPAIR) X(sensor_type, D::NSEN) X(sensor_objtype, D::NSEN)                   \
+  X(sensor_objid, D::NSEN) X(sensor_adr, D::NSEN) X(sensor_dim, D::NSEN)
 #define B2_MODEL_REAL_ARRAYS(X)                                                                                       \
   X(gravity, 3) X(wind, 3) X(body_pos, 3 * D::NB) X(body_quat, 4 * D::NB) X(body_ipos, 3 * D::NB)                     \
   X(body_iquat, 4 * D::NB) X(body_mass, D::NB) X(body_subtreemass, D::NB) X(body_inertia, 3 * D::NB)                  \
@@ -58,7 +60,7 @@ enum { ROW_LIMIT_JOINT = 0, ROW_LIMIT_TENDON = 1, ROW_CONTACT_1 = 2, ROW_CONTACT
   X(tendon_invweight0, D::NT) X(tendon_stiffness, D::NT) X(tendon_damping, D::NT) X(tendon_lengthspring, 2 * D::NT)   \
   X(wrap_coef, D::NW) X(actuator_gear, 6 * D::NU) X(actuator_ctrlrange, 2 * D::NU) X(actuator_forcerange, 2 * D::NU)  \
   X(actuator_gainprm, D::NU) X(actuator_biasprm, 3 * D::NU) X(pair_margin, D::NPAIR) X(pair_gap, D::NPAIR)            \
-  X(pair_friction, 2 * D::NPAIR) X(pair_solref, 2 * D::NPAIR) X(pair_solimp, 5 * D::NPAIR)
+  X(pair_friction, 2 * D::NPAIR) X(pair_solref, 2 * D::NPAIR) X(pair_solimp, 5 * D::NPAIR) X(sensor_cutoff, D::NSEN)
 
 template <typename T, class D>
 struct DevModel {
@@ -79,7 +81,8 @@ struct DevModel {
 template <class D>
 inline bool model_fits(const b2m_view& v) {
   return v.nbody <= D::NB && v.njnt <= D::NJ && v.nq <= D::NQ && v.nv <= D::NV && v.nu <= D::NU && v.ngeom <= D::NG &&
-         v.nsite <= D::NS && v.ntendon <= D::NT && v.nwrap <= D::NW && v.npair <= D::NPAIR && v.nv <= 32;
+         v.nsite <= D::NS && v.ntendon <= D::NT && v.nwrap <= D::NW && v.npair <= D::NPAIR && v.nv <= 32 && v.nsensor <= D::NSEN &&
+         v.nsensordata <= D::NSD;
 }
 
 template <typename T, typename S>
@@ -102,6 +105,10 @@ inline void fill_dev_model(DevModel<T, D>& m, const b2m_view& v, const int* actu
   m.nq = v.nq; m.nv = v.nv; m.nu = v.nu; m.nbody = v.nbody; m.njnt = v.njnt; m.ngeom = v.ngeom; m.nsite = v.nsite;
   m.ntendon = v.ntendon; m.npair = v.npair; m.integrator = v.integrator; m.iterations = v.iterations;
   m.ls_iterations = v.ls_iterations; m.has_fluid = v.has_fluid; m.has_dofdamping = v.has_dofdamping;
+  m.nsensor = v.nsensor; m.nsensordata = v.nsensordata;
+  fill(m.sensor_type, v.sensor_type, v.nsensor); fill(m.sensor_objtype, v.sensor_objtype, v.nsensor);
+  fill(m.sensor_objid, v.sensor_objid, v.nsensor); fill(m.sensor_adr, v.sensor_adr, v.nsensor);
+  fill(m.sensor_dim, v.sensor_dim, v.nsensor); fill(m.sensor_cutoff, v.sensor_cutoff, v.nsensor);
   m.timestep = (T)v.timestep; fill(m.gravity, v.gravity, 3); fill(m.wind, v.wind, 3);
   m.density = (T)v.density; m.viscosity = (T)v.viscosity; m.tolerance = (T)v.tolerance; m.ls_tolerance = (T)v.ls_tolerance;
   m.meaninertia = (T)v.meaninertia;

@@ -16,13 +16,13 @@ import struct
 import numpy as np
 
 MAGIC = 0x4A4D3242  # "B2MJ"
-VERSION = 3
+VERSION = 4
 
 # integer scalars, in blob order
 ISCALARS = (
     "nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon", "nwrap", "nkey",
     "npair", "integrator", "iterations", "ls_iterations", "has_fluid", "has_dofdamping",
-    "disableflags", "nmocap_unused",
+    "disableflags", "nmocap_unused", "nsensor", "nsensordata",
 )
 
 # double scalars / small fixed vectors, in blob order: (name, width)
@@ -86,6 +86,10 @@ ARRAYS = (
     ("pair_margin", "d", 1, "npair"), ("pair_gap", "d", 1, "npair"),
     ("pair_friction", "d", 5, "npair"), ("pair_solref", "d", 2, "npair"),
     ("pair_solimp", "d", 5, "npair"),
+    # sensors (type codes: mjcf.SENSOR_TYPES; objtype follows mjtObj: 1 body, 2 xbody, 3 joint, 5 geom, 6 site)
+    ("sensor_type", "i", 1, "nsensor"), ("sensor_objtype", "i", 1, "nsensor"),
+    ("sensor_objid", "i", 1, "nsensor"), ("sensor_adr", "i", 1, "nsensor"),
+    ("sensor_dim", "i", 1, "nsensor"), ("sensor_cutoff", "d", 1, "nsensor"),
 )
 
 

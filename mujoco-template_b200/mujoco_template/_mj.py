@@ -51,6 +51,7 @@ class mjtJoint:
 _OBJ_KIND = {
     mjtObj.mjOBJ_BODY: "body", mjtObj.mjOBJ_XBODY: "body", mjtObj.mjOBJ_JOINT: "joint", mjtObj.mjOBJ_GEOM: "geom",
     mjtObj.mjOBJ_SITE: "site", mjtObj.mjOBJ_TENDON: "tendon", mjtObj.mjOBJ_ACTUATOR: "actuator", mjtObj.mjOBJ_KEY: "key",
+    mjtObj.mjOBJ_SENSOR: "sensor",
 }
 
 
@@ -92,7 +93,7 @@ class MjModel:
     def __init__(self, compiled: dict):
         self._c = compiled
         self.names: dict[str, list[str | None]] = compiled["names"]
-        for key in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon", "nkey", "nsensordata"):
+        for key in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon", "nkey", "nsensor", "nsensordata"):
             setattr(self, key, int(compiled[key]))
         self.na = 0
         for key, val in compiled.items():
@@ -139,6 +140,10 @@ class MjModel:
             raise ConfigError(f"cannot load compiled model {path}: {exc}") from exc
         compiled.update(meta["scalars"])
         compiled["names"] = meta["names"]
+        if "nsensor" not in compiled:  # files written before sensors were compiled
+            compiled.update(nsensor=0, nsensordata=0, sensor_cutoff=np.zeros(0),
+                            **{k: np.zeros(0, np.int32) for k in ("sensor_type", "sensor_objtype", "sensor_objid", "sensor_adr", "sensor_dim")})
+            compiled["names"].setdefault("sensor", [])
         return cls(compiled)
 
     @property
@@ -181,7 +186,8 @@ _STATE_FIELDS = ("qpos", "qvel", "ctrl", "qacc_warmstart")
 def _field_dims(m: MjModel) -> dict[str, int]:
     return dict(qpos=m.nq, qvel=m.nv, ctrl=m.nu, qacc_warmstart=m.nv, xpos=3 * m.nbody, xquat=4 * m.nbody,
                 xipos=3 * m.nbody, geom_xpos=3 * m.ngeom, site_xpos=3 * m.nsite, subtree_com=3 * m.nbody,
-                qacc=m.nv, qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv)
+                qacc=m.nv, qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv,
+                sensordata=m.nsensordata)
 
 
 _INT_FIELDS = ("flags", "ncon", "nefc", "solver_iter")
@@ -237,7 +243,7 @@ class NativeBackend:
     def derived_struct(self) -> _capi.Derived:
         p = self._ptr
         return _capi.Derived(p("xpos"), p("xquat"), p("xipos"), p("geom_xpos"), p("site_xpos"), p("subtree_com"), p("qacc"),
-                             p("qfrc_bias"), p("ncon"), p("nefc"), p("solver_iter"))
+                             p("qfrc_bias"), p("ncon"), p("nefc"), p("solver_iter"), p("sensordata"))
 
     def _pre(self) -> None:
         # device tensors may have pending work on torch's current stream (controllers); order after it
@@ -389,7 +395,7 @@ class MjData(_DataBase):
         self.qfrc_inverse = b.array("qfrc_inverse")[:, 0]
         self.actuator_moment = b.array("actuator_moment")[:, 0].reshape(m.nu, m.nv)  # dense nu x nv
         self.act = np.zeros(0)
-        self.sensordata = np.zeros(0)
+        self.sensordata = b.array("sensordata")[:, 0]
         self.time = 0.0
         # data-less calls (mj_integratePos / mj_differentiatePos) reuse this env's backend scratch
         _HELPERS.setdefault(id(model), self.backend)

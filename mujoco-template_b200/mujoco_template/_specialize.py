@@ -20,7 +20,7 @@ from . import _layout
 
 # (field, kind) in the order of the X-macro lists in csrc/b2_model_dev.cuh
 INT_SCALARS = ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon", "npair", "integrator", "iterations",
-               "ls_iterations", "has_fluid", "has_dofdamping", "maxdepth")
+               "ls_iterations", "has_fluid", "has_dofdamping", "maxdepth", "nsensor", "nsensordata")
 REAL_SCALARS = ("timestep", "density", "viscosity", "tolerance", "ls_tolerance", "meaninertia")
 INT_ARRAYS = ("body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "body_dofnum", "body_dofadr", "body_anc",
               "body_depth", "jnt_type",
@@ -28,7 +28,8 @@ INT_ARRAYS = ("body_parentid", "body_rootid", "body_jntnum", "body_jntadr", "bod
               "dof_nanc", "dof_anclist",
               "geom_type", "geom_bodyid", "site_bodyid", "tendon_adr", "tendon_num", "tendon_limited", "wrap_jntid",
               "actuator_trntype", "actuator_trnid", "actuator_ctrllimited", "actuator_forcelimited", "actuator_disabled",
-              "pair_geom1", "pair_geom2", "pair_dim")
+              "pair_geom1", "pair_geom2", "pair_dim", "sensor_type", "sensor_objtype", "sensor_objid", "sensor_adr",
+              "sensor_dim")
 REAL_ARRAYS = ("gravity", "wind", "body_pos", "body_quat", "body_ipos", "body_iquat", "body_mass", "body_subtreemass",
                "body_inertia", "body_invweight0", "jnt_pos", "jnt_axis", "jnt_stiffness", "jnt_range", "jnt_margin",
                "jnt_solref", "jnt_solimp", "qpos0", "qpos_spring", "dof_armature", "dof_damping", "dof_invweight0",
@@ -36,7 +37,7 @@ REAL_ARRAYS = ("gravity", "wind", "body_pos", "body_quat", "body_ipos", "body_iq
                "tendon_margin", "tendon_solref", "tendon_solimp", "tendon_invweight0", "tendon_stiffness",
                "tendon_damping", "tendon_lengthspring", "wrap_coef", "actuator_gear", "actuator_ctrlrange",
                "actuator_forcerange", "actuator_gainprm", "actuator_biasprm", "pair_margin", "pair_gap", "pair_friction",
-               "pair_solref", "pair_solimp")
+               "pair_solref", "pair_solimp", "sensor_cutoff")
 
 _MAX_CONTACTS = {(0, 2): 1, (0, 3): 2, (0, 6): 4, (0, 4): 1, (2, 2): 1, (2, 3): 1, (3, 3): 2}
 
@@ -118,7 +119,8 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("namespace {")
     A("struct SDims {")
     A(f"  static constexpr int NB = {one(nb)}, NJ = {one(nj)}, NQ = {one(nq)}, NV = {one(nv)}, NU = {one(nu)}, NG = {one(ng)}, "
-      f"NS = {one(ns)}, NT = {one(nt)}, NW = {one(nw)}, NPAIR = {one(npair)}, NCON = {one(ncon)}, NEFC = {one(nefc)};")
+      f"NS = {one(ns)}, NT = {one(nt)}, NW = {one(nw)}, NPAIR = {one(npair)}, NCON = {one(ncon)}, NEFC = {one(nefc)}, "
+      f"NSEN = {one(int(c['nsensor']))}, NSD = {one(int(c['nsensordata']))};")
     A("};")
     A("template <typename T>")
     A("struct SModel {")

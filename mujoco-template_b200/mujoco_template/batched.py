@@ -16,6 +16,8 @@ Sharding across GPUs is by construction: one ``BatchedEnv`` per rank over its sl
 
 from __future__ import annotations
 
+import warnings
+
 from collections.abc import Iterable, Iterator
 from typing import Any
 
@@ -43,7 +45,13 @@ def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
 class BatchedObservationExtractor:
     """Tensor counterpart of ``ObservationExtractor``: same keys, trailing env axis."""
 
+    def _warn_once(self, key: str, msg: str) -> None:
+        if key not in self._warned:
+            self._warned.add(key)
+            warnings.warn(msg, RuntimeWarning, stacklevel=3)
+
     def __init__(self, model: mj.MjModel, spec: ObservationSpec):
+        self._warned: set[str] = set()
         self.model, self.spec = model, spec
         O = mj.mjtObj
 
@@ -81,7 +89,11 @@ class BatchedObservationExtractor:
         if s.include_ctrl:
             out["ctrl"] = pick(data.ctrl)
         if s.include_sensordata:
-            out["sensordata"] = data.qpos.new_zeros((0, data.nenv))
+            if self.model.nsensordata == 0:
+                self._warn_once("sensordata", "ObservationSpec requested sensordata but model has none; returning an empty array instead.")
+                out["sensordata"] = data.qpos.new_zeros((0, data.nenv))
+            else:
+                out["sensordata"] = pick(data.sensordata)
         if s.include_time:
             out["time"] = data.qpos.new_full((1, data.nenv), float(data.time))
         if self.site_ids:

@@ -41,6 +41,13 @@ GEOM_TYPES = {
 }
 JNT_FREE, JNT_BALL, JNT_SLIDE, JNT_HINGE = range(4)
 JNT_TYPES = {"free": JNT_FREE, "ball": JNT_BALL, "slide": JNT_SLIDE, "hinge": JNT_HINGE}
+# sensor tag -> (type code shared with the kernels and the oracle, output width)
+SENS_JOINTPOS, SENS_JOINTVEL, SENS_FRAMEPOS, SENS_FRAMEQUAT, SENS_GYRO, SENS_VELOCIMETER, SENS_ACCELEROMETER = range(7)
+SENSOR_TYPES = {
+    "jointpos": (SENS_JOINTPOS, 1), "jointvel": (SENS_JOINTVEL, 1), "framepos": (SENS_FRAMEPOS, 3),
+    "framequat": (SENS_FRAMEQUAT, 4), "gyro": (SENS_GYRO, 3), "velocimeter": (SENS_VELOCIMETER, 3),
+    "accelerometer": (SENS_ACCELEROMETER, 3),
+}
 TRN_JOINT, TRN_SITE = 0, 4
 INT_EULER, INT_RK4 = 0, 1
 
@@ -184,7 +191,7 @@ class _Compiler:
         self.tendons: list[dict] = []
         self.excludes: list[tuple[str, str]] = []
         self.keys: list[dict] = []
-        self.sensors: list[str] = []
+        self.sensors: list[dict] = []
         self.model_name = "model"
 
     # ---- xml loading with <include>
@@ -221,7 +228,7 @@ class _Compiler:
                 self.keys.append(dict(k.attrib))
         for node in root.findall("sensor"):
             for s in node:
-                self.sensors.append(s.tag)
+                self.sensors.append(dict(s.attrib, tag=s.tag))
         for node in root.findall("equality"):
             if len(node):
                 raise ConfigError("<equality> constraints are not supported by the B200 path")
@@ -939,11 +946,40 @@ def _finalize(c: _Compiler) -> dict:
         pair_solref=np.array([p[2]["solref"] for p in pairs]).reshape(npair, 2),
         pair_solimp=np.array([p[2]["solimp"] for p in pairs]).reshape(npair, 5),
     )
-    if c.sensors:
-        warnings.warn(
-            f"MJCF defines {len(c.sensors)} sensor(s); sensors are outside the B200 hot path "
-            "(nsensordata=0, see DESIGN.md).", RuntimeWarning, stacklevel=3)
-    m["nsensordata"] = 0
+    # --- sensors (subset: the kinds the reference's models and tests use, plus their velocity/frame siblings)
+    sens = []
+    adr = 0
+    for sd in c.sensors:
+        tag = sd["tag"]
+        if tag not in SENSOR_TYPES:
+            raise ConfigError(f"<sensor><{tag}> is not supported by the B200 path (supported: {sorted(SENSOR_TYPES)})")
+        code, dim = SENSOR_TYPES[tag]
+        if sd.get("reftype") or sd.get("refname"):
+            raise ConfigError(f"sensor {sd.get('name')!r}: reference frames (reftype/refname) are not supported")
+        if tag in ("jointpos", "jointvel"):
+            jid = lookup("joint", sd.get("joint"))
+            if int(m["jnt_type"][jid]) in (JNT_FREE, JNT_BALL):
+                raise ConfigError(f"sensor {sd.get('name')!r}: {tag} needs a slide or hinge joint")
+            objtype, objid = 3, jid
+        elif tag in ("gyro", "accelerometer", "velocimeter"):
+            objtype, objid = 6, lookup("site", sd.get("site"))
+        else:  # framepos / framequat
+            ot = sd.get("objtype")
+            kinds = dict(body=(1, "body"), xbody=(2, "body"), geom=(5, "geom"), site=(6, "site"))
+            if ot not in kinds:
+                raise ConfigError(f"sensor {sd.get('name')!r}: objtype {ot!r} is not supported")
+            objtype, objid = kinds[ot][0], lookup(kinds[ot][1], sd.get("objname"))
+        sens.append(dict(name=sd.get("name"), type=code, objtype=objtype, objid=objid, adr=adr, dim=dim,
+                         cutoff=float(sd.get("cutoff", 0.0))))
+        adr += dim
+    names["sensor"] = [x["name"] for x in sens]
+    m.update(nsensor=len(sens), nsensordata=adr,
+             sensor_type=np.array([x["type"] for x in sens], np.int32),
+             sensor_objtype=np.array([x["objtype"] for x in sens], np.int32),
+             sensor_objid=np.array([x["objid"] for x in sens], np.int32),
+             sensor_adr=np.array([x["adr"] for x in sens], np.int32),
+             sensor_dim=np.array([x["dim"] for x in sens], np.int32),
+             sensor_cutoff=np.array([x["cutoff"] for x in sens], float))
     _set_const(m)
     return m
 

@@ -55,6 +55,8 @@ typedef struct orc_data {
   double *cvel, *cdof_dot, *ten_velocity, *actuator_velocity, *qfrc_bias, *qfrc_passive;
   /* acceleration stage */
   double *actuator_force, *qfrc_actuator, *qfrc_smooth, *qacc_smooth, *qfrc_constraint;
+  /* sensors */
+  double *cacc, *sensordata;
   /* constraints */
   int ncon, nefc;
   orc_contact* contact;
@@ -94,6 +96,7 @@ orc_model* orc_model_create(const void* blob, size_t nbytes) {
 }
 void orc_model_free(orc_model* m) { if (m) { free(m->blob); free(m); } }
 const b2m_view* orc_model_view(const orc_model* m) { return &m->v; }
+int orc_model_nsensordata(const orc_model* m) { return m->v.nsensordata; }
 
 orc_data* orc_data_create(const orc_model* m) {
   const b2m_view* v = &m->v;
@@ -110,12 +113,13 @@ orc_data* orc_data_create(const orc_model* m) {
   d->qfrc_bias = ALLOC(nv); d->qfrc_passive = ALLOC(nv);
   d->actuator_force = ALLOC(nu); d->qfrc_actuator = ALLOC(nv); d->qfrc_smooth = ALLOC(nv); d->qacc_smooth = ALLOC(nv);
   d->qfrc_constraint = ALLOC(nv);
+  d->cacc = ALLOC(6 * nb); d->sensordata = ALLOC(v->nsensordata);
   d->contact = (orc_contact*)calloc((size_t)m->maxcon, sizeof(orc_contact));
   int me = m->maxefc;
   d->efc_type = (int*)calloc((size_t)me, sizeof(int)); d->efc_id = (int*)calloc((size_t)me, sizeof(int));
   d->efc_J = ALLOC(me * nv); d->efc_pos = ALLOC(me); d->efc_margin = ALLOC(me); d->efc_D = ALLOC(me); d->efc_R = ALLOC(me);
   d->efc_aref = ALLOC(me); d->efc_vel = ALLOC(me); d->efc_force = ALLOC(me); d->efc_diagApprox = ALLOC(me);
-  d->arena_cap = (size_t)(64 * (nq + nv + nu + 8) + 40 * nb + 8 * nv * nv + 12 * me + 16 * nv * 6 + 4096);
+  d->arena_cap = (size_t)(v->nsensordata + 64 * (nq + nv + nu + 8) + 40 * nb + 8 * nv * nv + 12 * me + 16 * nv * 6 + 4096);
   d->arena = ALLOC(d->arena_cap); d->arena_top = 0;
   return d;
 }
@@ -127,7 +131,8 @@ void orc_data_free(orc_data* d) {
                   &d->ten_length, &d->ten_J, &d->actuator_length, &d->actuator_moment, &d->cvel, &d->cdof_dot,
                   &d->ten_velocity, &d->actuator_velocity, &d->qfrc_bias, &d->qfrc_passive, &d->actuator_force,
                   &d->qfrc_actuator, &d->qfrc_smooth, &d->qacc_smooth, &d->qfrc_constraint, &d->efc_J, &d->efc_pos,
-                  &d->efc_margin, &d->efc_D, &d->efc_R, &d->efc_aref, &d->efc_vel, &d->efc_force, &d->efc_diagApprox};
+                  &d->efc_margin, &d->efc_D, &d->efc_R, &d->efc_aref, &d->efc_vel, &d->efc_force, &d->efc_diagApprox,
+                  &d->cacc, &d->sensordata};
   for (size_t i = 0; i < sizeof(p) / sizeof(p[0]); i++) free(*p[i]);
   free(d->arena); free(d->contact); free(d->efc_type); free(d->efc_id); free(d);
 }
@@ -1143,16 +1148,86 @@ static void orc_fwd_acceleration(const orc_model* m, orc_data* d) {
   }
   orc_solve_ld(v, d->qLD, d->qLDiagInv, d->qacc_smooth);
 }
-/* mj_forward (sensors are outside the hot path) */
-void orc_forward(const orc_model* m, orc_data* d) {
+/* ------------------------------------------------------------------ sensors
+ * mj_sensorPos / mj_sensorVel / mj_sensorAcc (engine_sensor.c) for the subset compiled by mjcf.py: jointpos, jointvel,
+ * framepos, framequat (no reference frame), gyro, velocimeter, accelerometer.  Type codes: mjcf.SENSOR_TYPES.
+ * Feeds data.sensordata behind ObservationSpec(include_sensordata=True) (reference mujoco_template/observations.py:117-127;
+ * sensors declared in reference examples/drone/x2.xml:83-87). */
+enum { SENS_JOINTPOS, SENS_JOINTVEL, SENS_FRAMEPOS, SENS_FRAMEQUAT, SENS_GYRO, SENS_VELOCIMETER, SENS_ACCELEROMETER };
+
+/* the body-frame acceleration pass of mj_rnePostConstraint: cacc = cacc_parent + cdof_dot*qvel + cdof*qacc */
+static void orc_body_acc(const b2m_view* v, orc_data* d) {
+  memset(d->cacc, 0, sizeof(double) * 6);
+  for (int k = 0; k < 3; k++) d->cacc[3 + k] = -v->gravity[k];
+  for (int i = 1; i < v->nbody; i++) {
+    int bda = v->body_dofadr[i];
+    double* a = d->cacc + 6 * i;
+    memcpy(a, d->cacc + 6 * v->body_parentid[i], sizeof(double) * 6);
+    for (int j = 0; j < v->body_dofnum[i]; j++)
+      for (int k = 0; k < 6; k++)
+        a[k] += d->cdof_dot[6 * (bda + j) + k] * d->qvel[bda + j] + d->cdof[6 * (bda + j) + k] * d->qacc[bda + j];
+  }
+}
+/* mj_objectVelocity / mj_objectAcceleration for a site, local frame */
+static void site_velocity(const b2m_view* v, const orc_data* d, int site, double* res) {
+  int b = v->site_bodyid[site];
+  sp_transform(res, d->cvel + 6 * b, 0, d->site_xpos + 3 * site, d->subtree_com + 3 * v->body_rootid[b], d->site_xmat + 9 * site);
+}
+static void site_acceleration(const b2m_view* v, const orc_data* d, int site, double* res) {
+  int b = v->site_bodyid[site];
+  double vel[6], corr[3];
+  site_velocity(v, d, site, vel);
+  sp_transform(res, d->cacc + 6 * b, 0, d->site_xpos + 3 * site, d->subtree_com + 3 * v->body_rootid[b], d->site_xmat + 9 * site);
+  v3_cross(corr, vel, vel + 3);
+  v3_addto(res + 3, corr);
+}
+static void orc_sensors(const orc_model* m, orc_data* d) {
+  const b2m_view* v = &m->v;
+  int need_acc = 0;
+  for (int s = 0; s < v->nsensor; s++) need_acc |= v->sensor_type[s] == SENS_ACCELEROMETER;
+  if (need_acc) orc_body_acc(v, d);
+  for (int s = 0; s < v->nsensor; s++) {
+    double* out = d->sensordata + v->sensor_adr[s];
+    int id = v->sensor_objid[s], ot = v->sensor_objtype[s], dim = v->sensor_dim[s];
+    double tmp[6];
+    switch (v->sensor_type[s]) {
+      case SENS_JOINTPOS: out[0] = d->qpos[v->jnt_qposadr[id]]; break;
+      case SENS_JOINTVEL: out[0] = d->qvel[v->jnt_dofadr[id]]; break;
+      case SENS_FRAMEPOS:
+        v3_copy(out, ot == 1 ? d->xipos + 3 * id : ot == 2 ? d->xpos + 3 * id : ot == 5 ? d->geom_xpos + 3 * id : d->site_xpos + 3 * id);
+        break;
+      case SENS_FRAMEQUAT:
+        if (ot == 2) memcpy(out, d->xquat + 4 * id, sizeof(double) * 4);
+        else if (ot == 1) q_mul(out, d->xquat + 4 * id, v->body_iquat + 4 * id);
+        else if (ot == 5) q_mul(out, d->xquat + 4 * v->geom_bodyid[id], v->geom_quat + 4 * id);
+        else q_mul(out, d->xquat + 4 * v->site_bodyid[id], v->site_quat + 4 * id);
+        q_normalize(out);
+        break;
+      case SENS_GYRO: site_velocity(v, d, id, tmp); v3_copy(out, tmp); break;
+      case SENS_VELOCIMETER: site_velocity(v, d, id, tmp); v3_copy(out, tmp + 3); break;
+      case SENS_ACCELEROMETER: site_acceleration(v, d, id, tmp); v3_copy(out, tmp + 3); break;
+      default: break;
+    }
+    /* cutoff applies to real-valued outputs only (quaternions are left alone) */
+    double cut = v->sensor_cutoff[s];
+    if (cut > 0 && v->sensor_type[s] != SENS_FRAMEQUAT)
+      for (int k = 0; k < dim; k++) out[k] = orc_clip(out[k], -cut, cut);
+  }
+}
+
+/* mj_forwardSkip(skipstage = none, skipsensor) */
+static void orc_forward_skip(const orc_model* m, orc_data* d, int skipsensor) {
   ARENA_MARK;
   orc_fwd_position(m, d);
   orc_fwd_velocity(m, d);
   orc_actuation(&m->v, d);
   orc_fwd_acceleration(m, d);
   orc_fwd_constraint(m, d);
+  if (m->v.nsensor && !skipsensor) orc_sensors(m, d);
   ARENA_RELEASE;
 }
+/* mj_forward */
+void orc_forward(const orc_model* m, orc_data* d) { orc_forward_skip(m, d, 0); }
 
 /* mj_inverse (continuous-time): qfrc_inverse = M*qacc + qfrc_bias - qfrc_passive - qfrc_constraint, with the
  * constraint forces of mj_invConstraint (the given qacc fixes every row's residual: f = -D * min(0, J qacc - aref)).
@@ -1251,7 +1326,7 @@ static void orc_rk4(const orc_model* m, orc_data* d) {
     for (int k = 0; k < nv; k++) X[i][nq + k] += h * dX[nv + k];
     memcpy(d->qpos, X[i], sizeof(double) * nq); memcpy(d->qvel, X[i] + nq, sizeof(double) * nv);
     d->time = T[i - 1];
-    orc_forward(m, d);
+    orc_forward_skip(m, d, 1); /* RK4 sub-stages do not refresh sensordata */
     memcpy(F[i], d->qacc, sizeof(double) * nv);
   }
   memset(dX, 0, sizeof(double) * 2 * nv);
@@ -1306,6 +1381,8 @@ void orc_transition_fd(const orc_model* m, orc_data* d, double eps, int centered
   orc_state s;
   state_save(v, d, &s);
   double *next = SCRATCH(nq + nv), *plus = SCRATCH(nq + nv), *minus = SCRATCH(nq + nv), *col = SCRATCH(ndx), *dpos = SCRATCH(nv);
+  double* sens = SCRATCH(v->nsensordata); /* FD rollouts run with skipsensor: sensordata is left as it was */
+  memcpy(sens, d->sensordata, sizeof(double) * v->nsensordata);
   orc_step(m, d);
   get_next(v, d, next);
   state_restore(v, d, &s);
@@ -1335,6 +1412,7 @@ void orc_transition_fd(const orc_model* m, orc_data* d, double eps, int centered
     state_diff(m, col, centered ? minus : next, plus, centered ? 2 * eps : eps);
     if (A) for (int r2 = 0; r2 < ndx; r2++) A[r2 * ndx + i] = col[r2];
   }
+  memcpy(d->sensordata, sens, sizeof(double) * v->nsensordata);
   ARENA_RELEASE;
 }
 
@@ -1344,7 +1422,7 @@ double* orc_ptr(orc_data* d, const char* name) {
   F(qpos) F(qvel) F(ctrl) F(qacc) F(qacc_warmstart) F(xpos) F(xquat) F(xmat) F(xipos) F(ximat) F(geom_xpos) F(geom_xmat)
   F(site_xpos) F(site_xmat) F(subtree_com) F(cdof) F(qM) F(qfrc_bias) F(qfrc_passive) F(qfrc_actuator) F(qfrc_smooth)
   F(qacc_smooth) F(qfrc_constraint) F(efc_J) F(efc_pos) F(efc_D) F(efc_R) F(efc_aref) F(efc_force) F(cvel) F(cinert)
-  F(actuator_moment) F(actuator_force) F(ten_length)
+  F(actuator_moment) F(actuator_force) F(ten_length) F(sensordata) F(cacc)
 #undef F
   return NULL;
 }

@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
         L.orc_model_create.restype = C.c_void_p
         L.orc_model_create.argtypes = [C.c_char_p, C.c_size_t]
         L.orc_model_free.argtypes = [C.c_void_p]
+        L.orc_model_nsensordata.argtypes = [C.c_void_p]
         L.orc_data_create.restype = C.c_void_p
         L.orc_data_create.argtypes = [C.c_void_p]
         L.orc_data_free.argtypes = [C.c_void_p]
@@ -77,6 +78,7 @@ class OracleModel:
         if not self.h:
             raise RuntimeError("oracle rejected model blob")
         self.dims = {k: int(dims[k]) for k in ("nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "ntendon")}
+        self.dims["nsensordata"] = int(self._L.orc_model_nsensordata(self.h))
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -126,6 +128,7 @@ class OracleData:
         self.qM = self._view("qM", (nv, nv)); self.cvel = self._view("cvel", (nb, 6))
         self.actuator_force = self._view("actuator_force", (d["nu"],))
         self.actuator_moment = self._view("actuator_moment", (d["nu"], nv))
+        self.sensordata = self._view("sensordata", (d["nsensordata"],)); self.cacc = self._view("cacc", (nb, 6))
         self.reset()
 
     def _view(self, name: str, shape):

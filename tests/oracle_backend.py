@@ -19,7 +19,7 @@ class OracleBackend:
         m = model
         dims = dict(qpos=m.nq, qvel=m.nv, ctrl=m.nu, qacc_warmstart=m.nv, xpos=3 * m.nbody, xquat=4 * m.nbody,
                     xipos=3 * m.nbody, geom_xpos=3 * m.ngeom, site_xpos=3 * m.nsite, subtree_com=3 * m.nbody, qacc=m.nv,
-                    qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv)
+                    qfrc_bias=m.nv, qfrc_inverse=m.nv, actuator_moment=m.nu * m.nv, sensordata=m.nsensordata)
         self.buf = {k: np.zeros((v, 1)) for k, v in dims.items()}
         for k in ("flags", "ncon", "nefc", "solver_iter"):
             self.buf[k] = np.zeros((1, 1), dtype=np.int32)
@@ -46,6 +46,7 @@ class OracleBackend:
         b["xpos"][:, 0] = od.xpos.ravel(); b["xquat"][:, 0] = od.xquat.ravel(); b["xipos"][:, 0] = od.xipos.ravel()
         b["geom_xpos"][:, 0] = od.geom_xpos.ravel(); b["site_xpos"][:, 0] = od.site_xpos.ravel()
         b["subtree_com"][:, 0] = od.subtree_com.ravel(); b["qacc"][:, 0] = od.qacc; b["qfrc_bias"][:, 0] = od.qfrc_bias
+        b["sensordata"][:, 0] = od.sensordata
         b["ncon"][0, 0] = od.ncon; b["nefc"][0, 0] = od.nefc; b["solver_iter"][0, 0] = od.solver_iter
 
     def step(self, nsteps=1, derived=True):

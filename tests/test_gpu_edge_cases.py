@@ -186,3 +186,71 @@ def test_inverse_dynamics_and_steady_ctrl0(name):
         expect = float(model.body_mass[1]) * 9.81 * 0.25 * np.sin(qpos[:, 0]) 
         # qvel != 0 adds no bias for a single hinge about a fixed axis; damping is zero
         assert np.allclose(u.cpu().numpy()[0], expect, atol=1e-10)
+
+
+def test_sensordata_matches_oracle_all_kinds_generic_kernels():
+    """Every compiled sensor kind (two-body chain + free body, generic kernels), N=1 Env view and a batch, FP64."""
+    import torch
+    import mujoco_template as mt
+    from mujoco_template import _mj as mj
+    from test_oracle_analytic import SENSOR_XML
+
+    model = _compile(SENSOR_XML.format(dt=0.002))
+    n = 33
+    rng = np.random.default_rng(11)
+    qpos = np.tile(model.qpos0, (n, 1)); qpos[:, :3] += rng.uniform(-0.5, 0.5, (n, 3))
+    quat = rng.normal(size=(n, 4)); qpos[:, 6:10] = quat / np.linalg.norm(quat, axis=1, keepdims=True)
+    qvel = rng.normal(size=(n, model.nv)); ctrl = rng.uniform(-1, 1, (n, model.nu))
+    data = mj.BatchData(model, n)
+    dev = data.qpos.device
+    data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev)); data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+    data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev))
+    om, od = oracle_for(model)
+    for phase in ("forward", "step"):
+        (mj.mj_forward if phase == "forward" else mj.mj_step)(model, data)
+        got = data.sensordata.cpu().numpy().T
+        assert got.shape == (n, model.nsensordata)
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+            od.forward()   # a step's sensordata is that of its pre-integration forward pass
+            assert _rel(got[e], od.sensordata) <= 1e-12, (phase, e)
+    # N = 1 Env: the observation is a zero-copy view of data.sensordata
+    env = mt.Env(mt.ModelHandle(model), obs_spec=mt.ObservationSpec(include_sensordata=True))
+    env.reset()
+    env.data.qvel[:] = qvel[0]
+    res = env.step()
+    assert np.shares_memory(res.obs["sensordata"], env.data.sensordata)
+    od.reset(); od.qvel[:] = qvel[0]; od.forward()
+    assert _rel(np.array(env.data.sensordata), od.sensordata) <= 1e-12
+
+
+@pytest.mark.parametrize("spec", [True, False])
+def test_drone_imu_sensors_specialised_and_generic(monkeypatch, spec):
+    import torch
+    import mujoco_template as mt
+    from conftest import random_states
+
+    if not spec:
+        monkeypatch.setenv("B2_DISABLE_SPEC", "1")
+    model = load_model("drone")
+    n = 64
+    qpos, qvel, ctrl = random_states(model, "drone", n, seed=4)
+    benv = mt.BatchedEnv(model, n, obs_spec=mt.ObservationSpec(include_sensordata=True))
+    assert benv.data.backend.batch.kernel_variant == ("drone" if spec else "generic")
+    dev = benv.data.qpos.device
+    benv.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev)); benv.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+    benv.data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev))
+    res = benv.step()
+    got = res.obs["sensordata"].cpu().numpy().T
+    om, od = oracle_for(model)
+    for e in range(n):
+        od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+        od.forward()
+        assert _rel(got[e], od.sensordata) <= 1e-11, e
+    # FP32 engine: same readings to single precision
+    b32 = mt.BatchedEnv(model, n, precision=32, obs_spec=mt.ObservationSpec(include_sensordata=True))
+    b32.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev, dtype=torch.float32))
+    b32.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev, dtype=torch.float32))
+    b32.data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev, dtype=torch.float32))
+    got32 = b32.step().obs["sensordata"].cpu().numpy().T.astype(float)
+    assert np.max(np.abs(got32 - got)) <= 5e-4 * max(1.0, np.max(np.abs(got)))

@@ -164,11 +164,22 @@ def test_observation_dict_flat_order_zero_copy_and_extras(handle):
                               bodies_pos=("torso",), geoms_pos=("torso_geom",), subtree_com=("torso",),
                               extras={"twice": lambda m, d: 2 * np.array(d.qpos)})
     ext = mt.ObservationExtractor(handle.model, spec)
-    with pytest.warns(RuntimeWarning, match="sensordata"):
-        obs = ext(handle.data)
+    handle.data.qpos[0] = 0.3
+    handle.forward()
     with warnings.catch_warnings():
         warnings.simplefilter("error")
-        ext(handle.data)                                  # warns only once
+        obs = ext(handle.data)                            # the model has a jointpos sensor: no warning
+    assert obs["sensordata"].shape == (handle.model.nsensordata,) == (1,)
+    assert np.shares_memory(obs["sensordata"], handle.data.sensordata) and obs["sensordata"][0] == 0.3
+    # reference tests/test_mujoco_template.py:291-314: a model without sensors warns once and returns an empty array
+    bare_model = mj.MjModel.from_xml_string(BASE_XML.replace("<sensor>", "<!--").replace("</sensor>", "-->"))
+    bare = mt.ModelHandle(bare_model, mj.MjData(bare_model, backend=OracleBackend(bare_model)))
+    ext0 = mt.ObservationExtractor(bare.model, mt.ObservationSpec(include_sensordata=True))
+    with pytest.warns(RuntimeWarning, match="sensordata"):
+        assert ext0(bare.data)["sensordata"].shape == (0,)
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")
+        ext0(bare.data)                                   # warns only once
     assert set(obs) == {"qpos", "qvel", "ctrl", "time", "sensordata", "sites_pos", "bodies_pos", "geoms_pos", "subtree_com", "twice"}
     assert np.shares_memory(obs["qpos"], handle.data.qpos) and obs["sites_pos"].shape == (1, 3) and obs["time"].shape == (1,)
     assert np.allclose(obs["sites_pos"][0], [0, 0, 0.2])

@@ -123,3 +123,20 @@ def test_compiled_model_roundtrip(tmp_path):
     m.save_compiled(str(path))
     m2 = mj.MjModel.from_compiled(str(path))
     assert m2.blob == m.blob and m2.names == m.names
+
+
+def test_sensor_compilation_and_unsupported_kinds():
+    from mujoco_template import ConfigError
+    from mujoco_template import _mj as mj
+    from test_oracle_analytic import SENSOR_XML
+
+    m = mj.MjModel.from_xml_string(SENSOR_XML.format(dt=0.002))
+    assert m.nsensor == 15 and list(m.sensor_adr[:4]) == [0, 1, 2, 5] and m.sensor_cutoff[-1] == 5.0
+    assert mj.mj_name2id(m, mj.mjtObj.mjOBJ_SENSOR, "gyro") == 9 and mj.mj_id2name(m, mj.mjtObj.mjOBJ_SENSOR, 0) == "s_pos"
+    drone = load_model("drone")
+    assert drone.nsensordata == 10 and drone.names["sensor"] == ["body_gyro", "body_linacc", "body_quat"]
+    base = '<mujoco><worldbody><body name="b"><joint name="j"/><geom size=".1"/><site name="s"/></body></worldbody><sensor>{}</sensor></mujoco>'
+    for bad in ('<touch site="s"/>', '<framepos objtype="site" objname="s" reftype="body" refname="b"/>',
+                '<jointpos joint="nope"/>', '<framequat objtype="camera" objname="s"/>'):
+        with pytest.raises(ConfigError):
+            mj.MjModel.from_xml_string(base.format(bad))

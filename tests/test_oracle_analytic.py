@@ -189,3 +189,120 @@ def test_setconst_cross_check_oracle_vs_compiler():
         assert np.allclose(body, model.body_invweight0, rtol=1e-10, atol=1e-14)
         if model.ntendon:
             assert np.allclose(ten, model.tendon_invweight0, rtol=1e-10)
+
+
+SENSOR_XML = """
+<mujoco model="sensor-rig">
+  <option timestep="{dt}" gravity="0.3 -0.2 -9.81"/>
+  <worldbody>
+    <body name="base" pos="0 0 1">
+      <joint name="swing" type="hinge" axis="0 1 0" damping="0.1"/>
+      <geom name="arm" type="capsule" fromto="0 0 0 0.4 0 0" size="0.03" mass="0.7"/>
+      <body name="probe" pos="0.4 0 0" quat="0.9 0.1 -0.3 0.2">
+        <joint name="slide" type="slide" axis="0 0 1"/>
+        <joint name="twist" type="hinge" axis="1 0 0" pos="0 0.05 0"/>
+        <geom name="tip" type="sphere" size="0.05" pos="0.02 0.1 -0.03" mass="0.4"/>
+        <site name="imu" pos="0.03 -0.07 0.11" quat="0.7 0.2 0.5 -0.4"/>
+      </body>
+    </body>
+    <body name="floater" pos="1 1 2">
+      <freejoint name="root"/>
+      <geom name="hull" type="box" size="0.1 0.2 0.05" mass="1.3" contype="0" conaffinity="0"/>
+      <site name="imu2" pos="0.05 0.02 -0.01" quat="0.5 0.5 -0.5 0.5"/>
+    </body>
+  </worldbody>
+  <actuator>
+    <motor name="m0" joint="swing"/>
+    <motor name="m1" joint="twist"/>
+  </actuator>
+  <sensor>
+    <jointpos name="s_pos" joint="slide"/>
+    <jointvel name="s_vel" joint="twist"/>
+    <framepos name="p_site" objtype="site" objname="imu"/>
+    <framepos name="p_body" objtype="body" objname="probe"/>
+    <framepos name="p_xbody" objtype="xbody" objname="probe"/>
+    <framepos name="p_geom" objtype="geom" objname="tip"/>
+    <framequat name="q_site" objtype="site" objname="imu"/>
+    <framequat name="q_xbody" objtype="xbody" objname="probe"/>
+    <framequat name="q_geom" objtype="geom" objname="tip"/>
+    <gyro name="gyro" site="imu"/>
+    <velocimeter name="velo" site="imu"/>
+    <accelerometer name="acc" site="imu"/>
+    <gyro name="gyro2" site="imu2"/>
+    <velocimeter name="velo2" site="imu2"/>
+    <accelerometer name="acc2" site="imu2" cutoff="5"/>
+  </sensor>
+</mujoco>
+"""
+
+
+def _sensor_rig(dt):
+    import warnings
+    from mujoco_template import _mj as mj
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return mj.MjModel.from_xml_string(SENSOR_XML.format(dt=dt))
+
+
+def _sens(model, d, name):
+    i = model.names["sensor"].index(name)
+    return np.array(d.sensordata[model.sensor_adr[i]: model.sensor_adr[i] + model.sensor_dim[i]])
+
+
+def _quat_mat(q):
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                     [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                     [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+
+def test_sensors_against_kinematic_identities():
+    """jointpos/jointvel read the state; frame sensors equal the pose arrays; gyro / velocimeter / accelerometer equal the
+    site-frame angular velocity, d/dt(site position) and d/dt(site velocity) - g, checked by differencing a tiny step."""
+    dt = 1e-6
+    model = _sensor_rig(dt)
+    assert model.nsensor == 15 and model.nsensordata == 2 + 4 * 3 + 3 * 4 + 6 * 3
+    om, d = oracle_for(model)
+    rng = np.random.default_rng(5)
+    d.qpos[:3] = rng.uniform(-0.5, 0.5, 3)
+    q = rng.normal(size=4); d.qpos[6:10] = q / np.linalg.norm(q)
+    d.qvel[:] = rng.normal(size=model.nv)
+    d.ctrl[:] = [0.3, -0.2]
+    d.forward()
+    s0 = {n: _sens(model, d, n) for n in model.names["sensor"]}
+    site = d.site_xpos.copy()
+    assert s0["s_pos"][0] == d.qpos[1] and s0["s_vel"][0] == d.qvel[2]
+    assert np.array_equal(s0["p_site"], d.site_xpos[0]) and np.array_equal(s0["p_xbody"], d.xpos[2])
+    assert np.array_equal(s0["p_body"], d.xipos[2]) and np.array_equal(s0["p_geom"], d.geom_xpos[1])
+    assert np.allclose(_quat_mat(s0["q_site"]), d.site_xmat[0].reshape(3, 3), atol=1e-14)
+    assert np.allclose(_quat_mat(s0["q_geom"]), d.geom_xmat[1].reshape(3, 3), atol=1e-14)
+    assert np.array_equal(s0["q_xbody"], d.xquat[2])
+    # free body: qvel[3:6] is the body-frame angular velocity; the site frame is a fixed rotation of it
+    Rs2 = _quat_mat([0.5, 0.5, -0.5, 0.5])
+    assert np.allclose(s0["gyro2"], Rs2.T @ d.qvel[6:9], atol=1e-13)
+    R1, R2 = d.site_xmat[0].reshape(3, 3).copy(), d.site_xmat[1].reshape(3, 3).copy()
+    v1_world, v2_world = R1 @ s0["velo"], R2 @ s0["velo2"]
+    d.step()
+    d.forward()
+    # velocimeter: site position differenced over the step (semi-implicit Euler moves positions with the NEW velocity)
+    s1 = {n: _sens(model, d, n) for n in model.names["sensor"]}
+    R1n, R2n = d.site_xmat[0].reshape(3, 3), d.site_xmat[1].reshape(3, 3)
+    assert np.allclose((d.site_xpos[0] - site[0]) / dt, R1n @ s1["velo"], atol=2e-5)
+    assert np.allclose((d.site_xpos[1] - site[1]) / dt, R2n @ s1["velo2"], atol=2e-5)
+    # accelerometer: world-frame site acceleration minus gravity, rotated into the site frame
+    g = np.array([0.3, -0.2, -9.81])
+    a1 = (R1n @ s1["velo"] - v1_world) / dt
+    a2 = (R2n @ s1["velo2"] - v2_world) / dt
+    assert np.allclose(R1.T @ (a1 - g), s0["acc"], atol=5e-4)
+    assert np.allclose(np.clip(R2.T @ (a2 - g), -5, 5), s0["acc2"], atol=5e-4)
+
+
+def test_sensors_rest_reading_and_rk4_stage_zero():
+    model = load_model("drone")
+    om, d = oracle_for(model)
+    d.reset(0); d.forward()
+    assert np.allclose(d.sensordata, [0, 0, 0, 0, 0, 9.81, 1, 0, 0, 0], atol=1e-10)  # hover: gyro 0, accel +g, level
+    # RK4: sensordata after a step is that of the step's initial state (sub-stages skip sensors)
+    pend = load_model("pendulum")
+    assert pend.nsensordata == 0
