@@ -306,3 +306,32 @@ def test_sensors_rest_reading_and_rk4_stage_zero():
     # RK4: sensordata after a step is that of the step's initial state (sub-stages skip sensors)
     pend = load_model("pendulum")
     assert pend.nsensordata == 0
+
+
+def test_free_body_momentum_is_conserved_without_gravity_and_fluid():
+    """SURVEY.md 8c pin 3: a torque-free rigid body keeps its linear momentum and world-frame angular momentum."""
+    import warnings
+    from mujoco_template import _mj as mj
+
+    xml = """<mujoco><option timestep="0.0005" gravity="0 0 0"/><worldbody><body pos="0 0 1"><freejoint/>
+      <geom type="box" size="0.1 0.25 0.05" mass="1.7" contype="0" conaffinity="0"/></body></worldbody></mujoco>"""
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = mj.MjModel.from_xml_string(xml)
+    om, d = oracle_for(model)
+    d.qvel[:] = [0.3, -0.2, 0.1, 2.0, -1.0, 3.0]
+    inertia = np.asarray(model.body_inertia[1])
+
+    def momenta():
+        R = d.xmat[1].reshape(3, 3)
+        return 1.7 * d.qvel[:3].copy(), R @ (inertia * d.qvel[3:6])
+
+    d.forward()
+    p0, L0 = momenta()
+    for _ in range(2000):
+        d.step()
+    d.forward()
+    p1, L1 = momenta()
+    assert np.allclose(p1, p0, atol=1e-13)
+    assert np.linalg.norm(L1 - L0) <= 2e-3 * np.linalg.norm(L0)        # first-order integrator: small drift only
+    assert abs(np.linalg.norm(d.qpos[3:7]) - 1.0) < 1e-12
