@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-host-controller", action="store_true", help="e2e leg: evaluate the LQR law in NumPy on the host instead of on the device")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     return ap.parse_args()
 
@@ -259,7 +260,7 @@ def main():
         flush.zero_()
         env.step(return_obs=False)
     torch.cuda.synchronize()
-    kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("linearize", "step")}
+    kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("lqr_control", "linearize", "step", "control_tick")}
     env.data.backend.profile = None
     c0 = _capi.launch_count()
     env.step(return_obs=False)
@@ -307,6 +308,8 @@ def main():
 
     # ---- roofline of the dominant kernel
     dom = "linearize" if lin else "step"
+    if lin and not kernel_ms["linearize"]:
+        dom = "control_tick"  # fused LQR + FD + step launch
     dom_ms = float(np.mean(kernel_ms[dom])) if kernel_ms[dom] else float("nan")
     alg_bytes = (LIN_BYTES[name] if lin else STEP_BYTES[name]) * nenv
     peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -353,7 +356,14 @@ def main():
         lo = float(model.actuator_ctrlrange[0, 0]) if model.nu else 0.0
         hi = float(model.actuator_ctrlrange[0, 1]) if model.nu else 0.0
 
+        device_lqr = K is not None and not args.e2e_host_controller
+        if device_lqr:
+            batch.lqr_set_gain(K, np.asarray(controller._qref_np, dtype=float), np.asarray(controller._uref_np, dtype=float))
+
         def host_step():
+            if device_lqr:  # control law on the device: H2D state, [LQR, FD, step] per chunk, D2H state + ctrl + (A, B)
+                batch.step_host(st, 1, lin, 1e-6, hA.data_ptr() if lin else None, hB.data_ptr() if lin else None, 0, device_lqr=True)
+                return
             if K is not None:  # host-side LQR tick on the host copy of the state: u = clip(-K [q; v]), no temporaries
                 rows = (qn[0], qn[1], vn[0], vn[1])
                 np.multiply(rows[0], -K[0, 0], out=un[0])
@@ -374,10 +384,10 @@ def main():
         tt = torch.tensor([dt], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        h2d = (nq + nv + nu + nv) * nenv * 8
-        d2h = (nq + nv + nv + (2 * nv * (2 * nv + nu) if lin else 0)) * nenv * 8
+        h2d = (nq + nv + (0 if device_lqr else nu) + nv) * nenv * 8
+        d2h = (nq + nv + nv + (nu if device_lqr else 0) + (2 * nv * (2 * nv + nu) if lin else 0)) * nenv * 8
         e2e = {"value": nenv * world * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "b2_step_host (C-ABI, pinned host buffers, host LQR tick)"}
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "b2_step_host (C-ABI, pinned host buffers, " + ("device LQR law, ctrl returned" if device_lqr else "host LQR tick") + ")"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -119,6 +119,14 @@ int b2_inverse(b2_batch* batch, const b2_state* state, const void* qacc, void* q
 int b2_lqr_set_gain(b2_batch* batch, const double* K, const double* qpos_ref, const double* ctrl_ref);
 int b2_lqr_control(b2_batch* batch, const b2_state* state, void* stream);
 
+/* One control tick of the reference's step loop (mujoco_template/env.py:177-191: controller, then (A, B) for a
+ * needs_linearization controller, then mj_step) for the whole batch: with use_lqr != 0 the control law set by
+ * b2_lqr_set_gain writes state.ctrl first; A/B as in b2_linearize at those controls; then one step as in b2_step.
+ * Models with a specialised fused kernel do all three in ONE launch (32 envs x (2nv+nu+1) warps per block, the last
+ * warp advancing the state in place after a block barrier); other models get the equivalent three launches. */
+int b2_control_tick(b2_batch* batch, const b2_state* state, const b2_derived* derived, int use_lqr, double eps,
+                    int centered, void* A, void* B, void* stream);
+
 /* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */
 int b2_integrate_pos(b2_batch* batch, void* qpos, const void* qvel, double dt, void* stream);
 int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void* qpos1, const void* qpos2, void* stream);
@@ -126,7 +134,11 @@ int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void*
 /* End-to-end variant with HOST buffers (pageable or pinned): copies qpos/qvel/ctrl[/warm]
  * host->device, runs `nsteps` steps (optionally one linearization first, as
  * reference env.py:178-190 does per control tick), copies qpos/qvel[/warm][/A,B] back, and
- * synchronises.  A/B may be NULL.  Used by bench.py's e2e leg. */
+ * synchronises.  A/B may be NULL.  `linearize` is a bit set: B2_HOST_LINEARIZE computes (A, B) before the step;
+ * B2_HOST_LQR evaluates the control law of b2_lqr_set_gain on the device first -- host_state.ctrl is then an OUTPUT
+ * (the controls that were applied) instead of an input.  Used by bench.py's e2e leg. */
+#define B2_HOST_LINEARIZE 1
+#define B2_HOST_LQR 2
 int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int linearize, double eps, void* host_A,
                  void* host_B, void* stream);
 

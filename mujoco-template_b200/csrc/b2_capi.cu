@@ -320,15 +320,43 @@ int b2_lqr_set_gain(b2_batch* b, const double* K, const double* qpos_ref, const 
   return B2_OK;
 }
 
+static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream) {
+  int rc = ensure_resident(b, stream);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_f64(b->model->cls, st, count, b->nenv, b->d_gain, stream)
+                              : b2::b2k_lqr_control_f32(b->model->cls, st, count, b->nenv, b->d_gain, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_lqr_control launch") : B2_OK;
+}
+
 int b2_lqr_control(b2_batch* b, const b2_state* st, void* stream) {
   B2_CHECK_STATE("b2_lqr_control");
   if (!b->d_gain) return fail(B2_ERR_ARG, "b2_lqr_control: call b2_lqr_set_gain first");
-  int rc = ensure_resident(b, stream);
+  return do_lqr_control(b, st, b->nenv, stream);
+}
+
+// One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).
+// A single fused launch when the model has a specialised k_tick; otherwise the same three launches a caller
+// would issue (b2_lqr_control, b2_linearize, b2_step), so the result does not depend on which path ran.
+int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, int use_lqr, double eps, int centered,
+                    void* A, void* B, void* stream) {
+  B2_CHECK_STATE("b2_control_tick");
+  if (!(eps > 0)) return fail(B2_ERR_LINEARIZE, "b2_control_tick: eps must be > 0");
+  if (!A && !B) return fail(B2_ERR_ARG, "b2_control_tick: A and B are both NULL");
+  if (use_lqr && !b->d_gain) return fail(B2_ERR_ARG, "b2_control_tick: call b2_lqr_set_gain first");
+  const b2::SpecKernels* k = active_spec(b);
+  const char* off = getenv("B2_DISABLE_FUSED_TICK");
+  if (k && k->tick[prec_index(b)] && !(off && off[0] == '1')) {
+    cudaError_t e = cudaSetDevice(b->device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const int rc = k->tick[prec_index(b)](st, derived, b->nenv, b->nenv, eps, centered, A, B, use_lqr ? b->d_gain : nullptr, stream);
+    g_launches++;
+    return rc ? cuda_fail((cudaError_t)rc, "control tick launch") : B2_OK;
+  }
+  int rc = use_lqr ? b2_lqr_control(b, st, stream) : B2_OK;
   if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_f64(b->model->cls, st, b->nenv, b->d_gain, stream)
-                              : b2::b2k_lqr_control_f32(b->model->cls, st, b->nenv, b->d_gain, stream);
-  g_launches++;
-  return rc ? cuda_fail((cudaError_t)rc, "b2_lqr_control launch") : B2_OK;
+  if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream))) return rc;
+  return do_step(b, st, b->nenv, 1, derived, stream);
 }
 
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {
@@ -357,6 +385,9 @@ int b2_differentiate_pos(b2_batch* b, void* out, double dt, const void* q1, cons
 int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, double eps, void* host_A, void* host_B, void* stream) {
   if (!b || !hs || !hs->qpos || !hs->qvel || (b->model->v.nu && !hs->ctrl)) return fail(B2_ERR_ARG, "b2_step_host: null pointer");
   if (nsteps < 1) return fail(B2_ERR_ARG, "b2_step_host: nsteps must be >= 1");
+  const bool lqr = (linearize & B2_HOST_LQR) != 0;  // ctrl is produced on the device by the b2_lqr_set_gain law and copied back
+  linearize &= B2_HOST_LINEARIZE;
+  if (lqr && !b->d_gain) return fail(B2_ERR_ARG, "b2_step_host: B2_HOST_LQR needs b2_lqr_set_gain first");
   cudaError_t e = cudaSetDevice(b->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const b2m_view& v = b->model->v;
@@ -368,9 +399,10 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   if (linearize && ((e = need(&b->d_A, nx * nx * N * es)) || (e = need(&b->d_B, nx * nu1 * N * es)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
   int rc = prepare_warp(b);
   if (rc) return rc;
-  if (!active_spec(b) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
+  if ((!active_spec(b) || lqr) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
   // chunking: warp-engine batches and small batches go through in one piece
-  const int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 4;
+  int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 4;
+  if (const char* env_chunks = getenv("B2_HOST_CHUNKS")) { const int c = atoi(env_chunks); if (c >= 1 && c <= 64 && nchunk > 1) nchunk = c; }
   if (!b->pipe_ready) {
     for (int i = 0; i < 3; i++) if ((e = cudaStreamCreateWithFlags(&b->pipe[i], cudaStreamNonBlocking))) return cuda_fail(e, "cudaStreamCreate");
     for (int i = 0; i < 3; i++) if ((e = cudaEventCreateWithFlags(&b->pipe_ev[i], cudaEventDisableTiming))) return cuda_fail(e, "cudaEventCreate");
@@ -381,7 +413,7 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   HostStepKey key;
   memset(&key, 0, sizeof(key));
   key.qpos = hs->qpos; key.qvel = hs->qvel; key.ctrl = hs->ctrl; key.warm = hs->qacc_warmstart; key.A = host_A; key.B = host_B;
-  key.nsteps = nsteps; key.linearize = linearize; key.eps = eps; key.model_serial = b->model->serial;
+  key.nsteps = nsteps; key.linearize = linearize | (lqr ? B2_HOST_LQR : 0) | (nchunk << 8); key.eps = eps; key.model_serial = b->model->serial;
   if (b->host_graph && memcmp(&key, &b->host_key, sizeof(key)) != 0) {
     cudaGraphExecDestroy(b->host_graph);
     b->host_graph = nullptr;
@@ -406,18 +438,20 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
       cudaStream_t s = b->pipe[c % 3];
       if ((e = copy_rows(b->d_qpos, hs->qpos, e0, cnt, v.nq, cudaMemcpyHostToDevice, s)) ||
           (e = copy_rows(b->d_qvel, hs->qvel, e0, cnt, v.nv, cudaMemcpyHostToDevice, s)) ||
-          (v.nu && (e = copy_rows(b->d_ctrl, hs->ctrl, e0, cnt, v.nu, cudaMemcpyHostToDevice, s))))
+          (v.nu && !lqr && (e = copy_rows(b->d_ctrl, hs->ctrl, e0, cnt, v.nu, cudaMemcpyHostToDevice, s))))
         break;
       if (hs->qacc_warmstart) e = copy_rows(b->d_warm, hs->qacc_warmstart, e0, cnt, v.nv, cudaMemcpyHostToDevice, s);
       else e = cudaMemset2DAsync((char*)b->d_warm + e0 * es, pitch, 0, cnt * es, v.nv, s);
       if (e) break;
       b2_state ds = {(char*)b->d_qpos + e0 * es, (char*)b->d_qvel + e0 * es, (char*)b->d_ctrl + e0 * es, (char*)b->d_warm + e0 * es, nullptr};
+      if (lqr && (err = do_lqr_control(b, &ds, (int)cnt, s))) break;
       if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, (char*)b->d_A + e0 * es, (char*)b->d_B + e0 * es, s))) break;
       if ((err = do_step(b, &ds, (int)cnt, nsteps, nullptr, s))) break;
       if ((e = copy_rows(hs->qpos, b->d_qpos, e0, cnt, v.nq, cudaMemcpyDeviceToHost, s)) ||
           (e = copy_rows(hs->qvel, b->d_qvel, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s)))
         break;
       if (hs->qacc_warmstart && (e = copy_rows(hs->qacc_warmstart, b->d_warm, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s))) break;
+      if (lqr && (e = copy_rows(hs->ctrl, b->d_ctrl, e0, cnt, v.nu, cudaMemcpyDeviceToHost, s))) break;
       if (linearize && host_A && (e = copy_rows(host_A, b->d_A, e0, cnt, nx * nx, cudaMemcpyDeviceToHost, s))) break;
       if (linearize && host_B && v.nu && (e = copy_rows(host_B, b->d_B, e0, cnt, nx * v.nu, cudaMemcpyDeviceToHost, s))) break;
     }

@@ -21,6 +21,13 @@
 namespace b2 {
 
 template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
+#ifndef B2_TICK_WARPS
+#define B2_TICK_WARPS 8
+#endif
+#ifndef B2_TICK_MIN_BLOCKS
+#define B2_TICK_MIN_BLOCKS 1
+#endif
+
 template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias, *sensordata; int *ncon, *nefc, *solver_iter; };
 
 template <typename T>
@@ -114,25 +121,41 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
 // Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state and
 // qacc_warmstart of every rollout start from the saved nominal values; control columns fall
 // back to one-sided differences at the ctrlrange bounds.
-template <typename T, class D, class M>
-__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
-  constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
+// One column of the FD linearisation (or, with nominal = true, the unperturbed step itself) for env e.
+// c < nv: tangent-space position column, c < 2nv: velocity column, else control column c - 2nv.
+// q0/v0/u0/w0: the env's nominal state in registers.  nominal: run the plain step, export derived arrays from
+// its pre-integration forward pass and leave the advanced state in env.qpos / env.qvel / env.warm.
+// The nominal state of a thread's env: held in registers (k_tick, which overwrites the state in place) ...
+template <typename T>
+struct NominalInRegisters {
+  const T *q0, *v0, *u0, *w0;
+  B2_DEV T q(int k) const { return q0[k]; }
+  B2_DEV T v(int k) const { return v0[k]; }
+  B2_DEV T u(int k) const { return u0[k]; }
+  B2_DEV T w(int k) const { return w0[k]; }
+};
+// ... or re-read from the SoA arrays at the start of every rollout (k_linearize: L1/L2 hits, and ~14 fewer live
+// registers across the physics, which is what the 168-register budget of three resident blocks is short of)
+template <typename T>
+struct NominalInMemory {
+  StateDev<T> st;
+  int N, e;
+  B2_DEV T q(int k) const { return __ldg(st.qpos + (size_t)k * N + e); }
+  B2_DEV T v(int k) const { return __ldg(st.qvel + (size_t)k * N + e); }
+  B2_DEV T u(int k) const { return __ldg(st.ctrl + (size_t)k * N + e); }
+  B2_DEV T w(int k) const { return st.warm ? __ldg(st.warm + (size_t)k * N + e) : T(0); }
+};
+
+template <typename T, class D, class M, class S>
+B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
+                      T eps, int centered, int N, int e, T* A, T* B, const DerivedDev<T>& out, int want_derived) {
+  constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)count * (ndx + nu)) return;
-  const int e = (int)(idx % count), c = (int)(idx / count);  // count envs, env stride N
-  RowStore<T, D> rows;
-  LaneEnv<T, D, M> env(rows);
-  T q0[NQ], v0[NV], u0[NU], w0[NV], yp[NQ + NV], ym[NQ + NV], yn[NQ + NV], col[2 * NV];
-  B2_UNROLL
-  for (int k = 0; k < nq; k++) q0[k] = st.qpos[(size_t)k * N + e];
-  B2_UNROLL
-  for (int k = 0; k < nv; k++) { v0[k] = st.qvel[(size_t)k * N + e]; w0[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
-  B2_UNROLL
-  for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
+  T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
   int kind, i;
   bool fwd = true, back = centered != 0;
-  if (c < nv) { kind = 1; i = c; }
+  if (nominal) { kind = 0; i = 0; fwd = back = false; }
+  else if (c < nv) { kind = 1; i = c; }
   else if (c < ndx) { kind = 2; i = c - nv; }
   else {
     kind = 3; i = c - ndx;
@@ -140,11 +163,11 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
     T lo = 0, hi = 0, u = 0;
     B2_UNROLL
     for (int a = 0; a < nu; a++)
-      if (a == i) { lim = M::actuator_ctrllimited(a); lo = M::actuator_ctrlrange(2 * a); hi = M::actuator_ctrlrange(2 * a + 1); u = u0[a]; }
+      if (a == i) { lim = M::actuator_ctrllimited(a); lo = M::actuator_ctrlrange(2 * a); hi = M::actuator_ctrlrange(2 * a + 1); u = nom.u(a); }
     fwd = !lim || (u >= lo && u <= hi && u + eps >= lo && u + eps <= hi);
     back = (centered || !fwd) && (!lim || (u - eps >= lo && u - eps <= hi && u >= lo && u <= hi));
   }
-  const int need = (fwd ? 1 : 0) | (back ? 2 : 0) | ((fwd != back) ? 4 : 0);  // plus, minus, nominal rollouts
+  const int need = nominal ? 4 : ((fwd ? 1 : 0) | (back ? 2 : 0) | ((fwd != back) ? 4 : 0));  // plus, minus, nominal rollouts
   // rolled phase loop: the physics is instantiated once; all array indices stay static
   bool pos_valid = false;
   B2_NOUNROLL
@@ -152,11 +175,11 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
     if (!((need >> phase) & 1)) continue;
     const T delta = phase == 0 ? eps : (phase == 1 ? -eps : T(0));
     B2_UNROLL
-    for (int k = 0; k < nq; k++) env.qpos[k] = q0[k];
+    for (int k = 0; k < nq; k++) env.qpos[k] = nom.q(k);
     B2_UNROLL
-    for (int k = 0; k < nv; k++) { env.qvel[k] = v0[k] + ((kind == 2 && k == i) ? delta : T(0)); env.warm[k] = w0[k]; }
+    for (int k = 0; k < nv; k++) { env.qvel[k] = nom.v(k) + ((kind == 2 && k == i) ? delta : T(0)); env.warm[k] = nom.w(k); }
     B2_UNROLL
-    for (int k = 0; k < nu; k++) env.ctrl[k] = u0[k] + ((kind == 3 && k == i) ? delta : T(0));
+    for (int k = 0; k < nu; k++) env.ctrl[k] = nom.u(k) + ((kind == 3 && k == i) ? delta : T(0));
     if (kind == 1 && phase < 2) {
       T dp[NV];
       B2_UNROLL
@@ -170,19 +193,20 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
     env.forward_rest();
     B2_UNROLL
     for (int k = 0; k < nv; k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
+    if (nominal && want_derived) store_derived(env, out, N, e);
     if (M::integrator() == 1) env.rk4(); else env.euler();
     pos_valid = kind != 1 && M::integrator() == 0;
+    // plus -> s2, minus -> s1, nominal -> whichever end the one-sided quotient is missing
+    const bool to2 = phase == 0 || (phase == 2 && !fwd);
     B2_UNROLL
     for (int k = 0; k < nq + nv; k++) {
       const T val = k < nq ? env.qpos[k < nq ? k : 0] : env.qvel[k >= nq ? k - nq : 0];
-      if (phase == 0) yp[k] = val; else if (phase == 1) ym[k] = val; else yn[k] = val;
+      if (to2) s2[k] = val; else s1[k] = val;
     }
   }
+  if (nominal) return;
   if (fwd || back) {
     const T h = (fwd && back) ? 2 * eps : eps;
-    T s1[NQ + NV], s2[NQ + NV];
-    B2_UNROLL
-    for (int k = 0; k < nq + nv; k++) { s1[k] = back ? ym[k] : yn[k]; s2[k] = fwd ? yp[k] : yn[k]; }
     env.differentiate_pos(col, h, s1, s2);
     const T ih = T(1) / h;
     B2_UNROLL
@@ -193,6 +217,85 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
   }
   if (c < ndx) { if (A) { B2_UNROLL for (int r = 0; r < ndx; r++) A[((size_t)r * ndx + c) * N + e] = col[r]; } }
   else if (B) { B2_UNROLL for (int r = 0; r < ndx; r++) B[((size_t)r * nu + (c - ndx)) * N + e] = col[r]; }
+}
+
+// Centred / one-sided finite differences of one step: one thread per (env, input column).
+// Columns 0..nv-1 perturb tangent-space position, nv..2nv-1 velocity, 2nv..2nv+nu-1 control.
+// Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state and
+// qacc_warmstart of every rollout start from the saved nominal values; control columns fall
+// back to one-sided differences at the ctrlrange bounds.
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
+  const int nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * (ndx + nu)) return;
+  const int e = (int)(idx % count), c = (int)(idx / count);  // count envs, env stride N
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  DerivedDev<T> none;
+  memset(&none, 0, sizeof(none));
+  const NominalInMemory<T> nom{st, N, e};
+  fd_column(env, nom, c, false, eps, centered, N, e, A, B, none, 0);
+  if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
+}
+
+// u = clip(u_ref - K [qpos (-) qpos_ref ; qvel], ctrlrange) for one env whose state is in registers.
+// gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
+template <typename T, class D, class M>
+B2_DEV void lqr_law(const LaneEnv<T, D, M>& env, const T* q, const T* v, const T* __restrict__ gain, T* u_out) {
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
+  T qr[D::NQ], x[2 * D::NV];
+  B2_UNROLL
+  for (int k = 0; k < nq; k++) qr[k] = gain[nu * 2 * nv + k];
+  env.differentiate_pos(x, T(1), qr, q);
+  B2_UNROLL
+  for (int k = 0; k < nv; k++) x[nv + k] = v[k];
+  B2_UNROLL
+  for (int a = 0; a < nu; a++) {
+    T u = gain[nu * 2 * nv + nq + a];
+    B2_UNROLL
+    for (int k = 0; k < 2 * nv; k++) u -= gain[a * 2 * nv + k] * x[k];
+    if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
+    u_out[a] = u;
+  }
+}
+
+// One control tick of a whole batch in ONE launch: [LQR control law] -> FD (A, B) at the new controls -> one step.
+// Block = 32 envs x (ncol + 1) warps: warp w < ncol computes FD column w of its 32 envs, the last warp advances them.
+// All warps load the nominal state first; the barrier orders those loads before the last warp's in-place write-back,
+// so no shadow copy of the state is needed.  Equivalent to k_lqr_control + k_linearize + k_step(nsteps = 1)
+// (reference env.py:177-191: controller, then (A, B), then step).
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(32 * B2_TICK_WARPS, B2_TICK_MIN_BLOCKS)
+k_tick(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
+  constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ncol = 2 * nv + nu;
+  const int e = blockIdx.x * 32 + threadIdx.x, c = threadIdx.y;
+  const bool live = e < count, nominal = c == ncol;
+  const int el = live ? e : 0;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  T q0[NQ], v0[NV], u0[NU], w0[NV];
+  B2_UNROLL
+  for (int k = 0; k < nq; k++) q0[k] = st.qpos[(size_t)k * N + el];
+  B2_UNROLL
+  for (int k = 0; k < nv; k++) { v0[k] = st.qvel[(size_t)k * N + el]; w0[k] = st.warm ? st.warm[(size_t)k * N + el] : T(0); }
+  if (gain) lqr_law(env, q0, v0, gain, u0);
+  else { B2_UNROLL for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + el]; }
+  __syncthreads();
+  if (!live) return;
+  DerivedDev<T> none;
+  memset(&none, 0, sizeof(none));
+  const NominalInRegisters<T> nom{q0, v0, u0, w0};
+  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, nominal ? out : none, want_derived);
+  if (nominal) {
+    B2_UNROLL
+    for (int k = 0; k < nq; k++) st.qpos[(size_t)k * N + e] = env.qpos[k];
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) st.qvel[(size_t)k * N + e] = env.qvel[k];
+    if (st.warm) { B2_UNROLL for (int k = 0; k < nv; k++) st.warm[(size_t)k * N + e] = env.warm[k]; }
+    if (gain) { B2_UNROLL for (int k = 0; k < nu; k++) st.ctrl[(size_t)k * N + e] = u0[k]; }
+  }
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
 }
 
@@ -256,22 +359,16 @@ __global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T*
 // (reference examples/drone/controllers/lqr.py:227-278, examples/humanoid/controllers/lqr.py:153-170).
 // gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int N, const T* __restrict__ gain) {
+__global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, int N, const T* __restrict__ gain) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= N) return;
-  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
+  if (e >= count) return;
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
-  T q[D::NQ], qr[D::NQ], x[2 * D::NV];
-  for (int k = 0; k < nq; k++) { q[k] = st.qpos[(size_t)k * N + e]; qr[k] = gain[nu * 2 * nv + k]; }
-  env.differentiate_pos(x, T(1), qr, q);
-  for (int k = 0; k < nv; k++) x[nv + k] = st.qvel[(size_t)k * N + e];
-  for (int a = 0; a < nu; a++) {
-    T u = gain[nu * 2 * nv + nq + a];
-    for (int k = 0; k < 2 * nv; k++) u -= gain[a * 2 * nv + k] * x[k];
-    if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
-    st.ctrl[(size_t)a * N + e] = u;
-  }
+  T q[D::NQ], v[D::NV], u[D::NU];
+  for (int k = 0; k < M::nq(); k++) q[k] = st.qpos[(size_t)k * N + e];
+  for (int k = 0; k < M::nv(); k++) v[k] = st.qvel[(size_t)k * N + e];
+  lqr_law(env, q, v, gain, u);
+  for (int a = 0; a < M::nu(); a++) st.ctrl[(size_t)a * N + e] = u[a];
 }
 
 template <typename T, class D, class M>

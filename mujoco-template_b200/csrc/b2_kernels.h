@@ -16,7 +16,7 @@ namespace b2 {
                          void* stream);                                                                                    \
   int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
   int b2k_inverse##SUF(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream);     \
-  int b2k_lqr_control##SUF(int cls, const b2_state* st, int N, const void* gain, void* stream);                           \
+  int b2k_lqr_control##SUF(int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \
   int b2k_integrate_pos##SUF(int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \
   int b2k_differentiate_pos##SUF(int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream);
 B2_DECL(_f64)

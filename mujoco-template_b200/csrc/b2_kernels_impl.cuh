@@ -192,10 +192,10 @@ int B2_FN(b2k_inverse)(int cls, const b2_state* st, int N, const void* qacc, voi
                        to_dev<real>(st), N, (const real*)qacc, (real*)qfrc, (real*)moment)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_lqr_control)(int cls, const b2_state* st, int N, const void* gain, void* stream) {
-  const int threads = 128, blocks = (N + threads - 1) / threads;
+int B2_FN(b2k_lqr_control)(int cls, const b2_state* st, int count, int N, const void* gain, void* stream) {
+  const int threads = 128, blocks = (count + threads - 1) / threads;
   B2_DISPATCH(cls, (k_lqr_control<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), N, (const real*)gain)));
+                       to_dev<real>(st), count, N, (const real*)gain)));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_integrate_pos)(int cls, void* qpos, const void* qvel, double dt, int N, void* stream) {

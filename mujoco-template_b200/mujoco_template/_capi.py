@@ -24,7 +24,7 @@ _lib: C.CDLL | None = None
 EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
-    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
 )
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
     L.b2_inverse.argtypes = [vp, C.POINTER(State), vp, vp, vp, vp]
     L.b2_lqr_set_gain.argtypes = [vp, C.POINTER(d), C.POINTER(d), C.POINTER(d)]
     L.b2_lqr_control.argtypes = [vp, C.POINTER(State), vp]
+    L.b2_control_tick.argtypes = [vp, C.POINTER(State), C.POINTER(Derived), i, C.c_double, i, vp, vp, vp]
     L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
@@ -173,14 +174,22 @@ class NativeBatch:
     def lqr_control(self, state: State, stream: int = 0) -> None:
         check(self._L.b2_lqr_control(self.handle, C.byref(state), stream))
 
+    def control_tick(self, state: State, derived: Derived | None, use_lqr: bool, eps: float, centered: bool, A: int, B: int,
+                     stream: int = 0) -> None:
+        check(self._L.b2_control_tick(self.handle, C.byref(state), C.byref(derived) if derived is not None else None,
+                                      int(bool(use_lqr)), float(eps), int(bool(centered)), A, B, stream))
+
     def integrate_pos(self, qpos: int, qvel: int, dt: float, stream: int = 0) -> None:
         check(self._L.b2_integrate_pos(self.handle, qpos, qvel, float(dt), stream))
 
     def differentiate_pos(self, out: int, dt: float, qpos1: int, qpos2: int, stream: int = 0) -> None:
         check(self._L.b2_differentiate_pos(self.handle, out, float(dt), qpos1, qpos2, stream))
 
-    def step_host(self, state: State, nsteps: int, linearize: bool, eps: float, A: int | None, B: int | None, stream: int = 0) -> None:
-        check(self._L.b2_step_host(self.handle, C.byref(state), int(nsteps), int(bool(linearize)), float(eps), A, B, stream))
+    def step_host(self, state: State, nsteps: int, linearize: bool, eps: float, A: int | None, B: int | None, stream: int = 0,
+                  device_lqr: bool = False) -> None:
+        """Host-buffer step; ``device_lqr`` evaluates the ``lqr_set_gain`` law on the device (``state.ctrl`` becomes an output)."""
+        flags = (1 if linearize else 0) | (2 if device_lqr else 0)
+        check(self._L.b2_step_host(self.handle, C.byref(state), int(nsteps), flags, float(eps), A, B, stream))
 
     def synchronize(self, stream: int = 0) -> None:
         check(self._L.b2_stream_synchronize(self.handle, stream))

@@ -279,6 +279,19 @@ class NativeBackend:
     def forward(self) -> None:
         self._launch("forward", self.batch.forward, self.state_struct(), self.derived_struct())
 
+    def control_tick(self, eps: float, centered: bool, use_lqr: bool, out=None):
+        """LQR law (optional) -> (A, B) -> one step, fused into one launch where the model has a specialised kernel."""
+        torch, m = self.torch, self.model
+        nx = 2 * m.nv
+        if out is not None:
+            A, B = out
+        else:
+            A = torch.empty((nx, nx, self.nenv), device=f"cuda:{self.device}", dtype=self.dtype)
+            B = torch.empty((nx, m.nu, self.nenv), device=f"cuda:{self.device}", dtype=self.dtype)
+        self._launch("control_tick", self.batch.control_tick, self.state_struct(), self.derived_struct(), use_lqr, eps,
+                     centered, A.data_ptr(), B.data_ptr() if m.nu else None)
+        return A, B
+
     def linearize(self, eps: float, centered: bool, out=None):
         """Returns (A, B) as SoA buffers of shape (2nv, 2nv, nenv) and (2nv, nu, nenv).
 

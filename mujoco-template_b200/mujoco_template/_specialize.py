@@ -112,6 +112,11 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("#define B2_STATIC_MODEL 1")
     # small models: ask for >= 3 resident blocks/SM in the FD kernel (<= 168 registers, measured best on B200)
     A(f"#define B2_LIN_MIN_BLOCKS {3 if nv <= 2 else 1}")
+    ncol = 2 * nv + nu
+    fused_tick = ncol + 1 <= 8  # one block = 32 envs x (ncol + 1) warps must fit the register file
+    if fused_tick:
+        A(f"#define B2_TICK_WARPS {ncol + 1}")
+        A("#define B2_TICK_MIN_BLOCKS 2")
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
     A("")
@@ -156,8 +161,15 @@ def emit_spec(compiled: dict, name: str) -> str:
         A(f"  k_jacobian<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), N, kind, objid, ({T}*)jacp, ({T}*)jacr);")
         A("  return (int)cudaGetLastError();")
         A("}")
+        if fused_tick:
+            A(f"int spec_tick{suf}(const b2_state* st, const b2_derived* out, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
+            A(f"  const dim3 block(32, {ncol + 1}); const int blocks = (count + 31) / 32;")
+            A(f"  k_tick<{T}, SDims, SModel<{T}>><<<blocks, block, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
+            A("  return (int)cudaGetLastError();")
+            A("}")
+    tick = "{spec_tick, spec_tick32}" if fused_tick else "{nullptr, nullptr}"
     A(f'const SpecKernels kSpec = {{"{name}", 0x{fnv1a(blob):016x}ull, {len(blob)}, {{spec_step, spec_step32}}, '
-      '{spec_linearize, spec_linearize32}, {spec_jacobian, spec_jacobian32}};')
+      f'{{spec_linearize, spec_linearize32}}, {{spec_jacobian, spec_jacobian32}}, {tick}}};')
     A("struct Registrar { Registrar() { register_spec(&kSpec); } } registrar;")
     A("}  // namespace")
     A("}  // namespace b2")

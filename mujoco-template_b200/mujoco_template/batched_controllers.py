@@ -76,13 +76,21 @@ class BatchedLQRController:
         self._free = bool(np.any(model.jnt_type == 0))
         self._qref_np, self._uref_np = qref, uref
 
+    def device_law_ready(self, data: Any) -> bool:
+        """True when the control law lives on the device (b2_lqr_set_gain done): ``BatchedEnv`` may then fold this
+        controller's tick, the (A, B) linearisation and the step into one ``b2_control_tick`` launch."""
+        b = data.backend
+        if not (self.fused and hasattr(b, "batch") and hasattr(data.qpos, "device")):
+            return False
+        if not self._gain_uploaded:
+            b.batch.lqr_set_gain(self.K, self._qref_np, self._uref_np)
+            self._gain_uploaded = True
+        return True
+
     def __call__(self, model: Any, data: Any, t: float) -> None:
         b = data.backend
-        if self.fused and hasattr(b, "batch") and hasattr(data.qpos, "device"):
+        if self.device_law_ready(data):
             # one kernel: tangent-space state error, gain product, ctrlrange clamp (b2_lqr_control)
-            if not self._gain_uploaded:
-                b.batch.lqr_set_gain(self.K, self._qref_np, self._uref_np)
-                self._gain_uploaded = True
             b._launch("lqr_control", b.batch.lqr_control, b.state_struct())
             return
         import torch

@@ -500,3 +500,59 @@ def test_batched_recorder_matches_single_env_csv(tmp_path):
         assert len(mine) == T
         for a, b in zip(mine, single.rows):
             assert np.allclose(np.array(a, dtype=float), np.array(b, dtype=float), rtol=0, atol=1e-13)
+
+
+@pytest.mark.parametrize("name,n", [("cartpole", 1000), ("pendulum", 33)])
+@pytest.mark.parametrize("precision", [64, 32])
+def test_fused_control_tick_equals_three_launch_sequence(name, n, precision):
+    """b2_control_tick (LQR law + (A, B) + step in one launch) == b2_lqr_control, b2_linearize, b2_step in sequence,
+    and the FP64 result matches the oracle driven by the same control law."""
+    import torch
+    import mujoco_template as mt
+
+    model = load_model(name)
+    qpos, qvel, _ = random_states(model, name, n, seed=21)
+    if name == "cartpole":
+        qpos[0] = [1.9995, 0.1]; qvel[0] = [3.0, 0.0]       # env 0 runs into the slider limit: constraint rows in the FD
+    out = {}
+    for fused in (True, False):
+        ctl = mt.batched_controllers.BatchedLQRController(qpos_ref=np.array(model.qpos0), Q=np.eye(2 * model.nv), R=np.eye(model.nu))
+        benv = mt.BatchedEnv(model, n, controller=ctl, precision=precision)
+        benv.fuse_control_tick = fused
+        dev, dt = benv.data.qpos.device, benv.data.qpos.dtype
+        benv.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev, dtype=dt))
+        benv.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev, dtype=dt))
+        c0 = mt._capi.launch_count()
+        hist = []
+        for _ in range(5):
+            res = benv.step(return_obs=False)
+            hist.append((res.info["A"].clone(), res.info["B"].clone(), benv.data.qpos.clone(), benv.data.qvel.clone(),
+                         benv.data.ctrl.clone(), benv.data.qacc.clone(), benv.data.xpos.clone()))
+        assert mt._capi.launch_count() - c0 == (5 if fused else 15)
+        out[fused] = hist
+    tol = 1e-12 if precision == 64 else 2e-4
+    for a, b in zip(out[True], out[False]):
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert x.shape == y.shape
+            if precision == 32 and k < 2:
+                continue  # FP32 differences at eps = 1e-6 are rounding noise in either path
+            # (A, B): rounding differences between the two kernels are amplified by 1/eps in the difference quotient
+            bound = (1e-7 if k < 2 else tol) * max(1.0, float(y.abs().max()))
+            assert float((x - y).abs().max()) <= bound, (k, float((x - y).abs().max()))
+    if precision == 64:
+        om, od = oracle_for(model)
+        K = ctl.K
+        for e in (0, 1, n - 1):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]
+            for s in range(5):
+                x = np.concatenate([od.qpos - model.qpos0, od.qvel])
+                u = -K @ x
+                lim = np.asarray(model.actuator_ctrllimited, bool)
+                od.ctrl[:] = np.where(lim, np.clip(u, model.actuator_ctrlrange[:, 0], model.actuator_ctrlrange[:, 1]), u)
+                Ao, Bo = od.transition_fd(1e-6, True)
+                A, B, q, v, uu, _, _ = out[True][s]
+                assert np.max(np.abs(A[e].cpu().numpy() - Ao)) <= 1e-6 * max(1.0, np.max(np.abs(Ao)))
+                assert np.max(np.abs(B[e].cpu().numpy() - Bo)) <= 1e-6 * max(1.0, np.max(np.abs(Bo)))
+                od.step()
+                assert np.max(np.abs(q[:, e].cpu().numpy() - od.qpos)) <= 1e-9 * max(1.0, np.max(np.abs(od.qpos)))
+                assert np.max(np.abs(v[:, e].cpu().numpy() - od.qvel)) <= 1e-9 * max(1.0, np.max(np.abs(od.qvel)))

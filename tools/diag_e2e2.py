@@ -27,3 +27,14 @@ def tick():
 t0=time.perf_counter()
 for _ in range(100): tick()
 print('tick ms',(time.perf_counter()-t0)/100*1e3)
+for mb in (1, 4, 13, 64):
+    x = torch.empty(mb * 1024 * 1024, dtype=torch.uint8, device='cuda'); h = torch.empty(mb * 1024 * 1024, dtype=torch.uint8).pin_memory()
+    for _ in range(3): h.copy_(x, non_blocking=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20): h.copy_(x, non_blocking=True)
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 20
+    for _ in range(3): x.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(20): x.copy_(h, non_blocking=True)
+    torch.cuda.synchronize(); dt2 = (time.perf_counter() - t0) / 20
+    print(f'{mb} MB: D2H {dt*1e3:.3f} ms {mb/1024/dt:.1f} GB/s   H2D {dt2*1e3:.3f} ms {mb/1024/dt2:.1f} GB/s')
