@@ -254,6 +254,8 @@ def main():
 
     # per-kernel device times for the roofline: a short eager pass with CUDA events around each launch
     env.data.backend.profile = {}
+    fuse_default = getattr(env, "fuse_control_tick", False)
+    env.fuse_control_tick = False  # time the controller / FD / step launches one by one in this pass
     for _ in range(max(args.warmup, 3)):
         env.step(return_obs=False)
     for _ in range(10):
@@ -262,6 +264,7 @@ def main():
     torch.cuda.synchronize()
     kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("lqr_control", "linearize", "step", "control_tick")}
     env.data.backend.profile = None
+    env.fuse_control_tick = fuse_default
     c0 = _capi.launch_count()
     env.step(return_obs=False)
     per_step_launches = _capi.launch_count() - c0  # library kernels per step (controller tick, FD, step)

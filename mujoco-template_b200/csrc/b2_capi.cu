@@ -188,16 +188,23 @@ static int prepare_warp(b2_batch* b) {
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
-static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, void* stream) {
+extern "C" { static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream); }
+
+static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, const void* gain,
+                               void* stream) {
   int rc = ensure_resident(b, stream);
   if (rc) return rc;
   if ((rc = prepare_warp(b))) return rc;
   const bool f64 = b->precision == B2_F64;
+  if (b->warp_mode == 1 && count == b->nenv && gain) {  // the warp engine has no in-kernel control law: separate launch
+    if ((rc = do_lqr_control(b, st, count, stream))) return rc;
+    gain = nullptr;
+  }
   if (b->warp_mode == 1 && count == b->nenv)
     return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream)
                : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream);
-  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, stream)
-             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, stream);
+  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream)
+             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream);
 }
 
 // make sure this batch's model is the image resident in constant memory on its device
@@ -223,31 +230,33 @@ static int ensure_resident(b2_batch* b, void* stream) {
 extern "C" {
 
 // count envs (a leading chunk of the arrays `st` points at; the env stride is always b->nenv)
-static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const b2_derived* derived, void* stream) {
+static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const b2_derived* derived, void* stream,
+                   const void* gain = nullptr) {
   int rc;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->step[prec_index(b)](st, derived, count, b->nenv, nsteps, stream);
+    rc = k->step[prec_index(b)](st, derived, count, b->nenv, nsteps, gain, stream);
   } else {
-    rc = launch_generic_step(b, st, derived, count, nsteps, stream);
+    rc = launch_generic_step(b, st, derived, count, nsteps, gain, stream);
     if (rc < 0) return rc;
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "step launch") : B2_OK;
 }
-static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, int centered, void* A, void* B, void* stream) {
+static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, int centered, void* A, void* B, void* stream,
+                        const void* gain = nullptr) {
   int rc;
   const int ncol = 2 * b->model->v.nv + b->model->v.nu;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, stream);
+    rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, gain, stream);
   } else {
     rc = ensure_resident(b, stream);
     if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, stream)
-                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, stream);
+    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, stream)
+                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, stream);
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "linearize launch") : B2_OK;
@@ -345,18 +354,20 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
   if (!A && !B) return fail(B2_ERR_ARG, "b2_control_tick: A and B are both NULL");
   if (use_lqr && !b->d_gain) return fail(B2_ERR_ARG, "b2_control_tick: call b2_lqr_set_gain first");
   const b2::SpecKernels* k = active_spec(b);
-  const char* off = getenv("B2_DISABLE_FUSED_TICK");
-  if (k && k->tick[prec_index(b)] && !(off && off[0] == '1')) {
+  const char* one = getenv("B2_SINGLE_LAUNCH_TICK");  // measured slower than the two launches below on B200
+  if (k && k->tick[prec_index(b)] && one && one[0] == '1') {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     const int rc = k->tick[prec_index(b)](st, derived, b->nenv, b->nenv, eps, centered, A, B, use_lqr ? b->d_gain : nullptr, stream);
     g_launches++;
     return rc ? cuda_fail((cudaError_t)rc, "control tick launch") : B2_OK;
   }
-  int rc = use_lqr ? b2_lqr_control(b, st, stream) : B2_OK;
+  // two launches: both kernels evaluate the control law themselves from (qpos, qvel) -- the FD kernel linearises about
+  // those controls, the step kernel applies them and writes them to state.ctrl -- so no separate controller launch
+  const void* gain = use_lqr ? b->d_gain : nullptr;
+  int rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream, gain);
   if (rc) return rc;
-  if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream))) return rc;
-  return do_step(b, st, b->nenv, 1, derived, stream);
+  return do_step(b, st, b->nenv, 1, derived, stream, gain);
 }
 
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {
@@ -444,9 +455,9 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
       else e = cudaMemset2DAsync((char*)b->d_warm + e0 * es, pitch, 0, cnt * es, v.nv, s);
       if (e) break;
       b2_state ds = {(char*)b->d_qpos + e0 * es, (char*)b->d_qvel + e0 * es, (char*)b->d_ctrl + e0 * es, (char*)b->d_warm + e0 * es, nullptr};
-      if (lqr && (err = do_lqr_control(b, &ds, (int)cnt, s))) break;
-      if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, (char*)b->d_A + e0 * es, (char*)b->d_B + e0 * es, s))) break;
-      if ((err = do_step(b, &ds, (int)cnt, nsteps, nullptr, s))) break;
+      const void* gain = lqr ? b->d_gain : nullptr;
+      if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, (char*)b->d_A + e0 * es, (char*)b->d_B + e0 * es, s, gain))) break;
+      if ((err = do_step(b, &ds, (int)cnt, nsteps, nullptr, s, gain))) break;
       if ((e = copy_rows(hs->qpos, b->d_qpos, e0, cnt, v.nq, cudaMemcpyDeviceToHost, s)) ||
           (e = copy_rows(hs->qvel, b->d_qvel, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s)))
         break;

@@ -86,16 +86,42 @@ B2_DEV void store_derived(LaneEnv<T, D, M>& env, const DerivedDev<T>& o, int N, 
   if (o.solver_iter) o.solver_iter[e] = env.niter;
 }
 
+// u = clip(u_ref - K [qpos (-) qpos_ref ; qvel], ctrlrange) for one env whose state is in registers.
+// gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
+template <typename T, class D, class M>
+B2_DEV void lqr_law(const LaneEnv<T, D, M>& env, const T* q, const T* v, const T* __restrict__ gain, T* u_out) {
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
+  T qr[D::NQ], x[2 * D::NV];
+  B2_UNROLL
+  for (int k = 0; k < nq; k++) qr[k] = gain[nu * 2 * nv + k];
+  env.differentiate_pos(x, T(1), qr, q);
+  B2_UNROLL
+  for (int k = 0; k < nv; k++) x[nv + k] = v[k];
+  B2_UNROLL
+  for (int a = 0; a < nu; a++) {
+    T u = gain[nu * 2 * nv + nq + a];
+    B2_UNROLL
+    for (int k = 0; k < 2 * nv; k++) u -= gain[a * 2 * nv + k] * x[k];
+    if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
+    u_out[a] = u;
+  }
+}
+
 // nsteps x mj_step with ctrl held; nsteps == 0 means mj_forward (no integration).
 // The step loop is rolled: one inlined copy of the physics per kernel.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps) {
+__global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps, const T* __restrict__ gain) {
   // count envs are processed; N is the env stride of the SoA arrays (count < N for a chunk of a larger batch)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
   load_state(env, st, N, e);
+  if (gain) {  // device-resident control law (b2_control_tick): ctrl is an output of this launch
+    lqr_law(env, env.qpos, env.qvel, gain, env.ctrl);
+    B2_UNROLL
+    for (int k = 0; k < M::nu(); k++) st.ctrl[(size_t)k * N + e] = env.ctrl[k];
+  }
   const int total = nsteps > 0 ? nsteps : 1;
   B2_NOUNROLL
   for (int s = 0; s < total; s++) {
@@ -140,9 +166,10 @@ template <typename T>
 struct NominalInMemory {
   StateDev<T> st;
   int N, e;
+  const T* u0;  // controls: registers (they may come from the control law rather than from st.ctrl)
   B2_DEV T q(int k) const { return __ldg(st.qpos + (size_t)k * N + e); }
   B2_DEV T v(int k) const { return __ldg(st.qvel + (size_t)k * N + e); }
-  B2_DEV T u(int k) const { return __ldg(st.ctrl + (size_t)k * N + e); }
+  B2_DEV T u(int k) const { return u0[k]; }
   B2_DEV T w(int k) const { return st.warm ? __ldg(st.warm + (size_t)k * N + e) : T(0); }
 };
 
@@ -225,8 +252,8 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // qacc_warmstart of every rollout start from the saved nominal values; control columns fall
 // back to one-sided differences at the ctrlrange bounds.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B) {
-  const int nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
+__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)count * (ndx + nu)) return;
   const int e = (int)(idx % count), c = (int)(idx / count);  // count envs, env stride N
@@ -234,30 +261,21 @@ __global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T
   LaneEnv<T, D, M> env(rows);
   DerivedDev<T> none;
   memset(&none, 0, sizeof(none));
-  const NominalInMemory<T> nom{st, N, e};
+  T u0[D::NU];
+  if (gain) {  // device-resident control law: linearise about the controls it produces (k_step applies the same law)
+    T q[D::NQ], v[D::NV];
+    B2_UNROLL
+    for (int k = 0; k < nq; k++) q[k] = st.qpos[(size_t)k * N + e];
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) v[k] = st.qvel[(size_t)k * N + e];
+    lqr_law(env, q, v, gain, u0);
+  } else {
+    B2_UNROLL
+    for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
+  }
+  const NominalInMemory<T> nom{st, N, e, u0};
   fd_column(env, nom, c, false, eps, centered, N, e, A, B, none, 0);
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
-}
-
-// u = clip(u_ref - K [qpos (-) qpos_ref ; qvel], ctrlrange) for one env whose state is in registers.
-// gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
-template <typename T, class D, class M>
-B2_DEV void lqr_law(const LaneEnv<T, D, M>& env, const T* q, const T* v, const T* __restrict__ gain, T* u_out) {
-  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
-  T qr[D::NQ], x[2 * D::NV];
-  B2_UNROLL
-  for (int k = 0; k < nq; k++) qr[k] = gain[nu * 2 * nv + k];
-  env.differentiate_pos(x, T(1), qr, q);
-  B2_UNROLL
-  for (int k = 0; k < nv; k++) x[nv + k] = v[k];
-  B2_UNROLL
-  for (int a = 0; a < nu; a++) {
-    T u = gain[nu * 2 * nv + nq + a];
-    B2_UNROLL
-    for (int k = 0; k < 2 * nv; k++) u -= gain[a * 2 * nv + k] * x[k];
-    if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
-    u_out[a] = u;
-  }
 }
 
 // One control tick of a whole batch in ONE launch: [LQR control law] -> FD (A, B) at the new controls -> one step.

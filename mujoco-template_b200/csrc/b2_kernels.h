@@ -11,9 +11,9 @@ namespace b2 {
   int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,  \
                          int wpb, int blocks, void* stream);                                                                                  \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
-  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);                  \
+  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);                  \
   int b2k_linearize##SUF(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
-                         void* stream);                                                                                    \
+                         const void* gain, void* stream);                                                                                    \
   int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
   int b2k_inverse##SUF(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream);     \
   int b2k_lqr_control##SUF(int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \

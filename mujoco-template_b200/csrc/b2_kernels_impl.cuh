@@ -132,10 +132,10 @@ double B2_FN(b2k_fma_peak)(void* stream) {
   const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
   return flops / (best * 1e-3) / 1e12;
 }
-int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream) {
+int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream) {
   const int threads = 128, blocks = (count + threads - 1) / threads;
   B2_DISPATCH(cls, (k_step<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps)));
+                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps, (const real*)gain)));
   return (int)cudaGetLastError();
 }
 // ---- warp engine (large models): launch geometry and per-warp scratch are sized by the host
@@ -172,12 +172,13 @@ int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived
       to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, warp_ws_reals_of(v));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B, void* stream) {
+int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,
+                         const void* gain, void* stream) {
   const int threads = 128;
   const long long total = (long long)count * ncol;
   const int blocks = (int)((total + threads - 1) / threads);
   B2_DISPATCH(cls, (k_linearize<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B)));
+                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B, (const real*)gain)));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_jacobian)(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {

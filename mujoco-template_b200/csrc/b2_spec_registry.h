@@ -13,8 +13,9 @@ struct SpecKernels {
   uint64_t blob_hash;
   size_t blob_size;
   // [0] FP64, [1] FP32; count envs, env stride N
-  int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, void* stream);
-  int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, void* stream);
+  // gain != null: the control law of b2_lqr_set_gain is evaluated inside the kernel (ctrl becomes an output of step)
+  int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);
+  int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream);
   int (*jacobian[2])(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
   // fused control tick (LQR law -> FD (A, B) -> one step) in one launch; null when the model has too many FD
   // columns for one block (ncol + 1 warps)

@@ -130,10 +130,9 @@ class BatchedEnv:
         self.controller = controller
         self.control_decimation = int(control_decimation)
         self.lin_eps = float(lin_eps)
-        # opt-in: fold a device-resident control law, (A, B) and the step into ONE launch (b2_control_tick).  Measured
-        # slower than the three separate launches on B200 for cartpole (86 vs 68 us/step at N=65536: the block of
-        # ncol+1 warps retires with its slowest column), so it is off by default.
-        self.fuse_control_tick = False
+        # a device-resident control law (BatchedLQRController) is evaluated inside the FD and step kernels
+        # (b2_control_tick: two launches per tick instead of controller + FD + step)
+        self.fuse_control_tick = True
         self.reward_fn, self.done_fn, self.info_fn = reward_fn, done_fn, info_fn
         self._obs_spec = obs_spec if obs_spec is not None else ObservationSpec(include_sensordata=False)
         self.extractor = BatchedObservationExtractor(model, self._obs_spec)
