@@ -333,9 +333,10 @@ def main():
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
-    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul): cartpole from the ncu capture in
-    # profiles/ncu_k_linearize_cartpole_spec_r01.txt; the others are the a-priori estimates of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 989.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul).  cartpole: counted by ncu on the kernels themselves
+    # (profiles/ncu_cartpole_kernels_r01d.txt: k_linearize 5.368e8 flops per 655,360 rollouts = 819 -- the velocity and
+    # control columns reuse the position stage -- and k_step 962 per step); the others are the a-priori estimates of BASELINE.md
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 819.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,

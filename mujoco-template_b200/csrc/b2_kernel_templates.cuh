@@ -11,6 +11,9 @@
 #include "b2_engine.cuh"
 
 // minimum resident blocks per SM requested for the FD kernel (caps registers per thread)
+#ifndef B2_LIN_THREADS
+#define B2_LIN_THREADS 128
+#endif
 #ifndef B2_LIN_MIN_BLOCKS
 #define B2_LIN_MIN_BLOCKS 1
 #endif
@@ -252,7 +255,7 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // qacc_warmstart of every rollout start from the saved nominal values; control columns fall
 // back to one-sided differences at the ctrlrange bounds.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
+__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)count * (ndx + nu)) return;

@@ -39,6 +39,10 @@ REAL_ARRAYS = ("gravity", "wind", "body_pos", "body_quat", "body_ipos", "body_iq
                "actuator_forcerange", "actuator_gainprm", "actuator_biasprm", "pair_margin", "pair_gap", "pair_friction",
                "pair_solref", "pair_solimp", "sensor_cutoff")
 
+# FD kernel block shape for small models: (threads per block, min resident blocks per SM)
+import os as _os
+LIN_SHAPE = tuple(int(x) for x in _os.environ.get("B2_LIN_SHAPE", "128,3").split(","))
+
 _MAX_CONTACTS = {(0, 2): 1, (0, 3): 2, (0, 6): 4, (0, 4): 1, (2, 2): 1, (2, 3): 1, (3, 3): 2}
 
 
@@ -111,7 +115,9 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("// Static model provider: every accessor folds to a compile-time constant after unrolling.")
     A("#define B2_STATIC_MODEL 1")
     # small models: ask for >= 3 resident blocks/SM in the FD kernel (<= 168 registers, measured best on B200)
-    A(f"#define B2_LIN_MIN_BLOCKS {3 if nv <= 2 else 1}")
+    lin_threads, lin_blocks = (LIN_SHAPE if nv <= 2 else (128, 1))
+    A(f"#define B2_LIN_THREADS {lin_threads}")
+    A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
     ncol = 2 * nv + nu
     fused_tick = ncol + 1 <= 8  # one block = 32 envs x (ncol + 1) warps must fit the register file
     if fused_tick:
@@ -151,7 +157,7 @@ def emit_spec(compiled: dict, name: str) -> str:
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
-        A(f"  const int threads = 128; const long long total = (long long)count * {2 * nv + nu};")
+        A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {2 * nv + nu};")
         A("  const int blocks = (int)((total + threads - 1) / threads);")
         A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
         A("  return (int)cudaGetLastError();")
