@@ -91,6 +91,7 @@ template <> cudaError_t upload_t<DimsLarge>(const b2m_view& v, const int* disabl
   cudaError_t e = cudaMemcpyToSymbolAsync(g_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
   if (e != cudaSuccess) return e;
   if ((e = upload_tri_tables(s)) != cudaSuccess) return e;
+  if ((e = upload_ld_plan(v, s)) != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 

@@ -38,6 +38,25 @@ inline cudaError_t upload_tri_tables(cudaStream_t s) {
   return cudaMemcpyToSymbolAsync(g_tri_col, col, sizeof(col), 0, cudaMemcpyHostToDevice, s);
 }
 
+// Work list of the tree-sparse L'DL factorisation (mj_factorM): for every pivot dof k the ancestor pairs (i, j), j <= i,
+// packed as tri(i,j) | tri(k,j) << 10 | i << 20; g_ld_off[k] .. g_ld_off[k+1] delimits pivot k.  Built on the host when
+// the model image is uploaded, so the factor loop does no index arithmetic.
+static __device__ int g_ld_plan[5456], g_ld_off[33];
+inline cudaError_t upload_ld_plan(const b2m_view& v, cudaStream_t s) {
+  static int plan[5456], off[33];
+  int n = 0;
+  auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
+  for (int k = 0; k < v.nv && k < 32; k++) {
+    off[k] = n;
+    for (int i = v.dof_parentid[k]; i >= 0; i = v.dof_parentid[i])
+      for (int j = i; j >= 0; j = v.dof_parentid[j]) plan[n++] = tri_h(i, j) | (tri_h(k, j) << 10) | (i << 20);
+  }
+  for (int k = v.nv < 32 ? v.nv : 32; k <= 32; k++) off[k] = n;
+  cudaError_t err = cudaMemcpyToSymbolAsync(g_ld_plan, plan, sizeof(int) * (n > 0 ? n : 1), 0, cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return err;
+  return cudaMemcpyToSymbolAsync(g_ld_off, off, sizeof(off), 0, cudaMemcpyHostToDevice, s);
+}
+
 struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
 
 // number of T elements of shared memory one env needs
@@ -47,7 +66,7 @@ template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, 
   const int overlayB = 6 * nv + 6 * nb;
   if (overlayB > overlayA) overlayA = overlayB;
   return (nq + 2 * nv + nu) + (3 + 4 + 9 + 3) * nb + overlayA + 6 * ng + 3 * nb + 10 * nb + 10 * nb + 6 * nv + 6 * nb +
-         2 * np + nv + nt + nt * nv + 11 * nv + 6 * (nv > nb ? nv : nb) + 13 * WarpCaps::NCON;
+         2 * np + 2 * nv + nt + nt * nv + 11 * nv + 6 * (nv > nb ? nv : nb) + 13 * WarpCaps::NCON;
 }
 
 template <typename T, class M>
@@ -56,7 +75,7 @@ struct WarpEnv {
   T *qpos, *qvel, *ctrl, *warm;
   T *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *cdof_dot, *cvel;
   T *geom_xpos, *geom_z, *com, *cinert, *crb, *cdof, *cacc;
-  T *Mp, *LDp, *dinv, *ten_len, *ten_J;
+  T *Mp, *LDp, *dinv, *hdinv, *ten_len, *ten_J;
   T *f_bias, *f_passive, *f_smooth, *f_con, *a_smooth, *qacc, *Ma, *Mv, *grad, *Mgrad, *search, *buf6;
   T *con_dist, *con_pos, *con_frame, *row_pos, *row_margin, *row_D, *row_aref, *Jaref, *Jv;
   int *con_pair, *row_meta;  // row_meta = type | id << 8
@@ -80,7 +99,7 @@ struct WarpEnv {
     p = ov + (ovA > ovB ? ovA : ovB);
     geom_xpos = take(3 * ng); geom_z = take(3 * ng); com = take(3 * nb); cinert = take(10 * nb); crb = take(10 * nb);
     cdof = take(6 * nv); cacc = take(6 * nb);
-    Mp = take(np); LDp = take(np); dinv = take(nv); ten_len = take(nt); ten_J = take(nt * nv);
+    Mp = take(np); LDp = take(np); dinv = take(nv); hdinv = take(nv); ten_len = take(nt); ten_J = take(nt * nv);
     f_bias = take(nv); f_passive = take(nv); f_smooth = take(nv); f_con = take(nv); a_smooth = take(nv); qacc = take(nv);
     Ma = take(nv); Mv = take(nv); grad = take(nv); Mgrad = take(nv); search = take(nv); buf6 = take(6 * (nv > nb ? nv : nb));
     con_dist = take(WarpCaps::NCON); con_pos = take(3 * WarpCaps::NCON); con_frame = take(9 * WarpCaps::NCON);
@@ -287,21 +306,22 @@ struct WarpEnv {
     for (int k = nv - 1; k >= 0; k--) {
       const int m = M::dof_nanc(k);  // proper ancestors of k, nearest first
       const T dkk = LDp[tri(k, k)];
+      // one division sequence per pivot: lanes < m scale their entry of row k, lane m produces 1 / d_k
+      const int i = lane < m ? M::dof_anclist(k * LS + lane) : 0;
+      const T q = (lane < m ? LDp[tri(k, i)] : T(1)) / dkk;
+      if (lane < m) tk[i] = q;
+      if (lane == m) dinv[k] = q;
       if (m) {
-        // t_i = L[k,i] / d_k once per ancestor i, then all ancestor pairs (i, j), j <= i, at once:
-        // L[i,j] -= t_i * L[k,j]   (the unscaled row k, exactly the scalar algorithm's operands)
-        if (lane < m) { const int i = M::dof_anclist(k * LS + lane); tk[i] = LDp[tri(k, i)] / dkk; }
         __syncwarp();
-        for (int e = lane; e < m * m; e += 32) {
-          const int a = e / m, b = e - a * m;
-          if (b < a) continue;  // the list is descending: position b >= a  <=>  dof j <= dof i
-          const int i = M::dof_anclist(k * LS + a), j = M::dof_anclist(k * LS + b);
-          LDp[tri(i, j)] -= tk[i] * LDp[tri(k, j)];
+        // all ancestor pairs (i, j), j <= i, at once: L[i,j] -= t_i * L[k,j]  (the unscaled row k, exactly the scalar
+        // algorithm's operands); the pairs and their packed indices come from the host-built work list
+        for (int e = __ldg(&g_ld_off[k]) + lane, end = __ldg(&g_ld_off[k + 1]); e < end; e += 32) {
+          const int w = __ldg(&g_ld_plan[e]);
+          LDp[w & 1023] -= tk[w >> 20] * LDp[(w >> 10) & 1023];
         }
         __syncwarp();
-        if (lane < m) { const int i = M::dof_anclist(k * LS + lane); LDp[tri(k, i)] = tk[i]; }
+        if (lane < m) LDp[tri(k, i)] = q;
       }
-      if (lane == 0) dinv[k] = T(1) / dkk;
       __syncwarp();
     }
   }
@@ -846,34 +866,38 @@ struct WarpEnv {
       H[e] = h;
     }
     __syncwarp();
-    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop
+    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop.  Lane r owns row
+    // j + 1 + r of the trailing block: the pivot-column operand H[c][j] is a broadcast read, no index inversion.
     for (int j = 0; j < nv; j++) {
       T t = H[tri(j, j)];
       if (t < Num<T>::minval()) t = Num<T>::minval();
       const T djj = sqrt(t), inv = T(1) / djj;
       __syncwarp();
       for (int i = j + lane; i < nv; i += 32) H[tri(i, j)] = (i == j) ? djj : H[tri(i, j)] * inv;
+      if (lane == 0) hdinv[j] = inv;
       __syncwarp();
-      const int m = nv - j - 1;  // trailing block: entries (j+1+a, j+1+b), b <= a
-      for (int e = lane; e < m * (m + 1) / 2; e += 32) {
-        int a, b;
-        untri(e, a, b);
-        H[tri(j + 1 + a, j + 1 + b)] -= H[tri(j + 1 + a, j)] * H[tri(j + 1 + b, j)];
+      const int i = j + 1 + lane;
+      if (i < nv) {
+        T* row = H + tri(i, 0);
+        const T lij = row[j];
+        int cj = tri(j + 1, j);  // packed index of H[c][j]
+        for (int c = j + 1; c <= i; c++) { row[c] -= lij * H[cj]; cj += c + 1; }
       }
       __syncwarp();
     }
     }  // !same
     WFOR(k, nv) Mgrad[k] = grad[k];
     __syncwarp();
+    // two triangular solves; the reciprocal pivots were stored by the factorisation
     for (int j = 0; j < nv; j++) {
-      const T xj = Mgrad[j] / H[tri(j, j)];
+      const T xj = Mgrad[j] * hdinv[j];
       __syncwarp();
       if (lane == 0) Mgrad[j] = xj;
       for (int i = j + 1 + lane; i < nv; i += 32) Mgrad[i] -= H[tri(i, j)] * xj;
       __syncwarp();
     }
     for (int j = nv - 1; j >= 0; j--) {
-      const T xj = Mgrad[j] / H[tri(j, j)];
+      const T xj = Mgrad[j] * hdinv[j];
       __syncwarp();
       if (lane == 0) Mgrad[j] = xj;
       WFOR(i, j) Mgrad[i] -= H[tri(j, i)] * xj;
