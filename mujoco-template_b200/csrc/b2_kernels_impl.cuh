@@ -92,6 +92,7 @@ template <> cudaError_t upload_t<DimsLarge>(const b2m_view& v, const int* disabl
   if (e != cudaSuccess) return e;
   if ((e = upload_tri_tables(s)) != cudaSuccess) return e;
   if ((e = upload_ld_plan(v, s)) != cudaSuccess) return e;
+  if ((e = upload_chol_plan(v.nv, s)) != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
@@ -144,7 +145,9 @@ static int warp_ws_reals_of(const b2m_view* v) {
   return warp_ws_reals<void>(v->nq, v->nv, v->nu, v->nbody, v->njnt, v->ngeom, v->ntendon);
 }
 static size_t warp_block_smem(const b2m_view* v, int wpb) {
-  return (size_t)wpb * ((size_t)warp_ws_reals_of(v) * sizeof(real) + (size_t)kWarpIntsAsReals * sizeof(double));
+  size_t extra = 0;
+  if (const char* x = getenv("B2_WARP_EXTRA_SMEM")) extra = (size_t)atoi(x);  // tuning: lowers the resident blocks per SM
+  return extra + (size_t)wpb * ((size_t)warp_ws_reals_of(v) * sizeof(real) + (size_t)kWarpIntsAsReals * sizeof(double));
 }
 // chooses warps-per-block / grid so that every SM is filled; returns the number of warp slots
 int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks) {

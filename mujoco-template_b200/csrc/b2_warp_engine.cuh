@@ -57,6 +57,25 @@ inline cudaError_t upload_ld_plan(const b2m_view& v, cudaStream_t s) {
   return cudaMemcpyToSymbolAsync(g_ld_off, off, sizeof(off), 0, cudaMemcpyHostToDevice, s);
 }
 
+// Work list of the dense nv x nv Cholesky of the Newton Hessian: for pivot column j the trailing entries (i, c),
+// j < c <= i, packed as tri(i,c) | tri(i,j) << 10 | tri(c,j) << 20; depends on nv only.
+static __device__ int g_chol_plan[5456], g_chol_off[33];
+inline cudaError_t upload_chol_plan(int nv, cudaStream_t s) {
+  static int plan[5456], off[33];
+  int n = 0;
+  auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
+  if (nv > 32) nv = 32;
+  for (int j = 0; j < nv; j++) {
+    off[j] = n;
+    for (int i = j + 1; i < nv; i++)
+      for (int c = j + 1; c <= i; c++) plan[n++] = tri_h(i, c) | (tri_h(i, j) << 10) | (tri_h(c, j) << 20);
+  }
+  for (int j = nv; j <= 32; j++) off[j] = n;
+  cudaError_t err = cudaMemcpyToSymbolAsync(g_chol_plan, plan, sizeof(int) * (n > 0 ? n : 1), 0, cudaMemcpyHostToDevice, s);
+  if (err != cudaSuccess) return err;
+  return cudaMemcpyToSymbolAsync(g_chol_off, off, sizeof(off), 0, cudaMemcpyHostToDevice, s);
+}
+
 struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
 
 // number of T elements of shared memory one env needs
@@ -68,6 +87,81 @@ template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, 
   return (nq + 2 * nv + nu) + (3 + 4 + 9 + 3) * nb + overlayA + 6 * ng + 3 * nb + 10 * nb + 10 * nb + 6 * nv + 6 * nb +
          2 * np + 2 * nv + nt + nt * nv + 11 * nv + 6 * (nv > nb ? nv : nb) + 13 * WarpCaps::NCON;
 }
+
+// in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once; tk: nv scratch reals
+template <typename T, class M>
+__device__ __noinline__ void factor_LD_impl(T* LDp, T* dinv, T* tk, int lane) {
+
+    const int nv = M::nv();
+    constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
+    for (int k = nv - 1; k >= 0; k--) {
+      const int m = M::dof_nanc(k);  // proper ancestors of k, nearest first
+      const T dkk = LDp[tri(k, k)];
+      // one division sequence per pivot: lanes < m scale their entry of row k, lane m produces 1 / d_k
+      const int i = lane < m ? M::dof_anclist(k * LS + lane) : 0;
+      const T q = (lane < m ? LDp[tri(k, i)] : T(1)) / dkk;
+      if (lane < m) tk[i] = q;
+      if (lane == m) dinv[k] = q;
+      if (m) {
+        __syncwarp();
+        // all ancestor pairs (i, j), j <= i, at once: L[i,j] -= t_i * L[k,j]  (the unscaled row k, exactly the scalar
+        // algorithm's operands); the pairs and their packed indices come from the host-built work list
+        for (int e0 = __ldg(&g_ld_off[k]) + lane, end = __ldg(&g_ld_off[k + 1]); e0 < end; e0 += 96) {
+          int w[3];
+          T a[3], b[3], c[3];
+#pragma unroll
+          for (int u = 0; u < 3; u++) w[u] = e0 + 32 * u < end ? __ldg(&g_ld_plan[e0 + 32 * u]) : -1;
+#pragma unroll
+          for (int u = 0; u < 3; u++) if (w[u] >= 0) { a[u] = LDp[w[u] & 1023]; b[u] = tk[w[u] >> 20]; c[u] = LDp[(w[u] >> 10) & 1023]; }
+#pragma unroll
+          for (int u = 0; u < 3; u++) if (w[u] >= 0) LDp[w[u] & 1023] = a[u] - b[u] * c[u];
+        }
+        __syncwarp();
+        if (lane < m) LDp[tri(k, i)] = q;
+      }
+      __syncwarp();
+    }
+  }
+
+// x <- (L'DL)^-1 x, column-oriented sweeps (no reductions).  One out-of-line copy shared by the three call sites:
+// the kernel is instruction-fetch bound (32 % of stall samples were "no instruction"), so code size matters.
+template <typename T, class M>
+__device__ __noinline__ void solve_LD_impl(const T* LDp, const T* dinv, T* x, int lane) {
+
+    const int nv = M::nv();
+    for (int i = nv - 1; i > 0; i--) {
+      const unsigned anc = ((unsigned)M::dof_anc(i)) & ~(1u << i);
+      const T xi = x[i];
+      WFOR(j, i) if ((anc >> j) & 1u) x[j] -= LDp[tri(i, j)] * xi;
+      __syncwarp();
+    }
+    WFOR(i, nv) x[i] *= dinv[i];
+    __syncwarp();
+    for (int j = 0; j < nv - 1; j++) {
+      const T xj = x[j];
+      for (int i = j + 1 + lane; i < nv; i += 32) if (((((unsigned)M::dof_anc(i)) >> j) & 1u)) x[i] -= LDp[tri(i, j)] * xj;
+      __syncwarp();
+    }
+  }
+
+// one evaluation of the exact piecewise-quadratic line-search objective (seven call sites share this copy);
+// out = {alpha, cost, d1, d2}
+template <typename T>
+__device__ __noinline__ void ls_eval_impl(const T* Jaref, const T* Jv, const T* row_D, int nefc, int lane, T qg0, T qg1, T qg2,
+                                          T alpha, T* out) {
+
+    T q0 = 0, q1 = 0, q2 = 0;
+    WFOR(i, nefc) {
+      if (Jaref[i] + alpha * Jv[i] < 0) {
+        const T dj = row_D[i] * Jaref[i];
+        q0 += T(0.5) * Jaref[i] * dj; q1 += Jv[i] * dj; q2 += T(0.5) * Jv[i] * row_D[i] * Jv[i];
+      }
+    }
+    q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
+    T d2 = 2 * q2;
+  if (d2 <= 0) d2 = Num<T>::minval();
+  out[0] = alpha; out[1] = alpha * alpha * q2 + alpha * q1 + q0; out[2] = 2 * alpha * q2 + q1; out[3] = d2;
+  }
 
 template <typename T, class M>
 struct WarpEnv {
@@ -84,6 +178,7 @@ struct WarpEnv {
   int ls_iter;
   unsigned active_sig[(WarpCaps::NEFC + 31) / 32];  // active-row bit set the factor in LDp was built for
   bool hess_valid;
+  int hess_ij[17];  // (row | col << 8) of the packed Hessian entries lane + 32 t this lane owns
 
   B2_DEV void bind(T* base, int* ibase, T* jscratch) {
     const int nq = M::nq(), nv = M::nv(), nu = M::nu(), nb = M::nbody(), nj = M::njnt(), ng = M::ngeom(), nt = M::ntendon();
@@ -111,6 +206,12 @@ struct WarpEnv {
     Jaref = rv + 4 * WarpCaps::NEFC; Jv = rv + 5 * WarpCaps::NEFC;
     lane = threadIdx.x & 31;
     ncon = nefc = niter = flags = 0;
+#pragma unroll
+    for (int t = 0; t < 17; t++) {
+      int i = 0, j = 0;
+      if (lane + 32 * t < np) untri(lane + 32 * t, i, j);
+      hess_ij[t] = i | (j << 8);
+    }
   }
   static B2_DEV bool dof_is_anc(int i, int j) { return (((unsigned)M::dof_anc(i)) >> j) & 1u; }
   static B2_DEV bool in_subtree(int root, int b) { return (((unsigned)M::body_anc(b)) >> root) & 1u; }
@@ -299,49 +400,8 @@ struct WarpEnv {
   }
 
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
-  B2_DEV void factor_LD() {
-    const int nv = M::nv();
-    T* tk = Mv;  // scratch: scaled pivot row (Mv is only live inside the line search)
-    constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
-    for (int k = nv - 1; k >= 0; k--) {
-      const int m = M::dof_nanc(k);  // proper ancestors of k, nearest first
-      const T dkk = LDp[tri(k, k)];
-      // one division sequence per pivot: lanes < m scale their entry of row k, lane m produces 1 / d_k
-      const int i = lane < m ? M::dof_anclist(k * LS + lane) : 0;
-      const T q = (lane < m ? LDp[tri(k, i)] : T(1)) / dkk;
-      if (lane < m) tk[i] = q;
-      if (lane == m) dinv[k] = q;
-      if (m) {
-        __syncwarp();
-        // all ancestor pairs (i, j), j <= i, at once: L[i,j] -= t_i * L[k,j]  (the unscaled row k, exactly the scalar
-        // algorithm's operands); the pairs and their packed indices come from the host-built work list
-        for (int e = __ldg(&g_ld_off[k]) + lane, end = __ldg(&g_ld_off[k + 1]); e < end; e += 32) {
-          const int w = __ldg(&g_ld_plan[e]);
-          LDp[w & 1023] -= tk[w >> 20] * LDp[(w >> 10) & 1023];
-        }
-        __syncwarp();
-        if (lane < m) LDp[tri(k, i)] = q;
-      }
-      __syncwarp();
-    }
-  }
-  // x <- (L'DL)^-1 x, column-oriented sweeps (no reductions)
-  B2_DEV void solve_LD(T* x) {
-    const int nv = M::nv();
-    for (int i = nv - 1; i > 0; i--) {
-      const unsigned anc = ((unsigned)M::dof_anc(i)) & ~(1u << i);
-      const T xi = x[i];
-      WFOR(j, i) if ((anc >> j) & 1u) x[j] -= LDp[tri(i, j)] * xi;
-      __syncwarp();
-    }
-    WFOR(i, nv) x[i] *= dinv[i];
-    __syncwarp();
-    for (int j = 0; j < nv - 1; j++) {
-      const T xj = x[j];
-      for (int i = j + 1 + lane; i < nv; i += 32) if (dof_is_anc(i, j)) x[i] -= LDp[tri(i, j)] * xj;
-      __syncwarp();
-    }
-  }
+  B2_DEV void factor_LD() { factor_LD_impl<T, M>(LDp, dinv, Mv, lane); }  // Mv: scratch, only live inside the line search
+  B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(LDp, dinv, x, lane); }
   B2_DEV void mul_M(T* r, const T* v) {
     const int nv = M::nv();
     WFOR(i, nv) {
@@ -764,16 +824,7 @@ struct WarpEnv {
   struct LsPoint { T alpha, cost, d1, d2; };
   B2_DEV void ls_eval(T alpha, LsPoint& p) {
     ls_iter++;
-    T q0 = 0, q1 = 0, q2 = 0;
-    WFOR(i, nefc) {
-      if (Jaref[i] + alpha * Jv[i] < 0) {
-        const T dj = row_D[i] * Jaref[i];
-        q0 += T(0.5) * Jaref[i] * dj; q1 += Jv[i] * dj; q2 += T(0.5) * Jv[i] * row_D[i] * Jv[i];
-      }
-    }
-    q0 = qg0 + warp_sum(q0); q1 = qg1 + warp_sum(q1); q2 = qg2 + warp_sum(q2);
-    p.alpha = alpha; p.cost = alpha * alpha * q2 + alpha * q1 + q0; p.d1 = 2 * alpha * q2 + q1; p.d2 = 2 * q2;
-    if (p.d2 <= 0) p.d2 = Num<T>::minval();
+    ls_eval_impl<T>(Jaref, Jv, row_D, nefc, lane, qg0, qg1, qg2, alpha, &p.alpha);
   }
   B2_DEV int ls_bracket(LsPoint& p, const LsPoint* cand, LsPoint& pnext) {
     int flag = 0;
@@ -853,21 +904,33 @@ struct WarpEnv {
     }
     hess_valid = true;
     if (!same) {
-    for (int e = lane; e < np; e += 32) {
-      int i, j;
-      untri(e, i, j);
-      T h = Mp[e];
-      for (int r = 0; r < nefc; r++) {
-        if (Jaref[r] >= 0) continue;
-        const T ji = J[r * nv + i];
-        if (ji == 0) continue;
-        h += (row_D[r] * ji) * J[r * nv + j];
+    {
+      // rows outer, entries inner: each lane accumulates its packed entries e = lane + 32 t in registers while the
+      // active rows are visited in increasing order (the summation order of the scalar algorithm)
+      constexpr int EPL = 17;  // ceil(32 * 33 / 2 / 32)
+      T h[EPL];
+#pragma unroll
+      for (int t = 0; t < EPL; t++) h[t] = lane + 32 * t < np ? Mp[lane + 32 * t] : T(0);
+#pragma unroll
+      for (int w = 0; w < (WarpCaps::NEFC + 31) / 32; w++) {
+        for (unsigned bits = sig[w]; bits; bits &= bits - 1) {
+          const int r = w * 32 + __ffs(bits) - 1;
+          const T* Jr = J + r * nv;
+          const T d = row_D[r];
+#pragma unroll
+          for (int t = 0; t < EPL; t++) {
+            if (lane + 32 * t < np) {
+              h[t] += (d * Jr[hess_ij[t] & 255]) * Jr[hess_ij[t] >> 8];
+            }
+          }
+        }
       }
-      H[e] = h;
+#pragma unroll
+      for (int t = 0; t < EPL; t++) if (lane + 32 * t < np) H[lane + 32 * t] = h[t];
     }
     __syncwarp();
-    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop.  Lane r owns row
-    // j + 1 + r of the trailing block: the pivot-column operand H[c][j] is a broadcast read, no index inversion.
+    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop; the trailing-block
+    // entries of every pivot column come from the host-built work list (no index inversion on the device)
     for (int j = 0; j < nv; j++) {
       T t = H[tri(j, j)];
       if (t < Num<T>::minval()) t = Num<T>::minval();
@@ -876,12 +939,16 @@ struct WarpEnv {
       for (int i = j + lane; i < nv; i += 32) H[tri(i, j)] = (i == j) ? djj : H[tri(i, j)] * inv;
       if (lane == 0) hdinv[j] = inv;
       __syncwarp();
-      const int i = j + 1 + lane;
-      if (i < nv) {
-        T* row = H + tri(i, 0);
-        const T lij = row[j];
-        int cj = tri(j + 1, j);  // packed index of H[c][j]
-        for (int c = j + 1; c <= i; c++) { row[c] -= lij * H[cj]; cj += c + 1; }
+      // the trailing entries of one pivot column are independent of each other: four per lane are in flight at once
+      for (int e0 = __ldg(&g_chol_off[j]) + lane, end = __ldg(&g_chol_off[j + 1]); e0 < end; e0 += 128) {
+        int w[4];
+        T a[4], b[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) w[u] = e0 + 32 * u < end ? __ldg(&g_chol_plan[e0 + 32 * u]) : -1;
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (w[u] >= 0) { a[u] = H[w[u] & 1023]; b[u] = H[(w[u] >> 10) & 1023]; c[u] = H[w[u] >> 20]; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (w[u] >= 0) H[w[u] & 1023] = a[u] - b[u] * c[u];
       }
       __syncwarp();
     }
