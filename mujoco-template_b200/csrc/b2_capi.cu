@@ -73,6 +73,7 @@ struct b2_batch {
   // warp engine (large models): -1 not yet decided, 0 lane engine, 1 warp engine
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
+  void* d_warp_counter = nullptr;  // inside d_jscratch
   void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
   cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
@@ -183,8 +184,9 @@ static int prepare_warp(b2_batch* b) {
                         : b2::b2k_warp_plan_f32(&b->model->v, b->nenv, &wpb, &blocks);
   if (slots <= 0) return B2_OK;  // not enough shared memory: stay on the lane engine
   const size_t bytes = f64 ? b2::b2k_warp_scratch_bytes_f64(&b->model->v, slots) : b2::b2k_warp_scratch_bytes_f32(&b->model->v, slots);
-  cudaError_t e = cudaMalloc(&b->d_jscratch, bytes);
+  cudaError_t e = cudaMalloc(&b->d_jscratch, bytes + 256);  // + the work-queue counter of the persistent kernel
   if (e != cudaSuccess) return cuda_fail(e, "warp-engine scratch cudaMalloc");
+  b->d_warp_counter = (char*)b->d_jscratch + bytes;
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
@@ -201,8 +203,8 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
     gain = nullptr;
   }
   if (b->warp_mode == 1 && count == b->nenv)
-    return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream)
-               : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->warp_wpb, b->warp_blocks, stream);
+    return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
   return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream)
              : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream);
 }

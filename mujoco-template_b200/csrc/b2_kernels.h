@@ -8,7 +8,7 @@ namespace b2 {
   double b2k_fma_peak##SUF(void* stream);                                                                                  \
   int b2k_warp_plan##SUF(const b2m_view* v, int N, int* out_wpb, int* out_blocks);                                        \
   size_t b2k_warp_scratch_bytes##SUF(const b2m_view* v, int slots);                                                        \
-  int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,  \
+  int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch, void* counter,  \
                          int wpb, int blocks, void* stream);                                                                                  \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
   int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);                  \

@@ -170,10 +170,13 @@ size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
   return (size_t)slots * WarpCaps::NEFC * (v->nv + 6) * sizeof(real);
 }
 int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
-                         int wpb, int blocks, void* stream) {
+                         void* counter, int wpb, int blocks, void* stream) {
   const size_t smem = warp_block_smem(v, wpb);
+  // envs are handed out through a work queue: the first gridDim * wpb statically, the rest by atomic counter
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
   k_warp_step<real, GlobalModelLarge><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-      to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, warp_ws_reals_of(v));
+      to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,

@@ -27,7 +27,7 @@ B2_DEV void warp_store_derived(const WarpEnv<T, M>& env, const DerivedDev<T>& o,
 // nsteps x mj_step (nsteps == 0: mj_forward) for envs gw, gw + nwarps, ...; one env per warp
 template <typename T, class M>
 __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps,
-                                                  T* jscratch, int ws_reals) {
+                                                  T* jscratch, int* queue, int ws_reals) {
   extern __shared__ double b2_smem[];
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> 
   WarpEnv<T, M> env;
   env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
   const int total = nsteps > 0 ? nsteps : 1;
-  for (int e = gw; e < N; e += nw) {
+  // dynamic scheduling: env costs differ (contacts, Newton iterations), a static stride leaves SMs idle at the tail
+  for (int e = gw; e < N; e = nw + __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(queue, 1) : 0, 0)) {
     WFOR(k, M::nq()) env.qpos[k] = st.qpos[(size_t)k * N + e];
     WFOR(k, M::nv()) { env.qvel[k] = st.qvel[(size_t)k * N + e]; env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
     WFOR(k, M::nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
