@@ -122,9 +122,10 @@ int b2_lqr_control(b2_batch* batch, const b2_state* state, void* stream);
 /* One control tick of the reference's step loop (mujoco_template/env.py:177-191: controller, then (A, B) for a
  * needs_linearization controller, then mj_step) for the whole batch: with use_lqr != 0 the control law set by
  * b2_lqr_set_gain produces the controls; A/B as in b2_linearize at those controls; then one step as in b2_step,
- * which also writes the applied controls to state.ctrl.  Two launches: the FD kernel and the step kernel each
- * evaluate the control law from (qpos, qvel) themselves, so there is no separate controller launch.
- * (B2_SINGLE_LAUNCH_TICK=1 selects an experimental one-launch kernel for models with <= 7 FD columns.) */
+ * which also writes the applied controls to state.ctrl.  The kernels evaluate the control law from (qpos, qvel)
+ * themselves, so there is no separate controller launch: two launches per tick (FD kernel, step kernel).
+ * (B2_MERGED_TICK=1: for small specialised models the step rides in the FD launch as one more column, advanced
+ * state to a shadow buffer committed by a second, tiny launch -- same results, measured slower.) */
 int b2_control_tick(b2_batch* batch, const b2_state* state, const b2_derived* derived, int use_lqr, double eps,
                     int centered, void* A, void* B, void* stream);
 

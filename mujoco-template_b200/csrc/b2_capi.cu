@@ -74,6 +74,7 @@ struct b2_batch {
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
   void* d_warp_counter = nullptr;  // inside d_jscratch
+  void* d_shadow = nullptr;        // shadow state of the merged FD + step launch (b2_control_tick)
   void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
   cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
@@ -151,7 +152,7 @@ int b2_batch_create(const b2_model* model, int nenv, int device, int precision, 
 }
 void b2_batch_destroy(b2_batch* b) {
   if (!b) return;
-  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch, b->d_gain};
+  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch, b->d_gain, b->d_shadow};
   for (void* q : p) if (q) cudaFree(q);
   if (b->host_graph) cudaGraphExecDestroy(b->host_graph);
   if (b->pipe_ready) { for (cudaStream_t st : b->pipe) cudaStreamDestroy(st); for (cudaEvent_t ev : b->pipe_ev) cudaEventDestroy(ev); }
@@ -347,8 +348,10 @@ int b2_lqr_control(b2_batch* b, const b2_state* st, void* stream) {
 }
 
 // One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).
-// A single fused launch when the model has a specialised k_tick; otherwise the same three launches a caller
-// would issue (b2_lqr_control, b2_linearize, b2_step), so the result does not depend on which path ran.
+// The FD and step kernels run back to back and evaluate the control law themselves (no controller launch).
+// B2_MERGED_TICK=1 (small specialised models): the step rides in the FD launch as an extra column and a tiny kernel
+// commits the shadow state (k_linearize_step + k_commit_state); same results, measured slower because the extra
+// path raises the FD kernel's register spills.
 int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, int use_lqr, double eps, int centered,
                     void* A, void* B, void* stream) {
   B2_CHECK_STATE("b2_control_tick");
@@ -356,12 +359,17 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
   if (!A && !B) return fail(B2_ERR_ARG, "b2_control_tick: A and B are both NULL");
   if (use_lqr && !b->d_gain) return fail(B2_ERR_ARG, "b2_control_tick: call b2_lqr_set_gain first");
   const b2::SpecKernels* k = active_spec(b);
-  const char* one = getenv("B2_SINGLE_LAUNCH_TICK");  // measured slower than the two launches below on B200
-  if (k && k->tick[prec_index(b)] && one && one[0] == '1') {
+  const char* merged = getenv("B2_MERGED_TICK");  // measured slower on B200 (70 vs 62 us per cartpole tick): opt-in
+  if (k && k->tick[prec_index(b)] && merged && merged[0] == '1') {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    const int rc = k->tick[prec_index(b)](st, derived, b->nenv, b->nenv, eps, centered, A, B, use_lqr ? b->d_gain : nullptr, stream);
-    g_launches++;
+    const b2m_view& v = b->model->v;
+    const size_t N = (size_t)b->nenv, es = b->esz, nu1 = v.nu ? v.nu : 1;
+    if (!b->d_shadow && (e = cudaMalloc(&b->d_shadow, (v.nq + 2 * (size_t)v.nv + nu1) * N * es))) return cuda_fail(e, "b2_control_tick: cudaMalloc");
+    char* p = (char*)b->d_shadow;
+    const b2_state shadow = {p, p + v.nq * N * es, p + (v.nq + v.nv) * N * es, p + (v.nq + v.nv + nu1) * N * es, nullptr};
+    const int rc = k->tick[prec_index(b)](st, &shadow, derived, b->nenv, b->nenv, eps, centered, A, B, use_lqr ? b->d_gain : nullptr, stream);
+    g_launches += 2;
     return rc ? cuda_fail((cudaError_t)rc, "control tick launch") : B2_OK;
   }
   // two launches: both kernels evaluate the control law themselves from (qpos, qvel) -- the FD kernel linearises about
@@ -414,7 +422,8 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   if (rc) return rc;
   if ((!active_spec(b) || lqr) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
   // chunking: warp-engine batches and small batches go through in one piece
-  int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 4;
+  // two chunks measured best at N = 65536 (1.72e8 vs 1.55e8 with 4, 0.94e8 with 16): every extra chunk adds ~11 copy nodes
+  int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 2;
   if (const char* env_chunks = getenv("B2_HOST_CHUNKS")) { const int c = atoi(env_chunks); if (c >= 1 && c <= 64 && nchunk > 1) nchunk = c; }
   if (!b->pipe_ready) {
     for (int i = 0; i < 3; i++) if ((e = cudaStreamCreateWithFlags(&b->pipe[i], cudaStreamNonBlocking))) return cuda_fail(e, "cudaStreamCreate");

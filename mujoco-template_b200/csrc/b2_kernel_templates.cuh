@@ -24,13 +24,6 @@
 namespace b2 {
 
 template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
-#ifndef B2_TICK_WARPS
-#define B2_TICK_WARPS 8
-#endif
-#ifndef B2_TICK_MIN_BLOCKS
-#define B2_TICK_MIN_BLOCKS 1
-#endif
-
 template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias, *sensordata; int *ncon, *nefc, *solver_iter; };
 
 template <typename T>
@@ -154,7 +147,7 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
 // c < nv: tangent-space position column, c < 2nv: velocity column, else control column c - 2nv.
 // q0/v0/u0/w0: the env's nominal state in registers.  nominal: run the plain step, export derived arrays from
 // its pre-integration forward pass and leave the advanced state in env.qpos / env.qvel / env.warm.
-// The nominal state of a thread's env: held in registers (k_tick, which overwrites the state in place) ...
+// The nominal state of a thread's env: held in registers ...
 template <typename T>
 struct NominalInRegisters {
   const T *q0, *v0, *u0, *w0;
@@ -281,43 +274,63 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
 }
 
-// One control tick of a whole batch in ONE launch: [LQR control law] -> FD (A, B) at the new controls -> one step.
-// Block = 32 envs x (ncol + 1) warps: warp w < ncol computes FD column w of its 32 envs, the last warp advances them.
-// All warps load the nominal state first; the barrier orders those loads before the last warp's in-place write-back,
-// so no shadow copy of the state is needed.  Equivalent to k_lqr_control + k_linearize + k_step(nsteps = 1)
-// (reference env.py:177-191: controller, then (A, B), then step).
+// One control tick of a whole batch: [LQR control law] -> FD (A, B) at the new controls -> one step, the step riding in the
+// FD launch as an extra "column": thread (e, c) with c == ncol advances env e.  The FD columns of an env keep reading its
+// nominal state throughout the launch, so the advanced state goes to shadow arrays and k_commit_state copies it back
+// afterwards.  The extra blocks are the last of the grid and do one rollout where an FD column does two: they fill the
+// tail of the FD launch instead of paying for a launch of their own at a batch size that cannot fill the GPU.
+// Equivalent to k_lqr_control + k_linearize + k_step(nsteps = 1) (reference env.py:177-191: controller, (A, B), step).
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(32 * B2_TICK_WARPS, B2_TICK_MIN_BLOCKS)
-k_tick(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
-  constexpr int NQ = D::NQ, NV = D::NV, NU = D::NU;
+__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS)
+k_linearize_step(StateDev<T> st, StateDev<T> shadow, DerivedDev<T> out, int want_derived, int count, int N, T eps, int centered,
+                 T* A, T* B, const T* __restrict__ gain) {
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ncol = 2 * nv + nu;
-  const int e = blockIdx.x * 32 + threadIdx.x, c = threadIdx.y;
-  const bool live = e < count, nominal = c == ncol;
-  const int el = live ? e : 0;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)count * (ncol + 1)) return;
+  const int e = (int)(idx % count), c = (int)(idx / count);
+  const bool nominal = c == ncol;
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
-  T q0[NQ], v0[NV], u0[NU], w0[NV];
-  B2_UNROLL
-  for (int k = 0; k < nq; k++) q0[k] = st.qpos[(size_t)k * N + el];
-  B2_UNROLL
-  for (int k = 0; k < nv; k++) { v0[k] = st.qvel[(size_t)k * N + el]; w0[k] = st.warm ? st.warm[(size_t)k * N + el] : T(0); }
-  if (gain) lqr_law(env, q0, v0, gain, u0);
-  else { B2_UNROLL for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + el]; }
-  __syncthreads();
-  if (!live) return;
-  DerivedDev<T> none;
-  memset(&none, 0, sizeof(none));
-  const NominalInRegisters<T> nom{q0, v0, u0, w0};
-  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, nominal ? out : none, want_derived);
+  T u0[D::NU];
+  if (gain) {
+    T q[D::NQ], v[D::NV];
+    B2_UNROLL
+    for (int k = 0; k < nq; k++) q[k] = st.qpos[(size_t)k * N + e];
+    B2_UNROLL
+    for (int k = 0; k < nv; k++) v[k] = st.qvel[(size_t)k * N + e];
+    lqr_law(env, q, v, gain, u0);
+  } else {
+    B2_UNROLL
+    for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
+  }
+  const NominalInMemory<T> nom{st, N, e, u0};
+  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, out, want_derived);
   if (nominal) {
     B2_UNROLL
-    for (int k = 0; k < nq; k++) st.qpos[(size_t)k * N + e] = env.qpos[k];
+    for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];
     B2_UNROLL
-    for (int k = 0; k < nv; k++) st.qvel[(size_t)k * N + e] = env.qvel[k];
-    if (st.warm) { B2_UNROLL for (int k = 0; k < nv; k++) st.warm[(size_t)k * N + e] = env.warm[k]; }
-    if (gain) { B2_UNROLL for (int k = 0; k < nu; k++) st.ctrl[(size_t)k * N + e] = u0[k]; }
+    for (int k = 0; k < nv; k++) { shadow.qvel[(size_t)k * N + e] = env.qvel[k]; shadow.warm[(size_t)k * N + e] = env.warm[k]; }
+    B2_UNROLL
+    for (int k = 0; k < nu; k++) shadow.ctrl[(size_t)k * N + e] = u0[k];
   }
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
+}
+
+// shadow -> state after k_linearize_step (rows of count elements, row stride N)
+template <typename T>
+__global__ void __launch_bounds__(256) k_commit_state(StateDev<T> st, StateDev<T> shadow, int count, int N, int nq, int nv, int nu) {
+  const long long total = (long long)count * (nq + 2 * nv + nu);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    int row = (int)(i / count);
+    const size_t at = (size_t)(i - (long long)row * count);
+    if (row < nq) { st.qpos[(size_t)row * N + at] = shadow.qpos[(size_t)row * N + at]; continue; }
+    row -= nq;
+    if (row < nv) { st.qvel[(size_t)row * N + at] = shadow.qvel[(size_t)row * N + at]; continue; }
+    row -= nv;
+    if (row < nv) { if (st.warm) st.warm[(size_t)row * N + at] = shadow.warm[(size_t)row * N + at]; continue; }
+    row -= nv;
+    st.ctrl[(size_t)row * N + at] = shadow.ctrl[(size_t)row * N + at];
+  }
 }
 
 // point Jacobians from the current qpos (mj_jacSite/Body/BodyCom/SubtreeCom)

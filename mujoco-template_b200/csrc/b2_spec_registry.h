@@ -17,10 +17,10 @@ struct SpecKernels {
   int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);
   int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream);
   int (*jacobian[2])(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
-  // fused control tick (LQR law -> FD (A, B) -> one step) in one launch; null when the model has too many FD
-  // columns for one block (ncol + 1 warps)
-  int (*tick[2])(const b2_state* st, const b2_derived* out, int count, int N, double eps, int centered, void* A, void* B,
-                 const void* gain, void* stream);
+  // control tick with the step riding in the FD launch (k_linearize_step + k_commit_state); null for larger models.
+  // shadow: scratch state arrays (qpos, qvel, ctrl, qacc_warmstart) of the same shape as st
+  int (*tick[2])(const b2_state* st, const b2_state* shadow, const b2_derived* out, int count, int N, double eps, int centered,
+                 void* A, void* B, const void* gain, void* stream);
 };
 
 void register_spec(const SpecKernels* k);

@@ -119,10 +119,7 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"#define B2_LIN_THREADS {lin_threads}")
     A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
     ncol = 2 * nv + nu
-    fused_tick = ncol + 1 <= 8  # one block = 32 envs x (ncol + 1) warps must fit the register file
-    if fused_tick:
-        A(f"#define B2_TICK_WARPS {ncol + 1}")
-        A("#define B2_TICK_MIN_BLOCKS 2")
+    fused_tick = nv <= 2  # small models: the step rides in the FD launch (k_linearize_step)
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
     A("")
@@ -168,9 +165,11 @@ def emit_spec(compiled: dict, name: str) -> str:
         A("  return (int)cudaGetLastError();")
         A("}")
         if fused_tick:
-            A(f"int spec_tick{suf}(const b2_state* st, const b2_derived* out, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
-            A(f"  const dim3 block(32, {ncol + 1}); const int blocks = (count + 31) / 32;")
-            A(f"  k_tick<{T}, SDims, SModel<{T}>><<<blocks, block, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
+            A(f"int spec_tick{suf}(const b2_state* st, const b2_state* shadow, const b2_derived* out, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
+            A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {ncol + 1};")
+            A("  const int blocks = (int)((total + threads - 1) / threads);")
+            A(f"  k_linearize_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(shadow), to_dev<{T}>(out), out != nullptr, count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
+            A(f"  k_commit_state<{T}><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(shadow), count, N, {nq}, {nv}, {nu});")
             A("  return (int)cudaGetLastError();")
             A("}")
     tick = "{spec_tick, spec_tick32}" if fused_tick else "{nullptr, nullptr}"

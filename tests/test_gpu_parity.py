@@ -504,13 +504,13 @@ def test_batched_recorder_matches_single_env_csv(tmp_path):
 
 @pytest.mark.parametrize("name,n", [("cartpole", 1000), ("pendulum", 33)])
 @pytest.mark.parametrize("precision", [64, 32])
-@pytest.mark.parametrize("single_launch", [False, True])
-def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, precision, single_launch):
-    """b2_control_tick (control law evaluated inside the FD and step kernels: two launches; or the experimental
-    one-launch kernel) == b2_lqr_control, b2_linearize, b2_step in sequence, and the FP64 result matches the oracle
-    driven by the same control law."""
-    if single_launch:
-        monkeypatch.setenv("B2_SINGLE_LAUNCH_TICK", "1")
+@pytest.mark.parametrize("merged", [False, True])
+def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, precision, merged):
+    """b2_control_tick (control law evaluated inside the FD and step kernels -- or, with B2_MERGED_TICK=1, the step
+    riding in the FD launch and a commit kernel copying the shadow state back) == b2_lqr_control, b2_linearize,
+    b2_step in sequence, and the FP64 result matches the oracle driven by the same control law."""
+    if merged:
+        monkeypatch.setenv("B2_MERGED_TICK", "1")
     import torch
     import mujoco_template as mt
 
@@ -532,7 +532,7 @@ def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, p
             res = benv.step(return_obs=False)
             hist.append((res.info["A"].clone(), res.info["B"].clone(), benv.data.qpos.clone(), benv.data.qvel.clone(),
                          benv.data.ctrl.clone(), benv.data.qacc.clone(), benv.data.xpos.clone()))
-        assert mt._capi.launch_count() - c0 == ((5 if single_launch else 10) if fused else 15)
+        assert mt._capi.launch_count() - c0 == (10 if fused else 15)
         out[fused] = hist
     tol = 1e-12 if precision == 64 else 2e-4
     for a, b in zip(out[True], out[False]):
