@@ -250,7 +250,8 @@ static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const
 static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, int centered, void* A, void* B, void* stream,
                         const void* gain = nullptr) {
   int rc;
-  const int ncol = 2 * b->model->v.nv + b->model->v.nu;
+  // FD tasks per env: see k_linearize (Euler: one thread for all velocity / control columns + one per position column)
+  const int ncol = b->model->v.integrator == 0 ? b->model->v.nv + 1 : 2 * b->model->v.nv + b->model->v.nu;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");

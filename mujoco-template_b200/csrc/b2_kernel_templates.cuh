@@ -138,11 +138,8 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
   if (st.flags && env.flags) st.flags[e] |= env.flags;
 }
 
-// Centred / one-sided finite differences of one step: one thread per (env, input column).
-// Columns 0..nv-1 perturb tangent-space position, nv..2nv-1 velocity, 2nv..2nv+nu-1 control.
-// Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state and
-// qacc_warmstart of every rollout start from the saved nominal values; control columns fall
-// back to one-sided differences at the ctrlrange bounds.
+// number of FD threads per env (see k_linearize)
+template <class M> B2_DEV int fd_tasks() { return M::integrator() == 0 ? M::nv() + 1 : 2 * M::nv() + M::nu(); }
 // One column of the FD linearisation (or, with nominal = true, the unperturbed step itself) for env e.
 // c < nv: tangent-space position column, c < 2nv: velocity column, else control column c - 2nv.
 // q0/v0/u0/w0: the env's nominal state in registers.  nominal: run the plain step, export derived arrays from
@@ -171,7 +168,7 @@ struct NominalInMemory {
 
 template <typename T, class D, class M, class S>
 B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
-                      T eps, int centered, int N, int e, T* A, T* B, const DerivedDev<T>& out, int want_derived) {
+                      T eps, int centered, int N, int e, T* A, T* B, const DerivedDev<T>& out, int want_derived, bool& pos_valid) {
   constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
@@ -191,8 +188,8 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     back = (centered || !fwd) && (!lim || (u - eps >= lo && u - eps <= hi && u >= lo && u <= hi));
   }
   const int need = nominal ? 4 : ((fwd ? 1 : 0) | (back ? 2 : 0) | ((fwd != back) ? 4 : 0));  // plus, minus, nominal rollouts
-  // rolled phase loop: the physics is instantiated once; all array indices stay static
-  bool pos_valid = false;
+  // rolled phase loop: the physics is instantiated once; all array indices stay static.  pos_valid (owned by the
+  // caller) says that env already holds the position stage of the nominal qpos from an earlier rollout of this thread
   B2_NOUNROLL
   for (int phase = 0; phase < 3; phase++) {
     if (!((need >> phase) & 1)) continue;
@@ -242,17 +239,20 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
   else if (B) { B2_UNROLL for (int r = 0; r < ndx; r++) B[((size_t)r * nu + (c - ndx)) * N + e] = col[r]; }
 }
 
-// Centred / one-sided finite differences of one step: one thread per (env, input column).
-// Columns 0..nv-1 perturb tangent-space position, nv..2nv-1 velocity, 2nv..2nv+nu-1 control.
-// Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state and
-// qacc_warmstart of every rollout start from the saved nominal values; control columns fall
-// back to one-sided differences at the ctrlrange bounds.
+// Centred / one-sided finite differences of one step.  Columns 0..nv-1 perturb tangent-space position, nv..2nv-1
+// velocity, 2nv..2nv+nu-1 control.  Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state
+// and qacc_warmstart of every rollout start from the saved nominal values; control columns fall back to one-sided
+// differences at the ctrlrange bounds.
+// Work split: under Euler the velocity and control columns all share the position stage of the nominal qpos, so ONE
+// thread per env runs that stage once and then the 2 (nv + nu) velocity / control rollouts (task 0, launched first: it
+// is the longest); each position column is a thread of its own (tasks 1..nv, two full rollouts).  RK4 models have
+// nothing to share between columns: one thread per (env, column).
 template <typename T, class D, class M>
 __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)count * (ndx + nu)) return;
-  const int e = (int)(idx % count), c = (int)(idx / count);  // count envs, env stride N
+  if (idx >= (long long)count * fd_tasks<M>()) return;
+  const int e = (int)(idx % count), task = (int)(idx / count);  // count envs, env stride N
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
   DerivedDev<T> none;
@@ -270,7 +270,12 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
     for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
   }
   const NominalInMemory<T> nom{st, N, e, u0};
-  fd_column(env, nom, c, false, eps, centered, N, e, A, B, none, 0);
+  const bool grouped = M::integrator() == 0;  // not a constant expression for the runtime provider
+  const int c0 = !grouped ? task : (task == 0 ? nv : task - 1);
+  const int c1 = !grouped ? task + 1 : (task == 0 ? ndx + nu : task);
+  bool pos_valid = false;
+  B2_NOUNROLL
+  for (int c = c0; c < c1; c++) fd_column(env, nom, c, false, eps, centered, N, e, A, B, none, 0, pos_valid);
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
 }
 
@@ -304,7 +309,8 @@ k_linearize_step(StateDev<T> st, StateDev<T> shadow, DerivedDev<T> out, int want
     for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
   }
   const NominalInMemory<T> nom{st, N, e, u0};
-  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, out, want_derived);
+  bool pos_valid = false;
+  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, out, want_derived, pos_valid);
   if (nominal) {
     B2_UNROLL
     for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];

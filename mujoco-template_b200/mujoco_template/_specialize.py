@@ -119,6 +119,7 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"#define B2_LIN_THREADS {lin_threads}")
     A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
     ncol = 2 * nv + nu
+    fd_tasks = nv + 1 if int(c["integrator"]) == 0 else ncol  # k_linearize: Euler groups the velocity / control columns
     fused_tick = nv <= 2  # small models: the step rides in the FD launch (k_linearize_step)
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
@@ -154,7 +155,7 @@ def emit_spec(compiled: dict, name: str) -> str:
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
-        A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {2 * nv + nu};")
+        A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {fd_tasks};")
         A("  const int blocks = (int)((total + threads - 1) / threads);")
         A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
         A("  return (int)cudaGetLastError();")
