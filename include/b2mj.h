@@ -121,13 +121,17 @@ int b2_lqr_control(b2_batch* batch, const b2_state* state, void* stream);
 
 /* One control tick of the reference's step loop (mujoco_template/env.py:177-191: controller, then (A, B) for a
  * needs_linearization controller, then mj_step) for the whole batch: with use_lqr != 0 the control law set by
- * b2_lqr_set_gain produces the controls; A/B as in b2_linearize at those controls; then one step as in b2_step,
- * which also writes the applied controls to state.ctrl.  The kernels evaluate the control law from (qpos, qvel)
- * themselves, so there is no separate controller launch: two launches per tick (FD kernel, step kernel).
- * (B2_MERGED_TICK=1: for small specialised models the step rides in the FD launch as one more column, advanced
- * state to a shadow buffer committed by a second, tiny launch -- same results, measured slower.) */
+ * b2_lqr_set_gain produces the controls (written to state.ctrl); A/B as in b2_linearize at those controls; then one
+ * step as in b2_step.  The kernels evaluate the control law themselves, so there is no controller launch.
+ * derived == NULL on an Euler model: the step rides in the FD launch (the thread that owns an env's velocity / control
+ * columns shares its position stage with the step) plus a small commit launch; the derived arrays of that step can
+ * still be obtained afterwards with b2_refresh_derived.  Otherwise: FD launch, then step launch. */
 int b2_control_tick(b2_batch* batch, const b2_state* state, const b2_derived* derived, int use_lqr, double eps,
                     int centered, void* A, void* B, void* stream);
+
+/* Derived arrays of the last b2_control_tick(derived = NULL): exactly what mj_step leaves in mjData after that step
+ * (the forward pass of the pre-step state, which the tick kept).  Error if there is no such tick. */
+int b2_refresh_derived(b2_batch* batch, const b2_derived* derived, void* stream);
 
 /* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */
 int b2_integrate_pos(b2_batch* batch, void* qpos, const void* qvel, double dt, void* stream);

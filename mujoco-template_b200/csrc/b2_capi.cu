@@ -74,7 +74,8 @@ struct b2_batch {
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
   void* d_warp_counter = nullptr;  // inside d_jscratch
-  void* d_shadow = nullptr;        // shadow state of the merged FD + step launch (b2_control_tick)
+  void* d_shadow = nullptr;        // shadow state of the FD launch that also advances the envs (b2_control_tick)
+  bool shadow_has_prestep = false;
   void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
   cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
@@ -248,19 +249,19 @@ static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const
   return rc ? cuda_fail((cudaError_t)rc, "step launch") : B2_OK;
 }
 static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, int centered, void* A, void* B, void* stream,
-                        const void* gain = nullptr) {
+                        const void* gain = nullptr, const b2_state* shadow = nullptr) {
   int rc;
   // FD tasks per env: see k_linearize (Euler: one thread for all velocity / control columns + one per position column)
   const int ncol = b->model->v.integrator == 0 ? b->model->v.nv + 1 : 2 * b->model->v.nv + b->model->v.nu;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, gain, stream);
+    rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, gain, shadow, stream);
   } else {
     rc = ensure_resident(b, stream);
     if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, stream)
-                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, stream);
+    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream)
+                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream);
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "linearize launch") : B2_OK;
@@ -348,37 +349,62 @@ int b2_lqr_control(b2_batch* b, const b2_state* st, void* stream) {
   return do_lqr_control(b, st, b->nenv, stream);
 }
 
-// One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).
-// The FD and step kernels run back to back and evaluate the control law themselves (no controller launch).
-// B2_MERGED_TICK=1 (small specialised models): the step rides in the FD launch as an extra column and a tiny kernel
-// commits the shadow state (k_linearize_step + k_commit_state); same results, measured slower because the extra
-// path raises the FD kernel's register spills.
+// Shadow state arrays of a batch (same shapes as the caller's): target of the env advance that rides in the FD launch.
+static int shadow_state(b2_batch* b, b2_state* out) {
+  const b2m_view& v = b->model->v;
+  const size_t N = (size_t)b->nenv, es = b->esz, nu1 = v.nu ? v.nu : 1;
+  if (!b->d_shadow) {
+    cudaError_t e = cudaMalloc(&b->d_shadow, (v.nq + 2 * (size_t)v.nv + nu1) * N * es);
+    if (e != cudaSuccess) return cuda_fail(e, "shadow state cudaMalloc");
+  }
+  char* p = (char*)b->d_shadow;
+  *out = b2_state{p, p + v.nq * N * es, p + (v.nq + v.nv) * N * es, p + (v.nq + v.nv + nu1) * N * es, nullptr};
+  return B2_OK;
+}
+
+// One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).  The kernels
+// evaluate the control law themselves (no controller launch).
+//  * derived == NULL and an Euler model: ONE physics launch.  The FD thread that owns an env's velocity / control columns
+//    has already run the position stage of the nominal state, so it also does the step (one more rollout instead of a
+//    k_step launch that cannot fill the GPU at this batch size) and writes the new state to the batch's shadow arrays;
+//    k_commit_state then swaps state and shadow.  The pre-step state stays in the shadow, so b2_refresh_derived can
+//    still produce the derived arrays of this tick on demand.
+//  * otherwise: FD kernel, then step kernel (which exports the derived arrays).
 int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, int use_lqr, double eps, int centered,
                     void* A, void* B, void* stream) {
   B2_CHECK_STATE("b2_control_tick");
   if (!(eps > 0)) return fail(B2_ERR_LINEARIZE, "b2_control_tick: eps must be > 0");
   if (!A && !B) return fail(B2_ERR_ARG, "b2_control_tick: A and B are both NULL");
   if (use_lqr && !b->d_gain) return fail(B2_ERR_ARG, "b2_control_tick: call b2_lqr_set_gain first");
-  const b2::SpecKernels* k = active_spec(b);
-  const char* merged = getenv("B2_MERGED_TICK");  // measured slower on B200 (70 vs 62 us per cartpole tick): opt-in
-  if (k && k->tick[prec_index(b)] && merged && merged[0] == '1') {
-    cudaError_t e = cudaSetDevice(b->device);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    const b2m_view& v = b->model->v;
-    const size_t N = (size_t)b->nenv, es = b->esz, nu1 = v.nu ? v.nu : 1;
-    if (!b->d_shadow && (e = cudaMalloc(&b->d_shadow, (v.nq + 2 * (size_t)v.nv + nu1) * N * es))) return cuda_fail(e, "b2_control_tick: cudaMalloc");
-    char* p = (char*)b->d_shadow;
-    const b2_state shadow = {p, p + v.nq * N * es, p + (v.nq + v.nv) * N * es, p + (v.nq + v.nv + nu1) * N * es, nullptr};
-    const int rc = k->tick[prec_index(b)](st, &shadow, derived, b->nenv, b->nenv, eps, centered, A, B, use_lqr ? b->d_gain : nullptr, stream);
-    g_launches += 2;
-    return rc ? cuda_fail((cudaError_t)rc, "control tick launch") : B2_OK;
-  }
-  // two launches: both kernels evaluate the control law themselves from (qpos, qvel) -- the FD kernel linearises about
-  // those controls, the step kernel applies them and writes them to state.ctrl -- so no separate controller launch
   const void* gain = use_lqr ? b->d_gain : nullptr;
+  const b2m_view& v = b->model->v;
+  b->shadow_has_prestep = false;
+  if (!derived && v.integrator == 0 && st->qacc_warmstart && (v.nu == 0 || st->ctrl)) {
+    b2_state shadow;
+    int rc = shadow_state(b, &shadow);
+    if (rc) return rc;
+    if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream, gain, &shadow))) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_commit_state_f64(st, &shadow, b->nenv, b->nenv, v.nq, v.nv, v.nu, stream)
+                                : b2::b2k_commit_state_f32(st, &shadow, b->nenv, b->nenv, v.nq, v.nv, v.nu, stream);
+    g_launches++;
+    if (rc) return cuda_fail((cudaError_t)rc, "commit launch");
+    b->shadow_has_prestep = true;
+    return B2_OK;
+  }
   int rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream, gain);
   if (rc) return rc;
   return do_step(b, st, b->nenv, 1, derived, stream, gain);
+}
+
+// Derived arrays (xpos, ..., sensordata) of the last b2_control_tick that ran without a `derived` argument: what mj_step
+// leaves in mjData after that step, i.e. the forward pass of the PRE-step state, which the tick kept in its shadow arrays.
+int b2_refresh_derived(b2_batch* b, const b2_derived* derived, void* stream) {
+  if (!b || !derived) return fail(B2_ERR_ARG, "b2_refresh_derived: null pointer");
+  if (!b->shadow_has_prestep) return fail(B2_ERR_ARG, "b2_refresh_derived: no control tick without derived outputs to refresh");
+  b2_state shadow;
+  int rc = shadow_state(b, &shadow);
+  if (rc) return rc;
+  return do_step(b, &shadow, b->nenv, 0, derived, stream);
 }
 
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {

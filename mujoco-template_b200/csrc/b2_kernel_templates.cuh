@@ -29,6 +29,7 @@ template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *
 template <typename T>
 static inline StateDev<T> to_dev(const b2_state* s) {
   StateDev<T> d;
+  if (!s) { d.qpos = d.qvel = d.ctrl = d.warm = nullptr; d.flags = nullptr; return d; }
   d.qpos = (T*)s->qpos; d.qvel = (T*)s->qvel; d.ctrl = (T*)s->ctrl; d.warm = (T*)s->qacc_warmstart; d.flags = s->flags;
   return d;
 }
@@ -140,35 +141,26 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
 
 // number of FD threads per env (see k_linearize)
 template <class M> B2_DEV int fd_tasks() { return M::integrator() == 0 ? M::nv() + 1 : 2 * M::nv() + M::nu(); }
-// One column of the FD linearisation (or, with nominal = true, the unperturbed step itself) for env e.
-// c < nv: tangent-space position column, c < 2nv: velocity column, else control column c - 2nv.
-// q0/v0/u0/w0: the env's nominal state in registers.  nominal: run the plain step, export derived arrays from
-// its pre-integration forward pass and leave the advanced state in env.qpos / env.qvel / env.warm.
-// The nominal state of a thread's env: held in registers ...
-template <typename T>
-struct NominalInRegisters {
-  const T *q0, *v0, *u0, *w0;
-  B2_DEV T q(int k) const { return q0[k]; }
-  B2_DEV T v(int k) const { return v0[k]; }
-  B2_DEV T u(int k) const { return u0[k]; }
-  B2_DEV T w(int k) const { return w0[k]; }
-};
-// ... or re-read from the SoA arrays at the start of every rollout (k_linearize: L1/L2 hits, and ~14 fewer live
-// registers across the physics, which is what the 168-register budget of three resident blocks is short of)
+// The nominal state of a thread's env is re-read from the SoA arrays at the start of every rollout (L1/L2 hits) rather
+// than held in registers: ~14 fewer live registers across the physics, which is what the 168-register budget of three
+// resident blocks is short of.  The controls are the exception (they may come from the control law, not from st.ctrl).
 template <typename T>
 struct NominalInMemory {
   StateDev<T> st;
   int N, e;
-  const T* u0;  // controls: registers (they may come from the control law rather than from st.ctrl)
+  const T* u0;
   B2_DEV T q(int k) const { return __ldg(st.qpos + (size_t)k * N + e); }
   B2_DEV T v(int k) const { return __ldg(st.qvel + (size_t)k * N + e); }
   B2_DEV T u(int k) const { return u0[k]; }
   B2_DEV T w(int k) const { return st.warm ? __ldg(st.warm + (size_t)k * N + e) : T(0); }
 };
 
+// One column of the FD linearisation for env e -- c < nv: tangent-space position column, c < 2nv: velocity column, else
+// control column c - 2nv -- or, with nominal = true, the unperturbed step itself, which leaves the advanced state in
+// env.qpos / env.qvel / env.warm.  nom: accessor of the env's nominal state.
 template <typename T, class D, class M, class S>
 B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
-                      T eps, int centered, int N, int e, T* A, T* B, const DerivedDev<T>& out, int want_derived, bool& pos_valid) {
+                      T eps, int centered, int N, int e, T* A, T* B, bool& pos_valid) {
   constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
@@ -213,7 +205,6 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     env.forward_rest();
     B2_UNROLL
     for (int k = 0; k < nv; k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
-    if (nominal && want_derived) store_derived(env, out, N, e);
     if (M::integrator() == 1) env.rk4(); else env.euler();
     pos_valid = kind != 1 && M::integrator() == 0;
     // plus -> s2, minus -> s1, nominal -> whichever end the one-sided quotient is missing
@@ -248,15 +239,13 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // is the longest); each position column is a thread of its own (tasks 1..nv, two full rollouts).  RK4 models have
 // nothing to share between columns: one thread per (env, column).
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain) {
+__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow) {
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)count * fd_tasks<M>()) return;
   const int e = (int)(idx % count), task = (int)(idx / count);  // count envs, env stride N
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
-  DerivedDev<T> none;
-  memset(&none, 0, sizeof(none));
   T u0[D::NU];
   if (gain) {  // device-resident control law: linearise about the controls it produces (k_step applies the same law)
     T q[D::NQ], v[D::NV];
@@ -272,46 +261,15 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   const NominalInMemory<T> nom{st, N, e, u0};
   const bool grouped = M::integrator() == 0;  // not a constant expression for the runtime provider
   const int c0 = !grouped ? task : (task == 0 ? nv : task - 1);
-  const int c1 = !grouped ? task + 1 : (task == 0 ? ndx + nu : task);
+  // shadow.qpos != null (grouped form only): the thread of the velocity / control columns also advances the env -- its
+  // position stage is the step's -- and leaves the new state in the shadow arrays (the other threads of the env still
+  // read the nominal state); k_commit_state swaps the two afterwards
+  const bool advance = grouped && task == 0 && shadow.qpos != nullptr;
+  const int c1 = !grouped ? task + 1 : (task == 0 ? ndx + nu + (advance ? 1 : 0) : task);
   bool pos_valid = false;
   B2_NOUNROLL
-  for (int c = c0; c < c1; c++) fd_column(env, nom, c, false, eps, centered, N, e, A, B, none, 0, pos_valid);
-  if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
-}
-
-// One control tick of a whole batch: [LQR control law] -> FD (A, B) at the new controls -> one step, the step riding in the
-// FD launch as an extra "column": thread (e, c) with c == ncol advances env e.  The FD columns of an env keep reading its
-// nominal state throughout the launch, so the advanced state goes to shadow arrays and k_commit_state copies it back
-// afterwards.  The extra blocks are the last of the grid and do one rollout where an FD column does two: they fill the
-// tail of the FD launch instead of paying for a launch of their own at a batch size that cannot fill the GPU.
-// Equivalent to k_lqr_control + k_linearize + k_step(nsteps = 1) (reference env.py:177-191: controller, (A, B), step).
-template <typename T, class D, class M>
-__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS)
-k_linearize_step(StateDev<T> st, StateDev<T> shadow, DerivedDev<T> out, int want_derived, int count, int N, T eps, int centered,
-                 T* A, T* B, const T* __restrict__ gain) {
-  const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ncol = 2 * nv + nu;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)count * (ncol + 1)) return;
-  const int e = (int)(idx % count), c = (int)(idx / count);
-  const bool nominal = c == ncol;
-  RowStore<T, D> rows;
-  LaneEnv<T, D, M> env(rows);
-  T u0[D::NU];
-  if (gain) {
-    T q[D::NQ], v[D::NV];
-    B2_UNROLL
-    for (int k = 0; k < nq; k++) q[k] = st.qpos[(size_t)k * N + e];
-    B2_UNROLL
-    for (int k = 0; k < nv; k++) v[k] = st.qvel[(size_t)k * N + e];
-    lqr_law(env, q, v, gain, u0);
-  } else {
-    B2_UNROLL
-    for (int k = 0; k < nu; k++) u0[k] = st.ctrl[(size_t)k * N + e];
-  }
-  const NominalInMemory<T> nom{st, N, e, u0};
-  bool pos_valid = false;
-  fd_column(env, nom, c, nominal, eps, centered, N, e, A, B, out, want_derived, pos_valid);
-  if (nominal) {
+  for (int c = c0; c < c1; c++) fd_column(env, nom, c, c == ndx + nu, eps, centered, N, e, A, B, pos_valid);
+  if (advance) {
     B2_UNROLL
     for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];
     B2_UNROLL
@@ -322,20 +280,24 @@ k_linearize_step(StateDev<T> st, StateDev<T> shadow, DerivedDev<T> out, int want
   if (st.flags && env.flags) atomicOr(st.flags + e, env.flags);
 }
 
-// shadow -> state after k_linearize_step (rows of count elements, row stride N)
+// After a launch that advanced envs into the shadow arrays: swap state and shadow (rows of count elements, row stride N).
+// The state arrays then hold the new state and the shadow the pre-step one, from which b2_refresh_derived can still
+// produce the derived arrays mj_step would have left behind.
 template <typename T>
 __global__ void __launch_bounds__(256) k_commit_state(StateDev<T> st, StateDev<T> shadow, int count, int N, int nq, int nv, int nu) {
   const long long total = (long long)count * (nq + 2 * nv + nu);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     int row = (int)(i / count);
     const size_t at = (size_t)(i - (long long)row * count);
-    if (row < nq) { st.qpos[(size_t)row * N + at] = shadow.qpos[(size_t)row * N + at]; continue; }
-    row -= nq;
-    if (row < nv) { st.qvel[(size_t)row * N + at] = shadow.qvel[(size_t)row * N + at]; continue; }
-    row -= nv;
-    if (row < nv) { if (st.warm) st.warm[(size_t)row * N + at] = shadow.warm[(size_t)row * N + at]; continue; }
-    row -= nv;
-    st.ctrl[(size_t)row * N + at] = shadow.ctrl[(size_t)row * N + at];
+    T *a, *b;
+    if (row < nq) { a = st.qpos; b = shadow.qpos; }
+    else if ((row -= nq) < nv) { a = st.qvel; b = shadow.qvel; }
+    else if ((row -= nv) < nv) { a = st.warm; b = shadow.warm; if (!a) continue; }
+    else { row -= nv; st.ctrl[(size_t)row * N + at] = shadow.ctrl[(size_t)row * N + at]; continue; }  // applied controls: both keep them
+    const size_t k = (size_t)row * N + at;
+    const T x = a[k];
+    a[k] = b[k];
+    b[k] = x;
   }
 }
 

@@ -13,7 +13,8 @@ namespace b2 {
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
   int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);                  \
   int b2k_linearize##SUF(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
-                         const void* gain, void* stream);                                                                                    \
+                         const void* gain, const b2_state* shadow, void* stream);                                                                                    \
+  int b2k_commit_state##SUF(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream); \
   int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
   int b2k_inverse##SUF(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream);     \
   int b2k_lqr_control##SUF(int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \

@@ -180,12 +180,16 @@ int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,
-                         const void* gain, void* stream) {
+                         const void* gain, const b2_state* shadow, void* stream) {
   const int threads = 128;
   const long long total = (long long)count * ncol;  // ncol: FD tasks per env (b2_capi: nv + 1 under Euler, else 2nv + nu)
   const int blocks = (int)((total + threads - 1) / threads);
   B2_DISPATCH(cls, (k_linearize<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B, (const real*)gain)));
+                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B, (const real*)gain, to_dev<real>(shadow))));
+  return (int)cudaGetLastError();
+}
+int B2_FN(b2k_commit_state)(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream) {
+  k_commit_state<real><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(to_dev<real>(st), to_dev<real>(shadow), count, N, nq, nv, nu);
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_jacobian)(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {

@@ -15,12 +15,10 @@ struct SpecKernels {
   // [0] FP64, [1] FP32; count envs, env stride N
   // gain != null: the control law of b2_lqr_set_gain is evaluated inside the kernel (ctrl becomes an output of step)
   int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);
-  int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream);
+  // shadow != null (Euler models): the FD launch also advances every env into the shadow arrays (see k_linearize)
+  int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain,
+                      const b2_state* shadow, void* stream);
   int (*jacobian[2])(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);
-  // control tick with the step riding in the FD launch (k_linearize_step + k_commit_state); null for larger models.
-  // shadow: scratch state arrays (qpos, qvel, ctrl, qacc_warmstart) of the same shape as st
-  int (*tick[2])(const b2_state* st, const b2_state* shadow, const b2_derived* out, int count, int N, double eps, int centered,
-                 void* A, void* B, const void* gain, void* stream);
 };
 
 void register_spec(const SpecKernels* k);

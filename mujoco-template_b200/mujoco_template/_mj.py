@@ -216,6 +216,7 @@ class NativeBackend:
         for name in _INT_FIELDS:
             self.buffers[name] = self._alloc(1, torch.int32)
         self._scratch: dict[str, Any] = {}
+        self.derived_stale = False  # a control tick deferred the derived arrays (see ensure_derived)
         self.stream = 0  # legacy default stream; device batches launch on torch's current stream (see _pre)
         self.profile: dict[str, list] | None = None  # name -> [(start_event, end_event)], filled when enabled
 
@@ -274,13 +275,22 @@ class NativeBackend:
         return [a.elapsed_time(b) for a, b in (self.profile or {}).get(name, [])]
 
     def step(self, nsteps: int = 1, derived: bool = True) -> None:
+        self.derived_stale = False
         self._launch("step", self.batch.step, self.state_struct(), nsteps, self.derived_struct() if derived else None)
 
     def forward(self) -> None:
+        self.derived_stale = False
         self._launch("forward", self.batch.forward, self.state_struct(), self.derived_struct())
 
-    def control_tick(self, eps: float, centered: bool, use_lqr: bool, out=None):
-        """LQR law (optional) -> (A, B) -> one step, fused into one launch where the model has a specialised kernel."""
+    def ensure_derived(self) -> None:
+        """Materialise the derived arrays of the last control tick that deferred them (``b2_refresh_derived``)."""
+        if self.derived_stale:
+            self.derived_stale = False
+            self._launch("refresh_derived", self.batch.refresh_derived, self.derived_struct())
+
+    def control_tick(self, eps: float, centered: bool, use_lqr: bool, out=None, derived: bool = True):
+        """LQR law (optional) -> (A, B) -> one step (``b2_control_tick``).  ``derived=False`` defers the derived arrays:
+        the step then rides in the FD launch, and ``ensure_derived()`` produces them later if someone reads them."""
         torch, m = self.torch, self.model
         nx = 2 * m.nv
         if out is not None:
@@ -288,8 +298,10 @@ class NativeBackend:
         else:
             A = torch.empty((nx, nx, self.nenv), device=f"cuda:{self.device}", dtype=self.dtype)
             B = torch.empty((nx, m.nu, self.nenv), device=f"cuda:{self.device}", dtype=self.dtype)
-        self._launch("control_tick", self.batch.control_tick, self.state_struct(), self.derived_struct(), use_lqr, eps,
-                     centered, A.data_ptr(), B.data_ptr() if m.nu else None)
+        defer = not derived and int(m.opt.integrator) == 0  # the library defers only for Euler models
+        self._launch("control_tick", self.batch.control_tick, self.state_struct(), None if defer else self.derived_struct(),
+                     use_lqr, eps, centered, A.data_ptr(), B.data_ptr() if m.nu else None)
+        self.derived_stale = defer
         return A, B
 
     def linearize(self, eps: float, centered: bool, out=None):
@@ -440,9 +452,27 @@ class BatchData(_DataBase):
         self.backend = backend if backend is not None else NativeBackend(model, nenv, device=device, precision=precision)
         b = self.backend
         for name in list(_field_dims(model)) + list(_INT_FIELDS):
-            setattr(self, name, b.array(name))
+            if name not in _LAZY_DERIVED:
+                setattr(self, name, b.array(name))
         self.time = 0.0
         mj_resetData(model, self)
+
+
+# Derived arrays of a batch are properties: a control tick may have deferred them (b2_control_tick without derived
+# outputs), in which case the first read materialises them -- with the values mj_step leaves in mjData -- in place.
+_LAZY_DERIVED = ("xpos", "xquat", "xipos", "geom_xpos", "site_xpos", "subtree_com", "qacc", "qfrc_bias", "sensordata",
+                 "ncon", "nefc", "solver_iter")
+
+
+def _lazy_derived(name: str):
+    def get(self):
+        self.backend.ensure_derived()
+        return self.backend.array(name)
+    return property(get)
+
+
+for _name in _LAZY_DERIVED:
+    setattr(BatchData, _name, _lazy_derived(_name))
 
 
 # ----------------------------------------------------------------------------- mujoco-shaped functions

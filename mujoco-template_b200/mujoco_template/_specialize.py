@@ -120,7 +120,6 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
     ncol = 2 * nv + nu
     fd_tasks = nv + 1 if int(c["integrator"]) == 0 else ncol  # k_linearize: Euler groups the velocity / control columns
-    fused_tick = nv <= 2  # small models: the step rides in the FD launch (k_linearize_step)
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
     A("")
@@ -154,10 +153,10 @@ def emit_spec(compiled: dict, name: str) -> str:
         A(f"  k_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, nsteps, (const {T}*)gain);")
         A("  return (int)cudaGetLastError();")
         A("}")
-        A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
+        A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, const b2_state* shadow, void* stream) {{")
         A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {fd_tasks};")
         A("  const int blocks = (int)((total + threads - 1) / threads);")
-        A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
+        A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain, to_dev<{T}>(shadow));")
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_jacobian{suf}(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {{")
@@ -165,17 +164,8 @@ def emit_spec(compiled: dict, name: str) -> str:
         A(f"  k_jacobian<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), N, kind, objid, ({T}*)jacp, ({T}*)jacr);")
         A("  return (int)cudaGetLastError();")
         A("}")
-        if fused_tick:
-            A(f"int spec_tick{suf}(const b2_state* st, const b2_state* shadow, const b2_derived* out, int count, int N, double eps, int centered, void* A, void* B, const void* gain, void* stream) {{")
-            A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {ncol + 1};")
-            A("  const int blocks = (int)((total + threads - 1) / threads);")
-            A(f"  k_linearize_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(shadow), to_dev<{T}>(out), out != nullptr, count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain);")
-            A(f"  k_commit_state<{T}><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(shadow), count, N, {nq}, {nv}, {nu});")
-            A("  return (int)cudaGetLastError();")
-            A("}")
-    tick = "{spec_tick, spec_tick32}" if fused_tick else "{nullptr, nullptr}"
     A(f'const SpecKernels kSpec = {{"{name}", 0x{fnv1a(blob):016x}ull, {len(blob)}, {{spec_step, spec_step32}}, '
-      f'{{spec_linearize, spec_linearize32}}, {{spec_jacobian, spec_jacobian32}}, {tick}}};')
+      f'{{spec_linearize, spec_linearize32}}, {{spec_jacobian, spec_jacobian32}}}};')
     A("struct Registrar { Registrar() { register_spec(&kSpec); } } registrar;")
     A("}  // namespace")
     A("}  // namespace b2")

@@ -213,7 +213,8 @@ class BatchedEnv:
                     pending = 0
                 if fuse and self.controller.device_law_ready(self.data):
                     # controller law + (A, B) + this step in one launch (b2_control_tick)
-                    A, B = backend.control_tick(self.lin_eps, True, True)
+                    A, B = backend.control_tick(self.lin_eps, True, True, derived=False)
+                    self._ticks_defer_derived = True
                     lin_A.append(A.permute(2, 0, 1))
                     lin_B.append(B.permute(2, 0, 1))
                     self._substep += 1
@@ -266,6 +267,8 @@ class BatchedEnv:
         else:
             self._substep += 1
         self._graph.replay()
+        if getattr(self, "_ticks_defer_derived", False):
+            self.data.backend.derived_stale = int(self.model.opt.integrator) == 0
         return self._graph_out
 
     def step(self, n: int = 1, *, return_obs: bool = True) -> StepResult:

@@ -504,17 +504,15 @@ def test_batched_recorder_matches_single_env_csv(tmp_path):
 
 @pytest.mark.parametrize("name,n", [("cartpole", 1000), ("pendulum", 33)])
 @pytest.mark.parametrize("precision", [64, 32])
-@pytest.mark.parametrize("merged", [False, True])
-def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, precision, merged):
-    """b2_control_tick (control law evaluated inside the FD and step kernels -- or, with B2_MERGED_TICK=1, the step
-    riding in the FD launch and a commit kernel copying the shadow state back) == b2_lqr_control, b2_linearize,
-    b2_step in sequence, and the FP64 result matches the oracle driven by the same control law."""
-    if merged:
-        monkeypatch.setenv("B2_MERGED_TICK", "1")
+def test_fused_control_tick_equals_three_launch_sequence(name, n, precision):
+    """b2_control_tick (control law evaluated inside the kernels; for Euler models the step rides in the FD launch and
+    the derived arrays are produced lazily by b2_refresh_derived) == b2_lqr_control, b2_linearize, b2_step in sequence,
+    and the FP64 result matches the oracle driven by the same control law."""
     import torch
     import mujoco_template as mt
 
     model = load_model(name)
+    euler = int(model.opt.integrator) == 0
     qpos, qvel, _ = random_states(model, name, n, seed=21)
     if name == "cartpole":
         qpos[0] = [1.9995, 0.1]; qvel[0] = [3.0, 0.0]       # env 0 runs into the slider limit: constraint rows in the FD
@@ -528,11 +526,18 @@ def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, p
         benv.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev, dtype=dt))
         c0 = mt._capi.launch_count()
         hist = []
-        for _ in range(5):
+        for s_ in range(5):
             res = benv.step(return_obs=False)
+            if fused and euler:
+                assert benv.data.backend.derived_stale      # nothing has read a derived array yet
+            launches = mt._capi.launch_count()
+            derived = (benv.data.qacc.clone(), benv.data.xpos.clone())   # first read materialises them (one forward launch)
+            if fused and euler:
+                assert mt._capi.launch_count() == launches + 1 and not benv.data.backend.derived_stale
             hist.append((res.info["A"].clone(), res.info["B"].clone(), benv.data.qpos.clone(), benv.data.qvel.clone(),
-                         benv.data.ctrl.clone(), benv.data.qacc.clone(), benv.data.xpos.clone()))
-        assert mt._capi.launch_count() - c0 == (10 if fused else 15)
+                         benv.data.ctrl.clone()) + derived)
+        per_tick = (3 if euler else 2) if fused else 3           # FD(+step) + commit + lazy forward | FD + step | law + FD + step
+        assert mt._capi.launch_count() - c0 == 5 * per_tick
         out[fused] = hist
     tol = 1e-12 if precision == 64 else 2e-4
     for a, b in zip(out[True], out[False]):
