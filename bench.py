@@ -330,13 +330,16 @@ def main():
                 "traffic": traffic, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": share,
+                "kernel_share_note": "kernels timed one by one in an eager pass (controller, FD, step); the timed loop itself runs "
+                                     "b2_control_tick, where the step rides in the FD launch",
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
     # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul).  cartpole: counted by ncu on the kernels themselves
-    # (profiles/ncu_cartpole_kernels_r01d.txt: k_linearize 5.368e8 flops per 655,360 rollouts = 819 -- the velocity and
-    # control columns reuse the position stage -- and k_step 962 per step); the others are the a-priori estimates of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 819.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    # (profiles/ncu_cartpole_kernels_r01e.txt: k_linearize 4.626e8 flops per 655,360 rollouts = 706 -- one thread per env
+    # runs the shared position stage once for all velocity / control columns -- and k_step 962 per step); the others are
+    # the a-priori estimates of BASELINE.md
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 706.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,

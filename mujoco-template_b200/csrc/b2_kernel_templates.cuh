@@ -285,19 +285,19 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
 // produce the derived arrays mj_step would have left behind.
 template <typename T>
 __global__ void __launch_bounds__(256) k_commit_state(StateDev<T> st, StateDev<T> shadow, int count, int N, int nq, int nv, int nu) {
-  const long long total = (long long)count * (nq + 2 * nv + nu);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    int row = (int)(i / count);
-    const size_t at = (size_t)(i - (long long)row * count);
-    T *a, *b;
-    if (row < nq) { a = st.qpos; b = shadow.qpos; }
-    else if ((row -= nq) < nv) { a = st.qvel; b = shadow.qvel; }
-    else if ((row -= nv) < nv) { a = st.warm; b = shadow.warm; if (!a) continue; }
-    else { row -= nv; st.ctrl[(size_t)row * N + at] = shadow.ctrl[(size_t)row * N + at]; continue; }  // applied controls: both keep them
-    const size_t k = (size_t)row * N + at;
-    const T x = a[k];
-    a[k] = b[k];
-    b[k] = x;
+  // blockIdx.y: row of the concatenated [qpos; qvel; warm; ctrl]; x: envs (two per thread, 16-byte accesses when aligned)
+  int row = blockIdx.y;
+  T *a, *b;
+  bool swap = true;
+  if (row < nq) { a = st.qpos; b = shadow.qpos; }
+  else if ((row -= nq) < nv) { a = st.qvel; b = shadow.qvel; }
+  else if ((row -= nv) < nv) { a = st.warm; b = shadow.warm; if (!a) return; }
+  else { row -= nv; a = st.ctrl; b = shadow.ctrl; swap = false; }  // applied controls: both sides keep them
+  a += (size_t)row * N; b += (size_t)row * N;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+    const T x = a[i];
+    a[i] = b[i];
+    if (swap) b[i] = x;
   }
 }
 

@@ -189,7 +189,9 @@ int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_commit_state)(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream) {
-  k_commit_state<real><<<148 * 4, 256, 0, (cudaStream_t)stream>>>(to_dev<real>(st), to_dev<real>(shadow), count, N, nq, nv, nu);
+  int bx = (count + 255) / 256;
+  if (bx > 148 * 8) bx = 148 * 8;
+  k_commit_state<real><<<dim3(bx, nq + 2 * nv + nu), 256, 0, (cudaStream_t)stream>>>(to_dev<real>(st), to_dev<real>(shadow), count, N, nq, nv, nu);
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_jacobian)(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {
