@@ -502,23 +502,28 @@ def test_batched_recorder_matches_single_env_csv(tmp_path):
             assert np.allclose(np.array(a, dtype=float), np.array(b, dtype=float), rtol=0, atol=1e-13)
 
 
-@pytest.mark.parametrize("name,n", [("cartpole", 1000), ("pendulum", 33)])
+@pytest.mark.parametrize("name,n", [("cartpole", 1000), ("pendulum", 33), ("drone", 70), ("cartpole-generic", 257)])
 @pytest.mark.parametrize("precision", [64, 32])
-def test_fused_control_tick_equals_three_launch_sequence(name, n, precision):
+def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, precision):
     """b2_control_tick (control law evaluated inside the kernels; for Euler models the step rides in the FD launch and
     the derived arrays are produced lazily by b2_refresh_derived) == b2_lqr_control, b2_linearize, b2_step in sequence,
     and the FP64 result matches the oracle driven by the same control law."""
     import torch
     import mujoco_template as mt
 
+    if name.endswith("-generic"):
+        monkeypatch.setenv("B2_DISABLE_SPEC", "1")
+        name = name.split("-")[0]
     model = load_model(name)
     euler = int(model.opt.integrator) == 0
     qpos, qvel, _ = random_states(model, name, n, seed=21)
+    qref = np.array(model.key_qpos[0]) if name == "drone" else np.array(model.qpos0)
+    uref = np.array(model.key_ctrl[0]) if name == "drone" else np.zeros(model.nu)
     if name == "cartpole":
         qpos[0] = [1.9995, 0.1]; qvel[0] = [3.0, 0.0]       # env 0 runs into the slider limit: constraint rows in the FD
     out = {}
     for fused in (True, False):
-        ctl = mt.batched_controllers.BatchedLQRController(qpos_ref=np.array(model.qpos0), Q=np.eye(2 * model.nv), R=np.eye(model.nu))
+        ctl = mt.batched_controllers.BatchedLQRController(qpos_ref=qref, ctrl_ref=uref, Q=np.eye(2 * model.nv), R=np.eye(model.nu))
         benv = mt.BatchedEnv(model, n, controller=ctl, precision=precision)
         benv.fuse_control_tick = fused
         dev, dt = benv.data.qpos.device, benv.data.qpos.dtype
@@ -554,8 +559,8 @@ def test_fused_control_tick_equals_three_launch_sequence(name, n, precision):
         for e in (0, 1, n - 1):
             od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]
             for s in range(5):
-                x = np.concatenate([od.qpos - model.qpos0, od.qvel])
-                u = -K @ x
+                x = np.concatenate([od.differentiate_pos(1.0, qref, np.array(od.qpos)), od.qvel])
+                u = uref - K @ x
                 lim = np.asarray(model.actuator_ctrllimited, bool)
                 od.ctrl[:] = np.where(lim, np.clip(u, model.actuator_ctrlrange[:, 0], model.actuator_ctrlrange[:, 1]), u)
                 Ao, Bo = od.transition_fd(1e-6, True)
