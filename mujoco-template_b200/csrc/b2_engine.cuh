@@ -523,6 +523,11 @@ struct LaneEnv {
           for (int k = 0; k < 3; k++) e[k] = p2[k] - z2[k] * s2[1];
           plane_sphere(p, margin, p1, z1, e, s2[0], z2);
         } else if (t2 == GEOM_BOX) {
+          // exact cull: the lowest corner sits reach = sum_k |n . axis_k| s_k below the centre along the plane normal
+          // (folds to a constant test when the box never rotates, e.g. a cart on a rail)
+          T reach = 0;
+          for (int k = 0; k < 3; k++) reach += fabs(z1[0] * R2[k] + z1[1] * R2[3 + k] + z1[2] * R2[6 + k]) * s2[k];
+          if (h - reach > margin) continue;
           int cnt = 0;
           B2_NOUNROLL
           for (int c = 0; c < 8 && cnt < 4; c++) {
