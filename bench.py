@@ -336,10 +336,10 @@ def main():
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
     # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul).  cartpole: counted by ncu on the kernels themselves
-    # (profiles/ncu_cartpole_kernels_r01e.txt: k_linearize 4.626e8 flops per 655,360 rollouts = 706 -- one thread per env
+    # (profiles/ncu_cartpole_kernels_r01f.txt: k_linearize 4.338e8 flops per 655,360 rollouts = 662 -- one thread per env
     # runs the shared position stage once for all velocity / control columns -- and k_step 962 per step); the others are
     # the a-priori estimates of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 706.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 662.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
