@@ -160,7 +160,7 @@ struct NominalInMemory {
 // env.qpos / env.qvel / env.warm.  nom: accessor of the env's nominal state.
 template <typename T, class D, class M, class S>
 B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
-                      T eps, int centered, int N, int e, T* A, T* B, bool& pos_valid) {
+                      T eps, T inv_eps, int centered, int N, int e, T* A, T* B, bool& pos_valid) {
   constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
@@ -200,7 +200,6 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     }
     // one mj_step; the position stage is skipped when an earlier rollout of this thread already ran
     // it at the same qpos (velocity / control columns under Euler)
-    env.check_state();
     if (!pos_valid) env.forward_position();
     env.forward_rest();
     B2_UNROLL
@@ -217,11 +216,11 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
   }
   if (nominal) return;
   if (fwd || back) {
-    const T h = (fwd && back) ? 2 * eps : eps;
-    env.differentiate_pos(col, h, s1, s2);
-    const T ih = T(1) / h;
+    // difference quotient with the reciprocal step (1 / (2 eps) = 0.5 / eps exactly): no division per entry
+    const T ih = (fwd && back) ? T(0.5) * inv_eps : inv_eps;
+    env.differentiate_pos(col, T(1), s1, s2);
     B2_UNROLL
-    for (int k = 0; k < nv; k++) col[nv + k] = (s2[nq + k] - s1[nq + k]) * ih;
+    for (int k = 0; k < nv; k++) { col[k] *= ih; col[nv + k] = (s2[nq + k] - s1[nq + k]) * ih; }
   } else {
     B2_UNROLL
     for (int k = 0; k < ndx; k++) col[k] = 0;
@@ -267,8 +266,15 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   const bool advance = grouped && task == 0 && shadow.qpos != nullptr;
   const int c1 = !grouped ? task + 1 : (task == 0 ? ndx + nu + (advance ? 1 : 0) : task);
   bool pos_valid = false;
+  const T inv_eps = T(1) / eps;
+  // mj_checkPos / mj_checkVel once on the nominal state (an eps perturbation of a finite state is finite)
+  B2_UNROLL
+  for (int k = 0; k < nq; k++) env.qpos[k] = nom.q(k);
+  B2_UNROLL
+  for (int k = 0; k < nv; k++) env.qvel[k] = nom.v(k);
+  env.check_state();
   B2_NOUNROLL
-  for (int c = c0; c < c1; c++) fd_column(env, nom, c, c == ndx + nu, eps, centered, N, e, A, B, pos_valid);
+  for (int c = c0; c < c1; c++) fd_column(env, nom, c, c == ndx + nu, eps, inv_eps, centered, N, e, A, B, pos_valid);
   if (advance) {
     B2_UNROLL
     for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];
