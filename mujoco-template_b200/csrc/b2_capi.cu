@@ -252,7 +252,7 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
                         const void* gain = nullptr, const b2_state* shadow = nullptr) {
   int rc;
   // FD tasks per env: see k_linearize (Euler: one thread for all velocity / control columns + one per position column)
-  const int ncol = b->model->v.integrator == 0 ? b->model->v.nv + 1 : 2 * b->model->v.nv + b->model->v.nu;
+  const int ncol = b2::fd_task_count(b->model->v.integrator, b->model->v.nv, b->model->v.nu);
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");

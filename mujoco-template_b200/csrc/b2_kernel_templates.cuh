@@ -140,7 +140,11 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
 }
 
 // number of FD threads per env (see k_linearize)
-template <class M> B2_DEV int fd_tasks() { return M::integrator() == 0 ? M::nv() + 1 : 2 * M::nv() + M::nu(); }
+// Euler: the nv + nu velocity / control columns are dealt out in groups of B2_FD_GROUP (one group if there are at most
+// that many: cartpole) -- each group is one thread that runs the shared position stage once -- followed by one thread
+// per position column.  Larger groups save more position stages but serialise more rollouts in one thread.
+// (B2_FD_GROUP, fd_group_count, fd_task_count: b2_model_dev.cuh, shared with the host launchers)
+template <class M> B2_DEV int fd_tasks() { return fd_task_count(M::integrator(), M::nv(), M::nu()); }
 // The nominal state of a thread's env is re-read from the SoA arrays at the start of every rollout (L1/L2 hits) rather
 // than held in registers: ~14 fewer live registers across the physics, which is what the 168-register budget of three
 // resident blocks is short of.  The controls are the exception (they may come from the control law, not from st.ctrl).
@@ -233,10 +237,10 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // velocity, 2nv..2nv+nu-1 control.  Replaces mjd_transitionFD (reference mujoco_template/linearization.py:16-35): state
 // and qacc_warmstart of every rollout start from the saved nominal values; control columns fall back to one-sided
 // differences at the ctrlrange bounds.
-// Work split: under Euler the velocity and control columns all share the position stage of the nominal qpos, so ONE
-// thread per env runs that stage once and then the 2 (nv + nu) velocity / control rollouts (task 0, launched first: it
-// is the longest); each position column is a thread of its own (tasks 1..nv, two full rollouts).  RK4 models have
-// nothing to share between columns: one thread per (env, column).
+// Work split: under Euler the velocity and control columns all share the position stage of the nominal qpos, so a
+// thread takes a group of up to B2_FD_GROUP of them, runs that stage once and then their rollouts (tasks 0..groups-1,
+// launched first: they are the longest); each position column is a thread of its own (two full rollouts).  RK4 models
+// have nothing to share between columns: one thread per (env, column).
 template <typename T, class D, class M>
 __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow) {
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
@@ -259,12 +263,16 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   }
   const NominalInMemory<T> nom{st, N, e, u0};
   const bool grouped = M::integrator() == 0;  // not a constant expression for the runtime provider
-  const int c0 = !grouped ? task : (task == 0 ? nv : task - 1);
+  const int groups = fd_group_count(nv, nu);
+  int c0 = task, c1 = task + 1;
+  if (grouped) {
+    if (task < groups) { c0 = nv + task * B2_FD_GROUP; c1 = c0 + B2_FD_GROUP < ndx + nu ? c0 + B2_FD_GROUP : ndx + nu; }
+    else { c0 = task - groups; c1 = c0 + 1; }
+  }
   // shadow.qpos != null (grouped form only): the thread of the velocity / control columns also advances the env -- its
   // position stage is the step's -- and leaves the new state in the shadow arrays (the other threads of the env still
   // read the nominal state); k_commit_state swaps the two afterwards
   const bool advance = grouped && task == 0 && shadow.qpos != nullptr;
-  const int c1 = !grouped ? task + 1 : (task == 0 ? ndx + nu + (advance ? 1 : 0) : task);
   bool pos_valid = false;
   const T inv_eps = T(1) / eps;
   // mj_checkPos / mj_checkVel once on the nominal state (an eps perturbation of a finite state is finite)
@@ -274,7 +282,10 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   for (int k = 0; k < nv; k++) env.qvel[k] = nom.v(k);
   env.check_state();
   B2_NOUNROLL
-  for (int c = c0; c < c1; c++) fd_column(env, nom, c, c == ndx + nu, eps, inv_eps, centered, N, e, A, B, pos_valid);
+  for (int c = c0; c < c1 + (advance ? 1 : 0); c++) {
+    const bool nominal = c == c1;  // the advance comes after the group's columns, on the same position stage
+    fd_column(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid);
+  }
   if (advance) {
     B2_UNROLL
     for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];

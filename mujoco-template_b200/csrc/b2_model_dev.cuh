@@ -29,6 +29,13 @@ struct DimsLarge {  // humanoid
   static constexpr int NB = 20, NJ = 24, NQ = 32, NV = 32, NU = 24, NG = 24, NS = 4, NT = 4, NW = 8, NPAIR = 176, NCON = 48, NEFC = 160, NSEN = 16, NSD = 48;
 };
 
+// FD linearisation work split (k_linearize): threads per env
+#define B2_FD_GROUP 4
+__host__ __device__ inline int fd_group_count(int nv, int nu) { return (nv + nu + B2_FD_GROUP - 1) / B2_FD_GROUP; }
+__host__ __device__ inline int fd_task_count(int integrator, int nv, int nu) {
+  return integrator == 0 ? fd_group_count(nv, nu) + nv : 2 * nv + nu;
+}
+
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4, GEOM_BOX = 6 };
 enum { TRN_JOINT = 0, TRN_SITE = 4 };

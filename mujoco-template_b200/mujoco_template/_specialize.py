@@ -119,7 +119,8 @@ def emit_spec(compiled: dict, name: str) -> str:
     A(f"#define B2_LIN_THREADS {lin_threads}")
     A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
     ncol = 2 * nv + nu
-    fd_tasks = nv + 1 if int(c["integrator"]) == 0 else ncol  # k_linearize: Euler groups the velocity / control columns
+    # k_linearize: Euler deals the velocity / control columns out in groups of B2_FD_GROUP = 4 (b2_kernel_templates.cuh)
+    fd_tasks = (nv + nu + 3) // 4 + nv if int(c["integrator"]) == 0 else ncol
     A('#include "../b2_kernel_templates.cuh"')
     A('#include "../b2_spec_registry.h"')
     A("")
