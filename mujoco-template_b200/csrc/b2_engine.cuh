@@ -1016,10 +1016,11 @@ struct LaneEnv {
       H[j * nv + j] = djj;
       const T inv = T(1) / djj;
       B2_UNROLL
-      for (int i = j + 1; i < nv; i++) {
+      for (int i = 0; i < nv; i++) {  // constant bounds + predicate: a triangular bound is not unrolled, and one runtime
+        if (i <= j) continue;         // index into a LaneEnv member keeps the whole struct in local memory
         T s = H[i * nv + j];
         B2_UNROLL
-        for (int k = 0; k < j; k++) s -= H[i * nv + k] * H[j * nv + k];
+        for (int k = 0; k < nv; k++) if (k < j) s -= H[i * nv + k] * H[j * nv + k];
         H[i * nv + j] = s * inv;
       }
     }

@@ -1,0 +1,26 @@
+"""Run a few steps (and optionally FD linearisations) of one model so that ncu can capture the kernels.
+  python tools/prof_model.py <model> <nenv> [--lin] [--ctrl-rand]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "mujoco-template_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
+
+from conftest import load_model, random_states
+from mujoco_template import _mj as mj
+
+name, n = sys.argv[1], int(sys.argv[2])
+model = load_model(name)
+d = mj.BatchData(model, n)
+qpos, qvel, ctrl = random_states(model, name, min(n, 8192), seed=0)
+reps = -(-n // qpos.shape[0])
+up = lambda a: torch.as_tensor(a.T.copy(), device="cuda").repeat(1, reps)[:, :n]
+d.qpos.copy_(up(qpos)); d.qvel.copy_(up(qvel)); d.ctrl.copy_(up(ctrl))
+for _ in range(4):
+    d.backend.step(1, derived=False)
+if "--lin" in sys.argv:
+    A, B = d.backend.linearize(1e-6, True)
+    d.backend.linearize(1e-6, True, out=(A, B))
+torch.cuda.synchronize()
+print("ok", d.backend.batch.kernel_variant, "bad flags", int((d.flags != 0).sum()))
