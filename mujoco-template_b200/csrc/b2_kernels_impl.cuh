@@ -149,11 +149,33 @@ static size_t warp_block_smem(const b2m_view* v, int wpb) {
   if (const char* x = getenv("B2_WARP_EXTRA_SMEM")) extra = (size_t)atoi(x);  // tuning: lowers the resident blocks per SM
   return extra + (size_t)wpb * ((size_t)warp_ws_reals_of(v) * sizeof(real) + (size_t)kWarpIntsAsReals * sizeof(double));
 }
+// lock-step launch shape (k_warp_step_ls): B2_WARP_LOCKSTEP=0 falls back to independent two-warp blocks
+static int warp_lockstep() {  // 0: independent warps, 1: lock step everywhere, 2: lock step outside the Newton loop
+  const char* x = getenv("B2_WARP_LOCKSTEP");
+  return x ? atoi(x) : 1;
+}
 // chooses warps-per-block / grid so that every SM is filled; returns the number of warp slots
 int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks) {
-  int dev = 0, sms = 0;
+  int dev = 0, sms = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  if (warp_lockstep()) {
+    // one block per SM with as many warps (envs) as the shared-memory workspace allows, at most 8
+    int wpb = 2;
+    if (const char* x = getenv("B2_WARP_LS_WPB")) wpb = atoi(x) > 0 && atoi(x) <= 8 ? atoi(x) : 2;
+    while (wpb > 1 && warp_block_smem(v, wpb) + 1024 > (size_t)smem_max) wpb--;
+    const size_t smem = warp_block_smem(v, wpb);
+    auto kern = warp_lockstep() == 2 ? k_warp_step_ls<real, GlobalModelLarge, 2> : k_warp_step_ls<real, GlobalModelLarge, 1>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return -1;
+    int blocks = sms * per_sm;
+    const int need = (N + wpb - 1) / wpb;
+    if (blocks > need) blocks = need;
+    *out_wpb = wpb; *out_blocks = blocks;
+    return blocks * wpb;
+  }
   const int wpb = 2;
   const size_t smem = warp_block_smem(v, wpb);
   auto kern = k_warp_step<real, GlobalModelLarge>;
@@ -175,8 +197,19 @@ int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived
   // envs are handed out through a work queue: the first gridDim * wpb statically, the rest by atomic counter
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  k_warp_step<real, GlobalModelLarge><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-      to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v));
+  // lock-step group: B2_WARP_LS_GROUP warps (default: the whole block), B2_WARP_LS_MAP picks which warps form a group
+  int gsize = wpb, map = 0;
+  if (const char* x = getenv("B2_WARP_LS_GROUP")) { const int g = atoi(x); if (g > 0 && wpb % g == 0) gsize = g; }
+  if (const char* x = getenv("B2_WARP_LS_MAP")) map = atoi(x) != 0;
+  if (warp_lockstep() == 2)
+    k_warp_step_ls<real, GlobalModelLarge, 2><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v), gsize, map);
+  else if (warp_lockstep())
+    k_warp_step_ls<real, GlobalModelLarge, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v), gsize, map);
+  else
+    k_warp_step<real, GlobalModelLarge><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,

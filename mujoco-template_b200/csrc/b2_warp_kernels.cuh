@@ -59,4 +59,55 @@ __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> 
   }
 }
 
+// Lock-step variant: the warps of a block form groups of `gsize` warps; a group takes gsize envs at a time from the work
+// queue and runs them stage by stage behind a named barrier (WarpEnv::forward<LS>).  Warps without an env of their own
+// at the tail of the batch recompute the last env and discard the result, so that every warp reaches every barrier.
+// map == 0: group = warp % ngroups (with 8 warps and pairs: warps w and w + 4, which share an SM sub-partition);
+// map == 1: group = warp / gsize (adjacent warps).
+template <typename T, class M, int LS>
+__global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps,
+                                                        T* jscratch, int* queue, int ws_reals, int gsize, int map) {
+  extern __shared__ double b2_smem[];
+  __shared__ int s_next[8];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+  const int ngroups = wpb / gsize;
+  const int grp = map ? wib / gsize : wib % ngroups, rank = map ? wib % gsize : wib / ngroups;
+  T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T)));
+  WarpEnv<T, M> env;
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  env.bar_id = 1 + grp; env.bar_cnt = 32 * gsize;
+  const int total = nsteps > 0 ? nsteps : 1;
+  int first = (blockIdx.x * ngroups + grp) * gsize;
+  while (first < N) {
+    const bool mine = first + rank < N;
+    const int e = mine ? first + rank : N - 1;
+    WFOR(k, M::nq()) env.qpos[k] = st.qpos[(size_t)k * N + e];
+    WFOR(k, M::nv()) { env.qvel[k] = st.qvel[(size_t)k * N + e]; env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
+    WFOR(k, M::nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
+    env.flags = 0;
+    __syncwarp();
+    for (int s = 0; s < total; s++) {
+      env.check_state();
+      env.template forward<LS>();
+      env.check_acc();
+      if (want_derived && s == total - 1 && mine) warp_store_derived(env, out, N, e);
+      env.template stage_sync<LS>();
+      if (nsteps > 0) env.euler();
+    }
+    if (mine) {
+      if (nsteps > 0) {
+        WFOR(k, M::nq()) st.qpos[(size_t)k * N + e] = env.qpos[k];
+        WFOR(k, M::nv()) st.qvel[(size_t)k * N + e] = env.qvel[k];
+      }
+      if (st.warm) WFOR(k, M::nv()) st.warm[(size_t)k * N + e] = env.warm[k];
+      if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
+    }
+    if (rank == 0 && lane == 0) s_next[grp] = nw + atomicAdd(queue, gsize);
+    env.template stage_sync<1>();
+    first = s_next[grp];
+    env.template stage_sync<1>();
+  }
+}
+
 }  // namespace b2
