@@ -198,9 +198,18 @@ def run_reference(args):
     }))
 
 
+# BASELINE.json configs[2] / configs[3]: i.i.d. random controls per step and actuator, generated on the device
+RANDOM_CTRL = {"drone": (0.0, 13.0), "humanoid": (-0.2, 0.2)}
+
+
 def workload_name(name: str, nenv: int, lin: bool) -> str:
-    return (f"{name} batched rollout, N={nenv} envs/GPU, FP64, " +
-            ("batched LQR + per-step FD (A,B) linearisation + 1 step" if lin else "1 step per launch, zero control"))
+    if lin:
+        tail = "batched LQR + per-step FD (A,B) linearisation + 1 step"
+    elif name in RANDOM_CTRL:
+        tail = "1 step per launch, random controls U(%g, %g) drawn on the device every step (Philox)" % RANDOM_CTRL[name]
+    else:
+        tail = "1 step per launch, zero control"
+    return f"{name} batched rollout, N={nenv} envs/GPU, FP64, " + tail
 
 
 def main():
@@ -239,6 +248,15 @@ def main():
                 def prepare(self, m, d): pass
                 def __call__(self, m, d, t): pass
             controller = HoldLin()
+    elif name in RANDOM_CTRL:
+        from mujoco_template import ControllerCapabilities
+
+        class RandomCtrl:  # counted as the controller, not as the path
+            capabilities = ControllerCapabilities()
+            lo, hi = RANDOM_CTRL[name]
+            def prepare(self, m, d): pass
+            def __call__(self, m, d, t): d.ctrl.uniform_(self.lo, self.hi)
+        controller = RandomCtrl()
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
     qpos, qvel = synth_states(model, name, nenv, seed=rank)  # each rank owns its own shard of envs
@@ -274,6 +292,12 @@ def main():
         for _ in range(3):  # eager call, capture + replay, replay
             env.step(return_obs=False)
     fp64_peak = _capi.fp_peak(64, local)
+    # the timed rollout starts from the configured initial-state distribution (the warm-up / profiling steps above have
+    # moved the envs: drones under random thrust eventually reach the floor, the humanoid falls)
+    env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev))
+    env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+    env.data.qacc_warmstart.zero_()
+    env.forward()
     barrier()
     launches0 = _capi.launch_count()
     sampler = ClockSampler(local)
@@ -408,6 +432,7 @@ def main():
             "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
                        "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
                        "launch": "CUDA graph replay of one env.step()" if use_graph else "eager launches",
+                       "rollout": f"timed steps are steps 0..{args.steps} of the rollout from the configured initial-state distribution",
                        "sharding": f"env batch split over {world} rank(s), no inter-step communication"},
             "linearizations_per_sec": (value if lin else 0.0),
             "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),
