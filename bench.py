@@ -22,6 +22,10 @@ import threading
 import time
 import warnings
 
+# NCCL_DEBUG=VERSION makes NCCL print its version banner to stdout, ahead of the one JSON line rank 0 owes the driver
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "mujoco-template_b200")):
     if p not in sys.path:
@@ -92,41 +96,68 @@ def synth_states(model, name: str, n: int, seed: int):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  The timed region of the
+    default workload lasts ~10 ms, so the samples are polled through NVML every ~2 ms (nvidia-smi -lms cannot sample
+    that fast); `nvidia-smi --query-gpu` once is the fallback when NVML is not importable."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, uuid: str | None = None):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows: list[list[str]] = []
-        self.proc = None
+        self.uuid = uuid
+        self.sm: list[float] = []
+        self.reasons: set[str] = set()
+        self.max_mhz = None
+        self._stop_evt = threading.Event()
+        self.first = threading.Event()
+        self.in_region = False
+        self.region_samples = 0
 
     def run(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + self.uuid) if not self.uuid.startswith("GPU-") else self.uuid)
+                except Exception:
+                    h = None
+            if h is None:
+                h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            while not self._stop_evt.is_set():
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                for name, bit in self.BAD.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                if self.in_region:
+                    self.region_samples += 1
+                self.first.set()
+                time.sleep(0.002)
         except Exception:
-            pass
+            try:  # one-shot fallback
+                q = "clocks.sm,clocks.max.sm"
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+                self.sm.append(float(out[0])); self.max_mhz = float(out[1])
+            except Exception:
+                pass
+            self.first.set()
 
     def stop(self) -> dict:
-        if self.proc is not None:
-            self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1])); mx.append(float(r[2]))
-            except (ValueError, IndexError):
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        if not sm:
+        self._stop_evt.set()
+        self.join(timeout=5)
+        if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm), "samples_in_timed_region": self.region_samples, "source": "NVML polled every 2 ms"}
 
 
 def cpu_oracle_rate(model, name: str, linearize: bool, target_seconds: float, seed: int = 123):
@@ -207,6 +238,8 @@ def workload_name(name: str, nenv: int, lin: bool) -> str:
         tail = "batched LQR + per-step FD (A,B) linearisation + 1 step"
     elif name in RANDOM_CTRL:
         tail = "1 step per launch, random controls U(%g, %g) drawn on the device every step (Philox)" % RANDOM_CTRL[name]
+        if name == "drone":
+            tail += ", episode reset to the initial state below z = 0.5 m"
     else:
         tail = "1 step per launch, zero control"
     return f"{name} batched rollout, N={nenv} envs/GPU, FP64, " + tail
@@ -254,8 +287,16 @@ def main():
         class RandomCtrl:  # counted as the controller, not as the path
             capabilities = ControllerCapabilities()
             lo, hi = RANDOM_CTRL[name]
+            init = None  # (qpos, qvel) tensors of the initial states: set below for the drone
             def prepare(self, m, d): pass
-            def __call__(self, m, d, t): d.ctrl.uniform_(self.lo, self.hi)
+            def __call__(self, m, d, t):
+                d.ctrl.uniform_(self.lo, self.hi)
+                if self.init is not None:
+                    # episode reset, as a batched rollout driver does it: a drone that comes within 0.5 m of the floor
+                    # starts again from its initial state (config #3 is free flight: "expect no ground contact")
+                    low = (d.qpos[2] < 0.5).unsqueeze(0)
+                    d.qpos.copy_(torch.where(low, self.init[0], d.qpos))
+                    d.qvel.copy_(torch.where(low, self.init[1], d.qvel))
         controller = RandomCtrl()
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
@@ -263,6 +304,8 @@ def main():
     env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev))
     env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
     env.forward()
+    if name == "drone" and not lin and controller is not None:
+        controller.init = (env.data.qpos.clone(), env.data.qvel.clone())
     flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
     def barrier():
@@ -300,12 +343,17 @@ def main():
     env.forward()
     barrier()
     launches0 = _capi.launch_count()
-    sampler = ClockSampler(local)
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local, gpu_uuid)
     sampler.start()
-    time.sleep(0.25)
+    sampler.first.wait(timeout=10)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     barrier()
+    sampler.in_region = True
     wall0 = time.perf_counter()
     for i in range(args.steps):
         flush.zero_()  # evict state / outputs from L2 between timed iterations (outside the event pair)
@@ -314,6 +362,7 @@ def main():
         stops[i].record()
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.in_region = False
     clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     total_ms = float(sum(step_ms))

@@ -1,5 +1,5 @@
 """Run a few steps (and optionally FD linearisations) of one model so that ncu can capture the kernels.
-  python tools/prof_model.py <model> <nenv> [--lin] [--ctrl-rand]"""
+  python tools/prof_model.py <model> <nenv> [--lin] [--presteps K]"""
 import os
 import sys
 
@@ -17,6 +17,11 @@ qpos, qvel, ctrl = random_states(model, name, min(n, 8192), seed=0)
 reps = -(-n // qpos.shape[0])
 up = lambda a: torch.as_tensor(a.T.copy(), device="cuda").repeat(1, reps)[:, :n]
 d.qpos.copy_(up(qpos)); d.qvel.copy_(up(qvel)); d.ctrl.copy_(up(ctrl))
+pre = int(sys.argv[sys.argv.index("--presteps") + 1]) if "--presteps" in sys.argv else 0
+lo, hi = {"drone": (0.0, 13.0), "humanoid": (-0.2, 0.2)}.get(name, (-1.0, 1.0))
+for _ in range(pre):  # age the batch under random controls (drones reach the floor, the humanoid falls)
+    d.ctrl.uniform_(lo, hi)
+    d.backend.step(1, derived=False)
 for _ in range(4):
     d.backend.step(1, derived=False)
 if "--lin" in sys.argv:
