@@ -123,6 +123,12 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
   B2_NOUNROLL
   for (int s = 0; s < total; s++) {
     env.check_state();
+    // a diverged env (NaN or |x| > 1e10: upstream would silently reset it) is flagged and frozen: stepping it on would
+    // only burn the Newton iteration cap on a meaningless state, and hold up the other 31 lanes of its warp
+    if (env.flags & 3) {
+      if (st.flags) st.flags[e] |= env.flags;
+      return;
+    }
     env.forward();
     B2_UNROLL
     for (int k = 0; k < M::nv(); k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;

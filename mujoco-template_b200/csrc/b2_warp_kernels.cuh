@@ -42,12 +42,19 @@ __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> 
     WFOR(k, M::nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
     env.flags = 0;
     __syncwarp();
-    for (int s = 0; s < total; s++) {
+    bool frozen = false;  // diverged env: flagged and left as it is (see k_step)
+    for (int s = 0; s < total && !frozen; s++) {
       env.check_state();
+      if (env.flags & 3) { frozen = true; break; }
       env.forward();
       env.check_acc();
       if (want_derived && s == total - 1) warp_store_derived(env, out, N, e);
       if (nsteps > 0) env.euler();
+    }
+    if (frozen) {
+      if (st.flags && lane == 0) st.flags[e] |= env.flags;
+      __syncwarp();
+      continue;
     }
     if (nsteps > 0) {
       WFOR(k, M::nq()) st.qpos[(size_t)k * N + e] = env.qpos[k];
@@ -87,15 +94,24 @@ __global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, Derived
     WFOR(k, M::nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
     env.flags = 0;
     __syncwarp();
+    bool frozen = false;  // diverged env: flagged and left as it is (see k_step); its warp keeps pace on the rest pose
     for (int s = 0; s < total; s++) {
       env.check_state();
+      if (!frozen && (env.flags & 3)) {
+        frozen = true;
+        if (mine && st.flags && lane == 0) st.flags[e] |= env.flags;
+        WFOR(k, M::nq()) env.qpos[k] = M::qpos0(k);
+        WFOR(k, M::nv()) { env.qvel[k] = 0; env.warm[k] = 0; }
+        WFOR(k, M::nu()) env.ctrl[k] = 0;
+        __syncwarp();
+      }
       env.template forward<LS>();
       env.check_acc();
-      if (want_derived && s == total - 1 && mine) warp_store_derived(env, out, N, e);
+      if (want_derived && s == total - 1 && mine && !frozen) warp_store_derived(env, out, N, e);
       env.template stage_sync<LS>();
       if (nsteps > 0) env.euler();
     }
-    if (mine) {
+    if (mine && !frozen) {
       if (nsteps > 0) {
         WFOR(k, M::nq()) st.qpos[(size_t)k * N + e] = env.qpos[k];
         WFOR(k, M::nv()) st.qvel[(size_t)k * N + e] = env.qvel[k];

@@ -22,8 +22,13 @@ lo, hi = {"drone": (0.0, 13.0), "humanoid": (-0.2, 0.2)}.get(name, (-1.0, 1.0))
 for _ in range(pre):  # age the batch under random controls (drones reach the floor, the humanoid falls)
     d.ctrl.uniform_(lo, hi)
     d.backend.step(1, derived=False)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
 for _ in range(4):
     d.backend.step(1, derived=False)
+e1.record()
+torch.cuda.synchronize()
+print("step_ms", e0.elapsed_time(e1) / 4, "ncon", float(d.ncon.float().mean()) if hasattr(d, "ncon") else None)
 if "--lin" in sys.argv:
     A, B = d.backend.linearize(1e-6, True)
     d.backend.linearize(1e-6, True, out=(A, B))
