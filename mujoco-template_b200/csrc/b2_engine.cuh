@@ -59,6 +59,16 @@ struct LaneEnv {
   T geom_xpos[3 * D::NG], geom_xmat[9 * D::NG], site_xpos[3 * D::NS], site_xmat[9 * D::NS];
   T com[3 * D::NB], cinert[10 * D::NB], cdof[6 * D::NV];
   T Mm[D::NV * D::NV], LD[D::NV * D::NV], dinv[D::NV];
+  // Small static models keep both factorisations of the position stage -- L'DL of M and of M + h*diag(damping), the
+  // Euler update's matrix -- alive across the rollouts of an FD thread that share qpos (the Newton Hessian then gets
+  // its own array instead of borrowing LD).  Larger / generic models refactor per rollout: registers (local memory) are
+  // the scarcer resource there.
+#ifdef B2_STATIC_MODEL
+  static constexpr bool kKeepFactors = D::NV <= 4;
+#else
+  static constexpr bool kKeepFactors = false;
+#endif
+  T LDe[kKeepFactors ? D::NV * D::NV : 1], dinve[kKeepFactors ? D::NV : 1], Hs[kKeepFactors ? D::NV * D::NV : 1];
   T ten_len[D::NT], ten_J[D::NT * D::NV], act_len[D::NU], act_moment[D::NU * D::NV];
   // ---- velocity-dependent
   T cvel[6 * D::NB], cdof_dot[6 * D::NV], spat[6 * D::NB], spat2[10 * D::NB];  // scratch: cacc / crb, cfrc
@@ -274,38 +284,54 @@ struct LaneEnv {
     }
   }
 
-  // in-place L'DL factorisation of the matrix held in LD (tree sparsity), dinv <- 1/D
-  B2_STAGE void factor_LD() {
+  // in-place L'DL factorisation of the matrix held in A (tree sparsity), di <- 1/D
+  B2_STAGE void factor_into(T* A, T* di) {
     const int nv = M::nv();
     B2_UNROLL
     for (int k = nv - 1; k >= 0; k--) {
-      const T dkk = LD[k * nv + k];
+      const T dkk = A[k * nv + k];
       B2_UNROLL
       for (int i = k - 1; i >= 0; i--) {
         if (!is_anc(k, i)) continue;
-        const T t = LD[k * nv + i] / dkk;
+        const T t = A[k * nv + i] / dkk;
         B2_UNROLL
-        for (int j = i; j >= 0; j--) if (is_anc(i, j)) LD[i * nv + j] -= t * LD[k * nv + j];
-        LD[k * nv + i] = t;
+        for (int j = i; j >= 0; j--) if (is_anc(i, j)) A[i * nv + j] -= t * A[k * nv + j];
+        A[k * nv + i] = t;
       }
-      dinv[k] = T(1) / dkk;
+      di[k] = T(1) / dkk;
     }
   }
-  B2_DEV void solve(T* x) const {
+  B2_STAGE void factor_LD() { factor_into(LD, dinv); }
+  // both factorisations of the position stage: M, and M + h*diag(damping) for the implicit-in-damping Euler update
+  B2_STAGE void factor_mass() {
+    const int nv = M::nv();
+    B2_UNROLL
+    for (int k = 0; k < nv * nv; k++) LD[k] = Mm[k];
+    factor_into(LD, dinv);
+    if (kKeepFactors && M::has_dofdamping()) {
+      B2_UNROLL
+      for (int k = 0; k < nv * nv; k++) LDe[k] = Mm[k];
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) LDe[k * nv + k] += M::timestep() * M::dof_damping(k);
+      factor_into(LDe, dinve);
+    }
+  }
+  B2_DEV void solve_with(const T* A, const T* di, T* x) const {
     const int nv = M::nv();
     B2_UNROLL
     for (int i = nv - 1; i >= 0; i--) {
       B2_UNROLL
-      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[j] -= LD[i * nv + j] * x[i];
+      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[j] -= A[i * nv + j] * x[i];
     }
     B2_UNROLL
-    for (int i = 0; i < nv; i++) x[i] *= dinv[i];
+    for (int i = 0; i < nv; i++) x[i] *= di[i];
     B2_UNROLL
     for (int i = 0; i < nv; i++) {
       B2_UNROLL
-      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[i] -= LD[i * nv + j] * x[j];
+      for (int j = i - 1; j >= 0; j--) if (is_anc(i, j)) x[i] -= A[i * nv + j] * x[j];
     }
   }
+  B2_DEV void solve(T* x) const { solve_with(LD, dinv, x); }
   B2_DEV void mul_M(T* r, const T* v) const {
     const int nv = M::nv();
     B2_UNROLL
@@ -991,7 +1017,7 @@ struct LaneEnv {
     B2_UNROLL
     for (int k = 0; k < nv; k++) grad[k] = Ma[k] - f_smooth[k] - f_con[k];
     // H = M + R.J' D_active R.J  (lower triangle, held in LD), dense Cholesky, Mgrad = H^-1 grad
-    T* H = LD;
+    T* H = kKeepFactors ? Hs : LD;
     B2_UNROLL
     for (int k = 0; k < nv * nv; k++) H[k] = Mm[k];
     B2_NOUNROLL
@@ -1111,19 +1137,26 @@ struct LaneEnv {
     com_frame();
     tendons();
     mass_matrix();
+    if (kKeepFactors) factor_mass();
     limit_rows();
     collide();
     transmission();
   }
-  B2_STAGE void forward_rest() {
-    B2_UNROLL
-    for (int k = 0; k < M::nv() * M::nv(); k++) LD[k] = Mm[k];
-    factor_LD();
+  // velocity-dependent part (depends on qpos and qvel only): reused by FD rollouts that perturb a control
+  // (upstream's mjSTAGE_VEL skip)
+  B2_STAGE void forward_velocity() {
     velocities();
     passive_forces();
     bias_forces();
+  }
+  B2_STAGE void forward_acc() {
+    if (!kKeepFactors) factor_mass();
     smooth_dynamics();
     constrained_acceleration();
+  }
+  B2_STAGE void forward_rest() {
+    forward_velocity();
+    forward_acc();
   }
   B2_DEV void forward() {
     forward_position();
@@ -1191,14 +1224,16 @@ struct LaneEnv {
     if (!M::has_dofdamping()) { B2_UNROLL for (int k = 0; k < nv; k++) acc[k] = qacc[k]; }
     else {
       // (M + h*diag(damping)) acc = f_smooth + f_con   (implicit in joint damping)
-      B2_UNROLL
-      for (int k = 0; k < nv * nv; k++) LD[k] = Mm[k];
-      B2_UNROLL
-      for (int k = 0; k < nv; k++) LD[k * nv + k] += h * M::dof_damping(k);
-      factor_LD();
+      if (!kKeepFactors) {
+        B2_UNROLL
+        for (int k = 0; k < nv * nv; k++) LD[k] = Mm[k];
+        B2_UNROLL
+        for (int k = 0; k < nv; k++) LD[k * nv + k] += h * M::dof_damping(k);
+        factor_LD();
+      }
       B2_UNROLL
       for (int k = 0; k < nv; k++) acc[k] = f_smooth[k] + f_con[k];
-      solve(acc);
+      solve_with(kKeepFactors ? LDe : LD, kKeepFactors ? dinve : dinv, acc);
     }
     B2_UNROLL
     for (int k = 0; k < nv; k++) qvel[k] += acc[k] * h;

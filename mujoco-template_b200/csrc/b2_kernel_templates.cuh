@@ -170,7 +170,7 @@ struct NominalInMemory {
 // env.qpos / env.qvel / env.warm.  nom: accessor of the env's nominal state.
 template <typename T, class D, class M, class S>
 B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
-                      T eps, T inv_eps, int centered, int N, int e, T* A, T* B, bool& pos_valid) {
+                      T eps, T inv_eps, int centered, int N, int e, T* A, T* B, bool& pos_valid, bool& vel_valid) {
   constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
@@ -210,11 +210,14 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     }
     // one mj_step; the position stage is skipped when an earlier rollout of this thread already ran
     // it at the same qpos (velocity / control columns under Euler)
+    // ... and so is the velocity stage when that rollout also ran at the nominal qvel (control columns, the advance)
     if (!pos_valid) env.forward_position();
-    env.forward_rest();
+    if (!(pos_valid && vel_valid && kind != 1 && kind != 2)) env.forward_velocity();
+    env.forward_acc();
     B2_UNROLL
     for (int k = 0; k < nv; k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
     if (M::integrator() == 1) env.rk4(); else env.euler();
+    vel_valid = kind != 1 && kind != 2 && M::integrator() == 0;  // this rollout's velocity stage was the nominal one
     pos_valid = kind != 1 && M::integrator() == 0;
     // plus -> s2, minus -> s1, nominal -> whichever end the one-sided quotient is missing
     const bool to2 = phase == 0 || (phase == 2 && !fwd);
@@ -279,7 +282,7 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   // position stage is the step's -- and leaves the new state in the shadow arrays (the other threads of the env still
   // read the nominal state); k_commit_state swaps the two afterwards
   const bool advance = grouped && task == 0 && shadow.qpos != nullptr;
-  bool pos_valid = false;
+  bool pos_valid = false, vel_valid = false;
   const T inv_eps = T(1) / eps;
   // mj_checkPos / mj_checkVel once on the nominal state (an eps perturbation of a finite state is finite)
   B2_UNROLL
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   B2_NOUNROLL
   for (int c = c0; c < c1 + (advance ? 1 : 0); c++) {
     const bool nominal = c == c1;  // the advance comes after the group's columns, on the same position stage
-    fd_column(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid);
+    fd_column(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid, vel_valid);
   }
   if (advance) {
     B2_UNROLL

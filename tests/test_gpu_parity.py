@@ -135,6 +135,37 @@ def test_bad_state_is_flagged_not_reset():
     flags = data.flags.cpu().numpy()[0]
     assert flags[0] == 0 and flags[3] == 0
     assert flags[1] & _capi.FLAG_BAD_QVEL and flags[2] & _capi.FLAG_BAD_QPOS
+    # ... and frozen: a flagged env is left exactly as it was, its neighbours step normally
+    q1, v1 = data.qpos.cpu().numpy().T, data.qvel.cpu().numpy().T
+    assert np.array_equal(q1[1], qpos[1]) and np.array_equal(v1[1], qvel[1])
+    assert np.array_equal(v1[2], qvel[2]) and np.array_equal(np.isnan(q1[2]), np.isnan(qpos[2]))
+    assert not np.array_equal(q1[0], qpos[0]) and not np.array_equal(q1[3], qpos[3])
+
+
+def test_bad_state_is_frozen_on_the_warp_engine():
+    from mujoco_template import _capi, _mj as mj
+
+    model = load_model("humanoid")
+    n = 5  # odd: the last lock-step pair has one env only
+    qpos, qvel, ctrl = random_states(model, "humanoid", n, seed=3)
+    qvel[1, 4] = -3e11
+    qpos[4, 9] = np.inf
+    data = _batch(model, n)
+    _upload(data, qpos, qvel, ctrl)
+    mj.mj_step(model, data, 2)
+    flags = data.flags.cpu().numpy()[0]
+    assert flags[0] == 0 and flags[2] == 0 and flags[3] == 0
+    assert flags[1] & _capi.FLAG_BAD_QVEL and flags[4] & _capi.FLAG_BAD_QPOS
+    q1, v1 = data.qpos.cpu().numpy().T, data.qvel.cpu().numpy().T
+    assert np.array_equal(q1[1], qpos[1]) and np.array_equal(v1[1], qvel[1])
+    assert np.array_equal(q1[4], qpos[4]) and np.array_equal(v1[4], qvel[4])
+    # the healthy envs match the oracle
+    om, od = oracle_for(model)
+    for e in (0, 2, 3):
+        od.reset()
+        od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+        od.step(2)
+        assert _rel(q1[e], od.qpos) <= STEP_RTOL and _rel(v1[e], od.qvel) <= 1e-8
 
 
 @pytest.mark.parametrize("name", MODEL_NAMES)
