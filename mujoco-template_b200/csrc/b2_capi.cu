@@ -260,6 +260,16 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
   } else {
     rc = ensure_resident(b, stream);
     if (rc) return rc;
+    // large models on the warp engine: one warp per (column, env) rollout pair (B2_WARP_FD=0: lane engine)
+    static const bool warp_fd = [] { const char* x = getenv("B2_WARP_FD"); return !(x && x[0] == '0'); }();
+    if ((rc = prepare_warp(b))) return rc;
+    if (warp_fd && b->warp_mode == 1 && count == b->nenv && !gain && !shadow) {
+      rc = b->precision == B2_F64
+               ? b2::b2k_warp_linearize_f64(&b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_linearize_f32(&b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
+      g_launches++;
+      return rc ? cuda_fail((cudaError_t)rc, "warp linearize launch") : B2_OK;
+    }
     rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream)
                                 : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream);
   }

@@ -212,6 +212,25 @@ int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived
         to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v));
   return (int)cudaGetLastError();
 }
+// FD linearisation on the warp engine: same grid and scratch slots as the step plan (wpb warps per block)
+int B2_FN(b2k_warp_linearize)(const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,
+                              void* counter, int wpb, int blocks, void* stream) {
+  const int extra = 2 * (v->nq + v->nv);
+  const size_t smem = warp_block_smem(v, wpb) + (size_t)wpb * extra * sizeof(real);
+  auto kern = k_warp_linearize<real, GlobalModelLarge, 1>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  if (blocks > sms * per_sm) blocks = sms * per_sm;  // persistent: never more blocks than fit at once (scratch slots are per block)
+  e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
+  if (e != cudaSuccess) return (int)e;
+  kern<<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(to_dev<real>(st), N, (real)eps, centered, (real*)A, (real*)B, (real*)jscratch,
+                                                         (int*)counter, warp_ws_reals_of(v), extra, wpb);
+  return (int)cudaGetLastError();
+}
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,
                          const void* gain, const b2_state* shadow, void* stream) {
   const int threads = 128;

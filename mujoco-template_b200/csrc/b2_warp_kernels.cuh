@@ -126,4 +126,100 @@ __global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, Derived
   }
 }
 
+// FD linearisation on the warp engine (large models): the work items are (column, env) pairs -- column-major, so that the
+// two warps of a lock-step pair run the same kind of column -- and an item is two full rollouts of one step from the
+// nominal state: plus / minus for a centred column, plus (or minus) and the nominal step where a control sits at its
+// range bound (mjd_transitionFD's one-sidedness, as k_linearize).  Every rollout restores qacc_warmstart.  The columns go
+// to A (2nv x 2nv x N) and B (2nv x nu x N), env fastest.  extra = 2 (nq + nv) reals per warp hold the two end states.
+template <typename T, class M, int LS>
+__global__ void __launch_bounds__(256, 1) k_warp_linearize(StateDev<T> st, int N, T eps, int centered, T* A, T* B, T* jscratch, int* queue,
+                                                          int ws_reals, int extra, int gsize) {
+  extern __shared__ double b2_smem[];
+  __shared__ int s_next[8];
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
+  const int ngroups = wpb / gsize, grp = wib % ngroups, rank = wib / ngroups;
+  const int ints = kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T));
+  T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + ints + extra);
+  WarpEnv<T, M> env;
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  env.bar_id = 1 + grp; env.bar_cnt = 32 * gsize;
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv, ncol = ndx + nu;
+  T* ends[2] = {base + ws_reals + ints, base + ws_reals + ints + nq + nv};  // [0]: minus side (s1), [1]: plus side (s2)
+  const int total = N * ncol;
+  int flags_all = 0;
+  int first = (blockIdx.x * ngroups + grp) * gsize;
+  while (first < total) {
+    const bool mine = first + rank < total;
+    const int item = mine ? first + rank : total - 1;
+    const int c = item / N, e = item - c * N;
+    int kind, i;
+    bool fwd = true, back = centered != 0;
+    if (c < nv) { kind = 1; i = c; }
+    else if (c < ndx) { kind = 2; i = c - nv; }
+    else {
+      kind = 3; i = c - ndx;
+      const T u = st.ctrl[(size_t)i * N + e], lo = M::actuator_ctrlrange(2 * i), hi = M::actuator_ctrlrange(2 * i + 1);
+      const bool lim = M::actuator_ctrllimited(i) != 0;
+      fwd = !lim || (u >= lo && u <= hi && u + eps >= lo && u + eps <= hi);
+      back = (centered || !fwd) && (!lim || (u - eps >= lo && u - eps <= hi && u >= lo && u <= hi));
+    }
+    // two rollouts per item whatever the column needs, so that both warps of a pair meet at every barrier
+    for (int side = 1; side >= 0; side--) {
+      const T delta = side ? (fwd ? eps : T(0)) : (back ? -eps : T(0));
+      WFOR(k, nq) env.qpos[k] = st.qpos[(size_t)k * N + e];
+      WFOR(k, nv) { env.qvel[k] = st.qvel[(size_t)k * N + e] + ((kind == 2 && k == i) ? delta : T(0)); env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
+      WFOR(k, nu) env.ctrl[k] = st.ctrl[(size_t)k * N + e] + ((kind == 3 && k == i) ? delta : T(0));
+      env.flags = 0;
+      __syncwarp();
+      if (kind == 1 && lane == 0) {  // tangent-space step along dof i (mj_integratePos of a unit vector)
+        const int j = M::dof_jntid(i), pa = M::jnt_qposadr(j), d = i - M::jnt_dofadr(j);
+        if (M::jnt_type(j) == JNT_FREE && d >= 3) {
+          T q[4] = {env.qpos[pa + 3], env.qpos[pa + 4], env.qpos[pa + 5], env.qpos[pa + 6]}, w[3] = {0, 0, 0};
+          w[d - 3] = 1;
+          quat_integrate(q, w, delta);
+          for (int k = 0; k < 4; k++) env.qpos[pa + 3 + k] = q[k];
+        } else env.qpos[pa + (M::jnt_type(j) == JNT_FREE ? d : 0)] += delta;
+      }
+      __syncwarp();
+      env.check_state();
+      env.template forward<LS>();
+      env.check_acc();
+      env.template stage_sync<LS>();
+      env.euler();
+      flags_all |= env.flags;
+      T* dst = ends[side];
+      WFOR(k, nq) dst[k] = env.qpos[k];
+      WFOR(k, nv) dst[nq + k] = env.qvel[k];
+      __syncwarp();
+    }
+    if (mine) {
+      const T* s1 = ends[0];
+      const T* s2 = ends[1];
+      const T ih = (fwd && back) ? T(0.5) / eps : ((fwd || back) ? T(1) / eps : T(0));
+      T* out = c < ndx ? A + ((size_t)c) * N + e : B + ((size_t)(c - ndx)) * N + e;
+      const size_t rs = (size_t)(c < ndx ? ndx : nu) * N;  // row stride
+      if (c < ndx ? A != nullptr : B != nullptr) {
+        WFOR(j, M::njnt()) {
+          const int pa = M::jnt_qposadr(j), va = M::jnt_dofadr(j);
+          if (M::jnt_type(j) == JNT_FREE) {
+            T neg[4] = {s1[pa + 3], -s1[pa + 4], -s1[pa + 5], -s1[pa + 6]}, q2[4] = {s2[pa + 3], s2[pa + 4], s2[pa + 5], s2[pa + 6]}, dq[4], rv[3];
+            quat_mul(dq, neg, q2);
+            quat_to_vel(rv, dq, T(1));
+            for (int k = 0; k < 3; k++) { out[(va + k) * rs] = (s2[pa + k] - s1[pa + k]) * ih; out[(va + 3 + k) * rs] = rv[k] * ih; }
+          } else out[va * rs] = (s2[pa] - s1[pa]) * ih;
+        }
+        WFOR(k, nv) out[(nv + k) * rs] = (s2[nq + k] - s1[nq + k]) * ih;
+      }
+      if (st.flags && flags_all && lane == 0) atomicOr(st.flags + e, flags_all);
+    }
+    flags_all = 0;
+    __syncwarp();
+    if (rank == 0 && lane == 0) s_next[grp] = nw + atomicAdd(queue, gsize);
+    env.template stage_sync<1>();
+    first = s_next[grp];
+    env.template stage_sync<1>();
+  }
+}
+
 }  // namespace b2
