@@ -261,7 +261,8 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
     rc = ensure_resident(b, stream);
     if (rc) return rc;
     // large models on the warp engine: one warp per (column, env) rollout pair (B2_WARP_FD=0: lane engine)
-    static const bool warp_fd = [] { const char* x = getenv("B2_WARP_FD"); return !(x && x[0] == '0'); }();
+    const char* wfd = getenv("B2_WARP_FD");
+    const bool warp_fd = !(wfd && wfd[0] == '0');
     if ((rc = prepare_warp(b))) return rc;
     if (warp_fd && b->warp_mode == 1 && count == b->nenv && !gain && !shadow) {
       rc = b->precision == B2_F64

@@ -177,7 +177,9 @@ def test_linearize_parity(name):
         ctrl[0, 0] = 0.0   # at the lower ctrlrange bound: forward one-sided difference
         ctrl[1, 1] = 13.0  # at the upper bound: backward difference
     if name == "humanoid":
-        ctrl[0, 3] = 1.0
+        ctrl[0, 3] = 1.0    # upper bound: backward difference
+        ctrl[1, 5] = -1.0   # lower bound: forward difference
+        ctrl[2, 7] = 1.5    # outside the range: mjd_transitionFD leaves the column at zero
     data = _batch(model, n)
     _upload(data, qpos, qvel, ctrl)
     eps = 1e-6
@@ -192,6 +194,25 @@ def test_linearize_parity(name):
         Ao, Bo = od.transition_fd(eps, True)
         assert _rel(A[e], Ao) <= AB_RTOL, (name, e, _rel(A[e], Ao))
         assert _rel(B[e], Bo) <= AB_RTOL, (name, e, _rel(B[e], Bo))
+
+
+def test_warp_engine_fd_matches_lane_engine_fd(monkeypatch):
+    """humanoid (A, B): k_warp_linearize (one warp per column rollout pair) vs the lane engine's k_linearize."""
+    model = load_model("humanoid")
+    n = 7  # odd: the last lock-step pair of the last column has one item only
+    qpos, qvel, ctrl = random_states(model, "humanoid", n, seed=13)
+    ctrl[3, 0] = -1.0
+    out = {}
+    for warp in ("1", "0"):
+        monkeypatch.setenv("B2_WARP_FD", warp)
+        data = _batch(model, n)
+        _upload(data, qpos, qvel, ctrl)
+        A, B = data.backend.linearize(1e-6, True)
+        out[warp] = (A.cpu().numpy(), B.cpu().numpy(), data.qpos.cpu().numpy().T.copy())
+    assert np.array_equal(out["1"][2], qpos) and np.array_equal(out["0"][2], qpos)
+    # same algorithm, different summation orders inside a step: roundoff amplified by 1 / eps
+    assert _rel(out["1"][0], out["0"][0]) <= 1e-7 and _rel(out["1"][1], out["0"][1]) <= 1e-7
+    assert np.abs(out["1"][0]).max() > 0.5 and np.abs(out["1"][1]).max() > 1e-3
 
 
 @pytest.mark.parametrize("name", MODEL_NAMES)

@@ -53,7 +53,7 @@ for name, ns in sizes.items():
             out = dict(model=name, nenv=n, precision=prec, kernel=d.backend.batch.kernel_variant, step_ms=ms,
                        env_steps_per_sec=n / ms * 1e3, bytes_per_step=(2 * model.nq + 2 * model.nv + model.nu + 2 * model.nv) * prec // 8)
             out["hbm_gbs"] = out["bytes_per_step"] * n / ms / 1e6
-            if prec == 64 and n <= 2**18 and not (name == "humanoid" and n > 2**12):
+            if prec == 64 and n <= 2**18 and not (name == "humanoid" and n > 2**14):
                 A, B = d.backend.linearize(1e-6, True)
                 lms = timed(lambda: d.backend.linearize(1e-6, True, out=(A, B)), 3)
                 out["linearize_ms"] = lms; out["linearizations_per_sec"] = n / lms * 1e3
