@@ -390,6 +390,29 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
   const void* gain = use_lqr ? b->d_gain : nullptr;
   const b2m_view& v = b->model->v;
   b->shadow_has_prestep = false;
+  if (!active_spec(b)) {
+    int rc = ensure_resident(b, stream);
+    if (rc || (rc = prepare_warp(b))) return rc;
+    if (b->warp_mode == 1) {
+      // large models: control-law launch, FD on the warp engine, step on the warp engine.  Without a `derived`
+      // argument the pre-step state is parked in the shadow arrays for b2_refresh_derived, as in the fused form.
+      if (gain && (rc = do_lqr_control(b, st, b->nenv, stream))) return rc;
+      if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream))) return rc;
+      if (!derived && st->qacc_warmstart) {
+        b2_state shadow;
+        if ((rc = shadow_state(b, &shadow))) return rc;
+        const size_t N = (size_t)b->nenv, es = b->esz;
+        cudaStream_t s = (cudaStream_t)stream;
+        cudaError_t e = cudaMemcpyAsync(shadow.qpos, st->qpos, v.nq * N * es, cudaMemcpyDeviceToDevice, s);
+        if (!e) e = cudaMemcpyAsync(shadow.qvel, st->qvel, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
+        if (!e) e = cudaMemcpyAsync(shadow.qacc_warmstart, st->qacc_warmstart, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
+        if (!e && v.nu) e = cudaMemcpyAsync(shadow.ctrl, st->ctrl, v.nu * N * es, cudaMemcpyDeviceToDevice, s);
+        if (e) return cuda_fail(e, "b2_control_tick: shadow copy");
+        b->shadow_has_prestep = true;
+      }
+      return do_step(b, st, b->nenv, 1, derived, stream);
+    }
+  }
   if (!derived && v.integrator == 0 && st->qacc_warmstart && (v.nu == 0 || st->ctrl)) {
     b2_state shadow;
     int rc = shadow_state(b, &shadow);

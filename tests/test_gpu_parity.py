@@ -489,6 +489,37 @@ def test_step_host_pipeline_matches_device_path(name, n):
             assert np.array_equal(hA.numpy(), A.cpu().numpy()) and np.array_equal(hB.numpy(), B.cpu().numpy()), rep
 
 
+def test_control_tick_on_the_warp_engine():
+    """humanoid: b2_control_tick = control-law launch + warp-engine FD + warp-engine step; the derived arrays of the
+    tick are produced lazily from the parked pre-step state, as on the small models."""
+    from mujoco_template import _mj as mj
+
+    model = load_model("humanoid")
+    n = 6
+    qpos, qvel, _ = random_states(model, "humanoid", n, seed=17)
+    rng = np.random.default_rng(0)
+    K = rng.normal(0, 0.02, (model.nu, 2 * model.nv))
+    qref, uref = np.array(model.key_qpos[1]), np.zeros(model.nu)
+    out = {}
+    for fused in (True, False):
+        data = _batch(model, n)
+        _upload(data, qpos, qvel, np.zeros((n, model.nu)))
+        data.backend.batch.lqr_set_gain(K, qref, uref)
+        for _ in range(3):
+            if fused:
+                A, B = data.backend.control_tick(1e-6, True, True, derived=False)
+                assert data.backend.derived_stale
+            else:
+                data.backend.batch.lqr_control(data.backend.state_struct())
+                A, B = data.backend.linearize(1e-6, True)
+                data.backend.step(1)
+        out[fused] = [x.clone() for x in (data.qpos, data.qvel, data.ctrl, A, B, data.xpos, data.qacc)]
+        assert not data.backend.derived_stale
+    for k, (a, b) in enumerate(zip(out[True], out[False])):
+        assert a.shape == b.shape and bool((a == b).all()), k   # the same kernels on the same inputs: bit-identical
+    assert float(out[True][2].abs().max()) > 1e-3               # the law did produce controls
+
+
 @pytest.mark.parametrize("name", ["cartpole", "drone"])
 def test_fused_lqr_control_kernel_matches_torch_reference(name):
     """b2_lqr_control (one launch) == the same tick written with torch ops, incl. quaternion error and ctrl clamp."""
