@@ -27,6 +27,52 @@ def dlqr_gain(A: np.ndarray, B: np.ndarray, Q: np.ndarray, R: np.ndarray) -> np.
     return np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
 
 
+def batched_dlqr_gain(A, B, Q, R, max_doublings: int = 40, tol: float = 1e-13):
+    """Infinite-horizon discrete LQR gains of a whole batch on the device.
+
+    ``A`` (N, nx, nx) and ``B`` (N, nx, nu) are torch tensors (any device; ``StepResult.info['A'/'B']`` of a
+    ``BatchedEnv`` have exactly this shape), ``Q`` (nx, nx) and ``R`` (nu, nu) are shared.  Returns ``(K, P)`` with
+    ``u = -K x``, ``K`` (N, nu, nx), ``P`` (N, nx, nx) the stabilising DARE solutions.  The DARE is solved by the
+    structure-preserving doubling iteration (k doublings = a Riccati recursion over 2**k steps, quadratic convergence):
+
+        W = I + G H;  A <- A W^-1 A;  G <- G + A W^-1 G A';  H <- H + A' H W^-1 A      (G0 = B R^-1 B', H0 = Q)
+
+    -- one batched solve and a few batched products per doubling, no per-env host work.  The single-system
+    reference recipe is ``scipy.linalg.solve_discrete_are`` (reference ``examples/drone/controllers/lqr.py:350-378``,
+    ``examples/humanoid/controllers/lqr.py:114-115``); ``dlqr_gain`` keeps that path for one system."""
+    import torch
+
+    A = torch.as_tensor(A)
+    B = torch.as_tensor(B, dtype=A.dtype, device=A.device)
+    if A.dim() == 2:
+        A, B = A[None], B[None]
+    Q = torch.as_tensor(Q, dtype=A.dtype, device=A.device)
+    R = torch.as_tensor(R, dtype=A.dtype, device=A.device)
+    n, nx = A.shape[0], A.shape[1]
+    eye = torch.eye(nx, dtype=A.dtype, device=A.device).expand(n, nx, nx)
+    Ak = A.clone()
+    G = B @ torch.linalg.solve(R, B.transpose(1, 2))
+    H = Q.expand(n, nx, nx).clone()
+    for k in range(max_doublings):
+        W = eye + G @ H
+        V = torch.linalg.solve(W, torch.cat([Ak, G], dim=2))  # W^-1 [A, G] in one batched solve
+        V1, V2 = V[:, :, :nx], V[:, :, nx:]
+        At = Ak.transpose(1, 2)
+        Hn = H + At @ H @ V1
+        G = G + Ak @ V2 @ At
+        Ak = Ak @ V1
+        Hn = 0.5 * (Hn + Hn.transpose(1, 2))
+        G = 0.5 * (G + G.transpose(1, 2))
+        done = k >= 3 and bool(((Hn - H).abs().amax(dim=(1, 2)) <= tol * Hn.abs().amax(dim=(1, 2)).clamp_min(1.0)).all())
+        H = Hn
+        if done:
+            break
+    P = H
+    BtP = B.transpose(1, 2) @ P
+    K = torch.linalg.solve(R + BtP @ B, BtP @ A)
+    return K, P
+
+
 class BatchedLQRController:
     def __init__(self, qpos_ref: np.ndarray | None = None, ctrl_ref: np.ndarray | None = None,
                  Q: np.ndarray | None = None, R: np.ndarray | None = None, eps: float = 1e-6,
@@ -110,4 +156,4 @@ class BatchedLQRController:
         data.ctrl.copy_(u)
 
 
-__all__ = ["BatchedLQRController", "dlqr_gain"]
+__all__ = ["BatchedLQRController", "batched_dlqr_gain", "dlqr_gain"]
