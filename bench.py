@@ -408,15 +408,16 @@ def main():
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
-    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul).  cartpole: counted by ncu on the kernels themselves
-    # (profiles/ncu_cartpole_kernels_r01f.txt: k_linearize 4.338e8 flops per 655,360 rollouts = 662 -- one thread per env
-    # runs the shared position stage once for all velocity / control columns -- and k_step 962 per step); the others are
-    # the a-priori estimates of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 662.0 if lin else 962.0, "drone": 1500.0, "humanoid": 100000.0}[name]
+    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
+    # themselves (profiles/ncu_*_r01h.txt): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per
+    # env runs the shared position stage once for all velocity / control columns, control columns skip the velocity stage
+    # too -- and k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 3.10e9 / 16,384 =
+    # 189,000 (mean 3.6 contacts, 2.9 Newton iterations); pendulum: a-priori estimate of BASELINE.md
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 189000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
-                     "flops_source": ("ncu-counted executed flops (profiles/)" if name == "cartpole" else "a-priori estimate (BASELINE.md section 4)"), "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
+                     "flops_source": ("ncu-counted executed flops (profiles/)" if name != "pendulum" else "a-priori estimate (BASELINE.md section 4)"), "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
 
     # ---- e2e: host buffers through the C-ABI (b2_step_host): H2D state+ctrl, linearise+step, D2H state+(A,B)
     e2e = None
