@@ -22,6 +22,9 @@ lo, hi = {"drone": (0.0, 13.0), "humanoid": (-0.2, 0.2)}.get(name, (-1.0, 1.0))
 for _ in range(pre):  # age the batch under random controls (drones reach the floor, the humanoid falls)
     d.ctrl.uniform_(lo, hi)
     d.backend.step(1, derived=False)
+for _ in range(3):
+    d.backend.step(1, derived=False)
+torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(4):
