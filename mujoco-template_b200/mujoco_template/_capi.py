@@ -54,7 +54,7 @@ def lib() -> C.CDLL:
         raise TemplateError(
             f"native library not found: {_LIB_PATH}. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(make -C mujoco-template_b200/csrc). There is no CPU fallback for the physics path.")
-    L = C.CDLL(_LIB_PATH)
+    L = C.CDLL(_LIB_PATH, mode=C.RTLD_GLOBAL)  # global: run-time specialisations (jit_specialize) link against it
     vp, i, d = C.c_void_p, C.c_int, C.c_double
     L.b2_last_error.restype = C.c_char_p
     L.b2_version.restype = C.c_char_p

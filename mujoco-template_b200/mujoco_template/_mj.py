@@ -18,6 +18,7 @@ read and write in place (zero-copy, like the reference's views of ``mjData``).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from types import SimpleNamespace
 from typing import Any
 
@@ -149,9 +150,22 @@ class MjModel:
     @property
     def native(self) -> _capi.NativeModel:
         if self._native is None:
+            if os.environ.get("B2_JIT_SPEC") == "1":  # opt-in: compile register-resident kernels for this model first
+                from ._specialize import jit_specialize
+
+                jit_specialize(self)
             self._native = _capi.NativeModel(self.blob)
             self._apply_disable_mask()
         return self._native
+
+    def specialize(self, name: str | None = None) -> str | None:
+        """Compile and register model-specialised kernels for this model (``_specialize.jit_specialize``).  Call it
+        before the first env / batch of the model is created; returns the cached shared object or None (nv > 8)."""
+        from ._specialize import jit_specialize
+
+        if self._native is not None:
+            raise ConfigError("MjModel.specialize(): call it before the model is first used on the device")
+        return jit_specialize(self, name)
 
     def _apply_disable_mask(self) -> None:
         if self._native is None or self.nu == 0:

@@ -186,3 +186,55 @@ def write_specs(models: dict[str, dict], outdir: str) -> list[str]:
                 fh.write(text)
         paths.append(path)
     return paths
+
+
+# ------------------------------------------------------------------ run-time specialisation of a user's model
+JIT_MAX_NV = 8  # beyond this the fully unrolled kernels stop paying (registers, compile time): generic / warp engine
+
+
+def jit_specialize(model, name: str | None = None, cache_dir: str | None = None, verbose: bool = False) -> str | None:
+    """Compile model-specialised (register-resident) kernels for ``model`` with nvcc and register them with the
+    loaded ``libb2mj.so``; later ``b2_model_create`` calls on the same blob pick them up (``kernel_variant`` then
+    reports ``name``).  The example models ship pre-compiled; this gives any other small model of the MJCF subset the
+    same kernels (reference ``Env.from_xml_path`` compiles the model at load time too: ``mujoco_template/env.py:99-143``).
+
+    Returns the path of the shared object, or ``None`` when the model is too large (nv > JIT_MAX_NV).  The object is
+    cached under ``cache_dir`` (default ``$B2_SPEC_CACHE`` or ``~/.cache/b2mj``) keyed by the blob hash, so the
+    ~1 minute compile happens once per model."""
+    import ctypes
+    import shutil
+    import subprocess
+
+    from . import _capi
+
+    c = model._c if hasattr(model, "_c") else model
+    if int(c["nv"]) > JIT_MAX_NV:
+        return None
+    blob = _layout.pack(c)
+    key = f"{fnv1a(blob):016x}_{len(blob)}"
+    name = name or f"jit_{key[:8]}"
+    cache_dir = cache_dir or os.environ.get("B2_SPEC_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "b2mj")
+    os.makedirs(cache_dir, exist_ok=True)
+    so = os.path.join(cache_dir, f"spec_{key}.so")
+    if not os.path.exists(so):
+        nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+        csrc = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
+        cu = os.path.join(cache_dir, f"spec_{key}.cu")
+        with open(cu, "w") as fh:
+            fh.write(emit_spec(c, name))
+        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+               "--expt-relaxed-constexpr", "-shared", "-I", os.path.join(csrc, "generated"), cu, "-o", so + ".tmp"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            from .exceptions import ConfigError
+
+            raise ConfigError("jit_specialize: nvcc failed\n" + r.stderr[-2000:])
+        os.replace(so + ".tmp", so)
+        if verbose:
+            print(f"jit_specialize: built {so}")
+    _capi.lib()  # libb2mj.so must be loaded (globally) first: the object's registrar calls b2::register_spec
+    _LOADED.setdefault(so, ctypes.CDLL(so, mode=ctypes.RTLD_GLOBAL))
+    return so
+
+
+_LOADED: dict = {}

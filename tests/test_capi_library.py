@@ -73,3 +73,28 @@ def test_generated_headers_are_current():
     for name in ("pendulum", "cartpole", "drone"):
         path = os.path.join(ROOT, "mujoco-template_b200", "csrc", "generated", f"spec_{name}.cu")
         assert open(path).read() == _specialize.emit_spec(load_model(name)._c, name)
+
+
+def test_jit_specialize_builds_and_registers(tmp_path, monkeypatch):
+    """Run-time specialisation of a user model: nvcc cross-compiles the generated translation unit for sm_100a and the
+    object's registrar resolves b2::register_spec against the loaded libb2mj.so (no GPU needed for either)."""
+    import shutil
+    import warnings
+
+    import pytest
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    from mujoco_template import _mj as mj
+    from mujoco_template._specialize import jit_specialize
+    from test_mjcf_compiler import ARM_XML
+
+    monkeypatch.setenv("B2_SPEC_CACHE", str(tmp_path))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = mj.MjModel.from_xml_string(ARM_XML.replace('timestep="0.004"', 'timestep="0.0045"'))
+    so = jit_specialize(model, "cpu_side_check")
+    assert so is not None and os.path.exists(so) and os.path.getsize(so) > 100_000
+    assert jit_specialize(model, "cpu_side_check") == so  # cached
+    big = mj.MjModel.from_compiled(os.path.join(os.path.dirname(__file__), "golden", "models", "humanoid.b2m"))
+    assert jit_specialize(big) is None  # nv = 27: stays on the generic / warp engine

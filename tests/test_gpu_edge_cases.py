@@ -1,5 +1,6 @@
 """GPU edge cases: ragged / tiny batches, models outside the compiled-in specialisations (generic kernels),
 no-actuator models, joint limits, RK4 with springs and servo actuators, capacity errors."""
+import os
 import warnings
 
 import numpy as np
@@ -87,6 +88,29 @@ def test_two_link_arm_rk4_springs_generic():
     qpos = rng.uniform(-1.2, 1.2, (n, 2)); qvel = rng.uniform(-2, 2, (n, 2)); ctrl = rng.uniform(-1.5, 1.5, (n, 2))
     qpos[0, 0] = 1.7                                   # past the +-90 degree shoulder limit
     _parity_rollout(model, qpos, qvel, ctrl, 25)
+
+
+def test_jit_specialised_kernels_for_a_user_model(tmp_path, monkeypatch):
+    """A model that is not one of the pre-compiled examples gets register-resident kernels at load time
+    (MjModel.specialize -> nvcc -> registered with libb2mj.so), with the same parity as the generic kernels."""
+    import shutil
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    monkeypatch.setenv("B2_SPEC_CACHE", str(tmp_path))
+    xml = ARM_XML.replace('timestep="0.004" integrator="RK4"', 'timestep="0.003"')  # its own blob (and Euler): other tests keep the generic kernels
+    assert xml != ARM_XML
+    model = _compile(xml)
+    so = model.specialize("user_arm")
+    assert so is not None and os.path.exists(so)
+    n = 40
+    rng = np.random.default_rng(2)
+    qpos = rng.uniform(-1.2, 1.2, (n, 2)); qvel = rng.uniform(-2, 2, (n, 2)); ctrl = rng.uniform(-1.5, 1.5, (n, 2))
+    qpos[0, 0] = 1.7
+    data = _parity_rollout(model, qpos, qvel, ctrl, 25)
+    assert data.backend.batch.kernel_variant == "user_arm"
+    with pytest.raises(Exception):
+        model.specialize()  # too late: the model is already on the device
 
 
 def test_model_without_actuators():
