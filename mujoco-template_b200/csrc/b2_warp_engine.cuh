@@ -22,7 +22,9 @@ namespace b2 {
 // being bound by instruction fetch, 2.6 % slower
 #define WFOR(i, n) _Pragma("unroll 1") for (int i = lane; i < (n); i += 32)
 
-template <typename T> B2_DEV T warp_sum(T v) {
+// out of line (as are the other helpers with many call sites below): the kernel is bound by instruction fetch, a butterfly of
+// five dependent shuffles gains nothing from being inlined 50 times
+template <typename T> __device__ __noinline__ T warp_sum(T v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
@@ -164,6 +166,27 @@ __device__ __noinline__ void ls_eval_impl(const T* Jaref, const T* Jv, const T* 
   if (d2 <= 0) d2 = Num<T>::minval();
   out[0] = alpha; out[1] = alpha * alpha * q2 + alpha * q1 + q0; out[2] = 2 * alpha * q2 + q1; out[3] = d2;
   }
+
+// r = M v with the packed lower triangle Mp (one row per lane); out = J v [- sub] (one constraint row per lane)
+template <typename T>
+__device__ __noinline__ void mul_M_impl(const T* Mp, T* r, const T* v, int nv, int lane) {
+  WFOR(i, nv) {
+    T s = 0;
+    for (int j = 0; j < nv; j++) s += (j <= i ? Mp[tri(i, j)] : Mp[tri(j, i)]) * v[j];
+    r[i] = s;
+  }
+  __syncwarp();
+}
+template <typename T>
+__device__ __noinline__ void mul_J_impl(const T* J, T* out, const T* v, const T* sub, int nefc, int nv, int lane) {
+  WFOR(i, nefc) {
+    T s = 0;
+    for (int k = 0; k < nv; k++) s += J[i * nv + k] * v[k];
+    out[i] = sub ? s - sub[i] : s;
+  }
+  __syncwarp();
+}
+template <typename T> __device__ __noinline__ void make_frame_shared(T* fr) { make_frame(fr); }
 
 template <typename T, class M>
 struct WarpEnv {
@@ -404,15 +427,7 @@ struct WarpEnv {
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
   B2_DEV void factor_LD() { factor_LD_impl<T, M>(LDp, dinv, Mv, lane); }  // Mv: scratch, only live inside the line search
   B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(LDp, dinv, x, lane); }
-  B2_DEV void mul_M(T* r, const T* v) {
-    const int nv = M::nv();
-    WFOR(i, nv) {
-      T s = 0;
-      for (int j = 0; j < nv; j++) s += (j <= i ? Mp[tri(i, j)] : Mp[tri(j, i)]) * v[j];
-      r[i] = s;
-    }
-    __syncwarp();
-  }
+  B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, M::nv(), lane); }
 
   // Jacobian column of dof d for a point on `body` at offset `off` from the root's subtree CoM; false if d does not move body
   B2_DEV bool jac_col(int last, int d, const T* off, T* jp) const {
@@ -529,7 +544,7 @@ struct WarpEnv {
         if (slot < WarpCaps::NCON) {
           T fr[9];
           for (int k = 0; k < 6; k++) fr[k] = cfr[6 * c + k];
-          make_frame(fr);
+          make_frame_shared(fr);
           con_dist[slot] = cd[c]; con_pair[slot] = p;
           for (int k = 0; k < 3; k++) con_pos[3 * slot + k] = cpos[3 * c + k];
           for (int k = 0; k < 9; k++) con_frame[9 * slot + k] = fr[k];
@@ -804,15 +819,7 @@ struct WarpEnv {
 
   // ------------------------------------------------------------------ Newton solver
   // J v for all rows: one row per lane
-  B2_DEV void mul_J(T* out, const T* v, const T* sub) {
-    const int nv = M::nv();
-    WFOR(i, nefc) {
-      T s = 0;
-      for (int k = 0; k < nv; k++) s += J[i * nv + k] * v[k];
-      out[i] = sub ? s - sub[i] : s;
-    }
-    __syncwarp();
-  }
+  B2_DEV void mul_J(T* out, const T* v, const T* sub) { mul_J_impl<T>(J, out, v, sub, nefc, M::nv(), lane); }
   B2_DEV T row_cost(const T* jar) {
     T c = 0;
     WFOR(i, nefc) if (jar[i] < 0) c += T(0.5) * row_D[i] * jar[i] * jar[i];
@@ -913,9 +920,9 @@ struct WarpEnv {
       T h[EPL];
 #pragma unroll
       for (int t = 0; t < EPL; t++) h[t] = lane + 32 * t < np ? Mp[lane + 32 * t] : T(0);
-#pragma unroll
+#pragma unroll 1
       for (int w = 0; w < (WarpCaps::NEFC + 31) / 32; w++) {
-        for (unsigned bits = sig[w]; bits; bits &= bits - 1) {
+        for (unsigned bits = w == 0 ? sig[0] : (w == 1 ? sig[1] : (w == 2 ? sig[2] : sig[3])); bits; bits &= bits - 1) {
           const int r = w * 32 + __ffs(bits) - 1;
           const T* Jr = J + r * nv;
           const T d = row_D[r];
