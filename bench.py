@@ -409,7 +409,7 @@ def main():
     # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
     # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
-    # themselves (profiles/ncu_*_r01h.txt): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per
+    # themselves (profiles/ncu_*_r01i.txt): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per
     # env runs the shared position stage once for all velocity / control columns, control columns skip the velocity stage
     # too -- and k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 3.10e9 / 16,384 =
     # 189,000 (mean 3.6 contacts, 2.9 Newton iterations); pendulum: a-priori estimate of BASELINE.md
