@@ -22,9 +22,10 @@ import threading
 import time
 import warnings
 
-# NCCL_DEBUG=VERSION makes NCCL print its version banner to stdout, ahead of the one JSON line rank 0 owes the driver
+# NCCL_DEBUG=VERSION makes NCCL print its version banner to stdout (WARN does too), ahead of the one JSON line rank 0 owes
+# the driver: drop the request (an explicit INFO / TRACE setting is left alone)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+    del os.environ["NCCL_DEBUG"]
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT, os.path.join(ROOT, "mujoco-template_b200")):
