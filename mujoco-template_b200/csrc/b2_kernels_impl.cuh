@@ -163,7 +163,7 @@ int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks
   if (warp_lockstep()) {
     // one block per SM with as many warps (envs) as the shared-memory workspace allows, at most 8
     int wpb = 2;
-    if (const char* x = getenv("B2_WARP_LS_WPB")) wpb = atoi(x) > 0 && atoi(x) <= 8 ? atoi(x) : 2;
+    if (const char* x = getenv("B2_WARP_LS_WPB")) wpb = atoi(x) == 1 ? 1 : 2;  // the kernels are compiled for 64-thread blocks
     while (wpb > 1 && warp_block_smem(v, wpb) + 1024 > (size_t)smem_max) wpb--;
     const size_t smem = warp_block_smem(v, wpb);
     auto kern = warp_lockstep() == 2 ? k_warp_step_ls<real, GlobalModelLarge, 2> : k_warp_step_ls<real, GlobalModelLarge, 1>;
@@ -189,7 +189,7 @@ int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks
   return blocks * wpb;
 }
 size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
-  return (size_t)slots * WarpCaps::NEFC * (v->nv + 6) * sizeof(real);
+  return (size_t)slots * warp_slot_reals(v->nv) * sizeof(real);
 }
 int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
                          void* counter, int wpb, int blocks, void* stream) {

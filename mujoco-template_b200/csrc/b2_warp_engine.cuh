@@ -81,6 +81,8 @@ inline cudaError_t upload_chol_plan(int nv, cudaStream_t s) {
 }
 
 struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
+// reals of global scratch one resident warp owns: J (NEFC x nv), six row vectors, and the contact records (dist, pos, frame)
+__host__ __device__ inline size_t warp_slot_reals(int nv) { return (size_t)WarpCaps::NEFC * (nv + 6) + 13 * WarpCaps::NCON; }
 
 // number of T elements of shared memory one env needs
 template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int nj, int ng, int nt) {
@@ -89,7 +91,7 @@ template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, 
   const int overlayB = 6 * nv + 6 * nb;
   if (overlayB > overlayA) overlayA = overlayB;
   return (nq + 2 * nv + nu) + (3 + 4 + 9 + 3) * nb + overlayA + 6 * ng + 3 * nb + 10 * nb + 10 * nb + 6 * nv + 6 * nb +
-         2 * np + 2 * nv + nt + nt * nv + 11 * nv + 6 * (nv > nb ? nv : nb) + 13 * WarpCaps::NCON;
+         2 * np + 2 * nv + nt + nt * nv + 11 * nv + (nb <= nv ? 0 : 6 * nb);  // buf6 aliases qacc .. search when it fits
 }
 
 // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once; tk: nv scratch reals
@@ -221,14 +223,18 @@ struct WarpEnv {
     cdof = take(6 * nv); cacc = take(6 * nb);
     Mp = take(np); LDp = take(np); dinv = take(nv); hdinv = take(nv); ten_len = take(nt); ten_J = take(nt * nv);
     f_bias = take(nv); f_passive = take(nv); f_smooth = take(nv); f_con = take(nv); a_smooth = take(nv); qacc = take(nv);
-    Ma = take(nv); Mv = take(nv); grad = take(nv); Mgrad = take(nv); search = take(nv); buf6 = take(6 * (nv > nb ? nv : nb));
-    con_dist = take(WarpCaps::NCON); con_pos = take(3 * WarpCaps::NCON); con_frame = take(9 * WarpCaps::NCON);
+    Ma = take(nv); Mv = take(nv); grad = take(nv); Mgrad = take(nv); search = take(nv);
+    // buf6 (6 reals per dof / body, live in mass_matrix and bias_forces only) shares the 6 nv reals of qacc .. search, which
+    // are first written after those stages; shared memory per env decides how many warps an SM holds
+    buf6 = nb <= nv ? qacc : take(6 * nb);
     con_pair = ibase; row_meta = ibase + WarpCaps::NCON;
     // per-row data lives in the warp's global scratch slot (L1/L2 resident): J, then six row vectors
     J = jscratch;
     T* rv = jscratch + WarpCaps::NEFC * nv;
     row_pos = rv; row_margin = rv + WarpCaps::NEFC; row_D = rv + 2 * WarpCaps::NEFC; row_aref = rv + 3 * WarpCaps::NEFC;
     Jaref = rv + 4 * WarpCaps::NEFC; Jv = rv + 5 * WarpCaps::NEFC;
+    T* cb = rv + 6 * WarpCaps::NEFC;  // contact records: written by collide, read by make_rows (once per step each)
+    con_dist = cb; con_pos = cb + WarpCaps::NCON; con_frame = cb + 4 * WarpCaps::NCON;
     lane = threadIdx.x & 31;
     ncon = nefc = niter = flags = 0;
 #pragma unroll

@@ -3,6 +3,10 @@
 #include "b2_kernel_templates.cuh"
 #include "b2_warp_engine.cuh"
 
+// The lock-step kernels are compiled for at most 200 registers (__maxnreg__): with 21.8 KB of shared memory per env that is
+// five two-warp blocks = 10 warps per SM (254 registers and 26.5 KB: 8 warps; +3 % humanoid throughput).  A 168-register
+// build (__launch_bounds__(64, 5) picks that) spills and is 5 % slower than the 8-warp one.
+
 namespace b2 {
 
 constexpr int kWarpIntsAsReals = (WarpCaps::NCON + WarpCaps::NEFC + 1) / 2;  // int metadata, counted in 8-byte units
@@ -33,7 +37,7 @@ __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> 
   const int gw = blockIdx.x * wpb + wib, nw = gridDim.x * wpb;
   T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T)));
   WarpEnv<T, M> env;
-  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * warp_slot_reals(M::nv()));
   const int total = nsteps > 0 ? nsteps : 1;
   // dynamic scheduling: env costs differ (contacts, Newton iterations), a static stride leaves SMs idle at the tail
   for (int e = gw; e < N; e = nw + __shfl_sync(0xffffffffu, lane == 0 ? atomicAdd(queue, 1) : 0, 0)) {
@@ -72,7 +76,7 @@ __global__ void __launch_bounds__(64) k_warp_step(StateDev<T> st, DerivedDev<T> 
 // map == 0: group = warp % ngroups (with 8 warps and pairs: warps w and w + 4, which share an SM sub-partition);
 // map == 1: group = warp / gsize (adjacent warps).
 template <typename T, class M, int LS>
-__global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps,
+__global__ void __maxnreg__(200) k_warp_step_ls(StateDev<T> st, DerivedDev<T> out, int want_derived, int N, int nsteps,
                                                         T* jscratch, int* queue, int ws_reals, int gsize, int map) {
   extern __shared__ double b2_smem[];
   __shared__ int s_next[8];
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, Derived
   const int grp = map ? wib / gsize : wib % ngroups, rank = map ? wib % gsize : wib / ngroups;
   T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T)));
   WarpEnv<T, M> env;
-  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * warp_slot_reals(M::nv()));
   env.bar_id = 1 + grp; env.bar_cnt = 32 * gsize;
   const int total = nsteps > 0 ? nsteps : 1;
   int first = (blockIdx.x * ngroups + grp) * gsize;
@@ -132,7 +136,7 @@ __global__ void __launch_bounds__(256, 1) k_warp_step_ls(StateDev<T> st, Derived
 // range bound (mjd_transitionFD's one-sidedness, as k_linearize).  Every rollout restores qacc_warmstart.  The columns go
 // to A (2nv x 2nv x N) and B (2nv x nu x N), env fastest.  extra = 2 (nq + nv) reals per warp hold the two end states.
 template <typename T, class M, int LS>
-__global__ void __launch_bounds__(256, 1) k_warp_linearize(StateDev<T> st, int N, T eps, int centered, T* A, T* B, T* jscratch, int* queue,
+__global__ void __maxnreg__(200) k_warp_linearize(StateDev<T> st, int N, T eps, int centered, T* A, T* B, T* jscratch, int* queue,
                                                           int ws_reals, int extra, int gsize) {
   extern __shared__ double b2_smem[];
   __shared__ int s_next[8];
@@ -142,7 +146,7 @@ __global__ void __launch_bounds__(256, 1) k_warp_linearize(StateDev<T> st, int N
   const int ints = kWarpIntsAsReals * (int)(sizeof(double) / sizeof(T));
   T* base = reinterpret_cast<T*>(b2_smem) + (size_t)wib * (ws_reals + ints + extra);
   WarpEnv<T, M> env;
-  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * WarpCaps::NEFC * (M::nv() + 6));
+  env.bind(base, reinterpret_cast<int*>(base + ws_reals), jscratch + (size_t)gw * warp_slot_reals(M::nv()));
   env.bar_id = 1 + grp; env.bar_cnt = 32 * gsize;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv, ncol = ndx + nu;
   T* ends[2] = {base + ws_reals + ints, base + ws_reals + ints + nq + nv};  // [0]: minus side (s1), [1]: plus side (s2)
