@@ -412,9 +412,9 @@ def main():
     # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
     # themselves (profiles/ncu_*_r01i.txt): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per
     # env runs the shared position stage once for all velocity / control columns, control columns skip the velocity stage
-    # too -- and k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 3.10e9 / 16,384 =
-    # 189,000 (mean 3.6 contacts, 2.9 Newton iterations); pendulum: a-priori estimate of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 189000.0}[name]
+    # too -- and k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 2.97e9 / 16,384 =
+    # 182,000 (mean 3.6 contacts, 2.9 Newton iterations); pendulum: a-priori estimate of BASELINE.md
+    flops_per_eval = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 182000.0}[name]
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
