@@ -398,10 +398,15 @@ def main():
     tfile = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
     if os.path.exists(tfile):
         traffic = json.load(open(tfile)).get(f"{name}:{dom}:{nenv}")
+    variant = env.data.backend.batch.kernel_variant
+    if "warp" in variant:  # large models: warp engine
+        kernel_label = "k_warp_linearize" if lin else "k_warp_step_ls"
+    else:
+        kernel_label = f"k_{dom}<{variant}>"
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
     share = {k: (float(np.mean(v)) * args.steps / total_ms if v else 0.0) for k, v in kernel_ms.items()}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
-                "traffic": traffic, "kernel": f"k_{dom}<DimsTiny>" if name in ("pendulum", "cartpole") else f"k_{dom}",
+                "traffic": traffic, "kernel": kernel_label,
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "kernel_share_of_step": share,
                 "kernel_share_note": "kernels timed one by one in an eager pass (controller, FD, step); the timed loop itself runs "
