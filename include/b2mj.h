@@ -129,8 +129,13 @@ int b2_lqr_control(b2_batch* batch, const b2_state* state, void* stream);
 int b2_control_tick(b2_batch* batch, const b2_state* state, const b2_derived* derived, int use_lqr, double eps,
                     int centered, void* A, void* B, void* stream);
 
-/* Derived arrays of the last b2_control_tick(derived = NULL): exactly what mj_step leaves in mjData after that step
- * (the forward pass of the pre-step state, which the tick kept).  Error if there is no such tick. */
+/* One mj_step (reference mujoco_template/model.py:56-57) without derived outputs, keeping the pre-step state so that
+ * b2_refresh_derived can still produce them on demand: writing ~100 derived reals per env costs more HBM traffic than
+ * the step itself, and a rollout that only consumes the state (Env.step(return_obs=False)) never reads them. */
+int b2_step_lazy(b2_batch* batch, const b2_state* state, void* stream);
+
+/* Derived arrays of the last b2_control_tick(derived = NULL) / b2_step_lazy: exactly what mj_step leaves in mjData after
+ * that step (the forward pass of the pre-step state, which the call kept).  Error if there is no such call. */
 int b2_refresh_derived(b2_batch* batch, const b2_derived* derived, void* stream);
 
 /* Replace mj.mj_integratePos / mj.mj_differentiatePos (reference linearization.py:10-13,55,67). */

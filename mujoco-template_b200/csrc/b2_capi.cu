@@ -373,6 +373,23 @@ static int shadow_state(b2_batch* b, b2_state* out) {
   return B2_OK;
 }
 
+// copy the state into the batch's shadow arrays: the pre-step state b2_refresh_derived works from
+static int park_state(b2_batch* b, const b2_state* st, void* stream) {
+  const b2m_view& v = b->model->v;
+  b2_state shadow;
+  int rc = shadow_state(b, &shadow);
+  if (rc) return rc;
+  const size_t N = (size_t)b->nenv, es = b->esz;
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaMemcpyAsync(shadow.qpos, st->qpos, v.nq * N * es, cudaMemcpyDeviceToDevice, s);
+  if (!e) e = cudaMemcpyAsync(shadow.qvel, st->qvel, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
+  if (!e) e = cudaMemcpyAsync(shadow.qacc_warmstart, st->qacc_warmstart, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
+  if (!e && v.nu) e = cudaMemcpyAsync(shadow.ctrl, st->ctrl, v.nu * N * es, cudaMemcpyDeviceToDevice, s);
+  if (e) return cuda_fail(e, "shadow copy of the pre-step state");
+  b->shadow_has_prestep = true;
+  return B2_OK;
+}
+
 // One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).  The kernels
 // evaluate the control law themselves (no controller launch).
 //  * derived == NULL and an Euler model: ONE physics launch.  The FD thread that owns an env's velocity / control columns
@@ -398,18 +415,7 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
       // argument the pre-step state is parked in the shadow arrays for b2_refresh_derived, as in the fused form.
       if (gain && (rc = do_lqr_control(b, st, b->nenv, stream))) return rc;
       if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream))) return rc;
-      if (!derived && st->qacc_warmstart) {
-        b2_state shadow;
-        if ((rc = shadow_state(b, &shadow))) return rc;
-        const size_t N = (size_t)b->nenv, es = b->esz;
-        cudaStream_t s = (cudaStream_t)stream;
-        cudaError_t e = cudaMemcpyAsync(shadow.qpos, st->qpos, v.nq * N * es, cudaMemcpyDeviceToDevice, s);
-        if (!e) e = cudaMemcpyAsync(shadow.qvel, st->qvel, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
-        if (!e) e = cudaMemcpyAsync(shadow.qacc_warmstart, st->qacc_warmstart, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
-        if (!e && v.nu) e = cudaMemcpyAsync(shadow.ctrl, st->ctrl, v.nu * N * es, cudaMemcpyDeviceToDevice, s);
-        if (e) return cuda_fail(e, "b2_control_tick: shadow copy");
-        b->shadow_has_prestep = true;
-      }
+      if (!derived && st->qacc_warmstart && (rc = park_state(b, st, stream))) return rc;
       return do_step(b, st, b->nenv, 1, derived, stream);
     }
   }
@@ -428,6 +434,14 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
   int rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream, gain);
   if (rc) return rc;
   return do_step(b, st, b->nenv, 1, derived, stream, gain);
+}
+
+int b2_step_lazy(b2_batch* b, const b2_state* st, void* stream) {
+  B2_CHECK_STATE("b2_step_lazy");
+  if (!st->qacc_warmstart) return fail(B2_ERR_ARG, "b2_step_lazy: state.qacc_warmstart is required");
+  int rc = park_state(b, st, stream);
+  if (rc) return rc;
+  return do_step(b, st, b->nenv, 1, nullptr, stream);
 }
 
 // Derived arrays (xpos, ..., sensordata) of the last b2_control_tick that ran without a `derived` argument: what mj_step

@@ -24,7 +24,7 @@ _lib: C.CDLL | None = None
 EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
-    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
 )
 
@@ -78,6 +78,7 @@ def lib() -> C.CDLL:
     L.b2_lqr_control.argtypes = [vp, C.POINTER(State), vp]
     L.b2_control_tick.argtypes = [vp, C.POINTER(State), C.POINTER(Derived), i, C.c_double, i, vp, vp, vp]
     L.b2_refresh_derived.argtypes = [vp, C.POINTER(Derived), vp]
+    L.b2_step_lazy.argtypes = [vp, C.POINTER(State), vp]
     L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
@@ -179,6 +180,9 @@ class NativeBatch:
                      stream: int = 0) -> None:
         check(self._L.b2_control_tick(self.handle, C.byref(state), C.byref(derived) if derived is not None else None,
                                       int(bool(use_lqr)), float(eps), int(bool(centered)), A, B, stream))
+
+    def step_lazy(self, state: State, stream: int = 0) -> None:
+        check(self._L.b2_step_lazy(self.handle, C.byref(state), stream))
 
     def refresh_derived(self, derived: Derived, stream: int = 0) -> None:
         check(self._L.b2_refresh_derived(self.handle, C.byref(derived), stream))

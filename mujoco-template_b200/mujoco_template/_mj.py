@@ -288,6 +288,11 @@ class NativeBackend:
         """Per-launch device times (ms) collected while ``profile`` was enabled."""
         return [a.elapsed_time(b) for a, b in (self.profile or {}).get(name, [])]
 
+    def step_lazy(self) -> None:
+        """One step without derived outputs (``b2_step_lazy``); ``ensure_derived()`` produces them if someone reads one."""
+        self._launch("step", self.batch.step_lazy, self.state_struct())
+        self.derived_stale = True
+
     def step(self, nsteps: int = 1, derived: bool = True) -> None:
         self.derived_stale = False
         self._launch("step", self.batch.step, self.state_struct(), nsteps, self.derived_struct() if derived else None)

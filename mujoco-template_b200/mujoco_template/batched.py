@@ -198,8 +198,12 @@ class BatchedEnv:
             out[token] = entry
         return out
 
-    def _device_work(self, n: int):
-        """Controller ticks, (A, B), Jacobians and n physics steps: device work only (no host sync)."""
+    def _device_work(self, n: int, lazy: bool = False):
+        """Controller ticks, (A, B), Jacobians and n physics steps: device work only (no host sync).
+
+        ``lazy``: the caller does not read derived arrays now (``step(return_obs=False)``), so the last step runs without
+        derived outputs and parks its pre-step state (``b2_step_lazy``); whoever reads ``data.xpos`` etc. later gets
+        them from ``b2_refresh_derived`` -- same values, produced on demand."""
         lin_A, lin_B, jacs = [], [], []
         backend = self.data.backend
         pending = 0  # consecutive steps with no controller tick are fused into one launch
@@ -230,7 +234,12 @@ class BatchedEnv:
             pending += 1
             self._substep += 1
         if pending:
-            backend.step(pending)
+            if lazy and hasattr(backend, "step_lazy") and int(self.model.opt.integrator) == 0:
+                if pending > 1:
+                    backend.step(pending - 1, derived=False)
+                backend.step_lazy()
+            else:
+                backend.step(pending)
         return lin_A, lin_B, jacs
 
     def _advance_time(self, n: int) -> None:
@@ -248,37 +257,38 @@ class BatchedEnv:
         if enabled and self.control_decimation != 1:
             raise ConfigError("CUDA-graph stepping requires control_decimation == 1")
         self._graph_enabled = bool(enabled)
-        self._graph = None
-        self._graph_warm = False
-        self._graph_out = None
+        self._graphs = {}  # one captured graph per flavour of step(): eager / lazy derived outputs
 
-    def _graphed_work(self):
+    def _graphed_work(self, lazy: bool = False):
         import torch
 
-        if not self._graph_warm:  # eager first call: loads the kernels, makes the model image resident
-            self._graph_warm = True
-            return self._device_work(1)
-        if self._graph is None:
+        g = self._graphs.setdefault(bool(lazy), {"warm": False, "graph": None, "out": None, "stale": False})
+        backend = self.data.backend
+        if not g["warm"]:  # eager first call: loads the kernels, makes the model image resident
+            g["warm"] = True
+            return self._device_work(1, lazy)
+        if g["graph"] is None:
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._graph_out = self._device_work(1)
-            self._graph = g
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                g["out"] = self._device_work(1, lazy)
+            g["graph"] = graph
+            g["stale"] = bool(backend.derived_stale)  # whether the captured work left the derived arrays for later
         else:
             self._substep += 1
-        self._graph.replay()
-        if getattr(self, "_ticks_defer_derived", False):
-            self.data.backend.derived_stale = int(self.model.opt.integrator) == 0
-        return self._graph_out
+        g["graph"].replay()
+        backend.derived_stale = g["stale"]
+        return g["out"]
 
     def step(self, n: int = 1, *, return_obs: bool = True) -> StepResult:
         if n < 1:
             raise ConfigError("BatchedEnv.step(n): n must be >= 1")
         info: InfoDict = {}
+        lazy = not return_obs
         if getattr(self, "_graph_enabled", False) and n == 1 and self.controller is not None:
-            lin_A, lin_B, jacs = self._graphed_work()
+            lin_A, lin_B, jacs = self._graphed_work(lazy)
         else:
-            lin_A, lin_B, jacs = self._device_work(n)
+            lin_A, lin_B, jacs = self._device_work(n, lazy)
         self._advance_time(n)
         if lin_A:
             info["A"], info["B"] = _one_or_many(lin_A), _one_or_many(lin_B)

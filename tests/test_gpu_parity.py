@@ -489,6 +489,46 @@ def test_step_host_pipeline_matches_device_path(name, n):
             assert np.array_equal(hA.numpy(), A.cpu().numpy()) and np.array_equal(hB.numpy(), B.cpu().numpy()), rep
 
 
+@pytest.mark.parametrize("name,graph", [("drone", False), ("drone", True), ("cartpole", False), ("humanoid", False)])
+def test_lazy_derived_outputs_equal_eager_ones(name, graph):
+    """step(return_obs=False) runs without derived outputs (b2_step_lazy: the pre-step state is parked); reading
+    data.xpos / sensordata / qacc afterwards materialises exactly what the eager step writes."""
+    import torch
+    import mujoco_template as mt
+
+    class Hold:  # a controller, so that the CUDA-graph path is exercised too
+        capabilities = mt.ControllerCapabilities()
+        def prepare(self, m, d): pass
+        def __call__(self, m, d, t): d.ctrl.mul_(1.0)
+
+    model = load_model(name)
+    n = 96
+    qpos, qvel, ctrl = random_states(model, name, n, seed=31)
+    out = {}
+    for lazy in (True, False):
+        env = mt.BatchedEnv(model, n, controller=Hold())
+        env.reset(1 if name == "humanoid" else None)
+        dev = env.data.qpos.device
+        env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev)); env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
+        env.data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev))
+        env.forward()
+        if graph:
+            env.enable_cuda_graph(True)
+        for _ in range(5):
+            env.step(return_obs=not lazy)
+            if lazy:
+                assert env.data.backend.derived_stale
+        names = ["qpos", "qvel", "xpos", "xquat", "geom_xpos", "subtree_com", "qacc", "qfrc_bias", "ncon", "nefc"]
+        if model.nsensordata:
+            names.append("sensordata")
+        if model.nsite:
+            names.append("site_xpos")
+        out[lazy] = {k: getattr(env.data, k).clone() for k in names}
+        assert not env.data.backend.derived_stale
+    for k in out[True]:
+        assert torch.equal(out[True][k], out[False][k]), k
+
+
 def test_control_tick_on_the_warp_engine():
     """humanoid: b2_control_tick = control-law launch + warp-engine FD + warp-engine step; the derived arrays of the
     tick are produced lazily from the parked pre-step state, as on the small models."""
@@ -624,7 +664,9 @@ def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, p
                 assert mt._capi.launch_count() == launches + 1 and not benv.data.backend.derived_stale
             hist.append((res.info["A"].clone(), res.info["B"].clone(), benv.data.qpos.clone(), benv.data.qvel.clone(),
                          benv.data.ctrl.clone()) + derived)
-        per_tick = (3 if euler else 2) if fused else 3           # FD(+step) + commit + lazy forward | FD + step | law + FD + step
+        # FD(+step) + commit + lazy forward | FD + step | law + FD + step (+ the lazy forward: step(return_obs=False) on an
+        # Euler model leaves the derived arrays to b2_refresh_derived as well)
+        per_tick = (3 if euler else 2) if fused else (4 if euler else 3)
         assert mt._capi.launch_count() - c0 == 5 * per_tick
         out[fused] = hist
     tol = 1e-12 if precision == 64 else 2e-4
