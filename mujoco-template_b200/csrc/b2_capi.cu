@@ -195,7 +195,7 @@ static int prepare_warp(b2_batch* b) {
 extern "C" { static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream); }
 
 static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, const void* gain,
-                               void* stream) {
+                               void* stream, const b2_state* park = nullptr) {
   int rc = ensure_resident(b, stream);
   if (rc) return rc;
   if ((rc = prepare_warp(b))) return rc;
@@ -207,8 +207,8 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
   if (b->warp_mode == 1 && count == b->nenv)
     return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
                : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
-  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream)
-             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, stream);
+  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
+             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
 }
 
 // make sure this batch's model is the image resident in constant memory on its device
@@ -235,14 +235,14 @@ extern "C" {
 
 // count envs (a leading chunk of the arrays `st` points at; the env stride is always b->nenv)
 static int do_step(b2_batch* b, const b2_state* st, int count, int nsteps, const b2_derived* derived, void* stream,
-                   const void* gain = nullptr) {
+                   const void* gain = nullptr, const b2_state* park = nullptr) {
   int rc;
   if (const b2::SpecKernels* k = active_spec(b)) {
     cudaError_t e = cudaSetDevice(b->device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    rc = k->step[prec_index(b)](st, derived, count, b->nenv, nsteps, gain, stream);
+    rc = k->step[prec_index(b)](st, derived, count, b->nenv, nsteps, gain, park, stream);
   } else {
-    rc = launch_generic_step(b, st, derived, count, nsteps, gain, stream);
+    rc = launch_generic_step(b, st, derived, count, nsteps, gain, stream, park);
     if (rc < 0) return rc;
   }
   g_launches++;
@@ -439,9 +439,20 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
 int b2_step_lazy(b2_batch* b, const b2_state* st, void* stream) {
   B2_CHECK_STATE("b2_step_lazy");
   if (!st->qacc_warmstart) return fail(B2_ERR_ARG, "b2_step_lazy: state.qacc_warmstart is required");
-  int rc = park_state(b, st, stream);
-  if (rc) return rc;
-  return do_step(b, st, b->nenv, 1, nullptr, stream);
+  int rc;
+  if (!active_spec(b)) {
+    if ((rc = ensure_resident(b, stream)) || (rc = prepare_warp(b))) return rc;
+    if (b->warp_mode == 1) {  // warp engine: park with device-to-device copies
+      if ((rc = park_state(b, st, stream))) return rc;
+      return do_step(b, st, b->nenv, 1, nullptr, stream);
+    }
+  }
+  // lane engine: the step kernel has the pre-step state in registers and writes it to the shadow arrays itself
+  b2_state shadow;
+  if ((rc = shadow_state(b, &shadow))) return rc;
+  if ((rc = do_step(b, st, b->nenv, 1, nullptr, stream, nullptr, &shadow))) return rc;
+  b->shadow_has_prestep = true;
+  return B2_OK;
 }
 
 // Derived arrays (xpos, ..., sensordata) of the last b2_control_tick that ran without a `derived` argument: what mj_step

@@ -107,7 +107,8 @@ B2_DEV void lqr_law(const LaneEnv<T, D, M>& env, const T* q, const T* v, const T
 // nsteps x mj_step with ctrl held; nsteps == 0 means mj_forward (no integration).
 // The step loop is rolled: one inlined copy of the physics per kernel.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps, const T* __restrict__ gain) {
+__global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps, const T* __restrict__ gain,
+                                                                  StateDev<T> park) {
   // count envs are processed; N is the env stride of the SoA arrays (count < N for a chunk of a larger batch)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
@@ -118,6 +119,14 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
     lqr_law(env, env.qpos, env.qvel, gain, env.ctrl);
     B2_UNROLL
     for (int k = 0; k < M::nu(); k++) st.ctrl[(size_t)k * N + e] = env.ctrl[k];
+  }
+  if (park.qpos) {  // b2_step_lazy: keep the pre-step state (it is in registers anyway) for b2_refresh_derived
+    B2_UNROLL
+    for (int k = 0; k < M::nq(); k++) park.qpos[(size_t)k * N + e] = env.qpos[k];
+    B2_UNROLL
+    for (int k = 0; k < M::nv(); k++) { park.qvel[(size_t)k * N + e] = env.qvel[k]; park.warm[(size_t)k * N + e] = env.warm[k]; }
+    B2_UNROLL
+    for (int k = 0; k < M::nu(); k++) park.ctrl[(size_t)k * N + e] = env.ctrl[k];
   }
   const int total = nsteps > 0 ? nsteps : 1;
   B2_NOUNROLL

@@ -13,7 +13,7 @@ namespace b2 {
   int b2k_warp_linearize##SUF(const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
                               void* counter, int wpb, int blocks, void* stream);                                                        \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
-  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);                  \
+  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park, void* stream);                  \
   int b2k_linearize##SUF(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
                          const void* gain, const b2_state* shadow, void* stream);                                                                                    \
   int b2k_commit_state##SUF(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream); \

@@ -134,10 +134,11 @@ double B2_FN(b2k_fma_peak)(void* stream) {
   const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
   return flops / (best * 1e-3) / 1e12;
 }
-int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream) {
+int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain,
+                    const b2_state* park, void* stream) {
   const int threads = 128, blocks = (count + threads - 1) / threads;
   B2_DISPATCH(cls, (k_step<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps, (const real*)gain)));
+                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps, (const real*)gain, to_dev<real>(park))));
   return (int)cudaGetLastError();
 }
 // ---- warp engine (large models): launch geometry and per-warp scratch are sized by the host

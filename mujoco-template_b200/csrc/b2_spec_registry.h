@@ -14,7 +14,9 @@ struct SpecKernels {
   size_t blob_size;
   // [0] FP64, [1] FP32; count envs, env stride N
   // gain != null: the control law of b2_lqr_set_gain is evaluated inside the kernel (ctrl becomes an output of step)
-  int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream);
+  // park != null: the kernel also copies the pre-step state there (b2_step_lazy)
+  int (*step[2])(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park,
+                 void* stream);
   // shadow != null (Euler models): the FD launch also advances every env into the shadow arrays (see k_linearize)
   int (*linearize[2])(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain,
                       const b2_state* shadow, void* stream);

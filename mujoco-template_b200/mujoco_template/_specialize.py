@@ -149,9 +149,9 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("};")
     A("")
     for T, suf in (("double", ""), ("float", "32")):
-        A(f"int spec_step{suf}(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, void* stream) {{")
+        A(f"int spec_step{suf}(const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park, void* stream) {{")
         A("  const int threads = 128, blocks = (count + threads - 1) / threads;")
-        A(f"  k_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, nsteps, (const {T}*)gain);")
+        A(f"  k_step<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), to_dev<{T}>(out), out != nullptr, count, N, nsteps, (const {T}*)gain, to_dev<{T}>(park));")
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, const b2_state* shadow, void* stream) {{")
