@@ -296,8 +296,8 @@ def main():
                     # episode reset, as a batched rollout driver does it: a drone that comes within 0.5 m of the floor
                     # starts again from its initial state (config #3 is free flight: "expect no ground contact")
                     low = (d.qpos[2] < 0.5).unsqueeze(0)
-                    d.qpos.copy_(torch.where(low, self.init[0], d.qpos))
-                    d.qvel.copy_(torch.where(low, self.init[1], d.qvel))
+                    torch.where(low, self.init[0], d.qpos, out=d.qpos)
+                    torch.where(low, self.init[1], d.qvel, out=d.qvel)
         controller = RandomCtrl()
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
