@@ -284,7 +284,15 @@ class BatchedEnv:
         if n < 1:
             raise ConfigError("BatchedEnv.step(n): n must be >= 1")
         info: InfoDict = {}
-        lazy = not return_obs
+        # derived arrays are produced on demand when the caller takes no observation -- unless it turns out that someone
+        # (a hook, a reward function, a recorder) reads them after such steps anyway: two lazy steps in a row that were
+        # each followed by a refresh switch this env back to eager derived outputs (a refresh costs a forward pass)
+        backend = self.data.backend
+        seen = getattr(backend, "refresh_count", 0)
+        if seen != getattr(self, "_refresh_seen", 0):
+            self._lazy_refreshes = getattr(self, "_lazy_refreshes", 0) + 1
+            self._refresh_seen = seen
+        lazy = not return_obs and getattr(self, "_lazy_refreshes", 0) < 2
         if getattr(self, "_graph_enabled", False) and n == 1 and self.controller is not None:
             lin_A, lin_B, jacs = self._graphed_work(lazy)
         else:
