@@ -1,30 +1,49 @@
-"""CLI smoke run (reference ``mujoco_template/__main__.py:10-33``):
+"""Command-line smoke run on the B200 path.
+
+Same flags and output as the reference's ``python -m mujoco_template`` (``mujoco_template/__main__.py:10-33``):
 
     python -m mujoco_template examples/pendulum/pendulum.xml --steps 300 --zero
+
+BASELINE config #1 is exactly this command on the pendulum model.
 """
 
 from __future__ import annotations
 
 import argparse
+import sys
 
 from .controllers import ZeroController
 from .env import Env
 
+_FLAGS = (
+    # name, kwargs
+    ("--steps", dict(type=int, default=300)),
+    ("--zero", dict(action="store_true", help="Use ZeroController")),
+    ("--groups", dict(type=int, nargs="*", default=None, help="Enable only these actuator groups")),
+    ("--decim", dict(type=int, default=1, help="Control decimation (>=1)")),
+)
+
+
+def _parser() -> argparse.ArgumentParser:
+    parser = argparse.ArgumentParser(prog="python -m mujoco_template",
+                                     description="MuJoCo template smoke test on the B200 path (fail-fast)")
+    parser.add_argument("xml", help="Path to MJCF XML")
+    for flag, kwargs in _FLAGS:
+        parser.add_argument(flag, **kwargs)
+    return parser
+
 
 def main(argv: list[str] | None = None) -> int:
-    ap = argparse.ArgumentParser(description="MuJoCo template smoke test on the B200 path (fail-fast)")
-    ap.add_argument("xml", help="Path to MJCF XML")
-    ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--zero", action="store_true", help="Use ZeroController")
-    ap.add_argument("--groups", type=int, nargs="*", default=None, help="Enable only these actuator groups")
-    ap.add_argument("--decim", type=int, default=1, help="Control decimation (>=1)")
-    args = ap.parse_args(argv)
-    env = Env.from_xml_path(args.xml, controller=ZeroController() if args.zero else None,
-                            enabled_groups=args.groups, control_decimation=args.decim)
-    steps = sum(1 for _ in env.passive(max_steps=args.steps))
-    print(f"Completed {steps} steps.")
-    return steps
+    """Build the env the flags describe, run ``--steps`` passive steps, report how many were taken."""
+    opts = _parser().parse_args(argv)
+    controller = ZeroController() if opts.zero else None
+    env = Env.from_xml_path(opts.xml, controller=controller, enabled_groups=opts.groups, control_decimation=opts.decim)
+    taken = 0
+    for _ in env.passive(max_steps=opts.steps):
+        taken += 1
+    print(f"Completed {taken} steps.")
+    return taken
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1:])

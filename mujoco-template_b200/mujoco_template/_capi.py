@@ -11,7 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-from .exceptions import ConfigError, LinearizationError, TemplateError
+from .exceptions import ConfigError, LinearizationError, TemplateError, error_for_status  # noqa: F401
 
 B2_F64, B2_F32 = 64, 32
 JAC_SITE, JAC_BODY, JAC_BODYCOM, JAC_SUBTREECOM = 0, 1, 2, 3
@@ -92,12 +92,7 @@ def check(rc: int) -> None:
     """Translate a C status code into the reference's exception types."""
     if rc == 0:
         return
-    msg = lib().b2_last_error().decode("utf-8", "replace")
-    if rc in (-1, -2, -3):
-        raise ConfigError(msg)
-    if rc == -5:
-        raise LinearizationError(msg)
-    raise TemplateError(msg)
+    raise error_for_status(rc, lib().b2_last_error().decode("utf-8", "replace"))
 
 
 def fp_peak(precision: int = B2_F64, device: int = 0) -> float:

@@ -35,6 +35,8 @@ from .observations import ObservationExtractor, ObservationSpec
 
 @dataclass
 class StepResult:
+    """What one ``Env.step`` call hands back (reference ``env.py:20-25``)."""
+
     obs: Observation | None
     reward: float | None
     done: bool
@@ -42,10 +44,36 @@ class StepResult:
 
 
 def _one_or_many(items: list) -> Any:
+    """The reference's shape rule for per-tick products: the object itself if there is exactly one, else the list."""
     return items[0] if len(items) == 1 else items
 
 
+class _TickProducts:
+    """Linearisations and Jacobians gathered over the control ticks of one ``step(n)`` call."""
+
+    __slots__ = ("A", "B", "jac")
+
+    def __init__(self) -> None:
+        self.A: list[np.ndarray] = []
+        self.B: list[np.ndarray] = []
+        self.jac: list[JacobiansDict] = []
+
+    def into(self, info: InfoDict) -> None:
+        if self.A:
+            info["A"] = _one_or_many(self.A)
+            info["B"] = _one_or_many(self.B)
+        if self.jac:
+            info["jacobians"] = _one_or_many(self.jac)
+
+
+def _declared_groups(controller: Controller | None) -> tuple[int, ...] | None:
+    groups = None if controller is None else controller.capabilities.actuator_groups
+    return None if groups is None else tuple(int(g) for g in groups)
+
+
 class Env:
+    """One environment: model handle + controller + observation extractor + optional reward / done / info hooks."""
+
     def __init__(
         self,
         handle: ModelHandle,
@@ -59,43 +87,42 @@ class Env:
     ):
         if control_decimation < 1:
             raise ConfigError("control_decimation must be >= 1")
-        self.handle = handle
-        self.model = handle.model
-        self.data = handle.data
-        self._obs_spec = obs_spec
-        self.extractor: ObservationExtractor | None = ObservationExtractor(handle.model, obs_spec) if obs_spec is not None else None
+        self.handle, self.model, self.data = handle, handle.model, handle.data
         self.controller = controller
-        self.reward_fn, self.done_fn, self.info_fn = reward_fn, done_fn, info_fn
         self.control_decimation = int(control_decimation)
+        self.reward_fn, self.done_fn, self.info_fn = reward_fn, done_fn, info_fn
+        self._obs_spec = obs_spec
+        self.extractor: ObservationExtractor | None = None if obs_spec is None else ObservationExtractor(handle.model, obs_spec)
         self._substep = 0
-        self._added_warnings = False
         self._compat_warnings: list[str] = []
-        self._configure_groups(enabled_groups)
+        self._added_warnings = False  # compat_warnings go into the first StepResult after construction / reset only
+        self._apply_group_selection(enabled_groups)
         if controller is not None:
-            controller.prepare(self.model, self.data)
-            report = check_controller_compat(self.model, controller.capabilities, self.handle.enabled_actuator_mask())
-            self._compat_warnings = list(report.warnings)
-            report.assert_ok()
+            self._prepare_and_check(controller)
 
-    def _configure_groups(self, enabled_groups: Iterable[int] | None) -> None:
-        caps_groups = None
-        if self.controller is not None and self.controller.capabilities.actuator_groups is not None:
-            caps_groups = tuple(int(g) for g in self.controller.capabilities.actuator_groups)
-        if enabled_groups is not None:
-            chosen = tuple(int(g) for g in enabled_groups)
-            if caps_groups is not None and set(caps_groups) != set(chosen):
-                self._note(
-                    f"Controller declares actuator groups {sorted(set(caps_groups))} but user requested "
-                    f"{sorted(set(chosen))}; proceeding with the user selection.")
-            self.handle.set_enabled_actuator_groups(chosen)
-        elif caps_groups is not None:
-            self._note(
-                f"Controller declares actuator groups {sorted(set(caps_groups))} but Env leaves actuator "
-                "availability unchanged by default.")
-
-    def _note(self, msg: str) -> None:
+    # ------------------------------------------------------------------ construction helpers
+    def _warn(self, msg: str) -> None:
         warnings.warn(msg, RuntimeWarning)
         self._compat_warnings.append(msg)
+
+    def _apply_group_selection(self, enabled_groups: Iterable[int] | None) -> None:
+        declared = _declared_groups(self.controller)
+        if enabled_groups is None:
+            if declared is not None:
+                self._warn(f"Controller declares actuator groups {sorted(set(declared))} but Env leaves actuator "
+                           "availability unchanged by default.")
+            return
+        chosen = tuple(int(g) for g in enabled_groups)
+        if declared is not None and set(declared) != set(chosen):
+            self._warn(f"Controller declares actuator groups {sorted(set(declared))} but user requested "
+                       f"{sorted(set(chosen))}; proceeding with the user selection.")
+        self.handle.set_enabled_actuator_groups(chosen)
+
+    def _prepare_and_check(self, controller: Controller) -> None:
+        controller.prepare(self.model, self.data)
+        report = check_controller_compat(self.model, controller.capabilities, self.handle.enabled_actuator_mask())
+        self._compat_warnings.extend(report.warnings)
+        report.assert_ok()
 
     @property
     def compat_warnings(self) -> list[str]:
@@ -116,39 +143,51 @@ class Env:
         auto_reset: bool = True,
         keyframe: int | str | None = None,
     ) -> "Env":
-        """Load an MJCF file, build the env and (by default) reset it.
+        """Compile the MJCF file, build the env around it and reset it (unless ``auto_reset=False``).
 
-        ``obs_spec`` defaults to ``ObservationSpec(include_sensordata=False)``.
+        Without an ``obs_spec`` the observation leaves out ``sensordata`` (reference ``env.py:122-123``).
         """
-        if obs_spec is None:
-            obs_spec = ObservationSpec(include_sensordata=False)
-        env = cls(
-            ModelHandle.from_xml_path(xml_path), obs_spec=obs_spec, controller=controller, reward_fn=reward_fn,
-            done_fn=done_fn, info_fn=info_fn, enabled_groups=enabled_groups, control_decimation=control_decimation)
         if keyframe is not None and not auto_reset:
             raise ConfigError("auto_reset=False is incompatible with specifying a keyframe")
+        env = cls(ModelHandle.from_xml_path(xml_path),
+                  obs_spec=ObservationSpec(include_sensordata=False) if obs_spec is None else obs_spec,
+                  controller=controller, reward_fn=reward_fn, done_fn=done_fn, info_fn=info_fn,
+                  enabled_groups=enabled_groups, control_decimation=control_decimation)
         if auto_reset:
             env.reset(keyframe)
         return env
 
-    def _ensure_extractor(self) -> ObservationExtractor:
+    # ------------------------------------------------------------------ observations
+    def _observe(self) -> Observation:
         if self.extractor is None:
-            if self._obs_spec is None:
-                self._obs_spec = ObservationSpec()
+            self._obs_spec = self._obs_spec or ObservationSpec()
             self.extractor = ObservationExtractor(self.model, self._obs_spec)
-        return self.extractor
+        return self.extractor(self.data)
 
+    # ------------------------------------------------------------------ reset / step
     def reset(self, keyframe: int | str | None = None) -> Observation:
+        """``mj_resetData[Keyframe]`` + ``mj_forward``; the controller is prepared again (reference ``env.py:152-162``)."""
         if keyframe is None:
             self.handle.reset()
         else:
             self.handle.reset_keyframe(keyframe)
         self.handle.forward()
-        self._substep = 0
-        self._added_warnings = False
+        self._substep, self._added_warnings = 0, False
         if self.controller is not None:
             self.controller.prepare(self.model, self.data)
-        return self._ensure_extractor()(self.data)
+        return self._observe()
+
+    def _control_tick(self, out: _TickProducts) -> None:
+        """Controller, then what its capabilities ask for -- (A, B) at the new controls, then Jacobians."""
+        controller = self.controller
+        controller(self.model, self.data, float(self.data.time))
+        caps = controller.capabilities
+        if caps.needs_linearization:
+            A, B = linearize_discrete(self.model, self.data, use_native=True)
+            out.A.append(A)
+            out.B.append(B)
+        if caps.needs_jacobians:
+            out.jac.append(compute_requested_jacobians(self.model, self.data, caps.needs_jacobians))
 
     def step(self, n: int = 1, *, return_obs: bool = True) -> StepResult:
         if n < 1:
@@ -157,47 +196,31 @@ class Env:
         if self._compat_warnings and not self._added_warnings:
             info["compat_warnings"] = list(self._compat_warnings)
             self._added_warnings = True
-
-        lin_A: list[np.ndarray] = []
-        lin_B: list[np.ndarray] = []
-        jacs: list[JacobiansDict] = []
+        products = _TickProducts()
         for _ in range(n):
             if self.controller is not None and self._substep % self.control_decimation == 0:
-                self.controller(self.model, self.data, float(self.data.time))
-                caps = self.controller.capabilities
-                if caps.needs_linearization:
-                    A, B = linearize_discrete(self.model, self.data, use_native=True)
-                    lin_A.append(A)
-                    lin_B.append(B)
-                if caps.needs_jacobians:
-                    jacs.append(compute_requested_jacobians(self.model, self.data, caps.needs_jacobians))
+                self._control_tick(products)
             self.handle.step()
             self._substep += 1
-        if lin_A:
-            info["A"], info["B"] = _one_or_many(lin_A), _one_or_many(lin_B)
-        if jacs:
-            info["jacobians"] = _one_or_many(jacs)
-
-        obs = self._ensure_extractor()(self.data) if return_obs else None
-        reward: float | None = None
-        done = False
-        if self.reward_fn:
-            reward = self.reward_fn(self.model, self.data, obs)
-        if self.done_fn:
-            done = bool(self.done_fn(self.model, self.data, obs))
+        products.into(info)
+        obs = self._observe() if return_obs else None
+        reward = self.reward_fn(self.model, self.data, obs) if self.reward_fn else None
+        done = bool(self.done_fn(self.model, self.data, obs)) if self.done_fn else False
         if self.info_fn:
-            for key, value in self.info_fn(self.model, self.data, obs).items():
-                if key in info:
-                    raise TemplateError(f"info key collision: {key}")
-                info[key] = value
+            extra = self.info_fn(self.model, self.data, obs)
+            clash = next((k for k in extra if k in info), None)
+            if clash is not None:
+                raise TemplateError(f"info key collision: {clash}")
+            info.update(extra)
         return StepResult(obs=obs, reward=reward, done=done, info=info)
 
     def linearize(self, eps: float = 1e-6, horizon_steps: int = 1) -> tuple[np.ndarray, np.ndarray]:
+        """(A, B) of one step at the current state and controls: ``b2_linearize`` behind ``linearize_discrete``."""
         return linearize_discrete(self.model, self.data, use_native=True, eps=eps, horizon_steps=horizon_steps)
 
     def passive(self, *, duration: float | None = None, max_steps: int | None = None, hooks=None,
                 return_obs: bool = True) -> Iterator[StepResult]:
-        """Yield steps via :func:`runtime.iterate_passive` (``return_obs=False`` skips extraction)."""
+        """Generator over steps until ``duration`` / ``max_steps`` (``runtime.iterate_passive``)."""
         from .runtime import iterate_passive
 
         yield from iterate_passive(self, duration=duration, max_steps=max_steps, hooks=hooks, return_obs=return_obs)

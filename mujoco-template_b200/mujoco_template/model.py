@@ -1,8 +1,9 @@
-"""ModelHandle: owns one ``(model, data)`` pair and forwards the hot-path calls to the GPU.
+"""``ModelHandle``: one compiled model plus one data block, with the hot-path calls routed to the GPU library.
 
-Same surface as reference ``mujoco_template/model.py:11-105``; ``step``/``forward``/``reset``
-land in ``libb2mj.so`` kernels instead of ``mj_step``/``mj_forward``/``mj_resetData``.
-``from_binary_path``/``save_binary`` use this package's own compiled-model file, not MJB.
+Public surface of reference ``mujoco_template/model.py:11-105`` (loaders, ``forward`` / ``step`` / ``reset`` /
+``reset_keyframe``, actuator-group masks).  ``step`` / ``forward`` / ``reset`` end in ``libb2mj.so`` kernels
+(``b2_step`` / ``b2_forward``) rather than in ``mj_step`` / ``mj_forward`` / ``mj_resetData``; the "binary" model file is
+this package's own compiled-model blob (``MjModel.save_compiled``), not MuJoCo's MJB.
 """
 
 from __future__ import annotations
@@ -14,34 +15,53 @@ import numpy as np
 from . import _mj as mj
 from .exceptions import CompatibilityError, ConfigError, NameLookupError, TemplateError
 
+_GROUP_BITS = 32  # width of opt.disableactuator
+
+
+def _keyframe_index(model: "mj.MjModel", key: int | str) -> int:
+    """Resolve a keyframe given by name or by index; errors follow the reference (name -> NameLookupError)."""
+    if isinstance(key, str):
+        found = mj.mj_name2id(model, mj.mjtObj.mjOBJ_KEY, key)
+        if found < 0:
+            raise NameLookupError(f"Keyframe name not found: {key}")
+        return found
+    index = int(key)
+    if not 0 <= index < model.nkey:
+        raise ConfigError(f"Keyframe index out of range: {index}")
+    return index
+
 
 class ModelHandle:
-    def __init__(self, model: mj.MjModel, data: mj.MjData | None = None):
-        self.model = model
-        if data is None:
-            data = mj.MjData(model)
-        elif data.model is not model:
-            raise ConfigError("Provided mj.MjData must reference the supplied model.")
-        self.data = data
+    """Owns ``(model, data)``; every method below is a thin, fail-fast forwarder."""
 
-    # ---- loaders
+    def __init__(self, model: "mj.MjModel", data: "mj.MjData | None" = None):
+        if data is not None and data.model is not model:
+            raise ConfigError("Provided mj.MjData must reference the supplied model.")
+        self.model = model
+        self.data = mj.MjData(model) if data is None else data
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def _from(cls, loader, source: str) -> "ModelHandle":
+        return cls(loader(source))
+
     @classmethod
     def from_xml_path(cls, xml_path: str) -> "ModelHandle":
-        return cls(mj.MjModel.from_xml_path(xml_path))
+        return cls._from(mj.MjModel.from_xml_path, xml_path)
 
     @classmethod
     def from_xml_string(cls, xml_text: str) -> "ModelHandle":
-        return cls(mj.MjModel.from_xml_string(xml_text))
+        return cls._from(mj.MjModel.from_xml_string, xml_text)
 
     @classmethod
     def from_binary_path(cls, mjb_path: str) -> "ModelHandle":
-        """Load a compiled-model file written by :meth:`save_binary` (not MuJoCo's MJB format)."""
-        return cls(mj.MjModel.from_compiled(mjb_path))
+        """Load what :meth:`save_binary` wrote (a compiled-model blob of this package)."""
+        return cls._from(mj.MjModel.from_compiled, mjb_path)
 
     @classmethod
-    def from_model_and_data(cls, model: mj.MjModel, data: mj.MjData) -> "ModelHandle":
-        """Adopt an existing pair; no buffers are allocated."""
-        return cls(model, data=data)
+    def from_model_and_data(cls, model: "mj.MjModel", data: "mj.MjData") -> "ModelHandle":
+        """Adopt a pair that already exists: nothing is allocated."""
+        return cls(model, data)
 
     def save_binary(self, mjb_path: str) -> None:
         try:
@@ -49,54 +69,46 @@ class ModelHandle:
         except OSError as exc:
             raise TemplateError(f"mj_saveModel failed for {mjb_path}: {exc}") from exc
 
-    # ---- hot path
-    def forward(self) -> None:
-        mj.mj_forward(self.model, self.data)
-
+    # ------------------------------------------------------------------ hot path (GPU)
     def step(self) -> None:
         mj.mj_step(self.model, self.data)
+
+    def forward(self) -> None:
+        mj.mj_forward(self.model, self.data)
 
     def reset(self) -> None:
         mj.mj_resetData(self.model, self.data)
 
     def reset_keyframe(self, key: int | str) -> None:
-        if isinstance(key, str):
-            idx = mj.mj_name2id(self.model, mj.mjtObj.mjOBJ_KEY, key)
-            if idx < 0:
-                raise NameLookupError(f"Keyframe name not found: {key}")
-        else:
-            idx = int(key)
-            if idx < 0 or idx >= self.model.nkey:
-                raise ConfigError(f"Keyframe index out of range: {idx}")
-        mj.mj_resetDataKeyframe(self.model, self.data, idx)
+        mj.mj_resetDataKeyframe(self.model, self.data, _keyframe_index(self.model, key))
 
-    # ---- actuator groups (API surface; the mask is applied inside the actuation stage)
+    # ------------------------------------------------------------------ actuator groups
+    # The mask lives in model.opt.disableactuator and is honoured by the actuation stage of the kernels.
     @property
     def actuator_groups(self) -> np.ndarray:
-        return np.array(self.model.actuator_group, dtype=int)
+        return np.asarray(self.model.actuator_group, dtype=int).copy()
+
+    def enabled_actuator_mask(self) -> np.ndarray:
+        """Boolean (nu,) array: True where the actuator's group is not disabled."""
+        off_bits = int(self.model.opt.disableactuator)
+        groups = self.actuator_groups[: self.model.nu]
+        return ((off_bits >> groups) & 1) == 0 if groups.size else np.zeros(0, dtype=bool)
 
     def set_enabled_actuator_groups(self, enabled_groups: Iterable[int]) -> None:
-        wanted = {int(g) for g in enabled_groups}
-        if not wanted:
+        keep = sorted({int(g) for g in enabled_groups})
+        if not keep:
             raise CompatibilityError("At least one actuator group must be enabled.")
-        if min(wanted) < 0 or max(wanted) > 31:
+        if keep[0] < 0 or keep[-1] >= _GROUP_BITS:
             raise ConfigError("Actuator groups must be in [0, 31].")
         if self.model.nu == 0:
             raise CompatibilityError("Model has no actuators (nu=0).")
-        present = {int(g) for g in self.model.actuator_group[: self.model.nu]}
-        if not (wanted & present):
+        in_model = set(self.actuator_groups[: self.model.nu].tolist())
+        if in_model.isdisjoint(keep):
             raise CompatibilityError("None of the requested groups exist in this model.")
-        mask = 0
-        for grp in present - wanted:
-            mask |= 1 << grp
-        self.model.opt.disableactuator = mask
-        mj.mj_forward(self.model, self.data)
+        self.model.opt.disableactuator = sum(1 << g for g in in_model.difference(keep))
+        self.forward()
         if not self.enabled_actuator_mask().any():
             raise CompatibilityError("All actuators disabled by group selection.")
-
-    def enabled_actuator_mask(self) -> np.ndarray:
-        disabled = int(self.model.opt.disableactuator)
-        return np.array([not ((disabled >> int(g)) & 1) for g in self.actuator_groups], dtype=bool).reshape(self.model.nu)
 
 
 __all__ = ["ModelHandle"]
