@@ -30,59 +30,59 @@ class CompatibilityReport:
         raise CompatibilityError("\n".join(lines))
 
 
-def _valid_range(pair) -> bool:
-    lo, hi = pair
-    return bool(np.isfinite(lo) and np.isfinite(hi) and hi > lo)
+def _range_notes(model: Any, indices: np.ndarray, flag_field: str, range_field: str, *, unflagged: str | None, label: str) -> list[str]:
+    """One pass over the enabled actuators for a (limited-flag, range) field pair of the model.
+
+    ``unflagged``: message template for an actuator whose flag is off (``None``: such actuators are fine and skipped);
+    a flagged actuator must have a finite, non-empty range, else it is reported under ``label``."""
+    flags = np.asarray(getattr(model, flag_field), dtype=bool)
+    ranges = np.asarray(getattr(model, range_field), dtype=float)
+    out: list[str] = []
+    for idx in indices:
+        if not flags[idx]:
+            if unflagged is not None:
+                out.append(unflagged.format(idx=idx))
+            continue
+        lo, hi = ranges[idx]
+        if not (np.isfinite(lo) and np.isfinite(hi) and hi > lo):
+            out.append(f"Invalid {label} for enabled actuator {idx}: [{lo}, {hi}]")
+    return out
+
+
+def _group_notes(model: Any, declared, active: np.ndarray) -> list[str]:
+    wanted = {int(g) for g in declared}
+    live = {int(g) for g in np.asarray(model.actuator_group)[active]}
+    out: list[str] = []
+    if not live:
+        out.append("Controller declared actuator groups but none are currently enabled; continuing without additional group gating.")
+    if wanted - live:
+        out.append(f"Controller requested actuator groups {sorted(wanted - live)} but they are not enabled; controller will still run with the available groups.")
+    if live - wanted:
+        out.append(f"Enabled actuators include groups {sorted(live - wanted)} beyond the controller request; behaviour matches MuJoCo but may require controller-side masking.")
+    return out
 
 
 def check_controller_compat(model: Any, ctrl_cap: ControllerCapabilities, enabled_mask: np.ndarray | None) -> CompatibilityReport:
-    reasons: list[str] = []
-    notes: list[str] = []
-    nu = model.nu
-    if nu == 0:
-        reasons.append("Model has no actuators (nu=0).")
-    mask = np.ones(nu, dtype=bool) if enabled_mask is None else enabled_mask
+    """Hard failures: no actuators, or none enabled.  Everything else becomes a warning string (reference wording)."""
+    nu = int(model.nu)
+    mask = np.ones(nu, dtype=bool) if enabled_mask is None else np.asarray(enabled_mask)
     if mask.shape[0] != nu:
         raise ConfigError("enabled_mask must have length model.nu")
-    if mask.sum() == 0:
-        reasons.append("All actuators are disabled by group selection.")
+    reasons = [msg for bad, msg in ((nu == 0, "Model has no actuators (nu=0)."),
+                                    (not mask.any(), "All actuators are disabled by group selection.")) if bad]
     active = np.flatnonzero(mask)
-
+    notes: list[str] = []
     if ctrl_cap.actuator_groups is not None:
-        wanted = {int(g) for g in ctrl_cap.actuator_groups}
-        live = {int(g) for g in np.asarray(model.actuator_group)[active]}
-        if not live:
-            notes.append("Controller declared actuator groups but none are currently enabled; continuing without additional group gating.")
-        missing, extra = sorted(wanted - live), sorted(live - wanted)
-        if missing:
-            notes.append(f"Controller requested actuator groups {missing} but they are not enabled; controller will still run with the available groups.")
-        if extra:
-            notes.append(f"Enabled actuators include groups {extra} beyond the controller request; behaviour matches MuJoCo but may require controller-side masking.")
-
+        notes += _group_notes(model, ctrl_cap.actuator_groups, active)
     space = ctrl_cap.control_space
     if space in _SERVO_SPACES:
-        limited = np.asarray(model.actuator_ctrllimited, dtype=bool)
-        for idx in active:
-            if not limited[idx]:
-                notes.append(f"Enabled actuator {idx} lacks ctrlrange limits required for servo control.")
-            elif not _valid_range(model.actuator_ctrlrange[idx]):
-                lo, hi = model.actuator_ctrlrange[idx]
-                notes.append(f"Invalid ctrlrange for enabled actuator {idx}: [{lo}, {hi}]")
+        notes += _range_notes(model, active, "actuator_ctrllimited", "actuator_ctrlrange", label="ctrlrange",
+                              unflagged="Enabled actuator {idx} lacks ctrlrange limits required for servo control.")
     if space == ControlSpace.INTVELOCITY:
-        actlim = np.asarray(model.actuator_actlimited, dtype=bool)
-        for idx in active:
-            if not actlim[idx]:
-                notes.append(f"Enabled actuator {idx} has no activation limits (actlimited=0) under intvelocity control.")
-            elif not _valid_range(model.actuator_actrange[idx]):
-                lo, hi = model.actuator_actrange[idx]
-                notes.append(f"Invalid actrange for enabled actuator {idx}: [{lo}, {hi}]")
+        notes += _range_notes(model, active, "actuator_actlimited", "actuator_actrange", label="actrange",
+                              unflagged="Enabled actuator {idx} has no activation limits (actlimited=0) under intvelocity control.")
     if space == ControlSpace.TORQUE:
-        flim = np.asarray(model.actuator_forcelimited, dtype=bool)
-        for idx in np.flatnonzero(flim & mask):
-            if not _valid_range(model.actuator_forcerange[idx]):
-                lo, hi = model.actuator_forcerange[idx]
-                notes.append(f"Invalid forcerange for enabled actuator {idx}: [{lo}, {hi}]")
-
+        notes += _range_notes(model, active, "actuator_forcelimited", "actuator_forcerange", label="forcerange", unflagged=None)
     notes.append("Note: joint/tendon constraints or other clamps may still limit motion/force beyond actuator-level checks.")
     return CompatibilityReport(ok=not reasons, reasons=reasons, warnings=notes)
 

@@ -56,90 +56,110 @@ class ObservationSpec:
 
 
 class ObservationExtractor:
-    def __init__(self, model: Any, spec: ObservationSpec):
-        self.model = model
-        self.spec = spec
-        O = mj.mjtObj
-        self.site_ids = self._ids(O.mjOBJ_SITE, spec.sites_pos)
-        self.body_ids = self._ids(O.mjOBJ_BODY, spec.bodies_pos)
-        self.geom_ids = self._ids(O.mjOBJ_GEOM, spec.geoms_pos)
-        self.subtree_ids = self._ids(O.mjOBJ_BODY, spec.subtree_com)
-        self.extra_items = tuple((name, self._as_producer(name, p)) for name, p in spec.extras.items())
-        self._warned: set[str] = set()
+    """Compiles an ``ObservationSpec`` into a fixed plan -- a list of ``(key, getter)`` pairs resolved once against the
+    model (names -> ids, which state slices, which position tables) -- and replays that plan on every call."""
 
-    def _ids(self, objtype: int, names: Sequence[str]) -> tuple[int, ...]:
-        out = []
-        for name in names:
-            idx = int(mj.mj_name2id(self.model, objtype, name))
+    _STATE_FIELDS = (("include_qpos", "qpos"), ("include_qvel", "qvel"))
+
+    def __init__(self, model: Any, spec: ObservationSpec):
+        self.model, self.spec = model, spec
+        self._warned: set[str] = set()
+        kinds = mj.mjtObj
+        self.site_ids = self._resolve(kinds.mjOBJ_SITE, spec.sites_pos)
+        self.body_ids = self._resolve(kinds.mjOBJ_BODY, spec.bodies_pos)
+        self.geom_ids = self._resolve(kinds.mjOBJ_GEOM, spec.geoms_pos)
+        self.subtree_ids = self._resolve(kinds.mjOBJ_BODY, spec.subtree_com)
+        self.extra_items = tuple((name, self._producer(name, p)) for name, p in spec.extras.items())
+        self._plan: list[tuple[str, Callable[[Any], np.ndarray]]] = self._compile()
+
+    # ------------------------------------------------------------------ plan construction
+    def _resolve(self, objtype: int, names: Sequence[str]) -> tuple[int, ...]:
+        ids = tuple(int(mj.mj_name2id(self.model, objtype, name)) for name in names)
+        for name, idx in zip(names, ids):
             if idx < 0:
                 raise NameLookupError(f"Name not found in model: {name}")
-            out.append(idx)
-        return tuple(out)
+        return ids
 
     @staticmethod
-    def _as_producer(name: str, p: Any) -> ObservationProducer:
+    def _producer(name: str, p: Any) -> ObservationProducer:
         if isinstance(p, ObservationProducer):
             return p
-        if callable(p):
-            return ObservationProducer(p)
-        raise TypeError(f"extras[{name!r}] must be callable or ObservationProducer")
+        if not callable(p):
+            raise TypeError(f"extras[{name!r}] must be callable or ObservationProducer")
+        return ObservationProducer(p)
+
+    def _view(self, arr: Any) -> np.ndarray:
+        """State slice: a zero-copy view of the (device-mapped) buffer unless the spec asks for copies."""
+        return np.array(arr, copy=True) if self.spec.copy else np.asarray(arr)
 
     def _warn_once(self, key: str, msg: str) -> None:
         if key not in self._warned:
             self._warned.add(key)
             warnings.warn(msg, RuntimeWarning)
 
-    def _slice(self, arr: Any) -> np.ndarray:
-        return np.array(arr, copy=True) if self.spec.copy else np.asarray(arr)
-
     @staticmethod
-    def _gather(src: Any, ids: tuple[int, ...]) -> np.ndarray:
-        pos = np.zeros((len(ids), 3))
+    def _rows(table: Any, ids: tuple[int, ...]) -> np.ndarray:
+        out = np.empty((len(ids), 3))
         for row, idx in enumerate(ids):
-            pos[row] = src[idx]
-        return pos
+            out[row] = table[idx]
+        return out
 
-    def __call__(self, data: Any) -> Observation:
-        s = self.spec
-        out: ObservationDict = {}
-        if s.include_qpos:
-            out["qpos"] = self._slice(data.qpos)
-        if s.include_qvel:
-            out["qvel"] = self._slice(data.qvel)
+    def _compile(self) -> list[tuple[str, Callable[[Any], np.ndarray]]]:
+        s, plan = self.spec, []
+        for flag, name in self._STATE_FIELDS:
+            if getattr(s, flag):
+                plan.append((name, lambda d, name=name: self._view(getattr(d, name))))
         if s.include_act:
-            if hasattr(data, "act"):
-                out["act"] = self._slice(data.act)
-            else:
-                self._warn_once("act", "ObservationSpec requested activations but data.act is missing; returning an empty array instead.")
-                out["act"] = np.zeros(0, dtype=float)
+            plan.append(("act", self._act))
         if s.include_ctrl:
-            out["ctrl"] = self._slice(data.ctrl)
+            plan.append(("ctrl", lambda d: self._view(d.ctrl)))
         if s.include_sensordata:
-            if self.model.nsensordata == 0:
-                self._warn_once("sensordata", "ObservationSpec requested sensordata but model has none; returning an empty array instead.")
-                out["sensordata"] = np.zeros(0, dtype=float)
-            else:
-                out["sensordata"] = self._slice(data.sensordata)
+            plan.append(("sensordata", self._sensordata))
         if s.include_time:
-            out["time"] = np.array([data.time], dtype=float)
+            plan.append(("time", lambda d: np.array([d.time], dtype=float)))
         if self.site_ids:
-            out["sites_pos"] = self._gather(data.site_xpos, self.site_ids)
+            plan.append(("sites_pos", lambda d: self._rows(d.site_xpos, self.site_ids)))
         if self.body_ids:
-            src = data.xipos if (s.bodies_inertial and hasattr(data, "xipos")) else data.xpos
-            out["bodies_pos"] = self._gather(src, self.body_ids)
+            plan.append(("bodies_pos", self._bodies))
         if self.geom_ids:
-            out["geoms_pos"] = self._gather(data.geom_xpos, self.geom_ids)
+            plan.append(("geoms_pos", lambda d: self._rows(d.geom_xpos, self.geom_ids)))
         if self.subtree_ids:
-            mj.mj_subtreeCoM(self.model, data)
-            out["subtree_com"] = self._gather(data.subtree_com, self.subtree_ids)
+            plan.append(("subtree_com", self._subtree))
+        return plan
+
+    # ------------------------------------------------------------------ getters with a story
+    def _act(self, data: Any) -> np.ndarray:
+        if hasattr(data, "act"):
+            return self._view(data.act)
+        self._warn_once("act", "ObservationSpec requested activations but data.act is missing; returning an empty array instead.")
+        return np.zeros(0, dtype=float)
+
+    def _sensordata(self, data: Any) -> np.ndarray:
+        if self.model.nsensordata:
+            return self._view(data.sensordata)
+        self._warn_once("sensordata", "ObservationSpec requested sensordata but model has none; returning an empty array instead.")
+        return np.zeros(0, dtype=float)
+
+    def _bodies(self, data: Any) -> np.ndarray:
+        inertial = self.spec.bodies_inertial and hasattr(data, "xipos")
+        return self._rows(data.xipos if inertial else data.xpos, self.body_ids)
+
+    def _subtree(self, data: Any) -> np.ndarray:
+        mj.mj_subtreeCoM(self.model, data)
+        return self._rows(data.subtree_com, self.subtree_ids)
+
+    # ------------------------------------------------------------------ per-step call
+    def __call__(self, data: Any) -> Observation:
+        out: ObservationDict = {key: get(data) for key, get in self._plan}
         for name, producer in self.extra_items:
             if name in out:
                 raise ValueError(f"extras[{name!r}] duplicates an existing observation key")
-            out[name] = producer.produce(self.model, data, s.copy)
-        if s.as_dict:
+            out[name] = producer.produce(self.model, data, self.spec.copy)
+        if self.spec.as_dict:
             return out
-        parts = [out[k].ravel() for k in sorted(out)]
-        return np.concatenate(parts) if parts else np.zeros(0)
+        if not out:
+            return np.zeros(0)
+        return np.concatenate([out[key].ravel() for key in sorted(out)])  # flattened form: keys in sorted order
 
 
 __all__ = ["ObservationSpec", "ObservationExtractor", "ObservationProducer"]
