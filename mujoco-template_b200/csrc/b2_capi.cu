@@ -38,6 +38,12 @@ struct b2_model {
   int cls;
   unsigned long long serial;
   const b2::SpecKernels* spec;  // model-specialised FP64 kernels, or nullptr (generic path)
+  // warp engine: the model image (constants + factorisation work lists) in device memory, per device and precision;
+  // kernels get it by pointer, so nothing about a large model is process-wide device state
+  mutable std::mutex image_mu;
+  mutable void* warp_image[16][2] = {};
+  mutable unsigned long long warp_image_serial[16][2] = {};
+  mutable std::vector<std::pair<int, void*>> retired_images;  // (device, pointer) replaced after a disable-mask change
 };
 
 namespace b2 {
@@ -127,7 +133,17 @@ int b2_model_create(const void* blob, size_t nbytes, b2_model** out) {
   *out = m;
   return B2_OK;
 }
-void b2_model_destroy(b2_model* m) { delete m; }
+void b2_model_destroy(b2_model* m) {
+  if (!m) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  for (int d = 0; d < 16; d++)
+    for (int p = 0; p < 2; p++)
+      if (m->warp_image[d][p]) { cudaSetDevice(d); cudaFree(m->warp_image[d][p]); }
+  for (auto& r : m->retired_images) { cudaSetDevice(r.first); cudaFree(r.second); }
+  cudaSetDevice(cur);
+  delete m;
+}
 
 int b2_model_set_actuator_disabled(b2_model* m, const int* disabled, int nu) {
   if (!m || (nu && !disabled) || nu != m->v.nu) return fail(B2_ERR_ARG, "b2_model_set_actuator_disabled: bad arguments");
@@ -192,6 +208,27 @@ static int prepare_warp(b2_batch* b) {
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
+// the model's warp-engine image on this batch's device (uploaded on first use and after a disable-mask change)
+static int warp_image_of(b2_batch* b, const void** out) {
+  const b2_model* m = b->model;
+  const int pi = b->precision == B2_F64 ? 0 : 1, dev = b->device;
+  std::lock_guard<std::mutex> lock(m->image_mu);
+  if (!m->warp_image[dev][pi] || m->warp_image_serial[dev][pi] != m->serial) {
+    const size_t bytes = pi == 0 ? b2::b2k_warp_image_bytes_f64() : b2::b2k_warp_image_bytes_f32();
+    std::vector<unsigned char> host(bytes);
+    if (pi == 0) b2::b2k_warp_image_fill_f64(&m->v, m->disabled.data(), host.data());
+    else b2::b2k_warp_image_fill_f32(&m->v, m->disabled.data(), host.data());
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "warp-engine model image cudaMalloc");
+    if ((e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return cuda_fail(e, "warp-engine model image upload"); }
+    if (m->warp_image[dev][pi]) m->retired_images.emplace_back(dev, m->warp_image[dev][pi]);  // kernels in flight may still read it
+    m->warp_image[dev][pi] = d;
+    m->warp_image_serial[dev][pi] = m->serial;
+  }
+  *out = m->warp_image[dev][pi];
+  return B2_OK;
+}
 extern "C" { static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream); }
 
 static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, const void* gain,
@@ -204,9 +241,12 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
     if ((rc = do_lqr_control(b, st, count, stream))) return rc;
     gain = nullptr;
   }
-  if (b->warp_mode == 1 && count == b->nenv)
-    return f64 ? b2::b2k_warp_step_f64(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
-               : b2::b2k_warp_step_f32(&b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
+  if (b->warp_mode == 1 && count == b->nenv) {
+    const void* image = nullptr;
+    if ((rc = warp_image_of(b, &image))) return rc;
+    return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
+  }
   return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
              : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
 }
@@ -265,9 +305,11 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
     const bool warp_fd = !(wfd && wfd[0] == '0');
     if ((rc = prepare_warp(b))) return rc;
     if (warp_fd && b->warp_mode == 1 && count == b->nenv && !gain && !shadow) {
+      const void* image = nullptr;
+      if ((rc = warp_image_of(b, &image))) return rc;
       rc = b->precision == B2_F64
-               ? b2::b2k_warp_linearize_f64(&b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
-               : b2::b2k_warp_linearize_f32(&b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
+               ? b2::b2k_warp_linearize_f64(image, &b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_linearize_f32(image, &b->model->v, st, b->nenv, eps, centered, A, B, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
       g_launches++;
       return rc ? cuda_fail((cudaError_t)rc, "warp linearize launch") : B2_OK;
     }

@@ -8,9 +8,11 @@ namespace b2 {
   double b2k_fma_peak##SUF(void* stream);                                                                                  \
   int b2k_warp_plan##SUF(const b2m_view* v, int N, int* out_wpb, int* out_blocks);                                        \
   size_t b2k_warp_scratch_bytes##SUF(const b2m_view* v, int slots);                                                        \
-  int b2k_warp_step##SUF(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch, void* counter,  \
+  size_t b2k_warp_image_bytes##SUF();                                                                                      \
+  void b2k_warp_image_fill##SUF(const b2m_view* v, const int* disabled, void* host);                                       \
+  int b2k_warp_step##SUF(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch, void* counter,  \
                          int wpb, int blocks, void* stream);                                                                                  \
-  int b2k_warp_linearize##SUF(const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
+  int b2k_warp_linearize##SUF(const void* image, const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
                               void* counter, int wpb, int blocks, void* stream);                                                        \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
   int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park, void* stream);                  \

@@ -4,6 +4,9 @@
 // precisions do not share the 64 KB constant bank.
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "b2_kernel_templates.cuh"
 #include "b2_kernels.h"
 #include "b2_warp_kernels.cuh"
@@ -39,26 +42,6 @@ struct RuntimeModel {
 #undef X
 };
 
-// Global-memory copy of the large image for the warp engine: its lanes read the model with
-// lane-dependent indices, which the constant cache would serialise (one address per cycle);
-// read-only global loads are gathered by L1 instead.
-__device__ DevModel<real, DimsLarge> g_model_large;
-struct GlobalModelLarge {
-  typedef DimsLarge D;
-#define X(name) static B2_DEV int name() { return __ldg(&g_model_large.name); }
-  B2_MODEL_INT_SCALARS(X)
-#undef X
-#define X(name) static B2_DEV real name() { return __ldg(&g_model_large.name); }
-  B2_MODEL_REAL_SCALARS(X)
-#undef X
-#define X(name, cap) static B2_DEV int name(int i) { return __ldg(&g_model_large.name[i]); }
-  B2_MODEL_INT_ARRAYS(X)
-#undef X
-#define X(name, cap) static B2_DEV real name(int i) { return __ldg(&g_model_large.name[i]); }
-  B2_MODEL_REAL_ARRAYS(X)
-#undef X
-};
-
 // register-resident FMA chain: measures the CUDA-core FP pipe peak the roofline is quoted against
 __global__ void __launch_bounds__(256) k_fma_peak(real* out, int iters, real a, real b) {
   real x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -88,11 +71,6 @@ template <> cudaError_t upload_t<DimsSmall>(const b2m_view& v, const int* disabl
 }
 template <> cudaError_t upload_t<DimsLarge>(const b2m_view& v, const int* disabled, cudaStream_t s) {
   static DevModel<real, DimsLarge> h; fill_dev_model(h, v, disabled);
-  cudaError_t e = cudaMemcpyToSymbolAsync(g_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
-  if (e != cudaSuccess) return e;
-  if ((e = upload_tri_tables(s)) != cudaSuccess) return e;
-  if ((e = upload_ld_plan(v, s)) != cudaSuccess) return e;
-  if ((e = upload_chol_plan(v.nv, s)) != cudaSuccess) return e;
   return cudaMemcpyToSymbolAsync(c_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
 }
 
@@ -142,94 +120,96 @@ int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int coun
   return (int)cudaGetLastError();
 }
 // ---- warp engine (large models): launch geometry and per-warp scratch are sized by the host
-static int warp_ws_reals_of(const b2m_view* v) {
-  return warp_ws_reals<void>(v->nq, v->nv, v->nu, v->nbody, v->njnt, v->ngeom, v->ntendon);
+// Sizes with a compiled-in kernel variant (every workspace offset and loop bound a constant): the humanoid's.
+typedef DimsStatic<28, 27, 21, 17, 22, 20, 2, 6> DimsHumanoid;
+static int view_maxdepth(const b2m_view* v) {
+  int best = 0;
+  for (int i = 1; i < v->nbody; i++) {
+    int depth = 0;
+    for (int j = i; j > 0; j = v->body_parentid[j]) depth++;
+    if (depth > best) best = depth;
+  }
+  return best;
 }
-static size_t warp_block_smem(const b2m_view* v, int wpb) {
+static bool dims_are_humanoid(const b2m_view* v) {
+  if (const char* x = getenv("B2_WARP_STATIC_DIMS")) if (x[0] == '0') return false;
+  typedef DimsHumanoid H;
+  return v->nq == H::NQ && v->nv == H::NV && v->nu == H::NU && v->nbody == H::NB && v->njnt == H::NJ && v->ngeom == H::NG &&
+         v->ntendon == H::NT && view_maxdepth(v) == H::DEPTH;
+}
+#define B2_WARP_DIMS(v, CALL)                                          \
+  if (dims_are_humanoid(v)) { typedef ImageModel<real, DimsHumanoid> WM; CALL; } \
+  else { typedef ImageModel<real, DimsRuntime> WM; CALL; }
+
+static int warp_ws_reals_of(const b2m_view* v) { return warp_ws_reals(v->nq, v->nv, v->nu, v->nbody, v->njnt, v->ngeom, v->ntendon); }
+static size_t warp_block_smem(const b2m_view* v, int wpb, int extra_reals) {
   size_t extra = 0;
   if (const char* x = getenv("B2_WARP_EXTRA_SMEM")) extra = (size_t)atoi(x);  // tuning: lowers the resident blocks per SM
-  return extra + (size_t)wpb * ((size_t)warp_ws_reals_of(v) * sizeof(real) + (size_t)kWarpIntsAsReals * sizeof(double));
+  return extra + (size_t)wpb * ((size_t)warp_ws_reals_of(v) + extra_reals) * sizeof(real);
 }
-// lock-step launch shape (k_warp_step_ls): B2_WARP_LOCKSTEP=0 falls back to independent two-warp blocks
-static int warp_lockstep() {  // 0: independent warps, 1: lock step everywhere, 2: lock step outside the Newton loop
-  const char* x = getenv("B2_WARP_LOCKSTEP");
-  return x ? atoi(x) : 1;
+static int warp_wpb() {  // warps (envs) per lock-step block
+  int wpb = 2;
+  if (const char* x = getenv("B2_WARP_LS_WPB")) { const int w = atoi(x); if (w >= 1 && w <= 8) wpb = w; }
+  return wpb;
 }
-// chooses warps-per-block / grid so that every SM is filled; returns the number of warp slots
+template <class K>
+static int warp_occupancy(K kern, int wpb, size_t smem, int* per_sm) {
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
+  // the whole L1 / shared-memory array as shared memory: the workspace per env decides how many warps an SM holds
+  cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, kern, wpb * 32, smem) != cudaSuccess || *per_sm < 1) return -1;
+  return 0;
+}
+size_t B2_FN(b2k_warp_image_bytes)() { return sizeof(WarpImage<real>); }
+void B2_FN(b2k_warp_image_fill)(const b2m_view* v, const int* disabled, void* host) {
+  fill_warp_image(*reinterpret_cast<WarpImage<real>*>(host), *v, disabled);
+}
+// chooses warps-per-block / grid so that every SM is filled; returns the number of warp slots (scratch slots)
 int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks) {
   int dev = 0, sms = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  if (warp_lockstep()) {
-    // one block per SM with as many warps (envs) as the shared-memory workspace allows, at most 8
-    int wpb = 2;
-    if (const char* x = getenv("B2_WARP_LS_WPB")) wpb = atoi(x) == 1 ? 1 : 2;  // the kernels are compiled for 64-thread blocks
-    while (wpb > 1 && warp_block_smem(v, wpb) + 1024 > (size_t)smem_max) wpb--;
-    const size_t smem = warp_block_smem(v, wpb);
-    auto kern = warp_lockstep() == 2 ? k_warp_step_ls<real, GlobalModelLarge, 2> : k_warp_step_ls<real, GlobalModelLarge, 1>;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return -1;
-    int blocks = sms * per_sm;
-    const int need = (N + wpb - 1) / wpb;
-    if (blocks > need) blocks = need;
-    *out_wpb = wpb; *out_blocks = blocks;
-    return blocks * wpb;
-  }
-  const int wpb = 2;
-  const size_t smem = warp_block_smem(v, wpb);
-  auto kern = k_warp_step<real, GlobalModelLarge>;
-  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -1;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return -1;
+  int wpb = warp_wpb();
+  while (wpb > 1 && warp_block_smem(v, wpb, 0) + 1024 > (size_t)smem_max) wpb--;
+  const size_t smem = warp_block_smem(v, wpb, 0);
+  int per_sm = 0, rc = 0;
+  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_step_ls<real, WM, 1>, wpb, smem, &per_sm)));
+  if (rc) return -1;
   int blocks = sms * per_sm;
   const int need = (N + wpb - 1) / wpb;
   if (blocks > need) blocks = need;
+  if (getenv("B2_WARP_DEBUG")) fprintf(stderr, "[b2mj] warp plan: %d warps/block, %d blocks/SM, %zu B shared memory/block, static dims %d\n", wpb, per_sm, smem, (int)dims_are_humanoid(v));
   *out_wpb = wpb; *out_blocks = blocks;
   return blocks * wpb;
 }
 size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
   return (size_t)slots * warp_slot_reals(v->nv) * sizeof(real);
 }
-int B2_FN(b2k_warp_step)(const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
+int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
                          void* counter, int wpb, int blocks, void* stream) {
-  const size_t smem = warp_block_smem(v, wpb);
+  const size_t smem = warp_block_smem(v, wpb, 0);
   // envs are handed out through a work queue: the first gridDim * wpb statically, the rest by atomic counter
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  // lock-step group: B2_WARP_LS_GROUP warps (default: the whole block), B2_WARP_LS_MAP picks which warps form a group
-  int gsize = wpb, map = 0;
-  if (const char* x = getenv("B2_WARP_LS_GROUP")) { const int g = atoi(x); if (g > 0 && wpb % g == 0) gsize = g; }
-  if (const char* x = getenv("B2_WARP_LS_MAP")) map = atoi(x) != 0;
-  if (warp_lockstep() == 2)
-    k_warp_step_ls<real, GlobalModelLarge, 2><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v), gsize, map);
-  else if (warp_lockstep())
-    k_warp_step_ls<real, GlobalModelLarge, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v), gsize, map);
-  else
-    k_warp_step<real, GlobalModelLarge><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-        to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter, warp_ws_reals_of(v));
+  B2_WARP_DIMS(v, (k_warp_step_ls<real, WM, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+                      (const WarpImage<real>*)image, to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter)));
   return (int)cudaGetLastError();
 }
-// FD linearisation on the warp engine: same grid and scratch slots as the step plan (wpb warps per block)
-int B2_FN(b2k_warp_linearize)(const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,
-                              void* counter, int wpb, int blocks, void* stream) {
-  const int extra = 2 * (v->nq + v->nv);
-  const size_t smem = warp_block_smem(v, wpb) + (size_t)wpb * extra * sizeof(real);
-  auto kern = k_warp_linearize<real, GlobalModelLarge, 1>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  int per_sm = 0, dev = 0, sms = 0;
+// FD linearisation on the warp engine: same scratch slots as the step plan (wpb warps per block)
+int B2_FN(b2k_warp_linearize)(const void* image, const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B,
+                              void* jscratch, void* counter, int wpb, int blocks, void* stream) {
+  const size_t smem = warp_block_smem(v, wpb, 2 * (v->nq + v->nv));
+  int per_sm = 0, dev = 0, sms = 0, rc = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, wpb * 32, smem) != cudaSuccess || per_sm < 1) return (int)cudaErrorLaunchOutOfResources;
+  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_linearize<real, WM, 1>, wpb, smem, &per_sm)));
+  if (rc) return (int)cudaErrorLaunchOutOfResources;
   if (blocks > sms * per_sm) blocks = sms * per_sm;  // persistent: never more blocks than fit at once (scratch slots are per block)
-  e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  kern<<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(to_dev<real>(st), N, (real)eps, centered, (real*)A, (real*)B, (real*)jscratch,
-                                                         (int*)counter, warp_ws_reals_of(v), extra, wpb);
+  B2_WARP_DIMS(v, (k_warp_linearize<real, WM, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+                      (const WarpImage<real>*)image, to_dev<real>(st), N, (real)eps, centered, (real*)A, (real*)B, (real*)jscratch, (int*)counter)));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,

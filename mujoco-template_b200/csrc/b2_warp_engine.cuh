@@ -30,81 +30,141 @@ template <typename T> __device__ __noinline__ T warp_sum(T v) {
   return v;
 }
 B2_DEV int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower triangle, j <= i
-// inverse of tri(): (row, col) of packed entry e, for matrices up to 32 x 32 (filled at load time)
-static __device__ unsigned char g_tri_row[528], g_tri_col[528];
-B2_DEV void untri(int e, int& i, int& j) { i = __ldg(&g_tri_row[e]); j = __ldg(&g_tri_col[e]); }
-inline cudaError_t upload_tri_tables(cudaStream_t s) {
-  static unsigned char row[528], col[528];
+
+// Everything a warp-engine kernel reads about one model, as ONE global-memory object owned by the b2_model (per device and
+// precision) and passed to the kernels by pointer -- no process-wide device symbols, so batches of different large models
+// can run concurrently on different streams.  Lanes read the model with lane-dependent indices, which the constant cache
+// would serialise (one address per cycle); read-only global loads are gathered by L1 instead.
+//  * ld_plan: work list of the tree-sparse L'DL factorisation (mj_factorM): for every pivot dof k the ancestor pairs (i, j),
+//    j <= i, packed as tri(i,j) | tri(k,j) << 10 | i << 20; ld_off[k] .. ld_off[k+1] delimits pivot k.
+//  * chol_plan: work list of the dense nv x nv Cholesky of the Newton Hessian: for pivot column j the trailing entries
+//    (i, c), j < c <= i, packed as tri(i,c) | tri(i,j) << 10 | tri(c,j) << 20; depends on nv only.
+//  * tri_row / tri_col: inverse of tri() for matrices up to 32 x 32.
+template <typename T>
+struct WarpImage {
+  DevModel<T, DimsLarge> model;
+  int ld_plan[5456], ld_off[33], chol_plan[5456], chol_off[33];
+  unsigned char tri_row[528], tri_col[528];
+};
+
+template <typename T>
+inline void fill_warp_image(WarpImage<T>& img, const b2m_view& v, const int* actuator_disabled) {
+  fill_dev_model(img.model, v, actuator_disabled);
+  auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
   int e = 0;
-  for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) { row[e] = (unsigned char)i; col[e] = (unsigned char)j; e++; }
-  cudaError_t err = cudaMemcpyToSymbolAsync(g_tri_row, row, sizeof(row), 0, cudaMemcpyHostToDevice, s);
-  if (err != cudaSuccess) return err;
-  return cudaMemcpyToSymbolAsync(g_tri_col, col, sizeof(col), 0, cudaMemcpyHostToDevice, s);
-}
-
-// Work list of the tree-sparse L'DL factorisation (mj_factorM): for every pivot dof k the ancestor pairs (i, j), j <= i,
-// packed as tri(i,j) | tri(k,j) << 10 | i << 20; g_ld_off[k] .. g_ld_off[k+1] delimits pivot k.  Built on the host when
-// the model image is uploaded, so the factor loop does no index arithmetic.
-static __device__ int g_ld_plan[5456], g_ld_off[33];
-inline cudaError_t upload_ld_plan(const b2m_view& v, cudaStream_t s) {
-  static int plan[5456], off[33];
+  for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) { img.tri_row[e] = (unsigned char)i; img.tri_col[e] = (unsigned char)j; e++; }
   int n = 0;
-  auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
   for (int k = 0; k < v.nv && k < 32; k++) {
-    off[k] = n;
+    img.ld_off[k] = n;
     for (int i = v.dof_parentid[k]; i >= 0; i = v.dof_parentid[i])
-      for (int j = i; j >= 0; j = v.dof_parentid[j]) plan[n++] = tri_h(i, j) | (tri_h(k, j) << 10) | (i << 20);
+      for (int j = i; j >= 0; j = v.dof_parentid[j]) img.ld_plan[n++] = tri_h(i, j) | (tri_h(k, j) << 10) | (i << 20);
   }
-  for (int k = v.nv < 32 ? v.nv : 32; k <= 32; k++) off[k] = n;
-  cudaError_t err = cudaMemcpyToSymbolAsync(g_ld_plan, plan, sizeof(int) * (n > 0 ? n : 1), 0, cudaMemcpyHostToDevice, s);
-  if (err != cudaSuccess) return err;
-  return cudaMemcpyToSymbolAsync(g_ld_off, off, sizeof(off), 0, cudaMemcpyHostToDevice, s);
+  for (int k = v.nv < 32 ? v.nv : 32; k <= 32; k++) img.ld_off[k] = n;
+  for (; n < 5456; n++) img.ld_plan[n] = 0;
+  n = 0;
+  const int nv = v.nv > 32 ? 32 : v.nv;
+  for (int j = 0; j < nv; j++) {
+    img.chol_off[j] = n;
+    for (int i = j + 1; i < nv; i++)
+      for (int c = j + 1; c <= i; c++) img.chol_plan[n++] = tri_h(i, c) | (tri_h(i, j) << 10) | (tri_h(c, j) << 20);
+  }
+  for (int j = nv; j <= 32; j++) img.chol_off[j] = n;
+  for (; n < 5456; n++) img.chol_plan[n] = 0;
 }
 
-// Work list of the dense nv x nv Cholesky of the Newton Hessian: for pivot column j the trailing entries (i, c),
-// j < c <= i, packed as tri(i,c) | tri(i,j) << 10 | tri(c,j) << 20; depends on nv only.
-static __device__ int g_chol_plan[5456], g_chol_off[33];
-inline cudaError_t upload_chol_plan(int nv, cudaStream_t s) {
-  static int plan[5456], off[33];
-  int n = 0;
-  auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
-  if (nv > 32) nv = 32;
-  for (int j = 0; j < nv; j++) {
-    off[j] = n;
-    for (int i = j + 1; i < nv; i++)
-      for (int c = j + 1; c <= i; c++) plan[n++] = tri_h(i, c) | (tri_h(i, j) << 10) | (tri_h(c, j) << 20);
-  }
-  for (int j = nv; j <= 32; j++) off[j] = n;
-  cudaError_t err = cudaMemcpyToSymbolAsync(g_chol_plan, plan, sizeof(int) * (n > 0 ? n : 1), 0, cudaMemcpyHostToDevice, s);
-  if (err != cudaSuccess) return err;
-  return cudaMemcpyToSymbolAsync(g_chol_off, off, sizeof(off), 0, cudaMemcpyHostToDevice, s);
-}
+// Model providers of the warp engine: an object that holds the image pointer; every field is a member accessor.
+// DimsRuntime reads the sizes from the image (any model of the large class); DimsStatic<...> makes them compile-time
+// constants, so that every workspace offset and loop bound folds (used when a model's sizes match an instantiated
+// kernel: the humanoid).  The field VALUES always come from the image.
+struct DimsRuntime { static constexpr bool STATIC = false; };
+template <int NQ_, int NV_, int NU_, int NB_, int NJ_, int NG_, int NT_, int DEPTH_>
+struct DimsStatic {
+  static constexpr bool STATIC = true;
+  static constexpr int NQ = NQ_, NV = NV_, NU = NU_, NB = NB_, NJ = NJ_, NG = NG_, NT = NT_, DEPTH = DEPTH_;
+};
+template <typename T>
+struct ImageModelBase {
+  typedef DimsLarge D;
+  const WarpImage<T>* img;
+#define X(name) B2_DEV int name() const { return __ldg(&img->model.name); }
+  B2_MODEL_INT_SCALARS(X)
+#undef X
+#define X(name) B2_DEV T name() const { return __ldg(&img->model.name); }
+  B2_MODEL_REAL_SCALARS(X)
+#undef X
+#define X(name, cap) B2_DEV int name(int i) const { return __ldg(&img->model.name[i]); }
+  B2_MODEL_INT_ARRAYS(X)
+#undef X
+#define X(name, cap) B2_DEV T name(int i) const { return __ldg(&img->model.name[i]); }
+  B2_MODEL_REAL_ARRAYS(X)
+#undef X
+  B2_DEV void untri(int e, int& i, int& j) const { i = __ldg(&img->tri_row[e]); j = __ldg(&img->tri_col[e]); }
+};
+template <typename T, class DM>
+struct ImageModel : ImageModelBase<T> {
+  typedef DM Dims;
+  B2_DEV int nq() const { return DM::NQ; }
+  B2_DEV int nv() const { return DM::NV; }
+  B2_DEV int nu() const { return DM::NU; }
+  B2_DEV int nbody() const { return DM::NB; }
+  B2_DEV int njnt() const { return DM::NJ; }
+  B2_DEV int ngeom() const { return DM::NG; }
+  B2_DEV int ntendon() const { return DM::NT; }
+  B2_DEV int maxdepth() const { return DM::DEPTH; }
+};
+template <typename T>
+struct ImageModel<T, DimsRuntime> : ImageModelBase<T> { typedef DimsRuntime Dims; };
 
 struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
-// reals of global scratch one resident warp owns: J (NEFC x nv), six row vectors, and the contact records (dist, pos, frame)
-__host__ __device__ inline size_t warp_slot_reals(int nv) { return (size_t)WarpCaps::NEFC * (nv + 6) + 13 * WarpCaps::NCON; }
+// reals of global scratch one resident warp owns: J (NEFC x nv), six row vectors, the contact records (dist, pos, frame) and
+// the int metadata of contacts and rows (counted as one real each)
+__host__ __device__ inline size_t warp_slot_reals(int nv) {
+  return (size_t)WarpCaps::NEFC * (nv + 6) + 13 * WarpCaps::NCON + WarpCaps::NCON + WarpCaps::NEFC;
+}
 
+// Shared-memory workspace of one env (offsets in reals).  How many warps an SM holds is decided by this size (and by the
+// registers), and the kernel is latency-bound, so arrays share storage wherever their live ranges allow:
+//   P  live across stages: state, packed M, bias / passive force, tendons, subtree CoM, cinert, cdof
+//   X  one region used three times over:
+//      A  kinematics   xpos xquat xipos xmat ximat xanchor xaxis geom_xpos geom_z   (dead once collide + com_frame ran)
+//      B  dynamics     crb buf6 cvel cdof_dot cacc                                   (mass matrix, velocities, RNE)
+//      C  solve        LDp dinv hdinv + nine nv-vectors                              (factorisations, Newton, Euler)
+// The stage order of forward() follows from it (collide right after kinematics, the first factorisation after RNE).
+struct WarpLayout {
+  int qpos, qvel, ctrl, warm, Mp, f_bias, f_passive, ten_len, ten_J, com, cinert, cdof, X, total;
+  int xpos, xquat, xipos, xmat, ximat, xanchor, xaxis, geom_xpos, geom_z;
+  int crb, buf6, cvel, cdof_dot, cacc;
+  int LDp, dinv, hdinv, f_smooth, f_con, a_smooth, qacc, Ma, Mv, grad, Mgrad, search;
+  __host__ __device__ constexpr WarpLayout(int nq, int nv, int nu, int nb, int nj, int ng, int nt)
+      : qpos(0), qvel(qpos + nq), ctrl(qvel + nv), warm(ctrl + nu), Mp(warm + nv), f_bias(Mp + nv * (nv + 1) / 2),
+        f_passive(f_bias + nv), ten_len(f_passive + nv), ten_J(ten_len + nt), com(ten_J + nt * nv), cinert(com + 3 * nb),
+        cdof(cinert + 10 * nb), X(cdof + 6 * nv), total(0),
+        xpos(X), xquat(xpos + 3 * nb), xipos(xquat + 4 * nb), xmat(xipos + 3 * nb), ximat(xmat + 9 * nb), xanchor(ximat + 9 * nb),
+        xaxis(xanchor + 3 * nj), geom_xpos(xaxis + 3 * nj), geom_z(geom_xpos + 3 * ng),
+        crb(X), buf6(crb + 10 * nb), cvel(buf6 + 6 * (nv > nb ? nv : nb)), cdof_dot(cvel + 6 * nb), cacc(cdof_dot + 6 * nv),
+        LDp(X), dinv(LDp + nv * (nv + 1) / 2), hdinv(dinv + nv), f_smooth(hdinv + nv), f_con(f_smooth + nv), a_smooth(f_con + nv),
+        qacc(a_smooth + nv), Ma(qacc + nv), Mv(Ma + nv), grad(Mv + nv), Mgrad(grad + nv), search(Mgrad + nv) {
+    int endA = geom_z + 3 * ng, endB = cacc + 6 * nb, endC = search + nv;
+    total = endA > endB ? endA : endB;
+    if (endC > total) total = endC;
+  }
+};
 // number of T elements of shared memory one env needs
-template <class M> __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int nj, int ng, int nt) {
-  const int np = nv * (nv + 1) / 2;
-  int overlayA = 9 * nb + 6 * nj;          // ximat + xanchor + xaxis   | cdof_dot + cvel
-  const int overlayB = 6 * nv + 6 * nb;
-  if (overlayB > overlayA) overlayA = overlayB;
-  return (nq + 2 * nv + nu) + (3 + 4 + 9 + 3) * nb + overlayA + 6 * ng + 3 * nb + 10 * nb + 10 * nb + 6 * nv + 6 * nb +
-         2 * np + 2 * nv + nt + nt * nv + 11 * nv + (nb <= nv ? 0 : 6 * nb);  // buf6 aliases qacc .. search when it fits
+__host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int nj, int ng, int nt) {
+  return WarpLayout(nq, nv, nu, nb, nj, ng, nt).total;
 }
 
 // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once; tk: nv scratch reals
 template <typename T, class M>
-__device__ __noinline__ void factor_LD_impl(T* LDp, T* dinv, T* tk, int lane) {
+__device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, T* tk, int lane) {
 
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
     for (int k = nv - 1; k >= 0; k--) {
-      const int m = M::dof_nanc(k);  // proper ancestors of k, nearest first
+      const int m = mdl.dof_nanc(k);  // proper ancestors of k, nearest first
       const T dkk = LDp[tri(k, k)];
       // one division sequence per pivot: lanes < m scale their entry of row k, lane m produces 1 / d_k
-      const int i = lane < m ? M::dof_anclist(k * LS + lane) : 0;
+      const int i = lane < m ? mdl.dof_anclist(k * LS + lane) : 0;
       const T q = (lane < m ? LDp[tri(k, i)] : T(1)) / dkk;
       if (lane < m) tk[i] = q;
       if (lane == m) dinv[k] = q;
@@ -112,11 +172,11 @@ __device__ __noinline__ void factor_LD_impl(T* LDp, T* dinv, T* tk, int lane) {
         __syncwarp();
         // all ancestor pairs (i, j), j <= i, at once: L[i,j] -= t_i * L[k,j]  (the unscaled row k, exactly the scalar
         // algorithm's operands); the pairs and their packed indices come from the host-built work list
-        for (int e0 = __ldg(&g_ld_off[k]) + lane, end = __ldg(&g_ld_off[k + 1]); e0 < end; e0 += 96) {
+        for (int e0 = __ldg(&mdl.img->ld_off[k]) + lane, end = __ldg(&mdl.img->ld_off[k + 1]); e0 < end; e0 += 96) {
           int w[3];
           T a[3], b[3], c[3];
 #pragma unroll
-          for (int u = 0; u < 3; u++) w[u] = e0 + 32 * u < end ? __ldg(&g_ld_plan[e0 + 32 * u]) : -1;
+          for (int u = 0; u < 3; u++) w[u] = e0 + 32 * u < end ? __ldg(&mdl.img->ld_plan[e0 + 32 * u]) : -1;
 #pragma unroll
           for (int u = 0; u < 3; u++) if (w[u] >= 0) { a[u] = LDp[w[u] & 1023]; b[u] = tk[w[u] >> 20]; c[u] = LDp[(w[u] >> 10) & 1023]; }
 #pragma unroll
@@ -132,11 +192,11 @@ __device__ __noinline__ void factor_LD_impl(T* LDp, T* dinv, T* tk, int lane) {
 // x <- (L'DL)^-1 x, column-oriented sweeps (no reductions).  One out-of-line copy shared by the three call sites:
 // the kernel is instruction-fetch bound (32 % of stall samples were "no instruction"), so code size matters.
 template <typename T, class M>
-__device__ __noinline__ void solve_LD_impl(const T* LDp, const T* dinv, T* x, int lane) {
+__device__ __noinline__ void solve_LD_impl(const M mdl, const T* LDp, const T* dinv, T* x, int lane) {
 
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     for (int i = nv - 1; i > 0; i--) {
-      const unsigned anc = ((unsigned)M::dof_anc(i)) & ~(1u << i);
+      const unsigned anc = ((unsigned)mdl.dof_anc(i)) & ~(1u << i);
       const T xi = x[i];
       WFOR(j, i) if ((anc >> j) & 1u) x[j] -= LDp[tri(i, j)] * xi;
       __syncwarp();
@@ -145,7 +205,7 @@ __device__ __noinline__ void solve_LD_impl(const T* LDp, const T* dinv, T* x, in
     __syncwarp();
     for (int j = 0; j < nv - 1; j++) {
       const T xj = x[j];
-      for (int i = j + 1 + lane; i < nv; i += 32) if (((((unsigned)M::dof_anc(i)) >> j) & 1u)) x[i] -= LDp[tri(i, j)] * xj;
+      for (int i = j + 1 + lane; i < nv; i += 32) if (((((unsigned)mdl.dof_anc(i)) >> j) & 1u)) x[i] -= LDp[tri(i, j)] * xj;
       __syncwarp();
     }
   }
@@ -192,6 +252,7 @@ template <typename T> __device__ __noinline__ void make_frame_shared(T* fr) { ma
 
 template <typename T, class M>
 struct WarpEnv {
+  M mdl;
   int lane, ncon, nefc, niter, flags;
   T *qpos, *qvel, *ctrl, *warm;
   T *xpos, *xquat, *xmat, *xipos, *ximat, *xanchor, *xaxis, *cdof_dot, *cvel;
@@ -207,27 +268,20 @@ struct WarpEnv {
   bool hess_valid;
   int hess_ij[17];  // (row | col << 8) of the packed Hessian entries lane + 32 t this lane owns
 
-  B2_DEV void bind(T* base, int* ibase, T* jscratch) {
-    const int nq = M::nq(), nv = M::nv(), nu = M::nu(), nb = M::nbody(), nj = M::njnt(), ng = M::ngeom(), nt = M::ntendon();
-    const int np = nv * (nv + 1) / 2;
-    T* p = base;
-    auto take = [&](int n) { T* r = p; p += n; return r; };
-    qpos = take(nq); qvel = take(nv); ctrl = take(nu); warm = take(nv);
-    xpos = take(3 * nb); xquat = take(4 * nb); xmat = take(9 * nb); xipos = take(3 * nb);
-    T* ov = p;
-    ximat = take(9 * nb); xanchor = take(3 * nj); xaxis = take(3 * nj);
-    cdof_dot = ov; cvel = ov + 6 * nv;
-    const int ovA = 9 * nb + 6 * nj, ovB = 6 * nv + 6 * nb;
-    p = ov + (ovA > ovB ? ovA : ovB);
-    geom_xpos = take(3 * ng); geom_z = take(3 * ng); com = take(3 * nb); cinert = take(10 * nb); crb = take(10 * nb);
-    cdof = take(6 * nv); cacc = take(6 * nb);
-    Mp = take(np); LDp = take(np); dinv = take(nv); hdinv = take(nv); ten_len = take(nt); ten_J = take(nt * nv);
-    f_bias = take(nv); f_passive = take(nv); f_smooth = take(nv); f_con = take(nv); a_smooth = take(nv); qacc = take(nv);
-    Ma = take(nv); Mv = take(nv); grad = take(nv); Mgrad = take(nv); search = take(nv);
-    // buf6 (6 reals per dof / body, live in mass_matrix and bias_forces only) shares the 6 nv reals of qacc .. search, which
-    // are first written after those stages; shared memory per env decides how many warps an SM holds
-    buf6 = nb <= nv ? qacc : take(6 * nb);
-    con_pair = ibase; row_meta = ibase + WarpCaps::NCON;
+  // base: this env's shared-memory workspace (WarpLayout); jscratch: the warp's global scratch slot
+  B2_DEV void bind(const WarpImage<T>* image, T* base, T* jscratch) {
+    mdl.img = image;
+    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
+    const WarpLayout L(mdl.nq(), nv, mdl.nu(), mdl.nbody(), mdl.njnt(), mdl.ngeom(), mdl.ntendon());
+    qpos = base + L.qpos; qvel = base + L.qvel; ctrl = base + L.ctrl; warm = base + L.warm; Mp = base + L.Mp;
+    f_bias = base + L.f_bias; f_passive = base + L.f_passive; ten_len = base + L.ten_len; ten_J = base + L.ten_J;
+    com = base + L.com; cinert = base + L.cinert; cdof = base + L.cdof;
+    xpos = base + L.xpos; xquat = base + L.xquat; xipos = base + L.xipos; xmat = base + L.xmat; ximat = base + L.ximat;
+    xanchor = base + L.xanchor; xaxis = base + L.xaxis; geom_xpos = base + L.geom_xpos; geom_z = base + L.geom_z;
+    crb = base + L.crb; buf6 = base + L.buf6; cvel = base + L.cvel; cdof_dot = base + L.cdof_dot; cacc = base + L.cacc;
+    LDp = base + L.LDp; dinv = base + L.dinv; hdinv = base + L.hdinv; f_smooth = base + L.f_smooth; f_con = base + L.f_con;
+    a_smooth = base + L.a_smooth; qacc = base + L.qacc; Ma = base + L.Ma; Mv = base + L.Mv; grad = base + L.grad;
+    Mgrad = base + L.Mgrad; search = base + L.search;
     // per-row data lives in the warp's global scratch slot (L1/L2 resident): J, then six row vectors
     J = jscratch;
     T* rv = jscratch + WarpCaps::NEFC * nv;
@@ -235,41 +289,42 @@ struct WarpEnv {
     Jaref = rv + 4 * WarpCaps::NEFC; Jv = rv + 5 * WarpCaps::NEFC;
     T* cb = rv + 6 * WarpCaps::NEFC;  // contact records: written by collide, read by make_rows (once per step each)
     con_dist = cb; con_pos = cb + WarpCaps::NCON; con_frame = cb + 4 * WarpCaps::NCON;
+    con_pair = reinterpret_cast<int*>(cb + 13 * WarpCaps::NCON); row_meta = con_pair + WarpCaps::NCON;
     lane = threadIdx.x & 31;
     ncon = nefc = niter = flags = 0;
 #pragma unroll
     for (int t = 0; t < 17; t++) {
       int i = 0, j = 0;
-      if (lane + 32 * t < np) untri(lane + 32 * t, i, j);
+      if (lane + 32 * t < np) mdl.untri(lane + 32 * t, i, j);
       hess_ij[t] = i | (j << 8);
     }
   }
-  static B2_DEV bool dof_is_anc(int i, int j) { return (((unsigned)M::dof_anc(i)) >> j) & 1u; }
-  static B2_DEV bool in_subtree(int root, int b) { return (((unsigned)M::body_anc(b)) >> root) & 1u; }
+  B2_DEV bool dof_is_anc(int i, int j) const { return (((unsigned)mdl.dof_anc(i)) >> j) & 1u; }
+  B2_DEV bool in_subtree(int root, int b) const { return (((unsigned)mdl.body_anc(b)) >> root) & 1u; }
 
   // ------------------------------------------------------------------ position stage
   B2_DEV void kinematics() {
-    const int nb = M::nbody();
+    const int nb = mdl.nbody();
     if (lane == 0) {
       for (int k = 0; k < 3; k++) { xpos[k] = 0; xipos[k] = 0; }
       xquat[0] = 1; xquat[1] = xquat[2] = xquat[3] = 0;
       quat_to_mat(xmat, xquat); quat_to_mat(ximat, xquat);
     }
     __syncwarp();
-    for (int level = 1; level <= M::maxdepth(); level++) {
+    for (int level = 1; level <= mdl.maxdepth(); level++) {
       const int i = lane;
-      if (i < nb && M::body_depth(i) == level) {
+      if (i < nb && mdl.body_depth(i) == level) {
         T p[3], q[4];
-        const int ja = M::body_jntadr(i), jn = M::body_jntnum(i), pid = M::body_parentid(i);
-        if (jn == 1 && M::jnt_type(ja) == JNT_FREE) {
-          const int qa = M::jnt_qposadr(ja);
+        const int ja = mdl.body_jntadr(i), jn = mdl.body_jntnum(i), pid = mdl.body_parentid(i);
+        if (jn == 1 && mdl.jnt_type(ja) == JNT_FREE) {
+          const int qa = mdl.jnt_qposadr(ja);
           for (int k = 0; k < 3; k++) p[k] = qpos[qa + k];
           for (int k = 0; k < 4; k++) q[k] = qpos[qa + 3 + k];
           normalize4(q);
-          for (int k = 0; k < 3; k++) { xanchor[3 * ja + k] = p[k]; xaxis[3 * ja + k] = M::jnt_axis(3 * ja + k); }
+          for (int k = 0; k < 3; k++) { xanchor[3 * ja + k] = p[k]; xaxis[3 * ja + k] = mdl.jnt_axis(3 * ja + k); }
         } else {
-          T bpos[3] = {M::body_pos(3 * i), M::body_pos(3 * i + 1), M::body_pos(3 * i + 2)};
-          T bquat[4] = {M::body_quat(4 * i), M::body_quat(4 * i + 1), M::body_quat(4 * i + 2), M::body_quat(4 * i + 3)};
+          T bpos[3] = {mdl.body_pos(3 * i), mdl.body_pos(3 * i + 1), mdl.body_pos(3 * i + 2)};
+          T bquat[4] = {mdl.body_quat(4 * i), mdl.body_quat(4 * i + 1), mdl.body_quat(4 * i + 2), mdl.body_quat(4 * i + 3)};
           if (pid) {
             T pm[9], pq[4];
             for (int k = 0; k < 9; k++) pm[k] = xmat[9 * pid + k];
@@ -283,14 +338,14 @@ struct WarpEnv {
           }
           for (int j = ja; j < ja + jn; j++) {
             T anchor[3], axis[3];
-            const int qa = M::jnt_qposadr(j);
-            T jaxis[3] = {M::jnt_axis(3 * j), M::jnt_axis(3 * j + 1), M::jnt_axis(3 * j + 2)};
-            T jpos[3] = {M::jnt_pos(3 * j), M::jnt_pos(3 * j + 1), M::jnt_pos(3 * j + 2)};
+            const int qa = mdl.jnt_qposadr(j);
+            T jaxis[3] = {mdl.jnt_axis(3 * j), mdl.jnt_axis(3 * j + 1), mdl.jnt_axis(3 * j + 2)};
+            T jpos[3] = {mdl.jnt_pos(3 * j), mdl.jnt_pos(3 * j + 1), mdl.jnt_pos(3 * j + 2)};
             quat_rot(axis, jaxis, q);
             quat_rot(anchor, jpos, q);
             for (int k = 0; k < 3; k++) anchor[k] += p[k];
-            const T disp = qpos[qa] - M::qpos0(qa);
-            if (M::jnt_type(j) == JNT_SLIDE) {
+            const T disp = qpos[qa] - mdl.qpos0(qa);
+            if (mdl.jnt_type(j) == JNT_SLIDE) {
               for (int k = 0; k < 3; k++) p[k] += axis[k] * disp;
             } else {
               T ql[4], off[3];
@@ -308,8 +363,8 @@ struct WarpEnv {
         for (int k = 0; k < 3; k++) xpos[3 * i + k] = p[k];
         for (int k = 0; k < 4; k++) xquat[4 * i + k] = q[k];
         for (int k = 0; k < 9; k++) xmat[9 * i + k] = m9[k];
-        T ipos[3] = {M::body_ipos(3 * i), M::body_ipos(3 * i + 1), M::body_ipos(3 * i + 2)};
-        T iquat[4] = {M::body_iquat(4 * i), M::body_iquat(4 * i + 1), M::body_iquat(4 * i + 2), M::body_iquat(4 * i + 3)};
+        T ipos[3] = {mdl.body_ipos(3 * i), mdl.body_ipos(3 * i + 1), mdl.body_ipos(3 * i + 2)};
+        T iquat[4] = {mdl.body_iquat(4 * i), mdl.body_iquat(4 * i + 1), mdl.body_iquat(4 * i + 2), mdl.body_iquat(4 * i + 3)};
         mat_vec(ip, m9, ipos);
         for (int k = 0; k < 3; k++) xipos[3 * i + k] = ip[k] + p[k];
         quat_mul(qi, q, iquat);
@@ -318,10 +373,10 @@ struct WarpEnv {
       }
       __syncwarp();
     }
-    WFOR(g, M::ngeom()) {
-      const int b = M::geom_bodyid(g);
-      T gp[3] = {M::geom_pos(3 * g), M::geom_pos(3 * g + 1), M::geom_pos(3 * g + 2)};
-      T gq[4] = {M::geom_quat(4 * g), M::geom_quat(4 * g + 1), M::geom_quat(4 * g + 2), M::geom_quat(4 * g + 3)};
+    WFOR(g, mdl.ngeom()) {
+      const int b = mdl.geom_bodyid(g);
+      T gp[3] = {mdl.geom_pos(3 * g), mdl.geom_pos(3 * g + 1), mdl.geom_pos(3 * g + 2)};
+      T gq[4] = {mdl.geom_quat(4 * g), mdl.geom_quat(4 * g + 1), mdl.geom_quat(4 * g + 2), mdl.geom_quat(4 * g + 3)};
       T bm[9], bq[4], r[3], q[4], m9[9];
       for (int k = 0; k < 9; k++) bm[k] = xmat[9 * b + k];
       for (int k = 0; k < 4; k++) bq[k] = xquat[4 * b + k];
@@ -336,13 +391,13 @@ struct WarpEnv {
 
   // subtree centres of mass, com-frame inertias, motion axes
   B2_DEV void com_frame() {
-    const int nb = M::nbody();
+    const int nb = mdl.nbody();
     WFOR(i, nb) {
       T s[3] = {0, 0, 0};
       for (int j = i; j < nb; j++)
-        if (in_subtree(i, j)) { const T mj = M::body_mass(j); for (int k = 0; k < 3; k++) s[k] += xipos[3 * j + k] * mj; }
-      if (M::body_subtreemass(i) < Num<T>::minval()) { for (int k = 0; k < 3; k++) s[k] = xipos[3 * i + k]; }
-      else { const T inv = T(1) / tmax(Num<T>::minval(), M::body_subtreemass(i)); for (int k = 0; k < 3; k++) s[k] *= inv; }
+        if (in_subtree(i, j)) { const T mj = mdl.body_mass(j); for (int k = 0; k < 3; k++) s[k] += xipos[3 * j + k] * mj; }
+      if (mdl.body_subtreemass(i) < Num<T>::minval()) { for (int k = 0; k < 3; k++) s[k] = xipos[3 * i + k]; }
+      else { const T inv = T(1) / tmax(Num<T>::minval(), mdl.body_subtreemass(i)); for (int k = 0; k < 3; k++) s[k] *= inv; }
       for (int k = 0; k < 3; k++) com[3 * i + k] = s[k];
     }
     __syncwarp();
@@ -350,20 +405,20 @@ struct WarpEnv {
       T ci[10];
       if (i == 0) { for (int k = 0; k < 10; k++) ci[k] = 0; }
       else {
-        const int r = M::body_rootid(i);
-        T off[3], inertia[3] = {M::body_inertia(3 * i), M::body_inertia(3 * i + 1), M::body_inertia(3 * i + 2)}, im[9];
+        const int r = mdl.body_rootid(i);
+        T off[3], inertia[3] = {mdl.body_inertia(3 * i), mdl.body_inertia(3 * i + 1), mdl.body_inertia(3 * i + 2)}, im[9];
         for (int k = 0; k < 3; k++) off[k] = xipos[3 * i + k] - com[3 * r + k];
         for (int k = 0; k < 9; k++) im[k] = ximat[9 * i + k];
-        inert_about(ci, inertia, im, off, M::body_mass(i));
+        inert_about(ci, inertia, im, off, mdl.body_mass(i));
       }
       for (int k = 0; k < 10; k++) cinert[10 * i + k] = ci[k];
     }
-    WFOR(j, M::njnt()) {
-      const int b = M::jnt_bodyid(j), r = M::body_rootid(b);
-      T* cd = cdof + 6 * M::jnt_dofadr(j);
+    WFOR(j, mdl.njnt()) {
+      const int b = mdl.jnt_bodyid(j), r = mdl.body_rootid(b);
+      T* cd = cdof + 6 * mdl.jnt_dofadr(j);
       T off[3], ax[3];
       for (int k = 0; k < 3; k++) off[k] = com[3 * r + k] - xanchor[3 * j + k];
-      const int t = M::jnt_type(j);
+      const int t = mdl.jnt_type(j);
       if (t == JNT_FREE) {
         for (int k = 0; k < 18; k++) cd[k] = 0;
         cd[3] = 1; cd[10] = 1; cd[17] = 1;
@@ -384,13 +439,13 @@ struct WarpEnv {
         for (int k = 0; k < 3; k++) { cd[k] = ax[k]; cd[3 + k] = c3[k]; }
       }
     }
-    WFOR(t, M::ntendon()) {
+    WFOR(t, mdl.ntendon()) {
       T L = 0;
-      for (int k = 0; k < M::nv(); k++) ten_J[t * M::nv() + k] = 0;
-      for (int w = M::tendon_adr(t); w < M::tendon_adr(t) + M::tendon_num(t); w++) {
-        const int j = M::wrap_jntid(w);
-        L += M::wrap_coef(w) * qpos[M::jnt_qposadr(j)];
-        ten_J[t * M::nv() + M::jnt_dofadr(j)] = M::wrap_coef(w);
+      for (int k = 0; k < mdl.nv(); k++) ten_J[t * mdl.nv() + k] = 0;
+      for (int w = mdl.tendon_adr(t); w < mdl.tendon_adr(t) + mdl.tendon_num(t); w++) {
+        const int j = mdl.wrap_jntid(w);
+        L += mdl.wrap_coef(w) * qpos[mdl.jnt_qposadr(j)];
+        ten_J[t * mdl.nv() + mdl.jnt_dofadr(j)] = mdl.wrap_coef(w);
       }
       ten_len[t] = L;
     }
@@ -399,7 +454,7 @@ struct WarpEnv {
 
   // composite inertias (subtree sums) and the packed lower-triangular mass matrix
   B2_DEV void mass_matrix() {
-    const int nb = M::nbody(), nv = M::nv();
+    const int nb = mdl.nbody(), nv = mdl.nv();
     WFOR(i, nb) {
       T s[10];
       for (int k = 0; k < 10; k++) s[k] = cinert[10 * i + k];
@@ -411,7 +466,7 @@ struct WarpEnv {
     __syncwarp();
     WFOR(d, nv) {
       T b6[6], c[10], cd[6];
-      const int b = M::dof_bodyid(d);
+      const int b = mdl.dof_bodyid(d);
       for (int k = 0; k < 10; k++) c[k] = crb[10 * b + k];
       for (int k = 0; k < 6; k++) cd[k] = cdof[6 * d + k];
       inert_mul(b6, c, cd);
@@ -421,19 +476,19 @@ struct WarpEnv {
     const int np = nv * (nv + 1) / 2;
     WFOR(e, np) {
       int i, j;
-      untri(e, i, j);
+      mdl.untri(e, i, j);
       T v = 0;
       if (dof_is_anc(i, j)) { for (int k = 0; k < 6; k++) v += cdof[6 * j + k] * buf6[6 * i + k]; }
-      if (i == j) v = M::dof_armature(i) + v;
+      if (i == j) v = mdl.dof_armature(i) + v;
       Mp[e] = v;
     }
     __syncwarp();
   }
 
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
-  B2_DEV void factor_LD() { factor_LD_impl<T, M>(LDp, dinv, Mv, lane); }  // Mv: scratch, only live inside the line search
-  B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(LDp, dinv, x, lane); }
-  B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, M::nv(), lane); }
+  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, Mv, lane); }  // Mv: scratch, only live inside the line search
+  B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(mdl, LDp, dinv, x, lane); }
+  B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, mdl.nv(), lane); }
 
   // Jacobian column of dof d for a point on `body` at offset `off` from the root's subtree CoM; false if d does not move body
   B2_DEV bool jac_col(int last, int d, const T* off, T* jp) const {
@@ -444,27 +499,27 @@ struct WarpEnv {
     jp[0] += c[3]; jp[1] += c[4]; jp[2] += c[5];
     return true;
   }
-  static B2_DEV int last_dof(int body) {
-    while (body && !M::body_dofnum(body)) body = M::body_parentid(body);
-    return body ? M::body_dofadr(body) + M::body_dofnum(body) - 1 : -1;
+  B2_DEV int last_dof(int body) const {
+    while (body && !mdl.body_dofnum(body)) body = mdl.body_parentid(body);
+    return body ? mdl.body_dofadr(body) + mdl.body_dofnum(body) - 1 : -1;
   }
 
   // ------------------------------------------------------------------ collision + rows
   // candidate pairs are tested 32 at a time; contacts are appended in pair order (ballot prefix)
   B2_DEV void collide() {
     ncon = 0;
-    const int np = M::npair();
+    const int np = mdl.npair();
     for (int base = 0; base < np; base += 32) {
       const int p = base + lane;
       int cnt = 0;
       T cd[2], cpos[6], cfr[12];
       if (p < np) {
-        const int g1 = M::pair_geom1(p), g2 = M::pair_geom2(p);
-        const T margin = M::pair_margin(p);
+        const int g1 = mdl.pair_geom1(p), g2 = mdl.pair_geom2(p);
+        const T margin = mdl.pair_margin(p);
         T p1[3], p2[3], z1[3], z2[3], d[3];
         for (int k = 0; k < 3; k++) { p1[k] = geom_xpos[3 * g1 + k]; p2[k] = geom_xpos[3 * g2 + k]; z1[k] = geom_z[3 * g1 + k]; z2[k] = geom_z[3 * g2 + k]; d[k] = p2[k] - p1[k]; }
-        const int t1 = M::geom_type(g1), t2 = M::geom_type(g2);
-        const T r1 = M::geom_size(3 * g1), l1 = M::geom_size(3 * g1 + 1), r2 = M::geom_size(3 * g2), l2 = M::geom_size(3 * g2 + 1);
+        const int t1 = mdl.geom_type(g1), t2 = mdl.geom_type(g2);
+        const T r1 = mdl.geom_size(3 * g1), l1 = mdl.geom_size(3 * g1 + 1), r2 = mdl.geom_size(3 * g2), l2 = mdl.geom_size(3 * g2 + 1);
         auto emit = [&](T dist, const T* pos, const T* n, const T* hint) {
           cd[cnt] = dist;
           for (int k = 0; k < 3; k++) { cpos[3 * cnt + k] = pos[k]; cfr[6 * cnt + k] = n[k]; cfr[6 * cnt + 3 + k] = hint ? hint[k] : T(0); }
@@ -491,7 +546,7 @@ struct WarpEnv {
           return 1;
         };
         if (t1 == GEOM_PLANE) {
-          if (dot3(d, z1) <= margin + M::geom_rbound(g2)) {
+          if (dot3(d, z1) <= margin + mdl.geom_rbound(g2)) {
             if (t2 == GEOM_SPHERE) plane_sphere(p2, r2, nullptr);
             else if (t2 == GEOM_CAPSULE) {
               T e[3];
@@ -502,7 +557,7 @@ struct WarpEnv {
             }
           }
         } else {
-          const T bound = margin + M::geom_rbound(g1) + M::geom_rbound(g2);
+          const T bound = margin + mdl.geom_rbound(g1) + mdl.geom_rbound(g2);
           if (dot3(d, d) <= bound * bound) {
             if (t1 == GEOM_SPHERE && t2 == GEOM_SPHERE) sphere_sphere(p1, r1, p2, r2);
             else if (t1 == GEOM_SPHERE && t2 == GEOM_CAPSULE) {
@@ -564,29 +619,29 @@ struct WarpEnv {
 
   // limit rows (joints, then tendons) followed by contact rows; J rows are written one dof per lane
   B2_DEV void make_rows() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     nefc = 0;
     auto zero_row = [&](int r) { WFOR(k, nv) J[r * nv + k] = 0; };
     // joint limits: sequential over joints keeps upstream row order; the test itself is uniform
-    for (int j = 0; j < M::njnt(); j++) {
-      if (!M::jnt_limited(j) || M::jnt_type(j) < JNT_SLIDE) continue;
-      const T value = qpos[M::jnt_qposadr(j)], margin = M::jnt_margin(j);
+    for (int j = 0; j < mdl.njnt(); j++) {
+      if (!mdl.jnt_limited(j) || mdl.jnt_type(j) < JNT_SLIDE) continue;
+      const T value = qpos[mdl.jnt_qposadr(j)], margin = mdl.jnt_margin(j);
       for (int side = -1; side <= 1; side += 2) {
-        const T dist = side * (M::jnt_range(2 * j + (side + 1) / 2) - value);
+        const T dist = side * (mdl.jnt_range(2 * j + (side + 1) / 2) - value);
         if (dist < margin) {
           if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
           const int r = nefc++;
           zero_row(r);
           __syncwarp();
-          if (lane == 0) { row_meta[r] = ROW_LIMIT_JOINT | (j << 8); row_pos[r] = dist; row_margin[r] = margin; J[r * nv + M::jnt_dofadr(j)] = T(-side); }
+          if (lane == 0) { row_meta[r] = ROW_LIMIT_JOINT | (j << 8); row_pos[r] = dist; row_margin[r] = margin; J[r * nv + mdl.jnt_dofadr(j)] = T(-side); }
         }
       }
     }
-    for (int t = 0; t < M::ntendon(); t++) {
-      if (!M::tendon_limited(t)) continue;
-      const T value = ten_len[t], margin = M::tendon_margin(t);
+    for (int t = 0; t < mdl.ntendon(); t++) {
+      if (!mdl.tendon_limited(t)) continue;
+      const T value = ten_len[t], margin = mdl.tendon_margin(t);
       for (int side = -1; side <= 1; side += 2) {
-        const T dist = side * (M::tendon_range(2 * t + (side + 1) / 2) - value);
+        const T dist = side * (mdl.tendon_range(2 * t + (side + 1) / 2) - value);
         if (dist < margin) {
           if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
           const int r = nefc++;
@@ -597,18 +652,18 @@ struct WarpEnv {
     }
     for (int c = 0; c < ncon; c++) {
       const int p = con_pair[c];
-      const T incl = M::pair_margin(p) - M::pair_gap(p), dist = con_dist[c];
+      const T incl = mdl.pair_margin(p) - mdl.pair_gap(p), dist = con_dist[c];
       if (dist >= incl) continue;
-      const int dim = M::pair_dim(p), nrow = dim == 1 ? 1 : 4;
+      const int dim = mdl.pair_dim(p), nrow = dim == 1 ? 1 : 4;
       if (nefc + nrow > WarpCaps::NEFC) { flags |= 8; break; }
       const int r0 = nefc;
       nefc += nrow;
-      const int b1 = M::geom_bodyid(M::pair_geom1(p)), b2 = M::geom_bodyid(M::pair_geom2(p));
+      const int b1 = mdl.geom_bodyid(mdl.pair_geom1(p)), b2 = mdl.geom_bodyid(mdl.pair_geom2(p));
       const int last1 = last_dof(b1), last2 = last_dof(b2);
-      const T mu = M::pair_friction(2 * p);
+      const T mu = mdl.pair_friction(2 * p);
       T fr[9], pos[3], off1[3], off2[3];
       for (int k = 0; k < 9; k++) fr[k] = con_frame[9 * c + k];
-      for (int k = 0; k < 3; k++) { pos[k] = con_pos[3 * c + k]; off1[k] = pos[k] - com[3 * M::body_rootid(b1) + k]; off2[k] = pos[k] - com[3 * M::body_rootid(b2) + k]; }
+      for (int k = 0; k < 3; k++) { pos[k] = con_pos[3 * c + k]; off1[k] = pos[k] - com[3 * mdl.body_rootid(b1) + k]; off2[k] = pos[k] - com[3 * mdl.body_rootid(b2) + k]; }
       WFOR(d, nv) {
         T acc[4] = {0, 0, 0, 0}, jp[3];
         // body 1 enters with a minus sign, then body 2 with a plus sign (same accumulation order as the lane engine)
@@ -643,25 +698,25 @@ struct WarpEnv {
     return dmin + y * (dmax - dmin);
   }
   B2_DEV void row_params() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     WFOR(i, nefc) {
       T sr[2], si[5], diag;
       const int type = row_meta[i] & 255, id = row_meta[i] >> 8;
       T mu = 0;
       if (type == ROW_LIMIT_JOINT) {
-        for (int k = 0; k < 2; k++) sr[k] = M::jnt_solref(2 * id + k);
-        for (int k = 0; k < 5; k++) si[k] = M::jnt_solimp(5 * id + k);
-        diag = M::dof_invweight0(M::jnt_dofadr(id));
+        for (int k = 0; k < 2; k++) sr[k] = mdl.jnt_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = mdl.jnt_solimp(5 * id + k);
+        diag = mdl.dof_invweight0(mdl.jnt_dofadr(id));
       } else if (type == ROW_LIMIT_TENDON) {
-        for (int k = 0; k < 2; k++) sr[k] = M::tendon_solref(2 * id + k);
-        for (int k = 0; k < 5; k++) si[k] = M::tendon_solimp(5 * id + k);
-        diag = M::tendon_invweight0(id);
+        for (int k = 0; k < 2; k++) sr[k] = mdl.tendon_solref(2 * id + k);
+        for (int k = 0; k < 5; k++) si[k] = mdl.tendon_solimp(5 * id + k);
+        diag = mdl.tendon_invweight0(id);
       } else {
         const int p = con_pair[id];
-        for (int k = 0; k < 2; k++) sr[k] = M::pair_solref(2 * p + k);
-        for (int k = 0; k < 5; k++) si[k] = M::pair_solimp(5 * p + k);
-        const T tran = M::body_invweight0(2 * M::geom_bodyid(M::pair_geom1(p))) + M::body_invweight0(2 * M::geom_bodyid(M::pair_geom2(p)));
-        mu = M::pair_friction(2 * p);
+        for (int k = 0; k < 2; k++) sr[k] = mdl.pair_solref(2 * p + k);
+        for (int k = 0; k < 5; k++) si[k] = mdl.pair_solimp(5 * p + k);
+        const T tran = mdl.body_invweight0(2 * mdl.geom_bodyid(mdl.pair_geom1(p))) + mdl.body_invweight0(2 * mdl.geom_bodyid(mdl.pair_geom2(p)));
+        mu = mdl.pair_friction(2 * p);
         diag = (type == ROW_CONTACT_1) ? tran : tran + mu * mu * tran;
       }
       const T pos = row_pos[i], margin = row_margin[i];
@@ -669,7 +724,7 @@ struct WarpEnv {
       const T dmax = tclip(si[1], T(0.0001), T(0.9999));
       T K, B;
       if (sr[0] > 0) {
-        const T tc = tmax(sr[0], 2 * M::timestep()), dr = sr[1];
+        const T tc = tmax(sr[0], 2 * mdl.timestep()), dr = sr[1];
         K = T(1) / tmax(Num<T>::minval(), dmax * dmax * tc * tc * dr * dr);
         B = T(2) / tmax(Num<T>::minval(), dmax * tc);
       } else {
@@ -688,16 +743,16 @@ struct WarpEnv {
 
   // ------------------------------------------------------------------ velocity stage
   B2_DEV void velocities() {
-    const int nb = M::nbody();
+    const int nb = mdl.nbody();
     if (lane < 6) cvel[lane] = 0;
     __syncwarp();
-    for (int level = 1; level <= M::maxdepth(); level++) {
+    for (int level = 1; level <= mdl.maxdepth(); level++) {
       const int i = lane;
-      if (i < nb && M::body_depth(i) == level) {
+      if (i < nb && mdl.body_depth(i) == level) {
         T v[6], cd[6], cdd[6];
-        const int da = M::body_dofadr(i), dn = M::body_dofnum(i), p = M::body_parentid(i);
+        const int da = mdl.body_dofadr(i), dn = mdl.body_dofnum(i), p = mdl.body_parentid(i);
         for (int k = 0; k < 6; k++) v[k] = cvel[6 * p + k];
-        if (dn == 6 && M::jnt_type(M::dof_jntid(da)) == JNT_FREE) {
+        if (dn == 6 && mdl.jnt_type(mdl.dof_jntid(da)) == JNT_FREE) {
           for (int k = 0; k < 18; k++) cdof_dot[6 * da + k] = 0;
           for (int k = 0; k < 6; k++) {
             T t = 0;
@@ -728,21 +783,21 @@ struct WarpEnv {
   }
 
   B2_DEV void passive_forces() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     WFOR(d, nv) {
-      const int j = M::dof_jntid(d);
+      const int j = mdl.dof_jntid(d);
       T f = 0;
-      const T st = M::jnt_stiffness(j);
-      if (st != 0 && M::jnt_type(j) >= JNT_SLIDE) { const int pa = M::jnt_qposadr(j); f -= st * (qpos[pa] - M::qpos_spring(pa)); }
-      f -= M::dof_damping(d) * qvel[d];
+      const T st = mdl.jnt_stiffness(j);
+      if (st != 0 && mdl.jnt_type(j) >= JNT_SLIDE) { const int pa = mdl.jnt_qposadr(j); f -= st * (qpos[pa] - mdl.qpos_spring(pa)); }
+      f -= mdl.dof_damping(d) * qvel[d];
       f_passive[d] = f;
     }
     __syncwarp();
-    for (int t = 0; t < M::ntendon(); t++) {
-      const T st = M::tendon_stiffness(t), dm = M::tendon_damping(t);
+    for (int t = 0; t < mdl.ntendon(); t++) {
+      const T st = mdl.tendon_stiffness(t), dm = mdl.tendon_damping(t);
       if (st == 0 && dm == 0) continue;
       T frc = 0, vel = 0;
-      const T lo = M::tendon_lengthspring(2 * t), hi = M::tendon_lengthspring(2 * t + 1), L = ten_len[t];
+      const T lo = mdl.tendon_lengthspring(2 * t), hi = mdl.tendon_lengthspring(2 * t + 1), L = ten_len[t];
       if (L > hi) frc = st * (hi - L); else if (L < lo) frc = st * (lo - L);
       for (int k = 0; k < nv; k++) vel += ten_J[t * nv + k] * qvel[k];
       frc -= dm * vel;
@@ -753,15 +808,15 @@ struct WarpEnv {
 
   // recursive Newton-Euler without accelerations
   B2_DEV void bias_forces() {
-    const int nb = M::nbody(), nv = M::nv();
-    if (lane < 6) cacc[lane] = lane < 3 ? T(0) : -M::gravity(lane - 3);
+    const int nb = mdl.nbody(), nv = mdl.nv();
+    if (lane < 6) cacc[lane] = lane < 3 ? T(0) : -mdl.gravity(lane - 3);
     __syncwarp();
-    for (int level = 1; level <= M::maxdepth(); level++) {
+    for (int level = 1; level <= mdl.maxdepth(); level++) {
       const int i = lane;
-      if (i < nb && M::body_depth(i) == level) {
-        const int da = M::body_dofadr(i), p = M::body_parentid(i);
+      if (i < nb && mdl.body_depth(i) == level) {
+        const int da = mdl.body_dofadr(i), p = mdl.body_parentid(i);
         T t[6] = {0, 0, 0, 0, 0, 0};
-        for (int j = 0; j < M::body_dofnum(i); j++)
+        for (int j = 0; j < mdl.body_dofnum(i); j++)
           for (int k = 0; k < 6; k++) t[k] += cdof_dot[6 * (da + j) + k] * qvel[da + j];
         for (int k = 0; k < 6; k++) cacc[6 * i + k] = cacc[6 * p + k] + t[k];
       }
@@ -792,7 +847,7 @@ struct WarpEnv {
     __syncwarp();
     WFOR(d, nv) {
       T s = 0;
-      const int b = M::dof_bodyid(d);
+      const int b = mdl.dof_bodyid(d);
       for (int k = 0; k < 6; k++) s += cdof[6 * d + k] * cfrc[6 * b + k];
       f_bias[d] = s;
     }
@@ -800,19 +855,19 @@ struct WarpEnv {
   }
 
   B2_DEV void smooth_dynamics() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     WFOR(d, nv) {
       T fa = 0;
-      for (int a = 0; a < M::nu(); a++) {
-        const int jid = M::actuator_trnid(a);
-        if (M::jnt_dofadr(jid) != d) continue;
+      for (int a = 0; a < mdl.nu(); a++) {
+        const int jid = mdl.actuator_trnid(a);
+        if (mdl.jnt_dofadr(jid) != d) continue;
         T u = ctrl[a];
-        if (M::actuator_ctrllimited(a)) u = tclip(u, M::actuator_ctrlrange(2 * a), M::actuator_ctrlrange(2 * a + 1));
-        const T gear = M::actuator_gear(6 * a);
-        const T len = qpos[M::jnt_qposadr(jid)] * gear, vel = gear * qvel[d];
-        T force = M::actuator_gainprm(a) * u + M::actuator_biasprm(3 * a) + M::actuator_biasprm(3 * a + 1) * len + M::actuator_biasprm(3 * a + 2) * vel;
-        if (M::actuator_forcelimited(a)) force = tclip(force, M::actuator_forcerange(2 * a), M::actuator_forcerange(2 * a + 1));
-        if (M::actuator_disabled(a)) force = 0;
+        if (mdl.actuator_ctrllimited(a)) u = tclip(u, mdl.actuator_ctrlrange(2 * a), mdl.actuator_ctrlrange(2 * a + 1));
+        const T gear = mdl.actuator_gear(6 * a);
+        const T len = qpos[mdl.jnt_qposadr(jid)] * gear, vel = gear * qvel[d];
+        T force = mdl.actuator_gainprm(a) * u + mdl.actuator_biasprm(3 * a) + mdl.actuator_biasprm(3 * a + 1) * len + mdl.actuator_biasprm(3 * a + 2) * vel;
+        if (mdl.actuator_forcelimited(a)) force = tclip(force, mdl.actuator_forcerange(2 * a), mdl.actuator_forcerange(2 * a + 1));
+        if (mdl.actuator_disabled(a)) force = 0;
         fa += gear * force;
       }
       T fs = f_passive[d] - f_bias[d];
@@ -825,7 +880,7 @@ struct WarpEnv {
 
   // ------------------------------------------------------------------ Newton solver
   // J v for all rows: one row per lane
-  B2_DEV void mul_J(T* out, const T* v, const T* sub) { mul_J_impl<T>(J, out, v, sub, nefc, M::nv(), lane); }
+  B2_DEV void mul_J(T* out, const T* v, const T* sub) { mul_J_impl<T>(J, out, v, sub, nefc, mdl.nv(), lane); }
   B2_DEV T row_cost(const T* jar) {
     T c = 0;
     WFOR(i, nefc) if (jar[i] < 0) c += T(0.5) * row_D[i] * jar[i] * jar[i];
@@ -833,7 +888,7 @@ struct WarpEnv {
   }
   B2_DEV T dotv(const T* a, const T* b) {
     T s = 0;
-    WFOR(k, M::nv()) s += a[k] * b[k];
+    WFOR(k, mdl.nv()) s += a[k] * b[k];
     return warp_sum(s);
   }
   struct LsPoint { T alpha, cost, d1, d2; };
@@ -851,13 +906,13 @@ struct WarpEnv {
     return flag;
   }
   B2_DEV T line_search() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     LsPoint p0, p1, p2, pmid, p1n, p2n;
     ls_iter = 0;
     const T sn = sqrt(dotv(search, search));
     if (sn < Num<T>::minval()) return 0;
-    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
-    const T gtol = M::tolerance() * M::ls_tolerance() * sn / scale;
+    const T scale = T(1) / (mdl.meaninertia() * T(nv > 1 ? nv : 1));
+    const T gtol = mdl.tolerance() * mdl.ls_tolerance() * sn / scale;
     mul_M(Mv, search);
     mul_J(Jv, search, nullptr);
     qg0 = gauss; qg1 = dotv(search, Ma) - dotv(f_smooth, search); qg2 = T(0.5) * dotv(search, Mv);
@@ -867,7 +922,7 @@ struct WarpEnv {
     if (fabs(p1.d1) < gtol) return p1.alpha;
     const int dir = p1.d1 < 0 ? 1 : -1;
     bool p2up = false;
-    const int maxls = M::ls_iterations();
+    const int maxls = mdl.ls_iterations();
     while (p1.d1 * dir <= -gtol && ls_iter < maxls) {
       p2 = p1; p2up = true;
       ls_eval(p1.alpha - p1.d1 / p1.d2, p1);
@@ -892,7 +947,7 @@ struct WarpEnv {
   }
   // cost, constraint force, gradient, and the Newton direction H^-1 grad (H = M + J' D_active J)
   B2_DEV void newton_refresh() {
-    const int nv = M::nv(), np = nv * (nv + 1) / 2;
+    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
     cost = row_cost(Jaref);
     WFOR(k, nv) {
       T f = 0;
@@ -955,11 +1010,11 @@ struct WarpEnv {
       if (lane == 0) hdinv[j] = inv;
       __syncwarp();
       // the trailing entries of one pivot column are independent of each other: four per lane are in flight at once
-      for (int e0 = __ldg(&g_chol_off[j]) + lane, end = __ldg(&g_chol_off[j + 1]); e0 < end; e0 += 128) {
+      for (int e0 = __ldg(&mdl.img->chol_off[j]) + lane, end = __ldg(&mdl.img->chol_off[j + 1]); e0 < end; e0 += 128) {
         int w[4];
         T a[4], b[4], c[4];
 #pragma unroll
-        for (int u = 0; u < 4; u++) w[u] = e0 + 32 * u < end ? __ldg(&g_chol_plan[e0 + 32 * u]) : -1;
+        for (int u = 0; u < 4; u++) w[u] = e0 + 32 * u < end ? __ldg(&mdl.img->chol_plan[e0 + 32 * u]) : -1;
 #pragma unroll
         for (int u = 0; u < 4; u++) if (w[u] >= 0) { a[u] = H[w[u] & 1023]; b[u] = H[(w[u] >> 10) & 1023]; c[u] = H[w[u] >> 20]; }
 #pragma unroll
@@ -990,20 +1045,16 @@ struct WarpEnv {
   // one instruction fetch from L2 serves all of them.  The kernel is bound by instruction-fetch bandwidth: its 276 KB of
   // SASS cannot stay in the 32 KB L1.5 instruction cache, and two resident warps per SM already reach 69 % of the
   // throughput of eight that run out of phase.
-  // LS: 0 none, 1 everywhere, 2 not inside the Newton loop.  The group is a named barrier (bar_id, bar_cnt threads).
-  int bar_id, bar_cnt;
+  // LS: 0 none, 1 everywhere, 2 not inside the Newton loop.  The lock-step group is the whole block and the barrier is
+  // barrier 0: a register-valued barrier id makes ptxas reserve all 16 barriers per block, which caps an SM at four
+  // blocks whatever the registers and shared memory would allow (ncu "Block Limit Barriers", profiles/ncu_hum_step_r01j.txt).
   template <int LS> B2_DEV void stage_sync() const {
-    if (LS) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(bar_cnt) : "memory");
+    if (LS) __syncthreads();
   }
-  B2_DEV bool group_or(bool p) const {
-    int r;
-    asm volatile("{ .reg .pred q, t; setp.ne.s32 q, %3, 0; bar.red.or.pred t, %1, %2, q; selp.s32 %0, 1, 0, t; }"
-                 : "=r"(r) : "r"(bar_id), "r"(bar_cnt), "r"((int)p) : "memory");
-    return r != 0;
-  }
+  B2_DEV bool group_or(bool p) const { return __syncthreads_or((int)p) != 0; }
   template <int LS>
   B2_DEV void constrained_acceleration() {
-    const int nv = M::nv();
+    const int nv = mdl.nv();
     niter = 0;
     bool done = false;
     if (!nefc) {
@@ -1031,7 +1082,7 @@ struct WarpEnv {
         mul_M(Ma, qacc);
       }
     }
-    const T scale = T(1) / (M::meaninertia() * T(nv > 1 ? nv : 1));
+    const T scale = T(1) / (mdl.meaninertia() * T(nv > 1 ? nv : 1));
     T old = 0;
     bool first = true;
     while (true) {
@@ -1043,13 +1094,13 @@ struct WarpEnv {
         if (!first) {
           const T gn = dotv(grad, grad);
           niter++;
-          if (scale * (old - cost) < M::tolerance() || scale * sqrt(gn) < M::tolerance()) done = true;
+          if (scale * (old - cost) < mdl.tolerance() || scale * sqrt(gn) < mdl.tolerance()) done = true;
         }
         if (!done) {
           first = false;
           WFOR(k, nv) search[k] = -Mgrad[k];
           __syncwarp();
-          if (niter >= M::iterations()) done = true;
+          if (niter >= mdl.iterations()) done = true;
         }
       }
       stage_sync<LS == 1>();
@@ -1071,27 +1122,30 @@ struct WarpEnv {
   }
 
   // ------------------------------------------------------------------ forward + Euler
-  template <int LS = 0>
-  B2_DEV void forward() {
-    const int nv = M::nv(), np = nv * (nv + 1) / 2;
+  // after_position(): called once the position-dependent arrays (xpos .. geom_xpos, com) are complete and before their
+  // storage is reused -- the kernels export the derived outputs there.
+  template <int LS, class F>
+  B2_DEV void forward(F&& after_position) {
+    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
     kinematics();
-    stage_sync<LS>();
-    com_frame();
-    stage_sync<LS>();
-    mass_matrix();
-    WFOR(e, np) LDp[e] = Mp[e];
-    __syncwarp();
-    stage_sync<LS>();
-    factor_LD();
     stage_sync<LS>();
     collide();
     stage_sync<LS>();
+    com_frame();
+    after_position();
+    stage_sync<LS>();
     make_rows();
+    stage_sync<LS>();
+    mass_matrix();  // from here on region X holds the dynamics arrays
     stage_sync<LS>();
     velocities();
     passive_forces();
     stage_sync<LS>();
     bias_forces();
+    WFOR(e, np) LDp[e] = Mp[e];  // ... and from here on the factor and the solver vectors
+    __syncwarp();
+    stage_sync<LS>();
+    factor_LD();
     stage_sync<LS>();
     smooth_dynamics();
     stage_sync<LS>();
@@ -1099,24 +1153,24 @@ struct WarpEnv {
   }
   B2_DEV void check_state() {
     int bad = 0;
-    WFOR(k, M::nq()) if (!(fabs(qpos[k]) <= T(1e10))) bad |= 1;
-    WFOR(k, M::nv()) if (!(fabs(qvel[k]) <= T(1e10))) bad |= 2;
+    WFOR(k, mdl.nq()) if (!(fabs(qpos[k]) <= T(1e10))) bad |= 1;
+    WFOR(k, mdl.nv()) if (!(fabs(qvel[k]) <= T(1e10))) bad |= 2;
     flags |= __reduce_or_sync(0xffffffffu, bad);
   }
   B2_DEV void check_acc() {
     int bad = 0;
-    WFOR(k, M::nv()) if (!(fabs(qacc[k]) <= T(1e10))) bad |= 4;
+    WFOR(k, mdl.nv()) if (!(fabs(qacc[k]) <= T(1e10))) bad |= 4;
     flags |= __reduce_or_sync(0xffffffffu, bad);
   }
   B2_DEV void euler() {
-    const int nv = M::nv(), np = nv * (nv + 1) / 2;
-    const T h = M::timestep();
+    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
+    const T h = mdl.timestep();
     T* acc = grad;
-    if (!M::has_dofdamping()) { WFOR(k, nv) acc[k] = qacc[k]; __syncwarp(); }
+    if (!mdl.has_dofdamping()) { WFOR(k, nv) acc[k] = qacc[k]; __syncwarp(); }
     else {
       WFOR(e, np) LDp[e] = Mp[e];
       __syncwarp();
-      WFOR(k, nv) LDp[tri(k, k)] += h * M::dof_damping(k);
+      WFOR(k, nv) LDp[tri(k, k)] += h * mdl.dof_damping(k);
       __syncwarp();
       factor_LD();
       WFOR(k, nv) acc[k] = f_smooth[k] + f_con[k];
@@ -1125,9 +1179,9 @@ struct WarpEnv {
     }
     WFOR(k, nv) qvel[k] += acc[k] * h;
     __syncwarp();
-    WFOR(j, M::njnt()) {
-      const int pa = M::jnt_qposadr(j), va = M::jnt_dofadr(j);
-      if (M::jnt_type(j) == JNT_FREE) {
+    WFOR(j, mdl.njnt()) {
+      const int pa = mdl.jnt_qposadr(j), va = mdl.jnt_dofadr(j);
+      if (mdl.jnt_type(j) == JNT_FREE) {
         T q[4], w[3];
         for (int k = 0; k < 3; k++) qpos[pa + k] += h * qvel[va + k];
         for (int k = 0; k < 4; k++) q[k] = qpos[pa + 3 + k];
