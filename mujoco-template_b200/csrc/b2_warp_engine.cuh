@@ -154,61 +154,72 @@ __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int
   return WarpLayout(nq, nv, nu, nb, nj, ng, nt).total;
 }
 
-// in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once; tk: nv scratch reals
+// In-place L'DL of the packed matrix in LDp (tree sparsity, mj_factorM).  Pivot k (leaves first): lane l owns the l-th
+// proper ancestor i_l of k (nearest first), keeps row k's entry L[k, i_l] and its quotient t_l = L[k, i_l] / d_k in registers,
+// and updates row i_l: L[i_l, i_{l+s}] -= t_l * L[k, i_{l+s}] for s = 0 .. m-1-l, the row-k value and the column index
+// coming from lane l+s by shuffle.  Nothing in the update loop waits on memory except its own read-modify-write, and the
+// next pivot's ancestor list is fetched while this one is being worked on (the kernel is latency-bound: the plan-driven
+// version of r01 spent 9 % of all stall samples on its load -> load -> FMA -> store chain).
 template <typename T, class M>
-__device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, T* tk, int lane) {
-
-    const int nv = mdl.nv();
-    constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
-    for (int k = nv - 1; k >= 0; k--) {
-      const int m = mdl.dof_nanc(k);  // proper ancestors of k, nearest first
-      const T dkk = LDp[tri(k, k)];
-      // one division sequence per pivot: lanes < m scale their entry of row k, lane m produces 1 / d_k
-      const int i = lane < m ? mdl.dof_anclist(k * LS + lane) : 0;
-      const T q = (lane < m ? LDp[tri(k, i)] : T(1)) / dkk;
-      if (lane < m) tk[i] = q;
-      if (lane == m) dinv[k] = q;
-      if (m) {
-        __syncwarp();
-        // all ancestor pairs (i, j), j <= i, at once: L[i,j] -= t_i * L[k,j]  (the unscaled row k, exactly the scalar
-        // algorithm's operands); the pairs and their packed indices come from the host-built work list
-        for (int e0 = __ldg(&mdl.img->ld_off[k]) + lane, end = __ldg(&mdl.img->ld_off[k + 1]); e0 < end; e0 += 96) {
-          int w[3];
-          T a[3], b[3], c[3];
-#pragma unroll
-          for (int u = 0; u < 3; u++) w[u] = e0 + 32 * u < end ? __ldg(&mdl.img->ld_plan[e0 + 32 * u]) : -1;
-#pragma unroll
-          for (int u = 0; u < 3; u++) if (w[u] >= 0) { a[u] = LDp[w[u] & 1023]; b[u] = tk[w[u] >> 20]; c[u] = LDp[(w[u] >> 10) & 1023]; }
-#pragma unroll
-          for (int u = 0; u < 3; u++) if (w[u] >= 0) LDp[w[u] & 1023] = a[u] - b[u] * c[u];
-        }
-        __syncwarp();
-        if (lane < m) LDp[tri(k, i)] = q;
+__device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, int lane) {
+  const int nv = mdl.nv();
+  constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
+  int m = mdl.dof_nanc(nv - 1), i = lane < m ? mdl.dof_anclist((nv - 1) * LS + lane) : 0;
+#pragma unroll 1
+  for (int k = nv - 1; k >= 0; k--) {
+    // prefetch the next pivot's list (independent of this pivot's arithmetic)
+    const int mn = k > 0 ? mdl.dof_nanc(k - 1) : 0;
+    const int in = (k > 0 && lane < mn) ? mdl.dof_anclist((k - 1) * LS + lane) : 0;
+    const int kk = tri(k, 0);
+    const T dkk = LDp[kk + k];
+    const T rk = lane < m ? LDp[kk + i] : T(1);
+    const T q = rk / dkk;  // lanes < m: t_l; lane m: 1 / d_k
+    if (lane == m) dinv[k] = q;
+    if (m) {
+      const int rowbase = tri(i, 0);
+#pragma unroll 2
+      for (int s = 0; s < m; s++) {
+        const T rks = __shfl_down_sync(0xffffffffu, rk, s);
+        const int js = __shfl_down_sync(0xffffffffu, i, s);
+        if (lane + s < m) LDp[rowbase + js] -= q * rks;
       }
-      __syncwarp();
+      if (lane < m) LDp[kk + i] = q;
     }
+    __syncwarp();
+    m = mn; i = in;
   }
+}
 
-// x <- (L'DL)^-1 x, column-oriented sweeps (no reductions).  One out-of-line copy shared by the three call sites:
-// the kernel is instruction-fetch bound (32 % of stall samples were "no instruction"), so code size matters.
+// x <- (L'DL)^-1 x with x_l in a register of lane l (nv <= 32): column sweeps by shuffle, no shared-memory traffic for x
+// and no warp barrier per column; the L entries of a column are loaded ahead of the value they multiply.
 template <typename T, class M>
 __device__ __noinline__ void solve_LD_impl(const M mdl, const T* LDp, const T* dinv, T* x, int lane) {
-
-    const int nv = mdl.nv();
-    for (int i = nv - 1; i > 0; i--) {
-      const unsigned anc = ((unsigned)mdl.dof_anc(i)) & ~(1u << i);
-      const T xi = x[i];
-      WFOR(j, i) if ((anc >> j) & 1u) x[j] -= LDp[tri(i, j)] * xi;
-      __syncwarp();
-    }
-    WFOR(i, nv) x[i] *= dinv[i];
-    __syncwarp();
-    for (int j = 0; j < nv - 1; j++) {
-      const T xj = x[j];
-      for (int i = j + 1 + lane; i < nv; i += 32) if (((((unsigned)mdl.dof_anc(i)) >> j) & 1u)) x[i] -= LDp[tri(i, j)] * xj;
-      __syncwarp();
-    }
+  const int nv = mdl.nv();
+  const unsigned anc = lane < nv ? ((unsigned)mdl.dof_anc(lane)) & ~(1u << lane) : 0u;  // proper ancestors of dof `lane`
+  const int rowbase = tri(lane < nv ? lane : 0, 0);
+  T xl = lane < nv ? x[lane] : T(0);
+  // x <- L^-T x : dof i (leaves first) pushes x_i into its ancestors j: x_j -= L[i,j] x_i.  Lane j needs bit j of anc(i),
+  // i.e. "i is a descendant of j": read from lane i's mask by shuffle.
+#pragma unroll 1
+  for (int i = nv - 1; i > 0; i--) {
+    const unsigned anci = __shfl_sync(0xffffffffu, anc, i);
+    const bool on = (anci >> lane) & 1u;
+    const T l = on ? LDp[tri(i, 0) + lane] : T(0);
+    const T xi = __shfl_sync(0xffffffffu, xl, i);
+    xl -= l * xi;
   }
+  xl *= lane < nv ? dinv[lane] : T(0);
+  // x <- L^-1 x : dof j (root first) pushes x_j into its descendants i: x_i -= L[i,j] x_j; lane i owns row i.
+#pragma unroll 1
+  for (int j = 0; j < nv - 1; j++) {
+    const bool on = (anc >> j) & 1u;
+    const T l = on ? LDp[rowbase + j] : T(0);
+    const T xj = __shfl_sync(0xffffffffu, xl, j);
+    xl -= l * xj;
+  }
+  if (lane < nv) x[lane] = xl;
+  __syncwarp();
+}
 
 // one evaluation of the exact piecewise-quadratic line-search objective (seven call sites share this copy);
 // out = {alpha, cost, d1, d2}
@@ -266,6 +277,7 @@ struct WarpEnv {
   int ls_iter;
   unsigned active_sig[(WarpCaps::NEFC + 31) / 32];  // active-row bit set the factor in LDp was built for
   bool hess_valid;
+  bool rows_tree;  // every constraint row touches one root-to-leaf chain only: H = M + J'DJ keeps M's tree sparsity
   int hess_ij[17];  // (row | col << 8) of the packed Hessian entries lane + 32 t this lane owns
 
   // base: this env's shared-memory workspace (WarpLayout); jscratch: the warp's global scratch slot
@@ -486,7 +498,7 @@ struct WarpEnv {
   }
 
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
-  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, Mv, lane); }  // Mv: scratch, only live inside the line search
+  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, lane); }  // Mv: scratch, only live inside the line search
   B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(mdl, LDp, dinv, x, lane); }
   B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, mdl.nv(), lane); }
 
@@ -621,6 +633,7 @@ struct WarpEnv {
   B2_DEV void make_rows() {
     const int nv = mdl.nv();
     nefc = 0;
+    rows_tree = true;
     auto zero_row = [&](int r) { WFOR(k, nv) J[r * nv + k] = 0; };
     // joint limits: sequential over joints keeps upstream row order; the test itself is uniform
     for (int j = 0; j < mdl.njnt(); j++) {
@@ -645,6 +658,12 @@ struct WarpEnv {
         if (dist < margin) {
           if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
           const int r = nefc++;
+          // a fixed tendon couples the dofs of its joints: chain-compatible if they are ancestors of one another
+          for (int w = mdl.tendon_adr(t) + 1; w < mdl.tendon_adr(t) + mdl.tendon_num(t); w++)
+            for (int u = mdl.tendon_adr(t); u < w; u++) {
+              const int d1 = mdl.jnt_dofadr(mdl.wrap_jntid(w)), d2 = mdl.jnt_dofadr(mdl.wrap_jntid(u));
+              if (!(d1 >= d2 ? dof_is_anc(d1, d2) : dof_is_anc(d2, d1))) rows_tree = false;
+            }
           WFOR(k, nv) J[r * nv + k] = -side * ten_J[t * nv + k];
           if (lane == 0) { row_meta[r] = ROW_LIMIT_TENDON | (t << 8); row_pos[r] = dist; row_margin[r] = margin; }
         }
@@ -660,6 +679,7 @@ struct WarpEnv {
       nefc += nrow;
       const int b1 = mdl.geom_bodyid(mdl.pair_geom1(p)), b2 = mdl.geom_bodyid(mdl.pair_geom2(p));
       const int last1 = last_dof(b1), last2 = last_dof(b2);
+      if (last1 >= 0 && last2 >= 0 && !(last1 >= last2 ? dof_is_anc(last1, last2) : dof_is_anc(last2, last1))) rows_tree = false;
       const T mu = mdl.pair_friction(2 * p);
       T fr[9], pos[3], off1[3], off2[3];
       for (int k = 0; k < 9; k++) fr[k] = con_frame[9 * c + k];
@@ -999,6 +1019,11 @@ struct WarpEnv {
       for (int t = 0; t < EPL; t++) if (lane + 32 * t < np) H[lane + 32 * t] = h[t];
     }
     __syncwarp();
+    if (rows_tree) {
+      // all active rows are chain rows (limits, contacts with the world or between a body and its own ancestor): H has the
+      // tree sparsity of M, so the tree-sparse L'DL of mj_factorM factorises it -- a third of the dense trailing updates
+      factor_LD_impl<T, M>(mdl, H, hdinv, lane);
+    } else {
     // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop; the trailing-block
     // entries of every pivot column come from the host-built work list (no index inversion on the device)
     for (int j = 0; j < nv; j++) {
@@ -1022,9 +1047,11 @@ struct WarpEnv {
       }
       __syncwarp();
     }
+    }  // dense
     }  // !same
     WFOR(k, nv) Mgrad[k] = grad[k];
     __syncwarp();
+    if (rows_tree) { solve_LD_impl<T, M>(mdl, H, hdinv, Mgrad, lane); return; }
     // two triangular solves; the reciprocal pivots were stored by the factorisation
     for (int j = 0; j < nv; j++) {
       const T xj = Mgrad[j] * hdinv[j];
