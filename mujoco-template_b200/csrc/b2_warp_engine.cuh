@@ -45,6 +45,7 @@ struct WarpImage {
   DevModel<T, DimsLarge> model;
   int ld_plan[5456], ld_off[33], chol_plan[5456], chol_off[33];
   unsigned char tri_row[528], tri_col[528];
+  unsigned short tri_ij[544];  // per packed entry e: row | col << 8 | (col is row itself or an ancestor of it) << 15
 };
 
 template <typename T>
@@ -53,6 +54,14 @@ inline void fill_warp_image(WarpImage<T>& img, const b2m_view& v, const int* act
   auto tri_h = [](int i, int j) { return i * (i + 1) / 2 + j; };
   int e = 0;
   for (int i = 0; i < 32; i++) for (int j = 0; j <= i; j++) { img.tri_row[e] = (unsigned char)i; img.tri_col[e] = (unsigned char)j; e++; }
+  for (int x = 0; x < 544; x++) img.tri_ij[x] = 0;
+  e = 0;
+  for (int i = 0; i < 32; i++)
+    for (int j = 0; j <= i; j++) {
+      bool anc = false;
+      if (i < v.nv) for (int a = i; a >= 0; a = v.dof_parentid[a]) if (a == j) { anc = true; break; }
+      img.tri_ij[e++] = (unsigned short)(i | (j << 8) | (anc ? 0x8000 : 0));
+    }
   int n = 0;
   for (int k = 0; k < v.nv && k < 32; k++) {
     img.ld_off[k] = n;
@@ -278,12 +287,11 @@ struct WarpEnv {
   unsigned active_sig[(WarpCaps::NEFC + 31) / 32];  // active-row bit set the factor in LDp was built for
   bool hess_valid;
   bool rows_tree;  // every constraint row touches one root-to-leaf chain only: H = M + J'DJ keeps M's tree sparsity
-  int hess_ij[17];  // (row | col << 8) of the packed Hessian entries lane + 32 t this lane owns
 
   // base: this env's shared-memory workspace (WarpLayout); jscratch: the warp's global scratch slot
   B2_DEV void bind(const WarpImage<T>* image, T* base, T* jscratch) {
     mdl.img = image;
-    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
+    const int nv = mdl.nv();
     const WarpLayout L(mdl.nq(), nv, mdl.nu(), mdl.nbody(), mdl.njnt(), mdl.ngeom(), mdl.ntendon());
     qpos = base + L.qpos; qvel = base + L.qvel; ctrl = base + L.ctrl; warm = base + L.warm; Mp = base + L.Mp;
     f_bias = base + L.f_bias; f_passive = base + L.f_passive; ten_len = base + L.ten_len; ten_J = base + L.ten_J;
@@ -304,12 +312,6 @@ struct WarpEnv {
     con_pair = reinterpret_cast<int*>(cb + 13 * WarpCaps::NCON); row_meta = con_pair + WarpCaps::NCON;
     lane = threadIdx.x & 31;
     ncon = nefc = niter = flags = 0;
-#pragma unroll
-    for (int t = 0; t < 17; t++) {
-      int i = 0, j = 0;
-      if (lane + 32 * t < np) mdl.untri(lane + 32 * t, i, j);
-      hess_ij[t] = i | (j << 8);
-    }
   }
   B2_DEV bool dof_is_anc(int i, int j) const { return (((unsigned)mdl.dof_anc(i)) >> j) & 1u; }
   B2_DEV bool in_subtree(int root, int b) const { return (((unsigned)mdl.body_anc(b)) >> root) & 1u; }
@@ -498,7 +500,7 @@ struct WarpEnv {
   }
 
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
-  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, lane); }  // Mv: scratch, only live inside the line search
+  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, lane); }
   B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(mdl, LDp, dinv, x, lane); }
   B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, mdl.nv(), lane); }
 
@@ -999,8 +1001,13 @@ struct WarpEnv {
       // active rows are visited in increasing order (the summation order of the scalar algorithm)
       constexpr int EPL = 17;  // ceil(32 * 33 / 2 / 32)
       T h[EPL];
+      int ij[EPL];  // row | col << 8 of this lane's entries, -1 beyond the end (skipping the entries outside the tree
+                    // pattern when every row is a chain row was measured 2.7 % slower: the predicate costs more than the FMAs)
 #pragma unroll
-      for (int t = 0; t < EPL; t++) h[t] = lane + 32 * t < np ? Mp[lane + 32 * t] : T(0);
+      for (int t = 0; t < EPL; t++) {
+        ij[t] = lane + 32 * t < np ? (int)__ldg(&mdl.img->tri_ij[lane + 32 * t]) & 0x7fff : -1;
+        h[t] = lane + 32 * t < np ? Mp[lane + 32 * t] : T(0);
+      }
 #pragma unroll 1
       for (int w = 0; w < (WarpCaps::NEFC + 31) / 32; w++) {
         for (unsigned bits = w == 0 ? sig[0] : (w == 1 ? sig[1] : (w == 2 ? sig[2] : sig[3])); bits; bits &= bits - 1) {
@@ -1009,8 +1016,8 @@ struct WarpEnv {
           const T d = row_D[r];
 #pragma unroll
           for (int t = 0; t < EPL; t++) {
-            if (lane + 32 * t < np) {
-              h[t] += (d * Jr[hess_ij[t] & 255]) * Jr[hess_ij[t] >> 8];
+            if (ij[t] >= 0) {
+              h[t] += (d * Jr[ij[t] & 255]) * Jr[ij[t] >> 8];
             }
           }
         }
@@ -1195,13 +1202,15 @@ struct WarpEnv {
     T* acc = grad;
     if (!mdl.has_dofdamping()) { WFOR(k, nv) acc[k] = qacc[k]; __syncwarp(); }
     else {
+      WFOR(k, nv) acc[k] = f_smooth[k] + f_con[k];
+      __syncwarp();
+      // implicit joint damping: (M + h diag(damping))^-1.  (Building this factor in the same sweep as M's, two matrices per
+      // pivot, was measured 2.3 % slower: tools/ab_run.sh, round 2.)
       WFOR(e, np) LDp[e] = Mp[e];
       __syncwarp();
       WFOR(k, nv) LDp[tri(k, k)] += h * mdl.dof_damping(k);
       __syncwarp();
       factor_LD();
-      WFOR(k, nv) acc[k] = f_smooth[k] + f_con[k];
-      __syncwarp();
       solve_LD(acc);
     }
     WFOR(k, nv) qvel[k] += acc[k] * h;
