@@ -54,6 +54,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="headline workload only (no drone / humanoid lines in `secondary`)")
     ap.add_argument("--e2e-host-controller", action="store_true", help="e2e leg: evaluate the LQR law in NumPy on the host instead of on the device")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU-baseline sample duration")
     return ap.parse_args()
@@ -96,10 +97,49 @@ def synth_states(model, name: str, n: int, seed: int):
     return qpos, qvel
 
 
+def bind_to_gpu_numa_node(local: int) -> dict:
+    """One process per GPU: run this rank's host threads (and therefore first-touch its pinned buffers) on the NUMA node
+    the GPU hangs off.  The e2e leg moves ~17 MB per step and rank across PCIe; with eight ranks on a two-socket host,
+    buffers on the far socket put that traffic on the socket interconnect.  Best effort: no sysfs entry, no binding."""
+    info = {"bound": False}
+    try:
+        import torch
+
+        import pynvml as nv
+
+        nv.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        bus_id = nv.nvmlDeviceGetPciInfo(h).busId
+        bus_id = (bus_id.decode() if isinstance(bus_id, bytes) else bus_id).lower()
+        node = -1
+        for cand in (bus_id, bus_id[-12:]):  # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            path = f"/sys/bus/pci/devices/{cand}/numa_node"
+            if os.path.exists(path):
+                node = int(open(path).read().strip())
+                break
+        if node < 0:
+            return info
+        cpus: set[int] = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info = {"bound": True, "numa_node": node, "cpus": len(cpus)}
+    except Exception as exc:  # pragma: no cover - depends on the host
+        info["error"] = str(exc)[:80]
+    return info
+
+
 class ClockSampler(threading.Thread):
-    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  The timed region of the
-    default workload lasts ~10 ms, so the samples are polled through NVML every ~2 ms (nvidia-smi -lms cannot sample
-    that fast); `nvidia-smi --query-gpu` once is the fallback when NVML is not importable."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe).  Polled through NVML every
+    10 ms (nvidia-smi -lms cannot sample that fast; a faster poll from eight ranks perturbs the host side of the
+    measurement), plus one explicit sample while the queued timed steps are executing (`sample_now`);
+    `nvidia-smi --query-gpu` once is the fallback when NVML is not importable."""
+
+    PERIOD_S = 0.010
 
     BAD = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
@@ -114,6 +154,7 @@ class ClockSampler(threading.Thread):
         self.first = threading.Event()
         self.in_region = False
         self.region_samples = 0
+        self._lock = threading.Lock()
 
     def run(self):
         try:
@@ -129,19 +170,11 @@ class ClockSampler(threading.Thread):
             if h is None:
                 h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
             self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._nv, self._h = nv, h
             while not self._stop_evt.is_set():
-                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
-                try:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
-                except Exception:
-                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
-                for name, bit in self.BAD.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                if self.in_region:
-                    self.region_samples += 1
+                self.sample_now()
                 self.first.set()
-                time.sleep(0.002)
+                time.sleep(self.PERIOD_S)
         except Exception:
             try:  # one-shot fallback
                 q = "clocks.sm,clocks.max.sm"
@@ -152,28 +185,61 @@ class ClockSampler(threading.Thread):
                 pass
             self.first.set()
 
+    def sample_now(self):
+        nv, h = getattr(self, "_nv", None), getattr(self, "_h", None)
+        if nv is None:
+            return
+        with self._lock:
+            self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+            try:
+                mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
+            except Exception:
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            for name, bit in self.BAD.items():
+                if mask & bit:
+                    self.reasons.add(name)
+            if self.in_region:
+                self.region_samples += 1
+
     def stop(self) -> dict:
         self._stop_evt.set()
         self.join(timeout=5)
         if not self.sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
-                "samples": len(self.sm), "samples_in_timed_region": self.region_samples, "source": "NVML polled every 2 ms"}
+                "samples": len(self.sm), "samples_in_timed_region": self.region_samples, "source": "NVML polled every 10 ms + one sample while the queued timed steps execute"}
+
+
+CPU_KIND_NOTE = ("oracle = C restatement of mj_step / mjd_transitionFD, built -O3 -march=native with FP contraction for this arm "
+                 "(oracle/_fast, compiled on this host); mujoco itself is not installable offline")
+
+
+def _cpu_model(model):
+    """The CPU arm's oracle: the optimised build (never the parity build)."""
+    from oracle.oracle import OracleModel
+
+    return OracleModel(model.blob, dict(nq=model.nq, nv=model.nv, nu=model.nu, nbody=model.nbody, njnt=model.njnt,
+                                        ngeom=model.ngeom, nsite=model.nsite, ntendon=model.ntendon), variant="fast")
+
+
+def _cpu_probe_rate(om, model, name: str, linearize: bool, cores: int, seed: int) -> float:
+    """env-steps/s of a short all-core run (after one throw-away call that starts the threads and faults the pages in)."""
+    n_probe = max(cores * 4, 64)
+    rate = 1.0
+    for rep in range(2):
+        qpos, qvel = synth_states(model, name, n_probe, seed)
+        ctrl = np.zeros((n_probe, model.nu))
+        t0 = time.perf_counter()
+        om.batch_rollout(qpos, qvel, ctrl, nsteps=2, lin=linearize, nthreads=cores)
+        rate = n_probe * 2 / max(time.perf_counter() - t0, 1e-6)
+    return rate
 
 
 def cpu_oracle_rate(model, name: str, linearize: bool, target_seconds: float, seed: int = 123):
     """Oracle (CPU restatement of mj_step / mjd_transitionFD) on all host cores over a bounded sample."""
-    from oracle.oracle import OracleModel
-
-    om = OracleModel(model.blob, dict(nq=model.nq, nv=model.nv, nu=model.nu, nbody=model.nbody, njnt=model.njnt,
-                                      ngeom=model.ngeom, nsite=model.nsite, ntendon=model.ntendon))
+    om = _cpu_model(model)
     cores = os.cpu_count() or 1
-    n_probe = max(cores * 4, 64)
-    qpos, qvel = synth_states(model, name, n_probe, seed)
-    ctrl = np.zeros((n_probe, model.nu))
-    t0 = time.perf_counter()
-    om.batch_rollout(qpos, qvel, ctrl, nsteps=2, lin=linearize, nthreads=cores)
-    probe_rate = n_probe * 2 / max(time.perf_counter() - t0, 1e-6)
+    probe_rate = _cpu_probe_rate(om, model, name, linearize, cores, seed)
     nsteps = 10
     n = int(min(max(probe_rate * target_seconds / nsteps, cores), 1 << 20))
     for _ in range(3):  # the short probe under-estimates the rate (thread start-up): grow the sample if needed
@@ -187,8 +253,7 @@ def cpu_oracle_rate(model, name: str, linearize: bool, target_seconds: float, se
         n = int(min(n * target_seconds / max(dt, 1e-3), 1 << 20))
     return dict(value=n * nsteps / dt, unit=UNIT, cores=cores, kind="port",
                 sample=f"{n} envs x {nsteps} steps of the same workload ({'FD linearisation + ' if linearize else ''}step), "
-                       f"{dt:.1f} s wall, pthread shards over {cores} threads; oracle = C restatement of mj_step "
-                       "(mujoco itself is not installable offline)")
+                       f"{dt:.1f} s wall, pthread shards over {cores} threads; " + CPU_KIND_NOTE)
 
 
 def run_reference(args):
@@ -200,15 +265,11 @@ def run_reference(args):
     name = args.model
     model = load_model(name)
     lin = not args.no_linearize
-    from oracle.oracle import OracleModel
-
-    om = OracleModel(model.blob, dict(nq=model.nq, nv=model.nv, nu=model.nu, nbody=model.nbody, njnt=model.njnt,
-                                      ngeom=model.ngeom, nsite=model.nsite, ntendon=model.ntendon))
+    om = _cpu_model(model)
     cores = os.cpu_count() or 1
-    per_step_cost = {"pendulum": 30e-6, "cartpole": 14e-6, "drone": 90e-6, "humanoid": 8e-3}[name] if lin else \
-        {"pendulum": 3e-6, "cartpole": 1e-6, "drone": 2.5e-6, "humanoid": 50e-6}[name]
-    # bounded sample: about 1.5 s of all-core work per step
-    n = int(max(cores, min(1 << 18, 1.5 * cores / per_step_cost)))
+    # bounded sample: about 1.5 s of all-core work per step, sized from a measured probe
+    rate = _cpu_probe_rate(om, model, name, lin, cores, 5)
+    n = int(max(cores, min(1 << 18, 1.5 * rate)))
     qpos, qvel = synth_states(model, name, n, 7)
     ctrl = np.zeros((n, model.nu))
     warm = np.zeros((n, model.nv))
@@ -219,7 +280,7 @@ def run_reference(args):
         om.batch_rollout(qpos, qvel, ctrl, warm, nsteps=1, lin=lin, nthreads=cores)
     dt = time.perf_counter() - t0
     value = n * args.steps / dt
-    sample = f"{n} envs per step (bounded sample of the {DEFAULT_NENV[name]}-env workload), all {cores} host threads"
+    sample = (f"{n} envs per step (bounded sample of the {DEFAULT_NENV[name]}-env workload), all {cores} host threads; " + CPU_KIND_NOTE)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -246,49 +307,27 @@ def workload_name(name: str, nenv: int, lin: bool) -> str:
     return f"{name} batched rollout, N={nenv} envs/GPU, FP64, " + tail
 
 
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def make_controller(name: str, lin: bool):
+    """The controller of a workload (counted as the controller, not as the path: SURVEY.md section 8d)."""
     import torch
-    import torch.distributed as dist
 
-    from mujoco_template import BatchedEnv, _capi
+    from mujoco_template import ControllerCapabilities
     from mujoco_template.batched_controllers import BatchedLQRController
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    dev = torch.device(f"cuda:{local}")
-    name = args.model
-    lin = not args.no_linearize
-    nenv = args.nenv or DEFAULT_NENV[name]
-    model = load_model(name)
-    controller = None
     if lin:
         if name == "cartpole":
-            controller = BatchedLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
-        else:
-            from mujoco_template import ControllerCapabilities
+            return BatchedLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
 
-            class HoldLin:
-                capabilities = ControllerCapabilities(needs_linearization=True)
-                def prepare(self, m, d): pass
-                def __call__(self, m, d, t): pass
-            controller = HoldLin()
-    elif name in RANDOM_CTRL:
-        from mujoco_template import ControllerCapabilities
-
-        class RandomCtrl:  # counted as the controller, not as the path
+        class HoldLin:
+            capabilities = ControllerCapabilities(needs_linearization=True)
+            def prepare(self, m, d): pass
+            def __call__(self, m, d, t): pass
+        return HoldLin()
+    if name in RANDOM_CTRL:
+        class RandomCtrl:
             capabilities = ControllerCapabilities()
             lo, hi = RANDOM_CTRL[name]
-            init = None  # (qpos, qvel) tensors of the initial states: set below for the drone
+            init = None  # (qpos, qvel) tensors of the initial states: set by the caller for the drone
             def prepare(self, m, d): pass
             def __call__(self, m, d, t):
                 d.ctrl.uniform_(self.lo, self.hi)
@@ -298,7 +337,27 @@ def main():
                     low = (d.qpos[2] < 0.5).unsqueeze(0)
                     torch.where(low, self.init[0], d.qpos, out=d.qpos)
                     torch.where(low, self.init[1], d.qvel, out=d.qvel)
-        controller = RandomCtrl()
+        return RandomCtrl()
+    return None
+
+
+def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, *, use_graph: bool, want_e2e: bool,
+                 e2e_host_controller: bool, cpu_seconds: float) -> dict:
+    """Times one workload on this rank's GPU and returns the fields of its JSON line (rank 0's copy is printed)."""
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_template import BatchedEnv, _capi
+
+    world, rank, local, dev, flush = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"], ctx["flush"]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    model = load_model(name)
+    controller = make_controller(name, lin)
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
     qpos, qvel = synth_states(model, name, nenv, seed=rank)  # each rank owns its own shard of envs
@@ -307,35 +366,35 @@ def main():
     env.forward()
     if name == "drone" and not lin and controller is not None:
         controller.init = (env.data.qpos.clone(), env.data.qvel.clone())
-    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # per-kernel device times for the roofline: a short eager pass with CUDA events around each launch
-    env.data.backend.profile = {}
+    # per-kernel device times for the roofline: short eager passes with CUDA events around each library launch --
+    # first the launches one by one (controller / FD / step), then the fused control tick the timed loop runs
     fuse_default = getattr(env, "fuse_control_tick", False)
-    env.fuse_control_tick = False  # time the controller / FD / step launches one by one in this pass
-    for _ in range(max(args.warmup, 3)):
-        env.step(return_obs=False)
-    for _ in range(10):
-        flush.zero_()
-        env.step(return_obs=False)
-    torch.cuda.synchronize()
-    kernel_ms = {k: env.data.backend.kernel_ms(k)[-10:] for k in ("lqr_control", "linearize", "step", "control_tick")}
+    kernel_ms = {}
+    for fused in ((False, True) if (lin and fuse_default) else (False,)):
+        env.data.backend.profile = {}
+        env.fuse_control_tick = fused
+        for _ in range(max(warmup, 3)):
+            env.step(return_obs=False)
+        env.data.backend.profile = {}
+        for _ in range(10):
+            flush.zero_()
+            env.step(return_obs=False)
+        torch.cuda.synchronize()
+        for k in ("lqr_control", "linearize", "step", "control_tick"):
+            v = env.data.backend.kernel_ms(k)[-10:]
+            if v:
+                kernel_ms[k] = v
     env.data.backend.profile = None
     env.fuse_control_tick = fuse_default
     c0 = _capi.launch_count()
     env.step(return_obs=False)
     per_step_launches = _capi.launch_count() - c0  # library kernels per step (controller tick, FD, step)
-    use_graph = controller is not None and not args.no_graph
+    use_graph = use_graph and controller is not None
     if use_graph:
         env.enable_cuda_graph(True)
         for _ in range(3):  # eager call, capture + replay, replay
             env.step(return_obs=False)
-    fp64_peak = _capi.fp_peak(64, local)
     # the timed rollout starts from the configured initial-state distribution (the warm-up / profiling steps above have
     # moved the envs: drones under random thrust eventually reach the floor, the humanoid falls)
     env.data.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=dev))
@@ -344,23 +403,26 @@ def main():
     env.forward()
     barrier()
     launches0 = _capi.launch_count()
-    try:
-        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
-    except Exception:
-        gpu_uuid = None
-    sampler = ClockSampler(local, gpu_uuid)
+    sampler = ClockSampler(local, ctx["gpu_uuid"])
     sampler.start()
     sampler.first.wait(timeout=10)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     barrier()
     sampler.in_region = True
     wall0 = time.perf_counter()
-    for i in range(args.steps):
+    # The host must never be the thing that is timed: the steps are queued behind a spin kernel (torch.cuda._sleep, outside
+    # every event pair), 64 at a time, so that each event pair brackets device work that was already waiting in the stream
+    # when the device got to it -- no Python, launch latency or rank-to-rank host contention inside the pairs.
+    spin_cycles = int(ctx["sm_hz"] * 0.004)
+    for i in range(steps):
+        if i % 64 == 0:
+            torch.cuda._sleep(spin_cycles)
         flush.zero_()  # evict state / outputs from L2 between timed iterations (outside the event pair)
         starts[i].record()
         env.step(return_obs=False)
         stops[i].record()
+    sampler.sample_now()  # the queued steps are executing now
     barrier()
     wall = time.perf_counter() - wall0
     sampler.in_region = False
@@ -368,12 +430,14 @@ def main():
     step_ms = [a.elapsed_time(b) for a, b in zip(starts, stops)]
     total_ms = float(sum(step_ms))
     # graph replays re-launch the captured kernels without passing through the C-ABI counter
-    launches = (_capi.launch_count() - launches0) if not use_graph else per_step_launches * args.steps
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    launches = (_capi.launch_count() - launches0) if not use_graph else per_step_launches * steps
+    rank_ms = [total_ms / steps]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    value = nenv * world * args.steps / (total_ms * 1e-3)
+        gathered = [torch.zeros(1, device=dev, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(gathered, torch.tensor([total_ms / steps], device=dev, dtype=torch.float64))
+        rank_ms = [float(g.item()) for g in gathered]
+    total_ms = max(rank_ms) * steps
+    value = nenv * world * steps / (total_ms * 1e-3)
 
     # untimed: the path's only collective -- gather per-env returns (here: final |x|) across ranks
     ret = env.data.qpos[0].abs().contiguous()
@@ -385,49 +449,48 @@ def main():
 
     # ---- roofline of the dominant kernel
     dom = "linearize" if lin else "step"
-    if lin and not kernel_ms["linearize"]:
+    if lin and not kernel_ms.get("linearize"):
         dom = "control_tick"  # fused LQR + FD + step launch
-    dom_ms = float(np.mean(kernel_ms[dom])) if kernel_ms[dom] else float("nan")
+    dom_ms = float(np.mean(kernel_ms[dom])) if kernel_ms.get(dom) else float("nan")
     alg_bytes = (LIN_BYTES[name] if lin else STEP_BYTES[name]) * nenv
-    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_file):
-        peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "ncu_traffic_r01.json")
-    if os.path.exists(tfile):
-        traffic = json.load(open(tfile)).get(f"{name}:{dom}:{nenv}")
+    for tname in ("ncu_traffic_r02.json", "ncu_traffic_r01.json"):
+        tfile = os.path.join(ROOT, "profiles", tname)
+        if traffic is None and os.path.exists(tfile):
+            traffic = json.load(open(tfile)).get(f"{name}:{dom}:{nenv}")
     variant = env.data.backend.batch.kernel_variant
     if "warp" in variant:  # large models: warp engine
         kernel_label = "k_warp_linearize" if lin else "k_warp_step_ls"
     else:
         kernel_label = f"k_{dom}<{variant}>"
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9
-    share = {k: (float(np.mean(v)) * args.steps / total_ms if v else 0.0) for k, v in kernel_ms.items()}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+    ms_step = total_ms / steps
+    mean_of = lambda k: float(np.mean(kernel_ms[k])) if kernel_ms.get(k) else None
+    # what the timed step consists of: the fused control tick (FD launch with the env advance riding in it + the state
+    # commit) when it is used, else the kernels launched one by one
+    in_step = ("control_tick",) if (lin and fuse_default and kernel_ms.get("control_tick")) else tuple(k for k in ("lqr_control", "linearize", "step") if kernel_ms.get(k))
+    share = {k: mean_of(k) / ms_step for k in in_step}
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx["peak_gbs"], "unit": "GB/s", "frac": achieved / ctx["peak_gbs"],
                 "traffic": traffic, "kernel": kernel_label,
-                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": ctx["peak_src"],
                 "kernel_share_of_step": share,
-                "kernel_share_note": "kernels timed one by one in an eager pass (controller, FD, step); the timed loop itself runs "
-                                     "b2_control_tick, where the step rides in the FD launch",
+                "kernel_ms_launched_separately": {k: mean_of(k) for k in ("lqr_control", "linearize", "step") if kernel_ms.get(k)},
+                "kernel_share_note": "share = device time of the launches the timed step consists of / ms_per_step; with a "
+                                     "linearising controller that is b2_control_tick (control law + FD + the env advance in one "
+                                     "launch, then the state commit); kernel_ms_launched_separately lists the same work as "
+                                     "individual launches (the roofline kernel is timed there)",
                 "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
-    # executed FP64 work: rollouts per launch x estimated flops per step-eval; peak measured live
+    # executed FP64 work: rollouts per launch x flops per step-evaluation
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
-    # executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
-    # themselves (profiles/ncu_*_r01i.txt): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per
-    # env runs the shared position stage once for all velocity / control columns, control columns skip the velocity stage
-    # too -- and k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 2.97e9 / 16,384 =
-    # 182,000 (mean 3.6 contacts, 2.9 Newton iterations); pendulum: a-priori estimate of BASELINE.md
-    flops_per_eval = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 182000.0}[name]
+    flops_per_eval, flops_src = flops_per_step_eval(name, lin)
     tf = evals * flops_per_eval / (dom_ms * 1e-3) / 1e12
-    roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tf / fp64_peak,
+    roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": ctx["fp64_peak"], "unit": "TFLOP/s", "frac": tf / ctx["fp64_peak"],
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
-                     "flops_source": ("ncu-counted executed flops (profiles/)" if name != "pendulum" else "a-priori estimate (BASELINE.md section 4)"), "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
+                     "flops_source": flops_src, "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
 
     # ---- e2e: host buffers through the C-ABI (b2_step_host): H2D state+ctrl, linearise+step, D2H state+(A,B)
     e2e = None
-    if not args.no_e2e:
+    if want_e2e:
         nq, nv, nu = model.nq, model.nv, model.nu
         hq = torch.as_tensor(qpos.T.copy()).pin_memory(); hv = torch.as_tensor(qvel.T.copy()).pin_memory()
         hu = torch.zeros((nu, nenv), dtype=torch.float64).pin_memory(); hw = torch.zeros((nv, nenv), dtype=torch.float64).pin_memory()
@@ -436,16 +499,21 @@ def main():
         st = _capi.State(hq.data_ptr(), hv.data_ptr(), hu.data_ptr(), hw.data_ptr(), None)
         K = getattr(controller, "K", None)
         batch = env.data.backend.batch
-        e2e_steps = max(3, min(args.steps, 50))
+        e2e_steps = max(3, min(steps, 50))
 
         qn, vn, un = hq.numpy(), hv.numpy(), hu.numpy()
         tmp = np.empty(nenv)
         lo = float(model.actuator_ctrlrange[0, 0]) if model.nu else 0.0
         hi = float(model.actuator_ctrlrange[0, 1]) if model.nu else 0.0
 
-        device_lqr = K is not None and not args.e2e_host_controller
+        device_lqr = K is not None and not e2e_host_controller
         if device_lqr:
             batch.lqr_set_gain(K, np.asarray(controller._qref_np, dtype=float), np.asarray(controller._uref_np, dtype=float))
+        rctrl = RANDOM_CTRL.get(name) if not lin else None
+        if rctrl is not None:
+            # the host-side controller of configs #3 / #4: random controls per env and actuator, drawn once and held over the
+            # e2e steps (drawing 1e6 doubles per step on the host would time NumPy's generator, not the path)
+            un[:] = np.random.default_rng(1234 + rank).uniform(rctrl[0], rctrl[1], un.shape)
 
         def host_step():
             if device_lqr:  # control law on the device: H2D state, [LQR, FD, step] per chunk, D2H state + ctrl + (A, B)
@@ -473,30 +541,108 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         h2d = (nq + nv + (0 if device_lqr else nu) + nv) * nenv * 8
         d2h = (nq + nv + nv + (nu if device_lqr else 0) + (2 * nv * (2 * nv + nu) if lin else 0)) * nenv * 8
-        e2e = {"value": nenv * world * e2e_steps / float(tt.item()), "unit": UNIT, "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "api": "b2_step_host (C-ABI, pinned host buffers, " + ("device LQR law, ctrl returned" if device_lqr else "host LQR tick") + ")"}
+        e2e_s = float(tt.item()) / e2e_steps
+        e2e = {"value": nenv * world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "steps": e2e_steps, "ms_per_step": e2e_s * 1e3,
+               "pcie_gbs_per_gpu": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9},
+               "pcie_note": "PCIe Gen5 x16 moves ~55 GB/s per direction in practice; d2h / 55 is the fraction of the link the "
+                            "(A, B) + state read-back uses",
+               "pcie_d2h_frac_of_55gbs": d2h / e2e_s / 1e9 / 55.0,
+               "api": "b2_step_host (C-ABI, pinned host buffers, " + ("device LQR law, ctrl returned" if device_lqr else ("host LQR tick" if K is not None else "controls held in the host buffer")) +
+                      (", (A, B) written by the FD kernel straight into the mapped host buffers" if lin and os.environ.get("B2_HOST_STAGED") != "1" else "") + ")"}
+        del hq, hv, hu, hw, hA, hB
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_oracle_rate(model, name, lin, args.cpu_seconds)
+    if rank == 0 and world == 1 and cpu_seconds > 0:
+        os.sched_setaffinity(0, ctx["affinity0"])  # the CPU baseline uses every host core
+        cpu = cpu_oracle_rate(model, name, lin, cpu_seconds)
 
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
+        "ms_per_step": ms_step, "ms_per_step_per_rank": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
+                   "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
+                   "launch": "CUDA graph replay of one env.step()" if use_graph else "eager launches",
+                   "timing": "CUDA event pair per step; steps queued 64 at a time behind a 4 ms spin kernel, so the pairs bracket "
+                             "device work only (no host latency inside); sum over steps, max over ranks",
+                   "rollout": f"timed steps are steps 0..{steps} of the rollout from the configured initial-state distribution",
+                   "sharding": f"env batch split over {world} rank(s), no inter-step communication"},
+        "linearizations_per_sec": (value if lin else 0.0),
+        "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),
+        "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
+        "bad_env_flags": flags_bad, "gathered_returns": int(allret.numel()), "contact_stats": contact_stats,
+        "kernel_variant": variant,
+    }
+    del env
+    torch.cuda.empty_cache()
+    return out
+
+
+def flops_per_step_eval(name: str, lin: bool):
+    """Executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
+    themselves (profiles/): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per env runs the
+    shared position stage once for all velocity / control columns, control columns skip the velocity stage too -- and
+    k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 182,000 (mean 3.6 contacts, 2.9
+    Newton iterations).  The oracle's op counter (oracle.op_count) gives the ALGORITHMIC count of one
+    mj_step for the same states; the executed count is what the pipe-utilisation figure needs."""
+    table = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 182000.0}
+    src = "ncu-counted executed flops (profiles/)" if name != "pendulum" else "a-priori estimate (BASELINE.md section 4)"
+    return table[name], src
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from mujoco_template import _capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    affinity0 = os.sched_getaffinity(0)
+    torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else {"bound": False, "note": "single rank: not bound"}
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = torch.device(f"cuda:{local}")
+    peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_file):
+        peak_gbs, peak_src = float(json.load(open(peaks_file))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak_gbs, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    try:
+        gpu_uuid = str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_uuid = None
+    ctx = {"world": world, "rank": rank, "local": local, "dev": dev, "affinity0": affinity0, "gpu_uuid": gpu_uuid,
+           "flush": torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev),  # > 126 MB L2
+           "fp64_peak": _capi.fp_peak(64, local), "peak_gbs": peak_gbs, "peak_src": peak_src,
+           "sm_hz": torch.cuda.get_device_properties(local).clock_rate * 1e3}
+    name = args.model
+    lin = not args.no_linearize
+    common = dict(use_graph=not args.no_graph, want_e2e=not args.no_e2e, e2e_host_controller=args.e2e_host_controller)
+    out = run_workload(ctx, name, lin, args.nenv or DEFAULT_NENV[name], args.steps, args.warmup,
+                       cpu_seconds=0.0 if args.no_cpu_baseline else args.cpu_seconds, **common)
+    out["host_binding"] = numa
+    # BASELINE.json configs[2] / configs[3] ride along with the headline workload (same run, same clocks, same rank
+    # count): drone free flight under random thrust and the humanoid with contacts, step only
+    if name == "cartpole" and lin and args.nenv is None and not args.no_secondary:
+        out["secondary"] = {}
+        for sname in ("drone", "humanoid"):
+            sec = run_workload(ctx, sname, False, DEFAULT_NENV[sname], min(args.steps, 100), args.warmup,
+                               cpu_seconds=0.0 if args.no_cpu_baseline else min(args.cpu_seconds, 5.0), **common)
+            out["secondary"][sname] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_per_rank", "steps", "config", "roofline",
+                                                           "roofline_fp64", "cpu_baseline", "e2e", "gpu_launches", "contact_stats",
+                                                           "bad_env_flags", "kernel_variant", "clocks")}
     if rank == 0:
-        out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
-                       "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
-                       "launch": "CUDA graph replay of one env.step()" if use_graph else "eager launches",
-                       "rollout": f"timed steps are steps 0..{args.steps} of the rollout from the configured initial-state distribution",
-                       "sharding": f"env batch split over {world} rank(s), no inter-step communication"},
-            "linearizations_per_sec": (value if lin else 0.0),
-            "step_evals_per_sec": value * ((2 * (2 * model.nv + model.nu) + 1) if lin else 1),
-            "roofline": roofline, "roofline_fp64": roofline_fp64, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall,
-            "bad_env_flags": flags_bad, "gathered_returns": int(allret.numel()), "contact_stats": contact_stats,
-            "kernel_variant": env.data.backend.batch.kernel_variant,
-        }
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

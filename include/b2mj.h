@@ -147,7 +147,9 @@ int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void*
  * reference env.py:178-190 does per control tick), copies qpos/qvel[/warm][/A,B] back, and
  * synchronises.  A/B may be NULL.  `linearize` is a bit set: B2_HOST_LINEARIZE computes (A, B) before the step;
  * B2_HOST_LQR evaluates the control law of b2_lqr_set_gain on the device first -- host_state.ctrl is then an OUTPUT
- * (the controls that were applied) instead of an input.  Used by bench.py's e2e leg. */
+ * (the controls that were applied) instead of an input.  host_A / host_B that are page-locked and device-mapped
+ * (cudaHostAlloc, cudaHostRegister, torch pin_memory()) are written by the FD kernel directly, with no staging copy in
+ * HBM; any other host memory goes through a staged device buffer.  Used by bench.py's e2e leg. */
 #define B2_HOST_LINEARIZE 1
 #define B2_HOST_LQR 2
 int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int linearize, double eps, void* host_A,

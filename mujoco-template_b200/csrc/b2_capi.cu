@@ -80,6 +80,7 @@ struct b2_batch {
   int warp_mode = -1, warp_wpb = 0, warp_blocks = 0, warp_slots = 0;
   void* d_jscratch = nullptr;
   void* d_warp_counter = nullptr;  // inside d_jscratch
+  void* d_warp_sort = nullptr;     // inside d_jscratch: cost-ordered queue (hist / cursor, cost[N], perm[N])
   void* d_shadow = nullptr;        // shadow state of the FD launch that also advances the envs (b2_control_tick)
   bool shadow_has_prestep = false;
   void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
@@ -202,9 +203,17 @@ static int prepare_warp(b2_batch* b) {
                         : b2::b2k_warp_plan_f32(&b->model->v, b->nenv, &wpb, &blocks);
   if (slots <= 0) return B2_OK;  // not enough shared memory: stay on the lane engine
   const size_t bytes = f64 ? b2::b2k_warp_scratch_bytes_f64(&b->model->v, slots) : b2::b2k_warp_scratch_bytes_f32(&b->model->v, slots);
-  cudaError_t e = cudaMalloc(&b->d_jscratch, bytes + 256);  // + the work-queue counter of the persistent kernel
+  // + the work-queue counter of the persistent kernel + the buffers of the cost-ordered queue (B2_WARP_SORT=0: plain order)
+  const char* srt = getenv("B2_WARP_SORT");
+  const bool sorted = !(srt && srt[0] == '0');
+  const size_t sort_bytes = sorted ? (f64 ? b2::b2k_warp_sort_bytes_f64(b->nenv) : b2::b2k_warp_sort_bytes_f32(b->nenv)) : 0;
+  cudaError_t e = cudaMalloc(&b->d_jscratch, bytes + 256 + sort_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "warp-engine scratch cudaMalloc");
   b->d_warp_counter = (char*)b->d_jscratch + bytes;
+  if (sorted) {
+    b->d_warp_sort = (char*)b->d_warp_counter + 256;
+    if ((e = cudaMemset(b->d_warp_sort, 0, sort_bytes)) != cudaSuccess) return cuda_fail(e, "warp-engine queue cudaMemset");
+  }
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
@@ -244,8 +253,8 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
   if (b->warp_mode == 1 && count == b->nenv) {
     const void* image = nullptr;
     if ((rc = warp_image_of(b, &image))) return rc;
-    return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream)
-               : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->warp_wpb, b->warp_blocks, stream);
+    return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream)
+               : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream);
   }
   return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
              : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
@@ -545,7 +554,25 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   if ((e = need(&b->d_qpos, v.nq * N * es)) || (e = need(&b->d_qvel, v.nv * N * es)) || (e = need(&b->d_ctrl, nu1 * N * es)) ||
       (e = need(&b->d_warm, v.nv * N * es)))
     return cuda_fail(e, "b2_step_host: cudaMalloc");
-  if (linearize && ((e = need(&b->d_A, nx * nx * N * es)) || (e = need(&b->d_B, nx * nu1 * N * es)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
+  // (A, B) are 8 (2nv)(2nv + nu) bytes per env against 8 (nq + 2nv) of state -- 89 % of the bytes that go back to the host for
+  // the cartpole.  When the caller's buffers are page-locked and mapped into this device's address space (cudaHostAlloc /
+  // cudaHostRegister under unified addressing: torch's pin_memory()), the FD kernel stores its columns straight into them --
+  // coalesced 256 B rows over PCIe while the kernel is still computing -- instead of staging them in HBM and copying
+  // afterwards.  B2_HOST_STAGED=1 keeps the staged form.
+  void *map_A = nullptr, *map_B = nullptr;
+  bool direct = linearize && host_A && (host_B || !v.nu);
+  if (const char* x = getenv("B2_HOST_STAGED")) if (x[0] == '1') direct = false;
+  if (direct) {
+    auto mapped = [&](void* host, void** dev) {
+      cudaPointerAttributes at;
+      if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return false; }
+      if (at.type != cudaMemoryTypeHost || !at.devicePointer) return false;
+      *dev = at.devicePointer;
+      return true;
+    };
+    direct = mapped(host_A, &map_A) && (!host_B || mapped(host_B, &map_B));
+  }
+  if (linearize && !direct && ((e = need(&b->d_A, nx * nx * N * es)) || (e = need(&b->d_B, nx * nu1 * N * es)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
   int rc = prepare_warp(b);
   if (rc) return rc;
   if ((!active_spec(b) || lqr) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
@@ -563,7 +590,7 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   HostStepKey key;
   memset(&key, 0, sizeof(key));
   key.qpos = hs->qpos; key.qvel = hs->qvel; key.ctrl = hs->ctrl; key.warm = hs->qacc_warmstart; key.A = host_A; key.B = host_B;
-  key.nsteps = nsteps; key.linearize = linearize | (lqr ? B2_HOST_LQR : 0) | (nchunk << 8); key.eps = eps; key.model_serial = b->model->serial;
+  key.nsteps = nsteps; key.linearize = linearize | (lqr ? B2_HOST_LQR : 0) | (nchunk << 8) | (direct ? 1 << 16 : 0); key.eps = eps; key.model_serial = b->model->serial;
   if (b->host_graph && memcmp(&key, &b->host_key, sizeof(key)) != 0) {
     cudaGraphExecDestroy(b->host_graph);
     b->host_graph = nullptr;
@@ -595,15 +622,17 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
       if (e) break;
       b2_state ds = {(char*)b->d_qpos + e0 * es, (char*)b->d_qvel + e0 * es, (char*)b->d_ctrl + e0 * es, (char*)b->d_warm + e0 * es, nullptr};
       const void* gain = lqr ? b->d_gain : nullptr;
-      if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, (char*)b->d_A + e0 * es, (char*)b->d_B + e0 * es, s, gain))) break;
+      void* out_A = direct ? (char*)map_A + e0 * es : (char*)b->d_A + e0 * es;
+      void* out_B = direct ? (map_B ? (char*)map_B + e0 * es : nullptr) : (char*)b->d_B + e0 * es;
+      if (linearize && (err = do_linearize(b, &ds, (int)cnt, eps, 1, out_A, out_B, s, gain))) break;
       if ((err = do_step(b, &ds, (int)cnt, nsteps, nullptr, s, gain))) break;
       if ((e = copy_rows(hs->qpos, b->d_qpos, e0, cnt, v.nq, cudaMemcpyDeviceToHost, s)) ||
           (e = copy_rows(hs->qvel, b->d_qvel, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s)))
         break;
       if (hs->qacc_warmstart && (e = copy_rows(hs->qacc_warmstart, b->d_warm, e0, cnt, v.nv, cudaMemcpyDeviceToHost, s))) break;
       if (lqr && (e = copy_rows(hs->ctrl, b->d_ctrl, e0, cnt, v.nu, cudaMemcpyDeviceToHost, s))) break;
-      if (linearize && host_A && (e = copy_rows(host_A, b->d_A, e0, cnt, nx * nx, cudaMemcpyDeviceToHost, s))) break;
-      if (linearize && host_B && v.nu && (e = copy_rows(host_B, b->d_B, e0, cnt, nx * v.nu, cudaMemcpyDeviceToHost, s))) break;
+      if (linearize && !direct && host_A && (e = copy_rows(host_A, b->d_A, e0, cnt, nx * nx, cudaMemcpyDeviceToHost, s))) break;
+      if (linearize && !direct && host_B && v.nu && (e = copy_rows(host_B, b->d_B, e0, cnt, nx * v.nu, cudaMemcpyDeviceToHost, s))) break;
     }
     // join the side streams back
     for (int i = 1; i < 3; i++) {

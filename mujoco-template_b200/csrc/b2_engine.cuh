@@ -1005,8 +1005,8 @@ struct LaneEnv {
     if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
     return 0;
   }
-  // cost, forces, gradient and Newton direction at the current qacc
-  B2_STAGE void newton_refresh() {
+  // cost, forces and gradient at the current qacc ...
+  B2_STAGE void newton_gradient() {
     const int nv = M::nv();
     cost = row_cost(R.Jaref, true);
     T g = 0;
@@ -1016,6 +1016,10 @@ struct LaneEnv {
     cost += gauss;
     B2_UNROLL
     for (int k = 0; k < nv; k++) grad[k] = Ma[k] - f_smooth[k] - f_con[k];
+  }
+  // ... and the Newton direction (not needed by the round that detects convergence: one factorisation fewer per solve)
+  B2_STAGE void newton_direction() {
+    const int nv = M::nv();
     // H = M + R.J' D_active R.J  (lower triangle, held in LD), dense Cholesky, Mgrad = H^-1 grad
     T* H = kKeepFactors ? Hs : LD;
     B2_UNROLL
@@ -1093,7 +1097,7 @@ struct LaneEnv {
     // one refresh / one line-search call site: the loop is the upstream iteration unrolled by half a turn
     B2_NOUNROLL
     while (true) {
-      newton_refresh();
+      newton_gradient();
       if (!first) {
         T gn = 0;
         B2_UNROLL
@@ -1102,9 +1106,10 @@ struct LaneEnv {
         if (scale * (old - cost) < M::tolerance() || scale * sqrt(gn) < M::tolerance()) break;
       }
       first = false;
+      if (niter >= M::iterations()) break;
+      newton_direction();
       B2_UNROLL
       for (int k = 0; k < nv; k++) search[k] = -Mgrad[k];
-      if (niter >= M::iterations()) break;
       const T alpha = line_search();
       if (alpha == 0) break;
       B2_UNROLL

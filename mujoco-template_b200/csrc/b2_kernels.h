@@ -10,8 +10,9 @@ namespace b2 {
   size_t b2k_warp_scratch_bytes##SUF(const b2m_view* v, int slots);                                                        \
   size_t b2k_warp_image_bytes##SUF();                                                                                      \
   void b2k_warp_image_fill##SUF(const b2m_view* v, const int* disabled, void* host);                                       \
+  size_t b2k_warp_sort_bytes##SUF(int N);                                                                                  \
   int b2k_warp_step##SUF(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch, void* counter,  \
-                         int wpb, int blocks, void* stream);                                                                                  \
+                         void* sortbuf, int wpb, int blocks, void* stream);                                                                   \
   int b2k_warp_linearize##SUF(const void* image, const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
                               void* counter, int wpb, int blocks, void* stream);                                                        \
   int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \

@@ -141,14 +141,21 @@ static bool dims_are_humanoid(const b2m_view* v) {
   if (dims_are_humanoid(v)) { typedef ImageModel<real, DimsHumanoid> WM; CALL; } \
   else { typedef ImageModel<real, DimsRuntime> WM; CALL; }
 
+// lock-step mode of the warp kernels (WarpEnv::forward<LS>): 1 = every stage and every Newton round behind the block
+// barrier, 2 = stages only (the Newton loop runs free), 0 = none.  Measured on the humanoid (200-step rollout, blocks of four
+// warps, cost-ordered queue): mode 2 7.44e6 env-steps/s, mode 1 7.30e6 -- the Newton loop's code is small enough to stay
+// in the instruction cache, and a warp no longer waits for its block mates in every round.
+#ifndef B2_WARP_LS_MODE
+#define B2_WARP_LS_MODE 2
+#endif
 static int warp_ws_reals_of(const b2m_view* v) { return warp_ws_reals(v->nq, v->nv, v->nu, v->nbody, v->njnt, v->ngeom, v->ntendon); }
 static size_t warp_block_smem(const b2m_view* v, int wpb, int extra_reals) {
   size_t extra = 0;
   if (const char* x = getenv("B2_WARP_EXTRA_SMEM")) extra = (size_t)atoi(x);  // tuning: lowers the resident blocks per SM
   return extra + (size_t)wpb * ((size_t)warp_ws_reals_of(v) + extra_reals) * sizeof(real);
 }
-static int warp_wpb() {  // warps (envs) per lock-step block
-  int wpb = 2;
+static int warp_wpb() {  // warps (envs) per lock-step block: 4 x 128 registers = 16 resident warps per SM, four to a fetch
+  int wpb = 4;
   if (const char* x = getenv("B2_WARP_LS_WPB")) { const int w = atoi(x); if (w >= 1 && w <= 8) wpb = w; }
   return wpb;
 }
@@ -174,7 +181,7 @@ int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks
   while (wpb > 1 && warp_block_smem(v, wpb, 0) + 1024 > (size_t)smem_max) wpb--;
   const size_t smem = warp_block_smem(v, wpb, 0);
   int per_sm = 0, rc = 0;
-  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_step_ls<real, WM, 1>, wpb, smem, &per_sm)));
+  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_step_ls<real, WM, B2_WARP_LS_MODE>, wpb, smem, &per_sm)));
   if (rc) return -1;
   int blocks = sms * per_sm;
   const int need = (N + wpb - 1) / wpb;
@@ -186,14 +193,28 @@ int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks
 size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
   return (size_t)slots * warp_slot_reals(v->nv) * sizeof(real);
 }
+// bytes of the cost-ordered queue's buffers behind the work-queue counter: [hist | cursor] (64 ints), cost[N], perm[N]
+size_t B2_FN(b2k_warp_sort_bytes)(int N) { return (64 + 2 * (size_t)N) * sizeof(int); }
 int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
-                         void* counter, int wpb, int blocks, void* stream) {
+                         void* counter, void* sortbuf, int wpb, int blocks, void* stream) {
   const size_t smem = warp_block_smem(v, wpb, 0);
+  cudaStream_t s = (cudaStream_t)stream;
   // envs are handed out through a work queue: the first gridDim * wpb statically, the rest by atomic counter
-  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
+  cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), s);
   if (e != cudaSuccess) return (int)e;
-  B2_WARP_DIMS(v, (k_warp_step_ls<real, WM, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
-                      (const WarpImage<real>*)image, to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter)));
+  int *cost = nullptr, *perm = nullptr;
+  if (sortbuf && wpb > 1 && nsteps > 0) {  // lock-step blocks: order the queue by the envs' last Newton iteration counts
+    int* hist = (int*)sortbuf;
+    cost = hist + 64; perm = cost + N;
+    if ((e = cudaMemsetAsync(hist, 0, 64 * sizeof(int), s)) != cudaSuccess) return (int)e;
+    int sb = (N + 255) / 256;
+    if (sb > 148 * 4) sb = 148 * 4;
+    k_cost_hist<kCostBins><<<sb, 256, 0, s>>>(cost, N, hist);
+    k_cost_scatter<kCostBins><<<sb, 256, 0, s>>>(cost, N, hist, hist + 32, perm);
+  }
+  B2_WARP_DIMS(v, (k_warp_step_ls<real, WM, B2_WARP_LS_MODE><<<blocks, wpb * 32, smem, s>>>(
+                      (const WarpImage<real>*)image, to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter,
+                      perm, cost)));
   return (int)cudaGetLastError();
 }
 // FD linearisation on the warp engine: same scratch slots as the step plan (wpb warps per block)
@@ -203,12 +224,12 @@ int B2_FN(b2k_warp_linearize)(const void* image, const b2m_view* v, const b2_sta
   int per_sm = 0, dev = 0, sms = 0, rc = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_linearize<real, WM, 1>, wpb, smem, &per_sm)));
+  B2_WARP_DIMS(v, (rc = warp_occupancy(k_warp_linearize<real, WM, B2_WARP_LS_MODE>, wpb, smem, &per_sm)));
   if (rc) return (int)cudaErrorLaunchOutOfResources;
   if (blocks > sms * per_sm) blocks = sms * per_sm;  // persistent: never more blocks than fit at once (scratch slots are per block)
   cudaError_t e = cudaMemsetAsync(counter, 0, sizeof(int), (cudaStream_t)stream);
   if (e != cudaSuccess) return (int)e;
-  B2_WARP_DIMS(v, (k_warp_linearize<real, WM, 1><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
+  B2_WARP_DIMS(v, (k_warp_linearize<real, WM, B2_WARP_LS_MODE><<<blocks, wpb * 32, smem, (cudaStream_t)stream>>>(
                       (const WarpImage<real>*)image, to_dev<real>(st), N, (real)eps, centered, (real*)A, (real*)B, (real*)jscratch, (int*)counter)));
   return (int)cudaGetLastError();
 }

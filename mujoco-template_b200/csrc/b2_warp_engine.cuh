@@ -171,31 +171,40 @@ __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int
 // version of r01 spent 9 % of all stall samples on its load -> load -> FMA -> store chain).
 template <typename T, class M>
 __device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, int lane) {
+  // The (l, s) pairs of a pivot form a triangle, and chains are short (humanoid: m <= 14): the warp is folded into 32 / W
+  // groups of W > m lanes, every group holds the same row-k registers, and group h takes the offsets s = h, h + 32 / W, ...
+  // -- a quarter (m < 8) or half (m < 16) of the sweeps of the one-group form, every entry still updated exactly once per
+  // pivot with the same operands (bit-identical).
   const int nv = mdl.nv();
   constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
-  int m = mdl.dof_nanc(nv - 1), i = lane < m ? mdl.dof_anclist((nv - 1) * LS + lane) : 0;
+  int m = mdl.dof_nanc(nv - 1);
+  int wl = m < 8 ? 3 : (m < 16 ? 4 : 5);  // log2 W
+  int i = (lane & ((1 << wl) - 1)) < m ? mdl.dof_anclist((nv - 1) * LS + (lane & ((1 << wl) - 1))) : 0;
 #pragma unroll 1
   for (int k = nv - 1; k >= 0; k--) {
     // prefetch the next pivot's list (independent of this pivot's arithmetic)
     const int mn = k > 0 ? mdl.dof_nanc(k - 1) : 0;
-    const int in = (k > 0 && lane < mn) ? mdl.dof_anclist((k - 1) * LS + lane) : 0;
+    const int wln = mn < 8 ? 3 : (mn < 16 ? 4 : 5);
+    const int ln = lane & ((1 << wln) - 1);
+    const int in = (k > 0 && ln < mn) ? mdl.dof_anclist((k - 1) * LS + ln) : 0;
+    const int l = lane & ((1 << wl) - 1), h = lane >> wl, hs = 32 >> wl;
     const int kk = tri(k, 0);
     const T dkk = LDp[kk + k];
-    const T rk = lane < m ? LDp[kk + i] : T(1);
-    const T q = rk / dkk;  // lanes < m: t_l; lane m: 1 / d_k
+    const T rk = l < m ? LDp[kk + i] : T(1);
+    const T q = rk / dkk;  // l < m: t_l; lane m (group 0, W > m): 1 / d_k
     if (lane == m) dinv[k] = q;
     if (m) {
       const int rowbase = tri(i, 0);
 #pragma unroll 2
-      for (int s = 0; s < m; s++) {
-        const T rks = __shfl_down_sync(0xffffffffu, rk, s);
-        const int js = __shfl_down_sync(0xffffffffu, i, s);
-        if (lane + s < m) LDp[rowbase + js] -= q * rks;
+      for (int s = h; s - h < m; s += hs) {
+        const T rks = __shfl_sync(0xffffffffu, rk, l + s);  // group 0 holds the row; l + s < m <= W there when it is used
+        const int js = __shfl_sync(0xffffffffu, i, l + s);
+        if (l + s < m) LDp[rowbase + js] -= q * rks;
       }
       if (lane < m) LDp[kk + i] = q;
     }
     __syncwarp();
-    m = mn; i = in;
+    m = mn; i = in; wl = wln;
   }
 }
 
@@ -967,9 +976,9 @@ struct WarpEnv {
     if (p2.cost <= p1.cost && p2.cost < p0.cost) return p2.alpha;
     return 0;
   }
-  // cost, constraint force, gradient, and the Newton direction H^-1 grad (H = M + J' D_active J)
-  B2_DEV void newton_refresh() {
-    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
+  // cost, constraint force and gradient at the current iterate ...
+  B2_DEV void newton_gradient() {
+    const int nv = mdl.nv();
     cost = row_cost(Jaref);
     WFOR(k, nv) {
       T f = 0;
@@ -981,6 +990,12 @@ struct WarpEnv {
     WFOR(k, nv) { g += (Ma[k] - f_smooth[k]) * (qacc[k] - a_smooth[k]); grad[k] = Ma[k] - f_smooth[k] - f_con[k]; }
     gauss = T(0.5) * warp_sum(g);
     cost += gauss;
+  }
+  // ... and the Newton direction H^-1 grad (H = M + J' D_active J).  Only called when the iterate is not accepted as
+  // converged: the round that detects convergence needs cost and gradient but no direction, which saves one of the
+  // ~4.5 Hessian factorisations of a humanoid step (same iterates, bit for bit).
+  B2_DEV void newton_direction() {
+    const int nv = mdl.nv(), np = nv * (nv + 1) / 2;
     // Hessian, packed lower triangle in LDp: each lane owns entries e = lane, lane + 32, ...
     // It only depends on the active set: when no row changed state since the last refresh the
     // factor in LDp is still valid (bit-identical to refactoring) and is reused.
@@ -1124,17 +1139,18 @@ struct WarpEnv {
       if (LS == 1) { if (!group_or(!done)) break; }
       else if (done) break;
       if (!done) {
-        newton_refresh();
+        newton_gradient();
         if (!first) {
           const T gn = dotv(grad, grad);
           niter++;
           if (scale * (old - cost) < mdl.tolerance() || scale * sqrt(gn) < mdl.tolerance()) done = true;
         }
+        if (!done && niter >= mdl.iterations()) done = true;  // iteration cap: the iterate stands, no further search
         if (!done) {
+          newton_direction();
           first = false;
           WFOR(k, nv) search[k] = -Mgrad[k];
           __syncwarp();
-          if (niter >= mdl.iterations()) done = true;
         }
       }
       stage_sync<LS == 1>();

@@ -4,9 +4,11 @@
 #include "b2_warp_engine.cuh"
 
 // Register budget (__maxnreg__): an SM sub-partition has 16 K registers, so 168 registers per thread allow three resident
-// warps per scheduler (12 per SM), 128 allow four; B2_WARP_MAXNREG is set by the build (csrc/Makefile).
+// warps per scheduler (12 per SM), 128 allow four.  The kernel is latency-bound: 128 registers (about 100 B of spills per
+// thread) with lock-step blocks of four warps measured +18 % over 168 registers with blocks of two on the humanoid
+// (round 2, gpurun A/B: 5.89e6 -> 6.98e6 env-steps/s; 112 and 96 registers spill too much).
 #ifndef B2_WARP_MAXNREG
-#define B2_WARP_MAXNREG 168
+#define B2_WARP_MAXNREG 128
 #endif
 #ifndef B2_WARP_MAXNREG_RUNTIME
 #define B2_WARP_MAXNREG_RUNTIME 200  // runtime sizes keep ~40 workspace pointers live: fewer registers only spill them
@@ -38,6 +40,50 @@ B2_DEV void warp_store_solution(const WarpEnv<T, M>& env, const DerivedDev<T>& o
   }
 }
 
+// Cost-ordered work queue.  The warps of a lock-step block leave the Newton loop together, i.e. a block pays for the
+// slowest of its envs; an env's Newton iteration count changes slowly from step to step, so the envs are handed out in
+// descending order of the count of their previous step (counting sort into kCostBins bins: histogram, then a scatter
+// that reserves a range per block and bin): block mates then need about the same number of rounds, and the expensive
+// envs start first.  Which env a warp runs has no effect on that env's result.
+constexpr int kCostBins = 16;
+template <int BINS>
+__global__ void __launch_bounds__(256) k_cost_hist(const int* __restrict__ cost, int N, int* hist) {
+  __shared__ int h[BINS];
+  if (threadIdx.x < BINS) h[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
+    const int c = cost[i];
+    atomicAdd(&h[c < BINS - 1 ? (c > 0 ? c : 0) : BINS - 1], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < BINS && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+template <int BINS>
+__global__ void __launch_bounds__(256) k_cost_scatter(const int* __restrict__ cost, int N, const int* __restrict__ hist, int* cursor, int* perm) {
+  __shared__ int base[BINS], cnt[BINS], off[BINS];
+  if (threadIdx.x < BINS) {  // descending cost: bin b starts after all bins above it
+    int s = 0;
+    for (int b = BINS - 1; b > (int)threadIdx.x; b--) s += hist[b];
+    base[threadIdx.x] = s;
+  }
+  for (int i0 = blockIdx.x * blockDim.x; i0 < N; i0 += gridDim.x * blockDim.x) {
+    if (threadIdx.x < BINS) cnt[threadIdx.x] = 0;
+    __syncthreads();
+    const int i = i0 + threadIdx.x;
+    int b = 0, r = 0;
+    if (i < N) {
+      const int c = cost[i];
+      b = c < BINS - 1 ? (c > 0 ? c : 0) : BINS - 1;
+      r = atomicAdd(&cnt[b], 1);
+    }
+    __syncthreads();
+    if (threadIdx.x < BINS) off[threadIdx.x] = cnt[threadIdx.x] ? atomicAdd(&cursor[threadIdx.x], cnt[threadIdx.x]) : 0;
+    __syncthreads();
+    if (i < N) perm[base[b] + off[b] + r] = i;
+    __syncthreads();
+  }
+}
+
 // nsteps x mj_step (nsteps == 0: mj_forward), one env per warp, persistent over envs: the first gridDim * wpb envs are
 // assigned statically, the rest through an atomic work queue (env costs differ with contacts and Newton iterations).
 // The warps of a block run their envs stage by stage behind the block barrier (WarpEnv::forward<LS>), so that one
@@ -45,7 +91,8 @@ B2_DEV void warp_store_solution(const WarpEnv<T, M>& env, const DerivedDev<T>& o
 // and discard the result, so that every warp reaches every barrier.
 template <typename T, class M, int LS>
 __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* __restrict__ img, StateDev<T> st, DerivedDev<T> out,
-                                                            int want_derived, int N, int nsteps, T* jscratch, int* queue) {
+                                                            int want_derived, int N, int nsteps, T* jscratch, int* queue,
+                                                            const int* __restrict__ perm, int* cost) {
   extern __shared__ double b2_smem[];
   __shared__ int s_next;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -58,7 +105,8 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
   int first = blockIdx.x * wpb;
   while (first < N) {
     const bool mine = first + wib < N;
-    const int e = mine ? first + wib : N - 1;
+    const int slot = mine ? first + wib : N - 1;
+    const int e = perm ? perm[slot] : slot;  // cost-ordered queue (see k_cost_scatter)
     WFOR(k, env.mdl.nq()) env.qpos[k] = st.qpos[(size_t)k * N + e];
     WFOR(k, env.mdl.nv()) { env.qvel[k] = st.qvel[(size_t)k * N + e]; env.warm[k] = st.warm ? st.warm[(size_t)k * N + e] : T(0); }
     WFOR(k, env.mdl.nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
@@ -90,6 +138,9 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
       if (st.warm) WFOR(k, env.mdl.nv()) st.warm[(size_t)k * N + e] = env.warm[k];
       if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
     }
+    // queue key of the next step: Newton rounds of this one, envs with dense (non-chain) rows -- three times the
+    // factorisation work per round -- in the upper half of the bins
+    if (mine && cost && lane == 0) cost[e] = frozen ? 0 : ((env.nefc && !env.rows_tree) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
     if (threadIdx.x == 0) s_next = nw + atomicAdd(queue, wpb);
     __syncthreads();
     first = s_next;

@@ -160,17 +160,26 @@ def emit_c_header() -> str:
         A(f"  const {'int' if dt == 'i' else 'double'}* {name};  /* {cnt} x {w} */")
     A("} b2m_view;")
     A("")
-    A("/* returns 0 on success, nonzero on malformed blob */")
+    A("/* returns 0 on success, nonzero on a malformed blob.  Everything is checked against nbytes before it is read:")
+    A(" * header and offset table inside the blob, dimensions non-negative and bounded, every array's recorded type and")
+    A(" * length equal to what the dimensions imply, its bytes inside the blob, and every index array within range of the")
+    A(" * arrays it indexes (codes: 1 magic, 2 version, 3 field counts, 4 truncated, 5 dimension, 6 table entry, 7 index). */")
     A("static inline int b2m_view_init(b2m_view* v, const void* blob, size_t nbytes) {")
     A("  const unsigned char* base = (const unsigned char*)blob;")
     A("  const int32_t* h = (const int32_t*)blob;")
     A("  if (nbytes < 20 || h[0] != (int32_t)B2M_MAGIC) return 1;")
     A("  if (h[1] != B2M_VERSION) return 2;")
     A(f"  if (h[2] != {len(ISCALARS)} || h[3] != {sum(w for _, w in DSCALARS)} || h[4] != {len(ARRAYS)}) return 3;")
+    nd = sum(w for _, w in DSCALARS)
+    off0 = (5 + len(ISCALARS)) * 4
+    off0 += (8 - off0 % 8) % 8
+    table_end = off0 + nd * 8 + len(ARRAYS) * 12
+    A(f"  if (nbytes < {table_end}) return 4;  /* scalars + offset table */")
     A("  const int32_t* is = h + 5;")
+    A(f"  for (int i = 0; i < {len(ISCALARS)}; i++) if (is[i] < 0 || is[i] > (1 << 20)) return 5;")
     for i, k in enumerate(ISCALARS):
         A(f"  v->{k} = is[{i}];")
-    A(f"  size_t off = (5 + {len(ISCALARS)}) * 4; if (off % 8) off += 8 - off % 8;")
+    A(f"  size_t off = {off0};")
     A("  const double* ds = (const double*)(base + off);")
     j = 0
     for name, w in DSCALARS:
@@ -182,10 +191,59 @@ def emit_c_header() -> str:
         j += w
     A(f"  off += {j} * 8;")
     A("  const int32_t* tab = (const int32_t*)(base + off);")
+    A("#define B2M_ARRAY(i, field, ctype, isdouble, count)                                                     \\")
+    A("  do {                                                                                                \\")
+    A("    const long long n_ = (long long)(count);                                                          \\")
+    A("    const int32_t o_ = tab[3 * (i) + 2];                                                              \\")
+    A("    if (tab[3 * (i)] != (isdouble) || (long long)tab[3 * (i) + 1] != n_ || o_ < 0 || (o_ & 7)) return 6; \\")
+    A("    if ((unsigned long long)o_ + (unsigned long long)n_ * sizeof(ctype) > (unsigned long long)nbytes) return 4; \\")
+    A("    v->field = (const ctype*)(base + o_);                                                              \\")
+    A("  } while (0)")
     for i, (name, dt, w, cnt) in enumerate(ARRAYS):
         ctype = "int" if dt == "i" else "double"
-        A(f"  if ((size_t)tab[{3 * i + 2}] > nbytes) return 4;")
-        A(f"  v->{name} = (const {ctype}*)(base + tab[{3 * i + 2}]);")
+        width = f"v->{w}" if isinstance(w, str) else str(w)
+        A(f"  B2M_ARRAY({i}, {name}, {ctype}, {0 if dt == 'i' else 1}, (long long)v->{cnt} * {width});")
+    A("#undef B2M_ARRAY")
+    A("  /* index arrays: every id the kernels dereference must lie inside the array it indexes */")
+    A("#define B2M_RANGE(arr, n, lo, hi) for (int i_ = 0; i_ < (n); i_++) if (v->arr[i_] < (lo) || v->arr[i_] >= (hi)) return 7")
+    A("  if (v->nbody < 1 || v->nsensordata > (1 << 16)) return 5;")
+    A("  for (int i = 0; i < v->nbody; i++) {")
+    A("    if (v->body_parentid[i] < 0 || v->body_parentid[i] > (i ? i - 1 : 0)) return 7;")
+    A("    if (v->body_jntnum[i] < 0 || v->body_dofnum[i] < 0) return 7;")
+    A("    if (v->body_jntnum[i] && (v->body_jntadr[i] < 0 || v->body_jntadr[i] + v->body_jntnum[i] > v->njnt)) return 7;")
+    A("    if (v->body_dofnum[i] && (v->body_dofadr[i] < 0 || v->body_dofadr[i] + v->body_dofnum[i] > v->nv)) return 7;")
+    A("  }")
+    A("  B2M_RANGE(body_rootid, v->nbody, 0, v->nbody);")
+    A("  B2M_RANGE(body_weldid, v->nbody, 0, v->nbody);")
+    A("  B2M_RANGE(jnt_type, v->njnt, 0, 4);")
+    A("  B2M_RANGE(jnt_bodyid, v->njnt, 0, v->nbody);")
+    A("  for (int j = 0; j < v->njnt; j++) {")
+    A("    const int t = v->jnt_type[j], wq = t == 0 ? 7 : (t == 1 ? 4 : 1), wv = t == 0 ? 6 : (t == 1 ? 3 : 1);")
+    A("    if (v->jnt_qposadr[j] < 0 || v->jnt_qposadr[j] + wq > v->nq || v->jnt_dofadr[j] < 0 || v->jnt_dofadr[j] + wv > v->nv) return 7;")
+    A("  }")
+    A("  B2M_RANGE(dof_bodyid, v->nv, 0, v->nbody);")
+    A("  B2M_RANGE(dof_jntid, v->nv, 0, v->njnt);")
+    A("  for (int i = 0; i < v->nv; i++) if (v->dof_parentid[i] < -1 || v->dof_parentid[i] >= i) return 7;")
+    A("  B2M_RANGE(geom_bodyid, v->ngeom, 0, v->nbody);")
+    A("  B2M_RANGE(geom_type, v->ngeom, 0, 8);")
+    A("  B2M_RANGE(site_bodyid, v->nsite, 0, v->nbody);")
+    A("  for (int t = 0; t < v->ntendon; t++)")
+    A("    if (v->tendon_adr[t] < 0 || v->tendon_num[t] < 0 || v->tendon_adr[t] + v->tendon_num[t] > v->nwrap) return 7;")
+    A("  B2M_RANGE(wrap_jntid, v->nwrap, 0, v->njnt);")
+    A("  for (int a = 0; a < v->nu; a++) {")
+    A("    const int t = v->actuator_trntype[a], id = v->actuator_trnid[a];")
+    A("    if (t == 0 ? (id < 0 || id >= v->njnt) : (t == 4 ? (id < 0 || id >= v->nsite) : 1)) return 7;")
+    A("  }")
+    A("  B2M_RANGE(pair_geom1, v->npair, 0, v->ngeom);")
+    A("  B2M_RANGE(pair_geom2, v->npair, 0, v->ngeom);")
+    A("  B2M_RANGE(pair_dim, v->npair, 1, 7);")
+    A("  for (int s = 0; s < v->nsensor; s++) {")
+    A("    const int ot = v->sensor_objtype[s], id = v->sensor_objid[s];")
+    A("    const int lim = ot == 1 || ot == 2 ? v->nbody : (ot == 3 ? v->njnt : (ot == 5 ? v->ngeom : (ot == 6 ? v->nsite : 0)));")
+    A("    if (id < 0 || id >= lim) return 7;")
+    A("    if (v->sensor_dim[s] < 0 || v->sensor_adr[s] < 0 || v->sensor_adr[s] + v->sensor_dim[s] > v->nsensordata) return 7;")
+    A("  }")
+    A("#undef B2M_RANGE")
     A("  return 0;")
     A("}")
     A("#endif")

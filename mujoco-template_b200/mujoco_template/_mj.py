@@ -439,6 +439,11 @@ class MjData(_DataBase):
         self.subtree_com = b.array("subtree_com")[:, 0].reshape(m.nbody, 3)
         self.qfrc_inverse = b.array("qfrc_inverse")[:, 0]
         self.actuator_moment = b.array("actuator_moment")[:, 0].reshape(m.nu, m.nv)  # dense nu x nv
+        # MuJoCo >= 3.2 stores the moment matrix row-compressed; callers densify it with mju_sparse2dense (reference
+        # setpoints.py:37-47, examples/humanoid/controllers/lqr.py:76-82).  Here every row is stored in full.
+        self.moment_rownnz = np.full(m.nu, m.nv, dtype=np.int32)
+        self.moment_rowadr = np.arange(m.nu, dtype=np.int32) * m.nv
+        self.moment_colind = np.tile(np.arange(m.nv, dtype=np.int32), m.nu)
         self.act = np.zeros(0)
         self.sensordata = b.array("sensordata")[:, 0]
         self.time = 0.0
@@ -590,6 +595,16 @@ def mj_jacBodyCom(model, data, jacp, jacr, body): _jac(model, data, _capi.JAC_BO
 def mj_jacSubtreeCom(model, data, jacp, body): _jac(model, data, _capi.JAC_SUBTREECOM, body, jacp, None)
 
 
+def mju_sparse2dense(res: np.ndarray, mat: np.ndarray, rownnz: np.ndarray, rowadr: np.ndarray, colind: np.ndarray) -> None:
+    """Expand a row-compressed matrix into the dense ``res`` (nr x nc), as mujoco.mju_sparse2dense does."""
+    res[...] = 0.0
+    mat = np.asarray(mat).reshape(-1)
+    colind = np.asarray(colind).reshape(-1)
+    for r in range(res.shape[0]):
+        a, n = int(rowadr[r]), int(rownnz[r])
+        res[r, colind[a:a + n]] = mat[a:a + n]
+
+
 def mj_subtreeCoM(model: MjModel, data: _DataBase) -> None:
     """``data.subtree_com`` is already produced by every forward pass; nothing to recompute."""
     return None
@@ -598,5 +613,5 @@ def mj_subtreeCoM(model: MjModel, data: _DataBase) -> None:
 __all__ = [
     "MjModel", "MjData", "BatchData", "NativeBackend", "mjtObj", "mjtJoint", "mj_name2id", "mj_id2name", "mj_resetData",
     "mj_resetDataKeyframe", "mj_forward", "mj_step", "mj_inverse", "mjd_transitionFD", "mj_integratePos", "mj_differentiatePos",
-    "mj_jacSite", "mj_jacBody", "mj_jacBodyCom", "mj_jacSubtreeCom", "mj_subtreeCoM",
+    "mj_jacSite", "mj_jacBody", "mj_jacBodyCom", "mj_jacSubtreeCom", "mj_subtreeCoM", "mju_sparse2dense",
 ]

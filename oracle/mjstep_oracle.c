@@ -27,6 +27,12 @@
 #include "../include/b2_model_layout.h"
 #include "orc_math.h"
 
+/* The op-counting build (make liborc_count.so, orc_count.h) compiles this file as C++ with `double` replaced by a
+ * counting class; the exported names stay C names. */
+#ifdef __cplusplus
+extern "C" {
+#endif
+
 enum { JNT_FREE = 0, JNT_BALL = 1, JNT_SLIDE = 2, JNT_HINGE = 3 };
 enum { GEOM_PLANE = 0, GEOM_SPHERE = 2, GEOM_CAPSULE = 3, GEOM_ELLIPSOID = 4, GEOM_BOX = 6 };
 enum { TRN_JOINT = 0, TRN_SITE = 4 };
@@ -1540,3 +1546,13 @@ void orc_batch_rollout(const orc_model* m, int N, double* qpos, double* qvel, do
   for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
   free(th); free(jobs);
 }
+
+#ifdef ORC_COUNT_OPS
+void orc_count_reset(void) { memset(&g_orc_ops, 0, sizeof(g_orc_ops)); }
+void orc_count_read(unsigned long long* out) {
+  out[0] = g_orc_ops.add; out[1] = g_orc_ops.mul; out[2] = g_orc_ops.div; out[3] = g_orc_ops.sqrt_; out[4] = g_orc_ops.trans;
+}
+#endif
+#ifdef __cplusplus
+}
+#endif

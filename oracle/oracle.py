@@ -19,20 +19,53 @@ _LIB = None
 _dp = C.POINTER(C.c_double)
 
 
-def build(force: bool = False) -> str:
-    so = os.path.join(_HERE, "liborc.so")
-    src = [os.path.join(_HERE, f) for f in ("mjstep_oracle.c", "orc_math.h")]
+def _cpu_stamp() -> str:
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown-cpu"
+
+
+def build(force: bool = False, variant: str = "strict") -> str:
+    """strict: -O2 -ffp-contract=off, the parity oracle.  count: the op-counting build (orc_count.h).  fast: -O3
+    -march=native with contraction, ONLY for bench.py's CPU arm -- rebuilt whenever the host CPU differs from the one it
+    was compiled on (the file travels from the build box to the GPU box)."""
+    target = {"strict": "liborc.so", "count": "liborc_count.so", "fast": os.path.join("_fast", "liborc_fast.so")}[variant]
+    so = os.path.join(_HERE, target)
+    src = [os.path.join(_HERE, f) for f in ("mjstep_oracle.c", "orc_math.h", "orc_count.h")]
     src.append(os.path.join(_HERE, "..", "include", "b2_model_layout.h"))
     stale = not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src)
+    stamp = os.path.join(_HERE, "_fast", "cpu.txt")
+    if variant == "fast" and not stale:
+        stale = not os.path.exists(stamp) or open(stamp).read() != _cpu_stamp()
     if force or stale:
-        subprocess.run(["make", "-C", _HERE, "-B", "liborc.so"], check=True, capture_output=True)
+        subprocess.run(["make", "-C", _HERE, "-B", target], check=True, capture_output=True)
+        if variant == "fast":
+            open(stamp, "w").write(_cpu_stamp())
     return so
 
 
-def lib() -> C.CDLL:
+_LIBS: dict[str, C.CDLL] = {}
+
+
+def lib(variant: str = "strict") -> C.CDLL:
     global _LIB
+    if variant != "strict":
+        if variant not in _LIBS:
+            _LIBS[variant] = _declare(C.CDLL(build(variant=variant)))
+            if variant == "count":
+                _LIBS[variant].orc_count_read.argtypes = [C.POINTER(C.c_ulonglong)]
+        return _LIBS[variant]
     if _LIB is None:
-        L = C.CDLL(build())
+        _LIB = _declare(C.CDLL(build()))
+    return _LIB
+
+
+def _declare(L: C.CDLL) -> C.CDLL:
+    if True:
         L.orc_model_create.restype = C.c_void_p
         L.orc_model_create.argtypes = [C.c_char_p, C.c_size_t]
         L.orc_model_free.argtypes = [C.c_void_p]
@@ -63,8 +96,30 @@ def lib() -> C.CDLL:
         L.orc_setconst_check.argtypes = [C.c_void_p, _dp, _dp, _dp]
         L.orc_batch_rollout.argtypes = [C.c_void_p, C.c_int, _dp, _dp, _dp, _dp, C.c_int, C.c_int, C.c_double,
                                         _dp, _dp, C.c_int]
-        _LIB = L
-    return _LIB
+    return L
+
+
+def op_count(blob: bytes, dims: dict, qpos, qvel, ctrl, *, linearize: bool = False, warm_steps: int = 1) -> dict:
+    """Algorithmic operation count of one mj_step (or one mjd_transitionFD + step) of the oracle on the given state:
+    runs `warm_steps` uncounted steps first (so that qacc_warmstart is a realistic one), then counts one.  Weights as in
+    SURVEY.md section 8(d): add / mul / div / sqrt = 1 flop, transcendental call = 20."""
+    om = OracleModel(blob, dims, variant="count")
+    od = OracleData(om)
+    od.qpos[:] = qpos; od.qvel[:] = qvel
+    if od.ctrl.size:
+        od.ctrl[:] = ctrl
+    for _ in range(warm_steps):
+        od.step()
+    L = om._L
+    L.orc_count_reset()
+    if linearize:
+        od.transition_fd(1e-6, True)
+    od.step()
+    c = (C.c_ulonglong * 5)()
+    L.orc_count_read(c)
+    add, mul, div, sq, tr = (int(x) for x in c)
+    return {"add": add, "mul": mul, "div": div, "sqrt": sq, "transcendental": tr, "flops": add + mul + div + sq + 20 * tr,
+            "ncon": int(od.ncon), "nefc": int(od.nefc), "solver_iter": int(od.solver_iter)}
 
 
 def _p(a: np.ndarray | None):
@@ -72,8 +127,8 @@ def _p(a: np.ndarray | None):
 
 
 class OracleModel:
-    def __init__(self, blob: bytes, dims: dict):
-        self._L = lib()
+    def __init__(self, blob: bytes, dims: dict, variant: str = "strict"):
+        self._L = lib(variant)
         self.h = self._L.orc_model_create(blob, len(blob))
         if not self.h:
             raise RuntimeError("oracle rejected model blob")

@@ -98,3 +98,74 @@ def test_jit_specialize_builds_and_registers(tmp_path, monkeypatch):
     assert jit_specialize(model, "cpu_side_check") == so  # cached
     big = mj.MjModel.from_compiled(os.path.join(os.path.dirname(__file__), "golden", "models", "humanoid.b2m"))
     assert jit_specialize(big) is None  # nv = 27: stays on the generic / warp engine
+
+
+def test_model_create_rejects_truncated_and_corrupt_blobs():
+    """b2_model_create validates the whole blob before anything dereferences it (offset table inside the blob, array
+    lengths equal to what the dimensions imply, index arrays in range): truncated or corrupted input gives B2_ERR_BLOB
+    (ConfigError), never an out-of-bounds read."""
+    import struct
+
+    import numpy as np
+
+    from mujoco_template import _capi, _layout
+
+    for name in ("cartpole", "drone", "humanoid"):
+        blob = bytes(load_model(name).blob)
+        assert _capi.NativeModel(blob).handle
+        # every truncation point in the header / table region, and a spread of points in the data region
+        cuts = list(range(0, 1300, 7)) + list(np.linspace(1300, len(blob) - 1, 60).astype(int))
+        for n in cuts:
+            with pytest.raises(_capi.ConfigError):
+                _capi.NativeModel(blob[:n])
+        head = (5 + len(_layout.ISCALARS)) * 4
+        head += (8 - head % 8) % 8
+        table = head + 8 * sum(w for _, w in _layout.DSCALARS)
+        # negative and absurd dimensions
+        for i in range(len(_layout.ISCALARS)):
+            for bad in (-1, 1 << 30):
+                b = bytearray(blob)
+                struct.pack_into("<i", b, 20 + 4 * i, bad)
+                if _layout.ISCALARS[i] in ("integrator", "iterations", "ls_iterations", "has_fluid", "has_dofdamping", "disableflags",
+                                           "nmocap_unused") and bad > 0:
+                    continue
+                with pytest.raises(_capi.ConfigError):
+                    _capi.NativeModel(bytes(b))
+        # a dimension that disagrees with the recorded array lengths
+        b = bytearray(blob)
+        struct.pack_into("<i", b, 20 + 4 * _layout.ISCALARS.index("nbody"), struct.unpack_from("<i", blob, 20 + 4 * 3)[0] + 1)
+        with pytest.raises(_capi.ConfigError):
+            _capi.NativeModel(bytes(b))
+        # offsets pointing outside the blob, negative, or misaligned; wrong type tag
+        for k in range(0, len(_layout.ARRAYS), 5):
+            for field, bad in ((2, len(blob) + 8), (2, -8), (2, 4), (0, 7)):
+                b = bytearray(blob)
+                n = struct.unpack_from("<i", blob, table + 12 * k + 4)[0]
+                if n == 0 and field == 2 and bad in (len(blob) + 8,):
+                    pass  # zero-length arrays must still have an in-range offset
+                struct.pack_into("<i", b, table + 12 * k + 4 * field, bad)
+                with pytest.raises(_capi.ConfigError):
+                    _capi.NativeModel(bytes(b))
+        # out-of-range ids in the index arrays the kernels dereference
+        names = [a[0] for a in _layout.ARRAYS]
+        for arr in ("body_parentid", "jnt_bodyid", "jnt_qposadr", "jnt_dofadr", "dof_bodyid", "dof_parentid", "geom_bodyid", "pair_geom1",
+                    "pair_geom2", "actuator_trnid"):
+            k = names.index(arr)
+            n, off = struct.unpack_from("<ii", blob, table + 12 * k + 4)
+            if n == 0:
+                continue
+            for bad in (10_000, -5):
+                b = bytearray(blob)
+                struct.pack_into("<i", b, off + 4 * (n - 1), bad)
+                with pytest.raises(_capi.ConfigError):
+                    _capi.NativeModel(bytes(b))
+    rng = np.random.default_rng(0)
+    blob = bytes(load_model("humanoid").blob)
+    for _ in range(300):  # random byte flips in the header / table: either rejected or still a consistent model -- never a crash
+        b = bytearray(blob)
+        for pos in rng.integers(0, 1300, 3):
+            b[pos] = int(rng.integers(0, 256))
+        try:
+            _capi.NativeModel(bytes(b))
+        except _capi.ConfigError:
+            pass
