@@ -13,7 +13,14 @@
  *  - Pointers may be device memory or page-locked host memory mapped into the device
  *    address space (the single-env `Env` uses the latter for zero-copy NumPy views).
  *  - Calls are asynchronous on `stream` (a cudaStream_t passed as void*; NULL = legacy
- *    default stream) unless stated otherwise.  The library never allocates in b2_step.
+ *    default stream) unless stated otherwise.  Device memory is allocated in b2_model_create /
+ *    b2_batch_create (model images, warp-engine scratch) and on the FIRST call of the entry points
+ *    that need extra buffers (b2_control_tick / b2_step_lazy: shadow state; b2_step_host: staging;
+ *    b2_lqr_set_gain); b2_step, b2_forward, b2_linearize and b2_jacobian never allocate.
+ *  - No process-wide model state: a model's constants live in per-model device images handed to
+ *    every launch, so batches of different models can be driven from different threads and streams,
+ *    and a captured CUDA graph replays with the model it was captured with.  One b2_batch must not be
+ *    used from two threads at once (its scratch is per batch).
  *  - Every function returns B2_OK (0) or a negative error code; b2_last_error() returns
  *    a thread-local message.  There is no CPU fallback: without a CUDA device every
  *    compute entry point fails with B2_ERR_CUDA.
@@ -161,11 +168,35 @@ int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int li
 int b2_fp_peak(int precision, int device, double* tflops);
 
 int b2_stream_synchronize(b2_batch* batch, void* stream);
+
+/* Batched discrete-time LQR synthesis on the device: for every env e the stabilising solution P_e of the DARE
+ *     P = A'PA - A'PB (R + B'PB)^-1 B'PA + Q
+ * and the gain K_e = (R + B'PB)^-1 B'PA (u = -K x) from that env's own (A_e, B_e) -- what the reference's example
+ * controllers compute once per system on the host (scipy.linalg.solve_discrete_are + solve:
+ * examples/drone/controllers/lqr.py:350-378, examples/humanoid/controllers/lqr.py:114-115).  A (nx, nx, nenv) and
+ * B (nx, nu, nenv) are DEVICE arrays in the layout b2_linearize writes (env fastest); K (nu, nx, nenv) and
+ * P (nx, nx, nenv) likewise; Q (nx x nx) and R (nu x nu) are HOST arrays, row-major, shared by all envs.  Structured
+ * doubling iteration, at most `max_doublings` (2^k Riccati steps), stopped when the relative change of P is <= tol.
+ * status (device, nenv ints, may be NULL): doublings used, negative if a pivot underflowed.  Not tied to a batch. */
+int b2_dlqr(int device, int precision, const void* A, const void* B, const double* Q, const double* R, int nx, int nu, int nenv,
+            int max_doublings, double tol, void* K, void* P, int* status, void* stream);
+
+/* Batched recorder sink: one CSV row per selected env and step, in the reference's column layout
+ * (reference logging.py:81-247: time_s, qpos.., qvel.., ctrl.., probe columns).  A recorder is a column table
+ * { array base (device pointer into a (dim, nenv) state / derived array of the batch), row } plus a selection of env
+ * indices; b2_recorder_record gathers one step into `out_slot` (ncol x nsel reals of the batch's precision, env fastest)
+ * in ONE launch, on `stream`, without a host synchronisation.  kind 0: array row, 1: the `time` argument, 2: NaN (the
+ * `ctrl[none]` column of a model without actuators). */
+typedef struct b2_recorder b2_recorder;
+typedef struct b2_record_col { const void* base; int row; int kind; } b2_record_col;
+int b2_recorder_create(b2_batch* batch, const b2_record_col* cols, int ncol, const int* env_index, int nsel, b2_recorder** out);
+int b2_recorder_record(b2_recorder* rec, double time, void* out_slot, void* stream);
+void b2_recorder_destroy(b2_recorder* rec);
 /* number of kernels launched by this library in the calling process (bench gpu_launches) */
 long long b2_launch_count(void);
 /* size class the model was mapped to: 0 tiny, 1 small, 2 large */
 int b2_batch_size_class(const b2_batch* batch);
-/* "generic" (constant-memory model, any MJCF in the subset) or the name of the compiled-in
+/* "generic" / "generic-warp" (runtime model image, any MJCF in the subset) or the name of the compiled-in
  * model-specialised kernel set the batch runs on (selected by blob hash; env B2_DISABLE_SPEC=1
  * forces generic) */
 const char* b2_batch_kernel_variant(const b2_batch* batch);

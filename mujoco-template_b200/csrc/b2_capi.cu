@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -21,9 +22,6 @@ namespace {
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 std::atomic<unsigned long long> g_serial{1};
-std::mutex g_mu;
-// which model image currently sits in constant memory: [device][precision 0/1][size class]
-unsigned long long g_resident[16][2][3];
 
 int fail(int code, const std::string& msg) { g_err = msg; return code; }
 int cuda_fail(cudaError_t e, const char* what) {
@@ -38,11 +36,13 @@ struct b2_model {
   int cls;
   unsigned long long serial;
   const b2::SpecKernels* spec;  // model-specialised FP64 kernels, or nullptr (generic path)
-  // warp engine: the model image (constants + factorisation work lists) in device memory, per device and precision;
-  // kernels get it by pointer, so nothing about a large model is process-wide device state
+  // The model's images in device memory, per device and precision: [.][.][0] the lane engine's (DevModel of the model's
+  // size class), [.][.][1] the warp engine's (constants + factorisation work lists).  Kernels get them by pointer, so
+  // nothing about a model is process-wide device state: batches of different models are independent of each other on
+  // any stream and thread, and a captured graph keeps the image it was captured with.
   mutable std::mutex image_mu;
-  mutable void* warp_image[16][2] = {};
-  mutable unsigned long long warp_image_serial[16][2] = {};
+  mutable void* image[16][2][2] = {};
+  mutable unsigned long long image_serial[16][2][2] = {};
   mutable std::vector<std::pair<int, void*>> retired_images;  // (device, pointer) replaced after a disable-mask change
 };
 
@@ -92,6 +92,8 @@ struct b2_batch {
   int host_graph_launches = 0;
 };
 
+static int b2_batch_setup(b2_batch* b, const void** image);
+
 // The warp engine covers the feature set of large articulated models (humanoid); everything else
 // in the large size class runs on the lane engine.
 static bool warp_engine_supports(const b2m_view& v) {
@@ -140,7 +142,8 @@ void b2_model_destroy(b2_model* m) {
   cudaGetDevice(&cur);
   for (int d = 0; d < 16; d++)
     for (int p = 0; p < 2; p++)
-      if (m->warp_image[d][p]) { cudaSetDevice(d); cudaFree(m->warp_image[d][p]); }
+      for (int k = 0; k < 2; k++)
+        if (m->image[d][p][k]) { cudaSetDevice(d); cudaFree(m->image[d][p][k]); }
   for (auto& r : m->retired_images) { cudaSetDevice(r.first); cudaFree(r.second); }
   cudaSetDevice(cur);
   delete m;
@@ -149,7 +152,7 @@ void b2_model_destroy(b2_model* m) {
 int b2_model_set_actuator_disabled(b2_model* m, const int* disabled, int nu) {
   if (!m || (nu && !disabled) || nu != m->v.nu) return fail(B2_ERR_ARG, "b2_model_set_actuator_disabled: bad arguments");
   m->disabled.assign(disabled, disabled + nu);
-  m->serial = g_serial.fetch_add(1);  // forces a constant-bank refresh
+  m->serial = g_serial.fetch_add(1);  // the device images are rebuilt on their next use
   for (int i = 0; i < nu; i++)
     if (disabled[i] != m->v.actuator_disabled[i]) m->spec = nullptr;  // the specialisation bakes the mask in
   return B2_OK;
@@ -165,6 +168,11 @@ int b2_batch_create(const b2_model* model, int nenv, int device, int precision, 
   b2_batch* b = new (std::nothrow) b2_batch();
   if (!b) return fail(B2_ERR_ARG, "out of host memory");
   b->model = model; b->nenv = nenv; b->device = device; b->precision = precision; b->esz = precision == B2_F64 ? 8 : 4;
+  // everything the step path needs on the device is set up here, so that b2_step / b2_linearize only launch: the model's
+  // images (shared by all batches of the model on this device) and, for large models, the warp engine's plan and scratch
+  const void* image = nullptr;
+  int rc = b2_batch_setup(b, &image);
+  if (rc) { b2_batch_destroy(b); return rc; }
   *out = b;
   return B2_OK;
 }
@@ -190,10 +198,12 @@ const char* b2_batch_kernel_variant(const b2_batch* b) {
 static inline const b2::SpecKernels* active_spec(const b2_batch* b) { return b->model->spec; }
 static inline int prec_index(const b2_batch* b) { return b->precision == B2_F64 ? 0 : 1; }
 
-static int ensure_resident(b2_batch* b, void* stream);
+static int lane_image(b2_batch* b, const void** image);
 
 // decide once per batch whether the large-model warp engine is used; plan its launch and scratch
 static int prepare_warp(b2_batch* b) {
+  cudaError_t e0 = cudaSetDevice(b->device);
+  if (e0 != cudaSuccess) return cuda_fail(e0, "cudaSetDevice");
   if (b->warp_mode >= 0) return B2_OK;
   b->warp_mode = 0;
   if (b->model->cls != 2 || !warp_engine_supports(b->model->v)) return B2_OK;
@@ -217,32 +227,43 @@ static int prepare_warp(b2_batch* b) {
   b->warp_mode = 1; b->warp_wpb = wpb; b->warp_blocks = blocks; b->warp_slots = slots;
   return B2_OK;
 }
-// the model's warp-engine image on this batch's device (uploaded on first use and after a disable-mask change)
-static int warp_image_of(b2_batch* b, const void** out) {
+// The model's image for this batch's device and precision (kind 0: lane engine, 1: warp engine): uploaded on first use
+// (b2_batch_create does that for the kinds the batch will launch) and again after a disable-mask change.
+static int image_of(b2_batch* b, int kind, const void** out) {
   const b2_model* m = b->model;
   const int pi = b->precision == B2_F64 ? 0 : 1, dev = b->device;
   std::lock_guard<std::mutex> lock(m->image_mu);
-  if (!m->warp_image[dev][pi] || m->warp_image_serial[dev][pi] != m->serial) {
-    const size_t bytes = pi == 0 ? b2::b2k_warp_image_bytes_f64() : b2::b2k_warp_image_bytes_f32();
+  if (!m->image[dev][pi][kind] || m->image_serial[dev][pi][kind] != m->serial) {
+    cudaError_t e = cudaSetDevice(dev);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    const size_t bytes = kind == 1 ? (pi == 0 ? b2::b2k_warp_image_bytes_f64() : b2::b2k_warp_image_bytes_f32())
+                                   : (pi == 0 ? b2::b2k_image_bytes_f64(m->cls) : b2::b2k_image_bytes_f32(m->cls));
     std::vector<unsigned char> host(bytes);
-    if (pi == 0) b2::b2k_warp_image_fill_f64(&m->v, m->disabled.data(), host.data());
-    else b2::b2k_warp_image_fill_f32(&m->v, m->disabled.data(), host.data());
+    if (kind == 1) {
+      if (pi == 0) b2::b2k_warp_image_fill_f64(&m->v, m->disabled.data(), host.data());
+      else b2::b2k_warp_image_fill_f32(&m->v, m->disabled.data(), host.data());
+    } else {
+      if (pi == 0) b2::b2k_image_fill_f64(m->cls, &m->v, m->disabled.data(), host.data());
+      else b2::b2k_image_fill_f32(m->cls, &m->v, m->disabled.data(), host.data());
+    }
     void* d = nullptr;
-    cudaError_t e = cudaMalloc(&d, bytes);
-    if (e != cudaSuccess) return cuda_fail(e, "warp-engine model image cudaMalloc");
-    if ((e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return cuda_fail(e, "warp-engine model image upload"); }
-    if (m->warp_image[dev][pi]) m->retired_images.emplace_back(dev, m->warp_image[dev][pi]);  // kernels in flight may still read it
-    m->warp_image[dev][pi] = d;
-    m->warp_image_serial[dev][pi] = m->serial;
+    e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "model image cudaMalloc");
+    if ((e = cudaMemcpy(d, host.data(), bytes, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(d); return cuda_fail(e, "model image upload"); }
+    if (m->image[dev][pi][kind]) m->retired_images.emplace_back(dev, m->image[dev][pi][kind]);  // kernels in flight may still read it
+    m->image[dev][pi][kind] = d;
+    m->image_serial[dev][pi][kind] = m->serial;
   }
-  *out = m->warp_image[dev][pi];
+  *out = m->image[dev][pi][kind];
   return B2_OK;
 }
+static int warp_image_of(b2_batch* b, const void** out) { return image_of(b, 1, out); }
 extern "C" { static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream); }
 
 static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived* derived, int count, int nsteps, const void* gain,
                                void* stream, const b2_state* park = nullptr) {
-  int rc = ensure_resident(b, stream);
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);
   if (rc) return rc;
   if ((rc = prepare_warp(b))) return rc;
   const bool f64 = b->precision == B2_F64;
@@ -256,25 +277,21 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
     return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream)
                : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream);
   }
-  return f64 ? b2::b2k_step_f64(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
-             : b2::b2k_step_f32(b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
+  return f64 ? b2::b2k_step_f64(lane, b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
+             : b2::b2k_step_f32(lane, b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
 }
 
-// make sure this batch's model is the image resident in constant memory on its device
-static int ensure_resident(b2_batch* b, void* stream) {
+// selects the batch's device and hands out the lane-engine image of its model
+static int b2_batch_setup(b2_batch* b, const void** image) {
+  int rc = prepare_warp(b);
+  if (rc || (rc = image_of(b, 0, image))) return rc;
+  if (b->warp_mode == 1) rc = image_of(b, 1, image);
+  return rc;
+}
+static int lane_image(b2_batch* b, const void** image) {
   cudaError_t e = cudaSetDevice(b->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  const int pi = b->precision == B2_F64 ? 0 : 1;
-  std::lock_guard<std::mutex> lock(g_mu);
-  if (g_resident[b->device][pi][b->model->cls] == b->model->serial) return B2_OK;
-  // kernels of another model may still be reading the constant bank on other streams
-  e = cudaDeviceSynchronize();
-  if (e != cudaSuccess) return cuda_fail(e, "cudaDeviceSynchronize");
-  int rc = pi == 0 ? b2::b2k_upload_f64(b->model->cls, &b->model->v, b->model->disabled.data(), stream)
-                   : b2::b2k_upload_f32(b->model->cls, &b->model->v, b->model->disabled.data(), stream);
-  if (rc) return cuda_fail((cudaError_t)rc, "constant-bank model upload");
-  g_resident[b->device][pi][b->model->cls] = b->model->serial;
-  return B2_OK;
+  return image_of(b, 0, image);
 }
 
 #define B2_CHECK_STATE(fn)                                                                         \
@@ -307,8 +324,8 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     rc = k->linearize[prec_index(b)](st, count, b->nenv, eps, centered, A, B, gain, shadow, stream);
   } else {
-    rc = ensure_resident(b, stream);
-    if (rc) return rc;
+    const void* lane = nullptr;
+    if ((rc = lane_image(b, &lane))) return rc;
     // large models on the warp engine: one warp per (column, env) rollout pair (B2_WARP_FD=0: lane engine)
     const char* wfd = getenv("B2_WARP_FD");
     const bool warp_fd = !(wfd && wfd[0] == '0');
@@ -322,8 +339,8 @@ static int do_linearize(b2_batch* b, const b2_state* st, int count, double eps, 
       g_launches++;
       return rc ? cuda_fail((cudaError_t)rc, "warp linearize launch") : B2_OK;
     }
-    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream)
-                                : b2::b2k_linearize_f32(b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream);
+    rc = b->precision == B2_F64 ? b2::b2k_linearize_f64(lane, b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream)
+                                : b2::b2k_linearize_f32(lane, b->model->cls, st, count, b->nenv, ncol, eps, centered, A, B, gain, shadow, stream);
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "linearize launch") : B2_OK;
@@ -359,10 +376,10 @@ int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     rc = k->jacobian[prec_index(b)](st, b->nenv, kind, objid, jacp, jacr, stream);
   } else {
-    rc = ensure_resident(b, stream);
-    if (rc) return rc;
-    rc = b->precision == B2_F64 ? b2::b2k_jacobian_f64(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream)
-                                : b2::b2k_jacobian_f32(b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream);
+    const void* lane = nullptr;
+    if ((rc = lane_image(b, &lane))) return rc;
+    rc = b->precision == B2_F64 ? b2::b2k_jacobian_f64(lane, b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream)
+                                : b2::b2k_jacobian_f32(lane, b->model->cls, st, b->nenv, kind, objid, jacp, jacr, stream);
   }
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_jacobian launch") : B2_OK;
@@ -371,10 +388,11 @@ int b2_jacobian(b2_batch* b, const b2_state* st, int kind, int objid, void* jacp
 int b2_inverse(b2_batch* b, const b2_state* st, const void* qacc, void* qfrc_inverse, void* actuator_moment, void* stream) {
   B2_CHECK_STATE("b2_inverse");
   if (!qfrc_inverse) return fail(B2_ERR_ARG, "b2_inverse: qfrc_inverse is NULL");
-  int rc = ensure_resident(b, stream);  // one-shot setup call: always the generic kernels
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);  // one-shot setup call: always the generic kernels
   if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_inverse_f64(b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream)
-                              : b2::b2k_inverse_f32(b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream);
+  rc = b->precision == B2_F64 ? b2::b2k_inverse_f64(lane, b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream)
+                              : b2::b2k_inverse_f32(lane, b->model->cls, st, b->nenv, qacc, qfrc_inverse, actuator_moment, stream);
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_inverse launch") : B2_OK;
 }
@@ -397,10 +415,11 @@ int b2_lqr_set_gain(b2_batch* b, const double* K, const double* qpos_ref, const 
 }
 
 static int do_lqr_control(b2_batch* b, const b2_state* st, int count, void* stream) {
-  int rc = ensure_resident(b, stream);
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);
   if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_f64(b->model->cls, st, count, b->nenv, b->d_gain, stream)
-                              : b2::b2k_lqr_control_f32(b->model->cls, st, count, b->nenv, b->d_gain, stream);
+  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_f64(lane, b->model->cls, st, count, b->nenv, b->d_gain, stream)
+                              : b2::b2k_lqr_control_f32(lane, b->model->cls, st, count, b->nenv, b->d_gain, stream);
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_lqr_control launch") : B2_OK;
 }
@@ -459,8 +478,8 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
   const b2m_view& v = b->model->v;
   b->shadow_has_prestep = false;
   if (!active_spec(b)) {
-    int rc = ensure_resident(b, stream);
-    if (rc || (rc = prepare_warp(b))) return rc;
+    int rc = prepare_warp(b);
+    if (rc) return rc;
     if (b->warp_mode == 1) {
       // large models: control-law launch, FD on the warp engine, step on the warp engine.  Without a `derived`
       // argument the pre-step state is parked in the shadow arrays for b2_refresh_derived, as in the fused form.
@@ -492,7 +511,7 @@ int b2_step_lazy(b2_batch* b, const b2_state* st, void* stream) {
   if (!st->qacc_warmstart) return fail(B2_ERR_ARG, "b2_step_lazy: state.qacc_warmstart is required");
   int rc;
   if (!active_spec(b)) {
-    if ((rc = ensure_resident(b, stream)) || (rc = prepare_warp(b))) return rc;
+    if ((rc = prepare_warp(b))) return rc;
     if (b->warp_mode == 1) {  // warp engine: park with device-to-device copies
       if ((rc = park_state(b, st, stream))) return rc;
       return do_step(b, st, b->nenv, 1, nullptr, stream);
@@ -519,10 +538,11 @@ int b2_refresh_derived(b2_batch* b, const b2_derived* derived, void* stream) {
 
 int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void* stream) {
   if (!b || !qpos || !qvel) return fail(B2_ERR_ARG, "b2_integrate_pos: null pointer");
-  int rc = ensure_resident(b, stream);
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);
   if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_integrate_pos_f64(b->model->cls, qpos, qvel, dt, b->nenv, stream)
-                              : b2::b2k_integrate_pos_f32(b->model->cls, qpos, qvel, dt, b->nenv, stream);
+  rc = b->precision == B2_F64 ? b2::b2k_integrate_pos_f64(lane, b->model->cls, qpos, qvel, dt, b->nenv, stream)
+                              : b2::b2k_integrate_pos_f32(lane, b->model->cls, qpos, qvel, dt, b->nenv, stream);
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_integrate_pos launch") : B2_OK;
 }
@@ -530,10 +550,11 @@ int b2_integrate_pos(b2_batch* b, void* qpos, const void* qvel, double dt, void*
 int b2_differentiate_pos(b2_batch* b, void* out, double dt, const void* q1, const void* q2, void* stream) {
   if (!b || !out || !q1 || !q2) return fail(B2_ERR_ARG, "b2_differentiate_pos: null pointer");
   if (dt == 0) return fail(B2_ERR_ARG, "b2_differentiate_pos: dt must be nonzero");
-  int rc = ensure_resident(b, stream);
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);
   if (rc) return rc;
-  rc = b->precision == B2_F64 ? b2::b2k_differentiate_pos_f64(b->model->cls, out, dt, q1, q2, b->nenv, stream)
-                              : b2::b2k_differentiate_pos_f32(b->model->cls, out, dt, q1, q2, b->nenv, stream);
+  rc = b->precision == B2_F64 ? b2::b2k_differentiate_pos_f64(lane, b->model->cls, out, dt, q1, q2, b->nenv, stream)
+                              : b2::b2k_differentiate_pos_f32(lane, b->model->cls, out, dt, q1, q2, b->nenv, stream);
   g_launches++;
   return rc ? cuda_fail((cudaError_t)rc, "b2_differentiate_pos launch") : B2_OK;
 }
@@ -575,7 +596,6 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   if (linearize && !direct && ((e = need(&b->d_A, nx * nx * N * es)) || (e = need(&b->d_B, nx * nu1 * N * es)))) return cuda_fail(e, "b2_step_host: cudaMalloc");
   int rc = prepare_warp(b);
   if (rc) return rc;
-  if ((!active_spec(b) || lqr) && (rc = ensure_resident(b, stream))) return rc;  // never switch the constant image mid-pipeline
   // chunking: warp-engine batches and small batches go through in one piece
   // two chunks measured best at N = 65536 (1.72e8 vs 1.55e8 with 4, 0.94e8 with 16): every extra chunk adds ~11 copy nodes
   int nchunk = (b->warp_mode == 1 || N < 4096) ? 1 : 2;
@@ -657,6 +677,91 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   g_launches += b->host_graph_launches;
   e = cudaStreamSynchronize(s0);
   return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
+}
+
+// Batched discrete LQR synthesis (see include/b2mj.h).  Q, R are host arrays shared by all envs; R is inverted here.
+int b2_dlqr(int device, int precision, const void* A, const void* B, const double* Q, const double* R, int nx, int nu, int nenv,
+            int max_doublings, double tol, void* K, void* P, int* status, void* stream) {
+  if (!A || !B || !Q || !R || !K || !P || nx < 1 || nu < 1 || nu > nx || nenv < 1 || max_doublings < 1 || !(tol > 0))
+    return fail(B2_ERR_ARG, "b2_dlqr: bad arguments");
+  if (precision != B2_F64 && precision != B2_F32) return fail(B2_ERR_ARG, "b2_dlqr: precision must be 64 or 32");
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  // Rinv by Gauss-Jordan with partial pivoting (nu x nu, host)
+  std::vector<double> aug((size_t)nu * 2 * nu, 0.0);
+  for (int i = 0; i < nu; i++) { for (int j = 0; j < nu; j++) aug[(size_t)i * 2 * nu + j] = R[i * nu + j]; aug[(size_t)i * 2 * nu + nu + i] = 1.0; }
+  for (int c = 0; c < nu; c++) {
+    int piv = c;
+    for (int r = c + 1; r < nu; r++) if (std::abs(aug[(size_t)r * 2 * nu + c]) > std::abs(aug[(size_t)piv * 2 * nu + c])) piv = r;
+    if (!(std::abs(aug[(size_t)piv * 2 * nu + c]) > 1e-300)) return fail(B2_ERR_ARG, "b2_dlqr: R is singular");
+    if (piv != c) for (int k = 0; k < 2 * nu; k++) std::swap(aug[(size_t)c * 2 * nu + k], aug[(size_t)piv * 2 * nu + k]);
+    const double inv = 1.0 / aug[(size_t)c * 2 * nu + c];
+    for (int k = 0; k < 2 * nu; k++) aug[(size_t)c * 2 * nu + k] *= inv;
+    for (int r = 0; r < nu; r++) if (r != c) { const double f = aug[(size_t)r * 2 * nu + c]; for (int k = 0; k < 2 * nu; k++) aug[(size_t)r * 2 * nu + k] -= f * aug[(size_t)c * 2 * nu + k]; }
+  }
+  const size_t nqr = (size_t)nx * nx + 2 * (size_t)nu * nu, esz = precision == B2_F64 ? 8 : 4;
+  std::vector<unsigned char> host(nqr * esz);
+  for (size_t i = 0; i < nqr; i++) {
+    const double x = i < (size_t)nx * nx ? Q[i] : (i < (size_t)nx * nx + (size_t)nu * nu ? R[i - (size_t)nx * nx]
+                                                   : aug[((i - (size_t)nx * nx - (size_t)nu * nu) / nu) * 2 * nu + nu + (i - (size_t)nx * nx - (size_t)nu * nu) % nu]);
+    if (precision == B2_F64) ((double*)host.data())[i] = x; else ((float*)host.data())[i] = (float)x;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  void* dqr = nullptr;
+  if ((e = cudaMallocAsync(&dqr, nqr * esz, s)) != cudaSuccess) return cuda_fail(e, "b2_dlqr: cudaMallocAsync");
+  if ((e = cudaMemcpyAsync(dqr, host.data(), nqr * esz, cudaMemcpyHostToDevice, s)) != cudaSuccess) { cudaFreeAsync(dqr, s); return cuda_fail(e, "b2_dlqr: upload"); }
+  const int rc = precision == B2_F64 ? b2::b2k_dare_f64(A, B, dqr, nx, nu, nenv, max_doublings, tol, K, P, status, stream)
+                                     : b2::b2k_dare_f32(A, B, dqr, nx, nu, nenv, max_doublings, tol, K, P, status, stream);
+  cudaFreeAsync(dqr, s);
+  g_launches++;
+  if (rc == (int)cudaErrorInvalidValue) return fail(B2_ERR_CAPACITY, "b2_dlqr: nx too large for the shared-memory workspace of one SM");
+  return rc ? cuda_fail((cudaError_t)rc, "b2_dlqr launch") : B2_OK;
+}
+
+struct b2_recorder {
+  b2_batch* batch;
+  void* d_cols;
+  int* d_index;
+  int ncol, nsel;
+};
+
+int b2_recorder_create(b2_batch* b, const b2_record_col* cols, int ncol, const int* env_index, int nsel, b2_recorder** out) {
+  if (!b || !cols || !env_index || !out || ncol < 1 || nsel < 1 || ncol > 65535) return fail(B2_ERR_ARG, "b2_recorder_create: bad arguments");
+  for (int c = 0; c < ncol; c++)
+    if (cols[c].kind < 0 || cols[c].kind > 2 || (cols[c].kind == 0 && (!cols[c].base || cols[c].row < 0)))
+      return fail(B2_ERR_ARG, "b2_recorder_create: bad column " + std::to_string(c));
+  for (int j = 0; j < nsel; j++)
+    if (env_index[j] < 0 || env_index[j] >= b->nenv) return fail(B2_ERR_ARG, "b2_recorder_create: env index out of range");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  b2_recorder* r = new (std::nothrow) b2_recorder();
+  if (!r) return fail(B2_ERR_ARG, "out of host memory");
+  r->batch = b; r->ncol = ncol; r->nsel = nsel; r->d_cols = nullptr; r->d_index = nullptr;
+  static_assert(sizeof(b2_record_col) == 16, "column table layout is shared with the kernel");
+  if ((e = cudaMalloc(&r->d_cols, sizeof(b2_record_col) * ncol)) || (e = cudaMalloc((void**)&r->d_index, sizeof(int) * nsel)) ||
+      (e = cudaMemcpy(r->d_cols, cols, sizeof(b2_record_col) * ncol, cudaMemcpyHostToDevice)) ||
+      (e = cudaMemcpy(r->d_index, env_index, sizeof(int) * nsel, cudaMemcpyHostToDevice))) {
+    b2_recorder_destroy(r);
+    return cuda_fail(e, "b2_recorder_create");
+  }
+  *out = r;
+  return B2_OK;
+}
+int b2_recorder_record(b2_recorder* r, double time, void* out_slot, void* stream) {
+  if (!r || !out_slot) return fail(B2_ERR_ARG, "b2_recorder_record: null pointer");
+  cudaError_t e = cudaSetDevice(r->batch->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  const int rc = r->batch->precision == B2_F64
+                     ? b2::b2k_record_rows_f64(r->d_cols, r->ncol, r->d_index, r->nsel, r->batch->nenv, time, out_slot, stream)
+                     : b2::b2k_record_rows_f32(r->d_cols, r->ncol, r->d_index, r->nsel, r->batch->nenv, time, out_slot, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_recorder_record launch") : B2_OK;
+}
+void b2_recorder_destroy(b2_recorder* r) {
+  if (!r) return;
+  if (r->d_cols) cudaFree(r->d_cols);
+  if (r->d_index) cudaFree(r->d_index);
+  delete r;
 }
 
 int b2_fp_peak(int precision, int device, double* tflops) {

@@ -23,6 +23,11 @@
 
 namespace b2 {
 
+// Runtime providers keep the model image in shared memory and fill it from the per-model image in device memory the launch
+// passes (`image`); static providers (generated, everything folded into the instruction stream) have no load().
+template <class M> B2_DEV auto model_load(const void* image, int) -> decltype(M::load(image)) { M::load(image); }
+template <class M> B2_DEV void model_load(const void*, long) {}
+
 template <typename T> struct StateDev { T *qpos, *qvel, *ctrl, *warm; int* flags; };
 template <typename T> struct DerivedDev { T *xpos, *xquat, *xipos, *geom_xpos, *site_xpos, *subtree_com, *qacc, *qfrc_bias, *sensordata; int *ncon, *nefc, *solver_iter; };
 
@@ -108,7 +113,8 @@ B2_DEV void lqr_law(const LaneEnv<T, D, M>& env, const T* q, const T* v, const T
 // The step loop is rolled: one inlined copy of the physics per kernel.
 template <typename T, class D, class M>
 __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st, DerivedDev<T> out, int want_derived, int count, int N, int nsteps, const T* __restrict__ gain,
-                                                                  StateDev<T> park) {
+                                                                  StateDev<T> park, const void* image = nullptr) {
+  model_load<M>(image, 0);
   // count envs are processed; N is the env stride of the SoA arrays (count < N for a chunk of a larger batch)
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
@@ -150,6 +156,8 @@ __global__ void __launch_bounds__(128, B2_STEP_MIN_BLOCKS) k_step(StateDev<T> st
     B2_UNROLL
     for (int k = 0; k < M::nv(); k++) st.qvel[(size_t)k * N + e] = env.qvel[k];
   }
+  // qacc_warmstart <- qacc at the end of the constraint stage (upstream mj_fwdConstraint: "save result for next step
+  // warmstart"), i.e. by mj_forward too -- which is why mjd_transitionFD saves and restores it around every rollout
   if (st.warm) { B2_UNROLL for (int k = 0; k < M::nv(); k++) st.warm[(size_t)k * N + e] = env.warm[k]; }
   if (st.flags && env.flags) st.flags[e] |= env.flags;
 }
@@ -260,7 +268,9 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // launched first: they are the longest); each position column is a thread of its own (two full rollouts).  RK4 models
 // have nothing to share between columns: one thread per (env, column).
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow) {
+__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow,
+                                                                                 const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)count * fd_tasks<M>()) return;
@@ -299,16 +309,18 @@ __global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize
   B2_UNROLL
   for (int k = 0; k < nv; k++) env.qvel[k] = nom.v(k);
   env.check_state();
+  // a diverged env is flagged and frozen, as in k_step: its "advanced" state is the state it has (one copy of the stores)
+  const bool frozen = advance && (env.flags & 3) != 0;
   B2_NOUNROLL
-  for (int c = c0; c < c1 + (advance ? 1 : 0); c++) {
+  for (int c = c0; c < c1 + (advance ? 1 : 0) && !frozen; c++) {
     const bool nominal = c == c1;  // the advance comes after the group's columns, on the same position stage
     fd_column(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid, vel_valid);
   }
   if (advance) {
     B2_UNROLL
-    for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = env.qpos[k];
+    for (int k = 0; k < nq; k++) shadow.qpos[(size_t)k * N + e] = frozen ? nom.q(k) : env.qpos[k];
     B2_UNROLL
-    for (int k = 0; k < nv; k++) { shadow.qvel[(size_t)k * N + e] = env.qvel[k]; shadow.warm[(size_t)k * N + e] = env.warm[k]; }
+    for (int k = 0; k < nv; k++) { shadow.qvel[(size_t)k * N + e] = frozen ? nom.v(k) : env.qvel[k]; shadow.warm[(size_t)k * N + e] = frozen ? nom.w(k) : env.warm[k]; }
     B2_UNROLL
     for (int k = 0; k < nu; k++) shadow.ctrl[(size_t)k * N + e] = u0[k];
   }
@@ -338,7 +350,8 @@ __global__ void __launch_bounds__(256) k_commit_state(StateDev<T> st, StateDev<T
 
 // point Jacobians from the current qpos (mj_jacSite/Body/BodyCom/SubtreeCom)
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kind, int objid, T* jacp, T* jacr) {
+__global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kind, int objid, T* jacp, T* jacr, const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   RowStore<T, D> rows;
@@ -377,7 +390,8 @@ __global__ void __launch_bounds__(128) k_jacobian(StateDev<T> st, int N, int kin
 // mj_inverse for a prescribed acceleration (steady_ctrl0: reference mujoco_template/setpoints.py:23-30);
 // optionally exports the dense actuator moment matrix (nu x nv) of every env
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T* qacc, T* qfrc, T* moment) {
+__global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T* qacc, T* qfrc, T* moment, const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   RowStore<T, D> rows;
@@ -396,7 +410,8 @@ __global__ void __launch_bounds__(128) k_inverse(StateDev<T> st, int N, const T*
 // (reference examples/drone/controllers/lqr.py:227-278, examples/humanoid/controllers/lqr.py:153-170).
 // gain: K (nu x 2nv row-major), then qpos_ref (nq), then ctrl_ref (nu), shared by all envs.
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, int N, const T* __restrict__ gain) {
+__global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, int N, const T* __restrict__ gain, const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= count) return;
   RowStore<T, D> rows;
@@ -408,8 +423,23 @@ __global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, 
   for (int a = 0; a < M::nu(); a++) st.ctrl[(size_t)a * N + e] = u[a];
 }
 
+// Recorder gather (reference logging.py:81-247 rows for a selection of envs): blockIdx.y = column, x = selected envs.
+struct RecordColDev { const void* base; int row; int kind; };
+template <typename T>
+__global__ void __launch_bounds__(128) k_record_rows(const RecordColDev* __restrict__ cols, const int* __restrict__ env_index, int nsel,
+                                                     int N, T time, T* out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (j >= nsel) return;
+  const RecordColDev col = cols[c];
+  T v;
+  if (col.kind == 0) v = static_cast<const T*>(col.base)[(size_t)col.row * N + env_index[j]];
+  else v = col.kind == 1 ? time : T(__int_as_float(0x7fc00000));
+  out[(size_t)c * nsel + j] = v;
+}
+
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T dt, int N) {
+__global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T dt, int N, const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   RowStore<T, D> rows;
@@ -420,7 +450,8 @@ __global__ void __launch_bounds__(128) k_integrate_pos(T* qpos, const T* qvel, T
   for (int k = 0; k < M::nq(); k++) qpos[(size_t)k * N + e] = env.qpos[k];
 }
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(128) k_differentiate_pos(T* out, T dt, const T* q1, const T* q2, int N) {
+__global__ void __launch_bounds__(128) k_differentiate_pos(T* out, T dt, const T* q1, const T* q2, int N, const void* image = nullptr) {
+  model_load<M>(image, 0);
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N) return;
   RowStore<T, D> rows;

@@ -15,16 +15,20 @@ namespace b2 {
                          void* sortbuf, int wpb, int blocks, void* stream);                                                                   \
   int b2k_warp_linearize##SUF(const void* image, const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
                               void* counter, int wpb, int blocks, void* stream);                                                        \
-  int b2k_upload##SUF(int cls, const b2m_view* v, const int* disabled, void* stream);                                      \
-  int b2k_step##SUF(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park, void* stream);                  \
-  int b2k_linearize##SUF(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
+  size_t b2k_image_bytes##SUF(int cls);                                                                                    \
+  void b2k_image_fill##SUF(int cls, const b2m_view* v, const int* disabled, void* host);                                   \
+  int b2k_step##SUF(const void* image, int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain, const b2_state* park, void* stream);                  \
+  int b2k_linearize##SUF(const void* image, int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,         \
                          const void* gain, const b2_state* shadow, void* stream);                                                                                    \
   int b2k_commit_state##SUF(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream); \
-  int b2k_jacobian##SUF(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
-  int b2k_inverse##SUF(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream);     \
-  int b2k_lqr_control##SUF(int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \
-  int b2k_integrate_pos##SUF(int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \
-  int b2k_differentiate_pos##SUF(int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream);
+  int b2k_jacobian##SUF(const void* image, int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream);    \
+  int b2k_inverse##SUF(const void* image, int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream);     \
+  int b2k_lqr_control##SUF(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \
+  int b2k_dare##SUF(const void* A, const void* B, const void* qr, int nx, int nu, int N, int max_doublings, double tol, void* K, void* P, \
+                    int* status, void* stream);                                                                            \
+  int b2k_record_rows##SUF(const void* cols, int ncol, const int* env_index, int nsel, int N, double time, void* out, void* stream); \
+  int b2k_integrate_pos##SUF(const void* image, int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \
+  int b2k_differentiate_pos##SUF(const void* image, int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream);
 B2_DECL(_f64)
 B2_DECL(_f32)
 #undef B2_DECL

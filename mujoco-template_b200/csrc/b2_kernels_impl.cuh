@@ -10,34 +10,47 @@
 #include "b2_kernel_templates.cuh"
 #include "b2_kernels.h"
 #include "b2_warp_kernels.cuh"
+#include "b2_dare.cuh"
 
 namespace b2 {
 
 typedef B2_REAL real;
 
-__constant__ DevModel<real, DimsTiny> c_model_tiny;
-__constant__ DevModel<real, DimsSmall> c_model_small;
-__constant__ DevModel<real, DimsLarge> c_model_large;
+// The generic kernels read the model from a copy in shared memory, filled at kernel start from the model's image in device
+// memory (one per model, device and precision, owned by the b2_model and passed to every launch).  Nothing about a model is
+// process-wide device state: two models of one size class can run on different streams and from different threads, and a
+// captured CUDA graph replays with the image it was captured with.  (Round 1 kept one image per size class in __constant__
+// memory, swapped under a lock -- a graph replay could then run with another model's constants.)
+__shared__ DevModel<real, DimsTiny> s_model_tiny;
+__shared__ DevModel<real, DimsSmall> s_model_small;
+__shared__ DevModel<real, DimsLarge> s_model_large;
 
-template <class D> struct ConstImage;
-template <> struct ConstImage<DimsTiny> { static B2_DEV const DevModel<real, DimsTiny>& get() { return c_model_tiny; } };
-template <> struct ConstImage<DimsSmall> { static B2_DEV const DevModel<real, DimsSmall>& get() { return c_model_small; } };
-template <> struct ConstImage<DimsLarge> { static B2_DEV const DevModel<real, DimsLarge>& get() { return c_model_large; } };
+template <class D> struct SharedImage;
+template <> struct SharedImage<DimsTiny> { static B2_DEV DevModel<real, DimsTiny>& get() { return s_model_tiny; } };
+template <> struct SharedImage<DimsSmall> { static B2_DEV DevModel<real, DimsSmall>& get() { return s_model_small; } };
+template <> struct SharedImage<DimsLarge> { static B2_DEV DevModel<real, DimsLarge>& get() { return s_model_large; } };
 
-// provider that reads the constant-bank image: uniform operands, any model of the size class
+// provider that reads the shared-memory image: uniform addresses (one broadcast read per warp), any model of the size class
 template <class DD>
 struct RuntimeModel {
   typedef DD D;
-#define X(name) static B2_DEV int name() { return ConstImage<D>::get().name; }
+  static B2_DEV void load(const void* image) {  // whole block, before anything else (and before any thread returns)
+    static_assert(sizeof(DevModel<real, D>) % 4 == 0, "model image is copied in 32-bit words");
+    const unsigned* src = reinterpret_cast<const unsigned*>(image);
+    unsigned* dst = reinterpret_cast<unsigned*>(&SharedImage<D>::get());
+    for (int i = threadIdx.x; i < (int)(sizeof(DevModel<real, D>) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+  }
+#define X(name) static B2_DEV int name() { return SharedImage<D>::get().name; }
   B2_MODEL_INT_SCALARS(X)
 #undef X
-#define X(name) static B2_DEV real name() { return ConstImage<D>::get().name; }
+#define X(name) static B2_DEV real name() { return SharedImage<D>::get().name; }
   B2_MODEL_REAL_SCALARS(X)
 #undef X
-#define X(name, cap) static B2_DEV int name(int i) { return ConstImage<D>::get().name[i]; }
+#define X(name, cap) static B2_DEV int name(int i) { return SharedImage<D>::get().name[i]; }
   B2_MODEL_INT_ARRAYS(X)
 #undef X
-#define X(name, cap) static B2_DEV real name(int i) { return ConstImage<D>::get().name[i]; }
+#define X(name, cap) static B2_DEV real name(int i) { return SharedImage<D>::get().name[i]; }
   B2_MODEL_REAL_ARRAYS(X)
 #undef X
 };
@@ -59,30 +72,18 @@ __global__ void __launch_bounds__(256) k_fma_peak(real* out, int iters, real a, 
     default: { typedef DimsLarge DD; CALL; break; }    \
   }
 
-template <class D>
-static cudaError_t upload_t(const b2m_view& v, const int* disabled, cudaStream_t s);
-template <> cudaError_t upload_t<DimsTiny>(const b2m_view& v, const int* disabled, cudaStream_t s) {
-  static DevModel<real, DimsTiny> h; fill_dev_model(h, v, disabled);
-  return cudaMemcpyToSymbolAsync(c_model_tiny, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
-}
-template <> cudaError_t upload_t<DimsSmall>(const b2m_view& v, const int* disabled, cudaStream_t s) {
-  static DevModel<real, DimsSmall> h; fill_dev_model(h, v, disabled);
-  return cudaMemcpyToSymbolAsync(c_model_small, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
-}
-template <> cudaError_t upload_t<DimsLarge>(const b2m_view& v, const int* disabled, cudaStream_t s) {
-  static DevModel<real, DimsLarge> h; fill_dev_model(h, v, disabled);
-  return cudaMemcpyToSymbolAsync(c_model_large, &h, sizeof(h), 0, cudaMemcpyHostToDevice, s);
-}
-
 #define B2_CAT_(a, b) a##b
 #define B2_CAT(a, b) B2_CAT_(a, b)
 #define B2_FN(name) B2_CAT(name, B2_SUFFIX)
 
-int B2_FN(b2k_upload)(int cls, const b2m_view* v, const int* disabled, void* stream) {
-  cudaError_t err = cudaSuccess;
-  B2_DISPATCH(cls, err = upload_t<DD>(*v, disabled, (cudaStream_t)stream));
-  if (err == cudaSuccess) err = cudaStreamSynchronize((cudaStream_t)stream);  // host image is static: finish before reuse
-  return (int)err;
+// the lane engine's model image of a size class: size, and fill on the host (uploaded once per model by the C-ABI layer)
+size_t B2_FN(b2k_image_bytes)(int cls) {
+  size_t n = 0;
+  B2_DISPATCH(cls, n = sizeof(DevModel<real, DD>));
+  return n;
+}
+void B2_FN(b2k_image_fill)(int cls, const b2m_view* v, const int* disabled, void* host) {
+  B2_DISPATCH(cls, fill_dev_model(*reinterpret_cast<DevModel<real, DD>*>(host), *v, disabled));
 }
 // returns measured TFLOP/s (2 flops per FMA) or a negative cudaError
 double B2_FN(b2k_fma_peak)(void* stream) {
@@ -112,11 +113,11 @@ double B2_FN(b2k_fma_peak)(void* stream) {
   const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
   return flops / (best * 1e-3) / 1e12;
 }
-int B2_FN(b2k_step)(int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain,
+int B2_FN(b2k_step)(const void* image, int cls, const b2_state* st, const b2_derived* out, int count, int N, int nsteps, const void* gain,
                     const b2_state* park, void* stream) {
   const int threads = 128, blocks = (count + threads - 1) / threads;
   B2_DISPATCH(cls, (k_step<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps, (const real*)gain, to_dev<real>(park))));
+                       to_dev<real>(st), to_dev<real>(out), out != nullptr, count, N, nsteps, (const real*)gain, to_dev<real>(park), image)));
   return (int)cudaGetLastError();
 }
 // ---- warp engine (large models): launch geometry and per-warp scratch are sized by the host
@@ -233,13 +234,13 @@ int B2_FN(b2k_warp_linearize)(const void* image, const b2m_view* v, const b2_sta
                       (const WarpImage<real>*)image, to_dev<real>(st), N, (real)eps, centered, (real*)A, (real*)B, (real*)jscratch, (int*)counter)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_linearize)(int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,
+int B2_FN(b2k_linearize)(const void* image, int cls, const b2_state* st, int count, int N, int ncol, double eps, int centered, void* A, void* B,
                          const void* gain, const b2_state* shadow, void* stream) {
   const int threads = 128;
   const long long total = (long long)count * ncol;  // ncol: FD tasks per env (b2_capi: nv + 1 under Euler, else 2nv + nu)
   const int blocks = (int)((total + threads - 1) / threads);
   B2_DISPATCH(cls, (k_linearize<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B, (const real*)gain, to_dev<real>(shadow))));
+                       to_dev<real>(st), count, N, (real)eps, centered, (real*)A, (real*)B, (const real*)gain, to_dev<real>(shadow), image)));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_commit_state)(const b2_state* st, const b2_state* shadow, int count, int N, int nq, int nv, int nu, void* stream) {
@@ -248,34 +249,57 @@ int B2_FN(b2k_commit_state)(const b2_state* st, const b2_state* shadow, int coun
   k_commit_state<real><<<dim3(bx, nq + 2 * nv + nu), 256, 0, (cudaStream_t)stream>>>(to_dev<real>(st), to_dev<real>(shadow), count, N, nq, nv, nu);
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_jacobian)(int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {
+int B2_FN(b2k_jacobian)(const void* image, int cls, const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_jacobian<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), N, kind, objid, (real*)jacp, (real*)jacr)));
+                       to_dev<real>(st), N, kind, objid, (real*)jacp, (real*)jacr, image)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_inverse)(int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream) {
+int B2_FN(b2k_inverse)(const void* image, int cls, const b2_state* st, int N, const void* qacc, void* qfrc, void* moment, void* stream) {
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_inverse<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), N, (const real*)qacc, (real*)qfrc, (real*)moment)));
+                       to_dev<real>(st), N, (const real*)qacc, (real*)qfrc, (real*)moment, image)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_lqr_control)(int cls, const b2_state* st, int count, int N, const void* gain, void* stream) {
+int B2_FN(b2k_lqr_control)(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, void* stream) {
   const int threads = 128, blocks = (count + threads - 1) / threads;
   B2_DISPATCH(cls, (k_lqr_control<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       to_dev<real>(st), count, N, (const real*)gain)));
+                       to_dev<real>(st), count, N, (const real*)gain, image)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_integrate_pos)(int cls, void* qpos, const void* qvel, double dt, int N, void* stream) {
+// batched DARE / LQR gains: one warp per env, as many warps per block as the shared-memory workspace allows (at most four)
+int B2_FN(b2k_dare)(const void* A, const void* B, const void* qr /* device: Q, R, Rinv */, int nx, int nu, int N, int max_doublings,
+                    double tol, void* K, void* P, int* status, void* stream) {
+  int dev = 0, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const size_t per = dare_ws_reals(nx, nu) * sizeof(real);
+  int wpb = (int)((size_t)smem_max / per);
+  if (wpb < 1) return (int)cudaErrorInvalidValue;  // nx too large for one SM's shared memory
+  if (wpb > 4) wpb = 4;
+  cudaError_t e = cudaFuncSetAttribute(k_dare<real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per * wpb));
+  if (e != cudaSuccess) return (int)e;
+  const real* q = (const real*)qr;
+  k_dare<real><<<(N + wpb - 1) / wpb, wpb * 32, per * wpb, (cudaStream_t)stream>>>(
+      (const real*)A, (const real*)B, q, q + nx * nx, q + nx * nx + nu * nu, nx, nu, N, max_doublings, (real)tol, (real*)K, (real*)P, status);
+  return (int)cudaGetLastError();
+}
+int B2_FN(b2k_record_rows)(const void* cols, int ncol, const int* env_index, int nsel, int N, double time, void* out, void* stream) {
+  const int threads = 128;
+  k_record_rows<real><<<dim3((nsel + threads - 1) / threads, ncol), threads, 0, (cudaStream_t)stream>>>(
+      (const RecordColDev*)cols, env_index, nsel, N, (real)time, (real*)out);
+  return (int)cudaGetLastError();
+}
+int B2_FN(b2k_integrate_pos)(const void* image, int cls, void* qpos, const void* qvel, double dt, int N, void* stream) {
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_integrate_pos<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       (real*)qpos, (const real*)qvel, (real)dt, N)));
+                       (real*)qpos, (const real*)qvel, (real)dt, N, image)));
   return (int)cudaGetLastError();
 }
-int B2_FN(b2k_differentiate_pos)(int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream) {
+int B2_FN(b2k_differentiate_pos)(const void* image, int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream) {
   const int threads = 128, blocks = (N + threads - 1) / threads;
   B2_DISPATCH(cls, (k_differentiate_pos<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
-                       (real*)out, (real)dt, (const real*)q1, (const real*)q2, N)));
+                       (real*)out, (real)dt, (const real*)q1, (const real*)q2, N, image)));
   return (int)cudaGetLastError();
 }
 

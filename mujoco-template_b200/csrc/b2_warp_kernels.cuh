@@ -135,7 +135,7 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
         WFOR(k, env.mdl.nq()) st.qpos[(size_t)k * N + e] = env.qpos[k];
         WFOR(k, env.mdl.nv()) st.qvel[(size_t)k * N + e] = env.qvel[k];
       }
-      if (st.warm) WFOR(k, env.mdl.nv()) st.warm[(size_t)k * N + e] = env.warm[k];
+      if (st.warm) WFOR(k, env.mdl.nv()) st.warm[(size_t)k * N + e] = env.warm[k];  // by mj_forward too (mj_fwdConstraint saves it)
       if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
     }
     // queue key of the next step: Newton rounds of this one, envs with dense (non-chain) rows -- three times the

@@ -19,7 +19,7 @@ from .env import Env, StepResult
 from .exceptions import CompatibilityError, ConfigError, LinearizationError, NameLookupError, TemplateError
 from .jacobians import compute_requested_jacobians
 from .linearization import linearize_discrete
-from .logging import BatchedStateControlRecorder, DataProbe, StateControlRecorder
+from .logging import ArrayProbe, BatchedStateControlRecorder, DataProbe, StateControlRecorder
 from .model import ModelHandle
 from .observations import ObservationExtractor, ObservationProducer, ObservationSpec
 from .runtime import StepHook, TrajectoryLogger, iterate_passive, run_passive_headless
@@ -34,7 +34,7 @@ __all__ = [
     "BatchedObservationExtractor", "shard_range", "ZeroController", "PositionTargetDemo",
     "check_controller_compat", "linearize_discrete", "compute_requested_jacobians", "steady_ctrl0",
     "batched_steady_ctrl0", "TrajectoryLogger",
-    "DataProbe", "StateControlRecorder", "BatchedStateControlRecorder", "StepHook", "iterate_passive", "run_passive_headless",
+    "DataProbe", "ArrayProbe", "StateControlRecorder", "BatchedStateControlRecorder", "StepHook", "iterate_passive", "run_passive_headless",
     "ObservationDict", "ObservationArray", "Observation", "JacobianDict", "JacobiansDict", "InfoDict",
     "StateSnapshot", "mj", "__version__",
 ]

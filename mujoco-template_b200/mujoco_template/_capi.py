@@ -26,7 +26,13 @@ EXPORTED_SYMBOLS = (
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
     "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
+    "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr",
 )
+
+
+class RecordCol(C.Structure):
+    """One column of the batched recorder (include/b2mj.h b2_record_col): kind 0 array row, 1 time, 2 NaN."""
+    _fields_ = [("base", C.c_void_p), ("row", C.c_int), ("kind", C.c_int)]
 
 
 class State(C.Structure):
@@ -83,6 +89,12 @@ def lib() -> C.CDLL:
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
     L.b2_stream_synchronize.argtypes = [vp, vp]
+    L.b2_dlqr.argtypes = [C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int,
+                          C.c_double, vp, vp, vp, vp]
+    L.b2_recorder_create.argtypes = [vp, C.POINTER(RecordCol), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
+    L.b2_recorder_record.argtypes = [vp, C.c_double, vp, vp]
+    L.b2_recorder_destroy.argtypes = [vp]
+    L.b2_recorder_destroy.restype = None
     L.b2_fp_peak.argtypes = [i, i, C.POINTER(d)]
     _lib = L
     return L
@@ -201,4 +213,35 @@ class NativeBatch:
         h = getattr(self, "handle", None)
         if h:
             self._L.b2_batch_destroy(h)
+            self.handle = None
+
+
+def dlqr(device: int, precision: int, A_ptr: int, B_ptr: int, Q, R, nx: int, nu: int, nenv: int, K_ptr: int, P_ptr: int,
+         status_ptr: int | None, max_doublings: int = 40, tol: float = 1e-13, stream: int = 0) -> None:
+    """``b2_dlqr``: batched DARE + gain on the device (A, B, K, P device pointers in the SoA layout; Q, R host arrays)."""
+    q = (C.c_double * (nx * nx))(*[float(x) for x in Q])
+    r = (C.c_double * (nu * nu))(*[float(x) for x in R])
+    check(lib().b2_dlqr(int(device), int(precision), A_ptr, B_ptr, q, r, int(nx), int(nu), int(nenv), int(max_doublings), float(tol),
+                        K_ptr, P_ptr, status_ptr, stream))
+
+
+class NativeRecorder:
+    """Owns a ``b2_recorder*``: column table + env selection on the device, one gather launch per recorded step."""
+
+    def __init__(self, batch: "NativeBatch", cols: list[tuple[int | None, int, int]], env_index: list[int]):
+        self._L = lib()
+        self.batch = batch  # keeps the batch alive
+        table = (RecordCol * len(cols))(*[RecordCol(base, int(row), int(kind)) for base, row, kind in cols])
+        idx = (C.c_int * len(env_index))(*[int(i) for i in env_index])
+        h = C.c_void_p()
+        check(self._L.b2_recorder_create(batch.handle, table, len(cols), idx, len(env_index), C.byref(h)))
+        self.handle = h
+
+    def record(self, time: float, out_ptr: int, stream: int = 0) -> None:
+        check(self._L.b2_recorder_record(self.handle, float(time), out_ptr, stream))
+
+    def __del__(self):
+        h = getattr(self, "handle", None)
+        if h:
+            self._L.b2_recorder_destroy(h)
             self.handle = None

@@ -335,9 +335,19 @@ class BatchedEnv:
         if not dist.is_available() or not dist.is_initialized():
             return tensor
         world = dist.get_world_size() if world_size is None else world_size
-        parts = [torch.empty_like(tensor) for _ in range(world)]
-        dist.all_gather(parts, tensor.contiguous())
-        return torch.cat(parts, dim=-1)
+        # shard_range hands out blocks that differ by one env when the total does not divide: exchange the block
+        # lengths first and pad to the longest
+        n_local = torch.tensor([tensor.shape[-1]], device=tensor.device, dtype=torch.int64)
+        counts = [torch.zeros_like(n_local) for _ in range(world)]
+        dist.all_gather(counts, n_local)
+        counts = [int(c.item()) for c in counts]
+        n_max = max(counts)
+        send = tensor.contiguous()
+        if send.shape[-1] < n_max:
+            send = torch.nn.functional.pad(send, (0, n_max - send.shape[-1]))
+        parts = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(parts, send)
+        return torch.cat([p[..., :c] for p, c in zip(parts, counts)], dim=-1)
 
 
 __all__ = ["BatchedEnv", "BatchedObservationExtractor", "shard_range"]

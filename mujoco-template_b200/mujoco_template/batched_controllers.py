@@ -19,58 +19,66 @@ from .control import ControlSpace, ControllerCapabilities
 from .exceptions import ConfigError
 
 
-def dlqr_gain(A: np.ndarray, B: np.ndarray, Q: np.ndarray, R: np.ndarray) -> np.ndarray:
-    """Infinite-horizon discrete LQR gain K (u = -K x) via SciPy's DARE solver."""
-    from scipy.linalg import solve_discrete_are
+def dlqr_gain(A: np.ndarray, B: np.ndarray, Q: np.ndarray, R: np.ndarray, device: int | None = None) -> np.ndarray:
+    """Infinite-horizon discrete LQR gain K (u = -K x) of ONE system: the library's DARE kernel (``b2_dlqr``) on a
+    one-env batch.  The reference recipe is ``scipy.linalg.solve_discrete_are`` + a solve (reference
+    ``examples/drone/controllers/lqr.py:350-378``); the two agree to ~1e-9 relative (tests/test_gpu_parity.py)."""
+    import torch
 
-    P = solve_discrete_are(A, B, Q, R)
-    return np.linalg.solve(R + B.T @ P @ B, B.T @ P @ A)
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else int(device)) if torch.cuda.is_available() else None
+    if dev is None:
+        from .exceptions import TemplateError
+
+        raise TemplateError("dlqr_gain: no CUDA device (this path has no CPU fallback)")
+    K, _ = batched_dlqr_gain(torch.as_tensor(np.asarray(A, dtype=float), device=dev)[None],
+                             torch.as_tensor(np.asarray(B, dtype=float), device=dev)[None], Q, R)
+    return K[0].cpu().numpy()
 
 
-def batched_dlqr_gain(A, B, Q, R, max_doublings: int = 40, tol: float = 1e-13):
-    """Infinite-horizon discrete LQR gains of a whole batch on the device.
+def batched_dlqr_gain(A, B, Q, R, max_doublings: int = 40, tol: float = 1e-13, return_status: bool = False):
+    """Infinite-horizon discrete LQR gains of a whole batch on the device: ``b2_dlqr``, one
+    warp per env, every env from its own ``(A, B)``.
 
-    ``A`` (N, nx, nx) and ``B`` (N, nx, nu) are torch tensors (any device; ``StepResult.info['A'/'B']`` of a
-    ``BatchedEnv`` have exactly this shape), ``Q`` (nx, nx) and ``R`` (nu, nu) are shared.  Returns ``(K, P)`` with
-    ``u = -K x``, ``K`` (N, nu, nx), ``P`` (N, nx, nx) the stabilising DARE solutions.  The DARE is solved by the
+    ``A`` (N, nx, nx) and ``B`` (N, nx, nu) are CUDA tensors -- ``StepResult.info['A'/'B']`` of a ``BatchedEnv`` have
+    exactly this shape, as permuted views of the ``(nx, nx, N)`` arrays ``b2_linearize`` writes, which the kernel reads
+    in place -- ``Q`` (nx, nx) and ``R`` (nu, nu) are shared.  Returns ``(K, P)`` with ``u = -K x``, ``K`` (N, nu, nx),
+    ``P`` (N, nx, nx) the stabilising DARE solutions (views of env-fastest storage).  The DARE is solved by the
     structure-preserving doubling iteration (k doublings = a Riccati recursion over 2**k steps, quadratic convergence):
 
         W = I + G H;  A <- A W^-1 A;  G <- G + A W^-1 G A';  H <- H + A' H W^-1 A      (G0 = B R^-1 B', H0 = Q)
 
-    -- one batched solve and a few batched products per doubling, no per-env host work.  The single-system
-    reference recipe is ``scipy.linalg.solve_discrete_are`` (reference ``examples/drone/controllers/lqr.py:350-378``,
-    ``examples/humanoid/controllers/lqr.py:114-115``); ``dlqr_gain`` keeps that path for one system."""
+    The single-system reference recipe is ``scipy.linalg.solve_discrete_are`` (reference
+    ``examples/drone/controllers/lqr.py:350-378``, ``examples/humanoid/controllers/lqr.py:114-115``)."""
     import torch
+
+    from . import _capi
+    from .exceptions import TemplateError
 
     A = torch.as_tensor(A)
     B = torch.as_tensor(B, dtype=A.dtype, device=A.device)
     if A.dim() == 2:
         A, B = A[None], B[None]
-    Q = torch.as_tensor(Q, dtype=A.dtype, device=A.device)
-    R = torch.as_tensor(R, dtype=A.dtype, device=A.device)
-    n, nx = A.shape[0], A.shape[1]
-    eye = torch.eye(nx, dtype=A.dtype, device=A.device).expand(n, nx, nx)
-    Ak = A.clone()
-    G = B @ torch.linalg.solve(R, B.transpose(1, 2))
-    H = Q.expand(n, nx, nx).clone()
-    for k in range(max_doublings):
-        W = eye + G @ H
-        V = torch.linalg.solve(W, torch.cat([Ak, G], dim=2))  # W^-1 [A, G] in one batched solve
-        V1, V2 = V[:, :, :nx], V[:, :, nx:]
-        At = Ak.transpose(1, 2)
-        Hn = H + At @ H @ V1
-        G = G + Ak @ V2 @ At
-        Ak = Ak @ V1
-        Hn = 0.5 * (Hn + Hn.transpose(1, 2))
-        G = 0.5 * (G + G.transpose(1, 2))
-        done = k >= 3 and bool(((Hn - H).abs().amax(dim=(1, 2)) <= tol * Hn.abs().amax(dim=(1, 2)).clamp_min(1.0)).all())
-        H = Hn
-        if done:
-            break
-    P = H
-    BtP = B.transpose(1, 2) @ P
-    K = torch.linalg.solve(R + BtP @ B, BtP @ A)
-    return K, P
+    if A.device.type != "cuda":
+        raise TemplateError("batched_dlqr_gain: A and B must be CUDA tensors (this path has no CPU fallback)")
+    if A.dtype not in (torch.float64, torch.float32):
+        raise ConfigError("batched_dlqr_gain: float64 or float32 tensors expected")
+    n, nx, nu = A.shape[0], A.shape[1], B.shape[2]
+    if A.shape != (n, nx, nx) or B.shape != (n, nx, nu) or nu > nx:
+        raise ConfigError("batched_dlqr_gain: A must be (N, nx, nx) and B (N, nx, nu) with nu <= nx")
+    Q = np.ascontiguousarray(np.asarray(Q.cpu() if hasattr(Q, "cpu") else Q, dtype=float)).reshape(nx * nx)
+    R = np.ascontiguousarray(np.asarray(R.cpu() if hasattr(R, "cpu") else R, dtype=float)).reshape(nu * nu)
+    # env-fastest storage: a permuted view of the (nx, nx, N) array costs nothing, anything else is copied once
+    As, Bs = A.permute(1, 2, 0), B.permute(1, 2, 0)
+    As = As if As.is_contiguous() else As.contiguous()
+    Bs = Bs if Bs.is_contiguous() else Bs.contiguous()
+    Ks = torch.empty((nu, nx, n), dtype=A.dtype, device=A.device)
+    Ps = torch.empty((nx, nx, n), dtype=A.dtype, device=A.device)
+    status = torch.zeros(n, dtype=torch.int32, device=A.device)
+    with torch.cuda.device(A.device):
+        _capi.dlqr(A.device.index, 64 if A.dtype == torch.float64 else 32, As.data_ptr(), Bs.data_ptr(), Q, R, nx, nu, n,
+                   Ks.data_ptr(), Ps.data_ptr(), status.data_ptr(), max_doublings, tol, torch.cuda.current_stream(A.device).cuda_stream)
+    K, P = Ks.permute(2, 0, 1), Ps.permute(2, 0, 1)
+    return (K, P, status) if return_status else (K, P)
 
 
 class BatchedLQRController:

@@ -121,7 +121,7 @@ class Env:
     def _prepare_and_check(self, controller: Controller) -> None:
         controller.prepare(self.model, self.data)
         report = check_controller_compat(self.model, controller.capabilities, self.handle.enabled_actuator_mask())
-        self._compat_warnings.extend(report.warnings)
+        self._compat_warnings = list(report.warnings)  # replaces the group warnings, as reference env.py:92 does
         report.assert_ok()
 
     @property

@@ -41,6 +41,17 @@ class DataProbe:
     extractor: Callable[[Any, Any], Any]
 
 
+@dataclass(frozen=True)
+class ArrayProbe:
+    """Extra CSV column of the batched recorder backed by one row of a ``(dim, nenv)`` array of ``env.data``
+    (``site_xpos``, ``subtree_com``, ``xpos``, ``sensordata``, ``qacc``, ...): gathered on the device with the state
+    columns, no Python per step.  ``row`` indexes the flattened leading dimension (site 2, z: ``3 * 2 + 2``)."""
+
+    name: str
+    array: str
+    row: int
+
+
 def _labels(table: dict, joint_type: int, count: int) -> Sequence[str]:
     known = table.get(joint_type)
     if known is None or len(known) != count:
@@ -170,10 +181,16 @@ class StateControlRecorder:
 class BatchedStateControlRecorder:
     """StepHook for ``BatchedEnv``: the reference's CSV rows for a selection of envs.
 
-    Every step appends ``[time, qpos.., qvel.., ctrl..]`` of the selected envs to a device-side ring buffer
-    with one gather (no host synchronisation in the step loop); full chunks are copied to pinned host memory
-    asynchronously and written out as CSV with the reference schema plus a leading ``env`` column.  Probes are
-    vectorised: ``extractor(env, result)`` must return one value per selected env (tensor or array)."""
+    Every step appends ``[time, qpos.., qvel.., ctrl.., probes..]`` of the selected envs to a device-side ring buffer
+    with ONE launch of the library's gather kernel (``b2_recorder_record``: a column table of (array, row) pairs built
+    once, no host synchronisation in the step loop); full chunks are copied to pinned host memory asynchronously and
+    written out as CSV with the reference schema plus a leading ``env`` column.
+
+    Probes come in two kinds.  ``ArrayProbe(name, array, row)`` names one row of a ``(dim, nenv)`` array of
+    ``env.data`` -- e.g. ``ArrayProbe("imu_z_m", "site_xpos", 3 * site_id + 2)`` for what the reference's drone example
+    logs through ``e.data.site_xpos[imu, 2]`` (``examples/drone/drone_common.py:52-57``) -- and is just another column
+    of the gather.  A ``DataProbe`` with a callable is vectorised: ``extractor(env, result)`` must return one value per
+    selected env (tensor or array); it is evaluated after the gather and written into its column."""
 
     def __init__(self, env: Any, *, log_path: str | Path | None = None, env_indices: Sequence[int] | None = None,
                  chunk_steps: int = 256, store_rows: bool = False, probes: Sequence[DataProbe] = ()) -> None:
@@ -181,7 +198,9 @@ class BatchedStateControlRecorder:
 
         self._env, self._model = env, env.model
         m = env.model
-        self._probes = StateControlRecorder._validate_probes(probes)
+        self._array_probes = {k: p for k, p in enumerate(probes) if isinstance(p, ArrayProbe)}
+        self._probes = StateControlRecorder._validate_probes([DataProbe(p.name, lambda e, r: None) if isinstance(p, ArrayProbe) else p
+                                                              for p in probes])
         cols, self._qi, self._vi, _ = build_schema(m, [p.name for p in self._probes])
         self.columns = ("env",) + cols
         n = env.data.qpos.shape[1]
@@ -206,6 +225,26 @@ class BatchedStateControlRecorder:
         self._file = None
         self._writer = None
         self.steps = 0
+        for p in self._array_probes.values():
+            arr = getattr(env.data, p.array, None)
+            if arr is None or not 0 <= int(p.row) < arr.shape[0]:
+                raise ConfigError(f"ArrayProbe {p.name!r}: env.data has no row {p.row} of array {p.array!r}")
+        # device path: the column table of the library's gather kernel (one launch per recorded step)
+        self._native = None
+        self._needs_derived = any(p.array not in ("qpos", "qvel", "ctrl", "qacc_warmstart") for p in self._array_probes.values())
+        if dev.type == "cuda":
+            from . import _capi
+
+            d = env.data
+            table: list[tuple[int | None, int, int]] = [(None, 0, 1)]  # time_s
+            table += [(d.qpos.data_ptr(), int(r), 0) for r in self._qi]
+            table += [(d.qvel.data_ptr(), int(r), 0) for r in self._vi]
+            table += [(d.ctrl.data_ptr(), a, 0) for a in range(m.nu)] if m.nu else [(None, 0, 2)]
+            for k in range(len(self._probes)):
+                p = self._array_probes.get(k)
+                table.append((getattr(d, p.array).data_ptr(), int(p.row), 0) if p is not None else (None, 0, 2))
+            assert len(table) == self._nrow
+            self._native = _capi.NativeRecorder(d.backend.batch, table, sel)
 
     def __enter__(self) -> "BatchedStateControlRecorder":
         if self._path is not None:
@@ -225,6 +264,20 @@ class BatchedStateControlRecorder:
 
         data, m = self._env.data, self._model
         slot = self._ring[self._fill]
+        if self._native is not None:
+            if self._needs_derived:
+                data.backend.ensure_derived()  # lazily stepped envs: produce xpos / site_xpos / ... of this step first
+            stream = torch.cuda.current_stream(slot.device).cuda_stream
+            self._native.record(float(data.time), slot.data_ptr(), stream)
+            base = 1 + m.nq + m.nv + max(m.nu, 1)
+            for k, probe in enumerate(self._probes):
+                if k not in self._array_probes:
+                    slot[base + k] = torch.as_tensor(probe.extractor(self._env, result), device=slot.device, dtype=slot.dtype)
+            self._fill += 1
+            self.steps += 1
+            if self._fill == self._chunk:
+                self.flush()
+            return
         slot[0] = float(data.time)
         slot[1: 1 + m.nq] = data.qpos[self._qi_t][:, self._sel]
         slot[1 + m.nq: 1 + m.nq + m.nv] = data.qvel[self._vi_t][:, self._sel]
@@ -235,7 +288,11 @@ class BatchedStateControlRecorder:
             slot[base] = float("nan")
         base += max(m.nu, 1)
         for k, probe in enumerate(self._probes):
-            slot[base + k] = torch.as_tensor(probe.extractor(self._env, result), device=slot.device, dtype=slot.dtype)
+            if k in self._array_probes:
+                p = self._array_probes[k]
+                slot[base + k] = getattr(data, p.array)[int(p.row)][self._sel]
+            else:
+                slot[base + k] = torch.as_tensor(probe.extractor(self._env, result), device=slot.device, dtype=slot.dtype)
         self._fill += 1
         self.steps += 1
         if self._fill == self._chunk:
@@ -277,4 +334,4 @@ class BatchedStateControlRecorder:
         self._writer = None
 
 
-__all__ = ["DataProbe", "StateControlRecorder", "BatchedStateControlRecorder", "build_schema"]
+__all__ = ["DataProbe", "ArrayProbe", "StateControlRecorder", "BatchedStateControlRecorder", "build_schema"]

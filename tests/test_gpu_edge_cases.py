@@ -278,3 +278,101 @@ def test_drone_imu_sensors_specialised_and_generic(monkeypatch, spec):
     b32.data.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=dev, dtype=torch.float32))
     got32 = b32.step().obs["sensordata"].cpu().numpy().T.astype(float)
     assert np.max(np.abs(got32 - got)) <= 5e-4 * max(1.0, np.max(np.abs(got)))
+
+
+def _variant_of(model, **changes):
+    """A second model of the same size class: the compiled model with some constants changed (new blob, new handle)."""
+    import copy
+
+    from mujoco_template import _mj as mj
+
+    c = copy.deepcopy(model._c)
+    for k, v in changes.items():
+        c[k] = np.asarray(v, dtype=np.asarray(c[k]).dtype) if isinstance(c[k], np.ndarray) else v
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return mj.MjModel(c)
+
+
+@pytest.mark.parametrize("family", ["tiny-generic", "large-warp", "large-lane"])
+def test_two_models_of_one_size_class_interleaved_on_two_streams(family, monkeypatch):
+    """No process-wide model state: batches of two different models of the same size class, launched alternately on two
+    streams with no synchronisation in between, each follow their own oracle (round 1 kept one constant-memory image per
+    size class and swapped it under a lock; a launch could pick up the other model's constants)."""
+    import torch
+    from mujoco_template import _mj as mj
+
+    if family == "tiny-generic":
+        monkeypatch.setenv("B2_DISABLE_SPEC", "1")
+        a = _compile(ARM_XML)
+        b = _variant_of(a, timestep=0.003, gravity=[0.0, 0.0, -3.0])
+        n, nsteps, tol = 64, 20, 1e-9
+    else:
+        if family == "large-lane":
+            monkeypatch.setenv("B2_DISABLE_WARP", "1")
+        a = load_model("humanoid")
+        b = _variant_of(a, timestep=0.004, gravity=[0.0, 0.0, -5.0])
+        n, nsteps, tol = 8, 6, 1e-9
+    rng = np.random.default_rng(5)
+    models, datas, streams, states = (a, b), [], [torch.cuda.Stream(), torch.cuda.Stream()], []
+    for m in models:
+        if m.nq == 2:
+            qpos = rng.uniform(-1.0, 1.0, (n, 2)); qvel = rng.uniform(-1, 1, (n, 2))
+        else:
+            qpos = np.tile(m.key_qpos[1], (n, 1)); qpos[:, 7:] += rng.normal(0, 0.02, (n, m.nq - 7)); qvel = rng.normal(0, 0.01, (n, m.nv))
+        ctrl = rng.uniform(-0.3, 0.3, (n, m.nu))
+        d = mj.BatchData(m, n)
+        d.qpos.copy_(torch.as_tensor(qpos.T.copy(), device=d.qpos.device)); d.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=d.qpos.device))
+        d.ctrl.copy_(torch.as_tensor(ctrl.T.copy(), device=d.qpos.device))
+        datas.append(d); states.append((qpos, qvel, ctrl))
+    assert datas[0].backend.batch.size_class == datas[1].backend.batch.size_class
+    torch.cuda.synchronize()
+    for _ in range(nsteps):  # alternate launches, each batch on its own stream, nothing waits for anything
+        for d, s in zip(datas, streams):
+            with torch.cuda.stream(s):
+                d.backend.stream = s.cuda_stream
+                d.backend.step(1, derived=False)
+    torch.cuda.synchronize()
+    for m, d, (qpos, qvel, ctrl) in zip(models, datas, states):
+        om, od = oracle_for(m)
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]
+            for _ in range(nsteps):
+                od.step()
+            qpos[e] = od.qpos; qvel[e] = od.qvel
+        assert _rel(d.qpos.cpu().numpy().T, qpos) <= tol * nsteps
+        assert _rel(d.qvel.cpu().numpy().T, qvel) <= tol * nsteps
+    # the two models really differ (the test would pass trivially otherwise)
+    assert float(models[0].opt.timestep) != float(models[1].opt.timestep)
+
+
+def test_graph_replay_keeps_its_model_when_another_model_runs_in_between(monkeypatch):
+    """A captured BatchedEnv step replays with the model it was captured with, whatever ran on the device since."""
+    import torch
+    import mujoco_template as mt
+
+    monkeypatch.setenv("B2_DISABLE_SPEC", "1")
+    a = _compile(ARM_XML)
+    b = _variant_of(a, timestep=0.002, gravity=[0.0, 0.0, -1.0])
+    n = 32
+    envs = [mt.BatchedEnv(m, n, controller=mt.ZeroController()) for m in (a, b)]
+    rng = np.random.default_rng(9)
+    q0 = rng.uniform(-1, 1, (n, 2))
+    for env in envs:
+        env.reset()
+        env.data.qpos.copy_(torch.as_tensor(q0.T.copy(), device=env.data.qpos.device))
+        env.forward()
+        env.enable_cuda_graph(True)
+    for _ in range(6):
+        for env in envs:
+            env.step(return_obs=False)
+    torch.cuda.synchronize()
+    for m, env in zip((a, b), envs):
+        om, od = oracle_for(m)
+        ref = np.empty((n, 2))
+        for e in range(n):
+            od.reset(); od.qpos[:] = q0[e]
+            for _ in range(6):
+                od.step()
+            ref[e] = od.qpos
+        assert _rel(env.data.qpos.cpu().numpy().T, ref) <= 1e-8

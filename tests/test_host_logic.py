@@ -312,38 +312,13 @@ def test_steady_ctrl0_preserves_state_and_holds_the_pose(handle):
     assert np.allclose(u, 1.325 * 9.81 / 4, atol=1e-9)
 
 
-def test_batched_dlqr_gain_matches_scipy_dare():
-    """Doubling-iteration DARE on a batch (torch, here on the CPU) == scipy.linalg.solve_discrete_are per system:
-    cartpole and drone (A, B) from the oracle's FD at perturbed setpoints, and random stabilisable systems."""
+def test_batched_dlqr_gain_needs_the_device():
+    """LQR synthesis is a library kernel (b2_dlqr): CPU tensors are refused, there is no host fallback."""
     import torch
-    from scipy.linalg import solve_discrete_are
 
-    from conftest import load_model, oracle_for, random_states
+    import mujoco_template as mt
     from mujoco_template.batched_controllers import batched_dlqr_gain
 
-    for name, nsys in (("cartpole", 6), ("drone", 3)):
-        model = load_model(name)
-        om, od = oracle_for(model)
-        qpos, qvel, ctrl = random_states(model, name, nsys, seed=4)
-        As, Bs = [], []
-        for e in range(nsys):
-            od.reset()
-            od.qpos[:] = qpos[e]; od.qvel[:] = 0.1 * qvel[e]; od.ctrl[:] = ctrl[e] if name == "drone" else 0.0
-            A, B = od.transition_fd(1e-6, True)
-            As.append(A); Bs.append(B)
-        A, B = np.stack(As), np.stack(Bs)
-        nx, nu = A.shape[1], B.shape[2]
-        Q, R = np.diag(np.linspace(1.0, 3.0, nx)), 0.1 * np.eye(nu)
-        K, P = batched_dlqr_gain(torch.as_tensor(A), torch.as_tensor(B), Q, R)
-        for e in range(nsys):
-            Pe = solve_discrete_are(A[e], B[e], Q, R)
-            Ke = np.linalg.solve(R + B[e].T @ Pe @ B[e], B[e].T @ Pe @ A[e])
-            assert np.max(np.abs(P[e].numpy() - Pe)) <= 1e-8 * np.max(np.abs(Pe)), (name, e)
-            assert np.max(np.abs(K[e].numpy() - Ke)) <= 1e-8 * max(1.0, np.max(np.abs(Ke))), (name, e)
-            assert np.max(np.abs(np.linalg.eigvals(A[e] - B[e] @ K[e].numpy()))) < 1.0
-    rng = np.random.default_rng(0)
-    A = rng.normal(0, 0.6, (32, 5, 5)); B = rng.normal(0, 1.0, (32, 5, 2))
-    K, P = batched_dlqr_gain(torch.as_tensor(A), torch.as_tensor(B), np.eye(5), np.eye(2))
-    for e in range(32):
-        Pe = solve_discrete_are(A[e], B[e], np.eye(5), np.eye(2))
-        assert np.max(np.abs(P[e].numpy() - Pe)) <= 1e-8 * np.max(np.abs(Pe))
+    with pytest.raises(mt.TemplateError, match="CUDA"):
+        batched_dlqr_gain(torch.eye(4)[None].double(), torch.ones(1, 4, 1).double(), np.eye(4), np.eye(1))
+

@@ -2,7 +2,7 @@
 
 Step-only throughput (zero/hover control, one mj_step per launch, CUDA events, L2 flushed between
 launches) and FP64 linearizations/s.  Prints one JSON object per line; the committed output lives in
-profiles/sweep_r01.jsonl.   python tools/sweep.py [--quick]
+profiles/sweep_r02.jsonl.   python tools/sweep.py [--quick]
 """
 import json
 import os
@@ -31,8 +31,8 @@ def timed(fn, reps):
     return float(np.median(ts))
 
 
-sizes = {"pendulum": [2**10, 2**14, 2**18, 2**22], "cartpole": [2**10, 2**14, 2**16, 2**18, 2**22],
-         "drone": [2**10, 2**14, 2**18, 2**20], "humanoid": [2**10, 2**12, 2**14, 2**16]}
+sizes = {"pendulum": [2**10, 2**12, 2**14, 2**16, 2**18, 2**20, 2**22], "cartpole": [2**10, 2**12, 2**14, 2**16, 2**18, 2**20, 2**22],
+         "drone": [2**10, 2**14, 2**18, 2**20, 2**22], "humanoid": [2**10, 2**12, 2**14, 2**16, 2**18, 2**20, 2**22]}
 if quick:
     sizes = {k: v[:2] for k, v in sizes.items()}
 for name, ns in sizes.items():
@@ -49,7 +49,7 @@ for name, ns in sizes.items():
                 d.ctrl.fill_(3.2495625)
             for _ in range(3):
                 mj.mj_step(model, d)
-            ms = timed(lambda: d.backend.step(1, derived=False), 7 if name != "humanoid" else 3)
+            ms = timed(lambda: d.backend.step(1, derived=False), 7 if name != "humanoid" else (3 if n <= 2**16 else 1))
             out = dict(model=name, nenv=n, precision=prec, kernel=d.backend.batch.kernel_variant, step_ms=ms,
                        env_steps_per_sec=n / ms * 1e3, bytes_per_step=(2 * model.nq + 2 * model.nv + model.nu + 2 * model.nv) * prec // 8)
             out["hbm_gbs"] = out["bytes_per_step"] * n / ms / 1e6
