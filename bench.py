@@ -223,15 +223,20 @@ def _cpu_model(model):
 
 
 def _cpu_probe_rate(om, model, name: str, linearize: bool, cores: int, seed: int) -> float:
-    """env-steps/s of a short all-core run (after one throw-away call that starts the threads and faults the pages in)."""
+    """env-steps/s of a short all-core run: the sample grows until it takes >= 0.1 s, so that thread start-up and page
+    faults do not dominate the estimate."""
     n_probe = max(cores * 4, 64)
     rate = 1.0
-    for rep in range(2):
+    for _ in range(8):
         qpos, qvel = synth_states(model, name, n_probe, seed)
         ctrl = np.zeros((n_probe, model.nu))
         t0 = time.perf_counter()
         om.batch_rollout(qpos, qvel, ctrl, nsteps=2, lin=linearize, nthreads=cores)
-        rate = n_probe * 2 / max(time.perf_counter() - t0, 1e-6)
+        dt = max(time.perf_counter() - t0, 1e-6)
+        rate = n_probe * 2 / dt
+        if dt >= 0.1:
+            break
+        n_probe = int(min(n_probe * 8, 1 << 20))
     return rate
 
 
@@ -299,7 +304,7 @@ def workload_name(name: str, nenv: int, lin: bool) -> str:
     if lin:
         tail = "batched LQR + per-step FD (A,B) linearisation + 1 step"
     elif name in RANDOM_CTRL:
-        tail = "1 step per launch, random controls U(%g, %g) drawn on the device every step (Philox)" % RANDOM_CTRL[name]
+        tail = "1 step per launch, random controls U(%g, %g) drawn on the device every step (Philox, b2_random_controls)" % RANDOM_CTRL[name]
         if name == "drone":
             tail += ", episode reset to the initial state below z = 0.5 m"
     else:
@@ -307,7 +312,7 @@ def workload_name(name: str, nenv: int, lin: bool) -> str:
     return f"{name} batched rollout, N={nenv} envs/GPU, FP64, " + tail
 
 
-def make_controller(name: str, lin: bool):
+def make_controller(name: str, lin: bool, seed: int = 0):
     """The controller of a workload (counted as the controller, not as the path: SURVEY.md section 8d)."""
     import torch
 
@@ -324,20 +329,13 @@ def make_controller(name: str, lin: bool):
             def __call__(self, m, d, t): pass
         return HoldLin()
     if name in RANDOM_CTRL:
-        class RandomCtrl:
-            capabilities = ControllerCapabilities()
-            lo, hi = RANDOM_CTRL[name]
-            init = None  # (qpos, qvel) tensors of the initial states: set by the caller for the drone
-            def prepare(self, m, d): pass
-            def __call__(self, m, d, t):
-                d.ctrl.uniform_(self.lo, self.hi)
-                if self.init is not None:
-                    # episode reset, as a batched rollout driver does it: a drone that comes within 0.5 m of the floor
-                    # starts again from its initial state (config #3 is free flight: "expect no ground contact")
-                    low = (d.qpos[2] < 0.5).unsqueeze(0)
-                    torch.where(low, self.init[0], d.qpos, out=d.qpos)
-                    torch.where(low, self.init[1], d.qvel, out=d.qvel)
-        return RandomCtrl()
+        from mujoco_template.batched_controllers import BatchedRandomController
+
+        # one library launch per tick (b2_random_controls): Philox controls + for the drone the episode reset of a batched
+        # rollout driver -- a drone that comes within 0.5 m of the floor starts again from its initial state (config #3 is
+        # free flight: "expect no ground contact")
+        lo, hi = RANDOM_CTRL[name]
+        return BatchedRandomController(lo, hi, seed=seed, reset_below=(2, 0.5) if name == "drone" else None)
     return None
 
 
@@ -357,7 +355,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
         torch.cuda.synchronize()
 
     model = load_model(name)
-    controller = make_controller(name, lin)
+    controller = make_controller(name, lin, seed=rank)
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
     qpos, qvel = synth_states(model, name, nenv, seed=rank)  # each rank owns its own shard of envs
@@ -365,7 +363,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
     env.data.qvel.copy_(torch.as_tensor(qvel.T.copy(), device=dev))
     env.forward()
     if name == "drone" and not lin and controller is not None:
-        controller.init = (env.data.qpos.clone(), env.data.qvel.clone())
+        controller.set_reset_state(env.data.qpos, env.data.qvel)
 
     # per-kernel device times for the roofline: short eager passes with CUDA events around each library launch --
     # first the launches one by one (controller / FD / step), then the fused control tick the timed loop runs
@@ -381,7 +379,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
             flush.zero_()
             env.step(return_obs=False)
         torch.cuda.synchronize()
-        for k in ("lqr_control", "linearize", "step", "control_tick"):
+        for k in ("random_controls", "lqr_control", "linearize", "step", "control_tick"):
             v = env.data.backend.kernel_ms(k)[-10:]
             if v:
                 kernel_ms[k] = v
@@ -468,13 +466,13 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
     mean_of = lambda k: float(np.mean(kernel_ms[k])) if kernel_ms.get(k) else None
     # what the timed step consists of: the fused control tick (FD launch with the env advance riding in it + the state
     # commit) when it is used, else the kernels launched one by one
-    in_step = ("control_tick",) if (lin and fuse_default and kernel_ms.get("control_tick")) else tuple(k for k in ("lqr_control", "linearize", "step") if kernel_ms.get(k))
+    in_step = ("control_tick",) if (lin and fuse_default and kernel_ms.get("control_tick")) else tuple(k for k in ("random_controls", "lqr_control", "linearize", "step") if kernel_ms.get(k))
     share = {k: mean_of(k) / ms_step for k in in_step}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": ctx["peak_gbs"], "unit": "GB/s", "frac": achieved / ctx["peak_gbs"],
                 "traffic": traffic, "kernel": kernel_label,
                 "kernel_ms": dom_ms, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": ctx["peak_src"],
                 "kernel_share_of_step": share,
-                "kernel_ms_launched_separately": {k: mean_of(k) for k in ("lqr_control", "linearize", "step") if kernel_ms.get(k)},
+                "kernel_ms_launched_separately": {k: mean_of(k) for k in ("random_controls", "lqr_control", "linearize", "step") if kernel_ms.get(k)},
                 "kernel_share_note": "share = device time of the launches the timed step consists of / ms_per_step; with a "
                                      "linearising controller that is b2_control_tick (control law + FD + the env advance in one "
                                      "launch, then the state commit); kernel_ms_launched_separately lists the same work as "
@@ -487,6 +485,17 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
     roofline_fp64 = {"bound": "fp64_fma", "achieved": tf, "peak": ctx["fp64_peak"], "unit": "TFLOP/s", "frac": tf / ctx["fp64_peak"],
                      "step_evals_per_launch": evals, "flops_per_step_eval": flops_per_eval,
                      "flops_source": flops_src, "peak_source": "b2_fp_peak DFMA microbenchmark, this run"}
+    # the ALGORITHMIC count of the same work: the oracle's op counter (tools/op_count.py -> profiles/op_count_r02.json)
+    oc_file = os.path.join(ROOT, "profiles", "op_count_r02.json")
+    if os.path.exists(oc_file):
+        oc = json.load(open(oc_file))["models"][name]
+        alg = (oc["linearize_plus_step"]["flops"] - oc["step"]["flops"]) if lin else oc["step"]["flops"]
+        roofline_fp64["algorithmic_flops_per_launch_unit"] = alg
+        roofline_fp64["algorithmic_unit"] = "one mjd_transitionFD (1 + 2(2nv+nu) serial mj_steps upstream)" if lin else "one mj_step"
+        roofline_fp64["algorithmic_tflops"] = alg * nenv / (dom_ms * 1e-3) / 1e12
+        roofline_fp64["algorithmic_note"] = ("oracle op count (add/mul/div/sqrt = 1, transcendental call = 20) of the scalar algorithm on this "
+                                             "workload's states; the kernels execute fewer flops than that where they reuse stages across "
+                                             "rollouts or fold the model into the instruction stream")
 
     # ---- e2e: host buffers through the C-ABI (b2_step_host): H2D state+ctrl, linearise+step, D2H state+(A,B)
     e2e = None
@@ -550,6 +559,27 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
                "pcie_d2h_frac_of_55gbs": d2h / e2e_s / 1e9 / 55.0,
                "api": "b2_step_host (C-ABI, pinned host buffers, " + ("device LQR law, ctrl returned" if device_lqr else ("host LQR tick" if K is not None else "controls held in the host buffer")) +
                       (", (A, B) written by the FD kernel straight into the mapped host buffers" if lin and os.environ.get("B2_HOST_STAGED") != "1" else "") + ")"}
+        if lin:
+            # the same tick when the consumer of (A, B) lives on the device (a device-side gain synthesis such as b2_dlqr, or
+            # the control law itself): (A, B) stay in HBM, the host exchanges state and controls only
+            def host_step_ab_on_device():
+                batch.step_host(st, 1, lin, 1e-6, None, None, 0, device_lqr=device_lqr)
+
+            for _ in range(3):
+                host_step_ab_on_device()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                host_step_ab_on_device()
+            barrier()
+            tt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            s2 = float(tt.item()) / e2e_steps
+            e2e["ab_kept_on_device"] = {"value": nenv * world / s2, "unit": UNIT, "ms_per_step": s2 * 1e3, "h2d_bytes_per_step": h2d,
+                                        "d2h_bytes_per_step": d2h - 2 * nv * (2 * nv + nu) * nenv * 8,
+                                        "note": "b2_step_host with host_A = host_B = NULL: (A, B) are computed every step and left in "
+                                                "device memory for a device-side consumer; not the headline e2e"}
         del hq, hv, hu, hw, hA, hB
 
     cpu = None
@@ -584,10 +614,11 @@ def flops_per_step_eval(name: str, lin: bool):
     """Executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
     themselves (profiles/): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per env runs the
     shared position stage once for all velocity / control columns, control columns skip the velocity stage too -- and
-    k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 182,000 (mean 3.6 contacts, 2.9
-    Newton iterations).  The oracle's op counter (oracle.op_count) gives the ALGORITHMIC count of one
+    k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 3.70e9 / 16,384 = 226,000 in the
+    round-2 capture (profiles/ncu_hum_step_r02d.txt: 100 steps into the fall, ~5 contacts, 3.5 Newton iterations; 182,000
+    in round 1's lighter state).  The oracle's op counter (oracle.op_count) gives the ALGORITHMIC count of one
     mj_step for the same states; the executed count is what the pipe-utilisation figure needs."""
-    table = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 182000.0}
+    table = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 226000.0}
     src = "ncu-counted executed flops (profiles/)" if name != "pendulum" else "a-priori estimate (BASELINE.md section 4)"
     return table[name], src
 
@@ -637,7 +668,7 @@ def main():
     if name == "cartpole" and lin and args.nenv is None and not args.no_secondary:
         out["secondary"] = {}
         for sname in ("drone", "humanoid"):
-            sec = run_workload(ctx, sname, False, DEFAULT_NENV[sname], min(args.steps, 100), args.warmup,
+            sec = run_workload(ctx, sname, False, DEFAULT_NENV[sname], args.steps, args.warmup,
                                cpu_seconds=0.0 if args.no_cpu_baseline else min(args.cpu_seconds, 5.0), **common)
             out["secondary"][sname] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_per_rank", "steps", "config", "roofline",
                                                            "roofline_fp64", "cpu_baseline", "e2e", "gpu_launches", "contact_stats",

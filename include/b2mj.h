@@ -169,6 +169,15 @@ int b2_fp_peak(int precision, int device, double* tflops);
 
 int b2_stream_synchronize(b2_batch* batch, void* stream);
 
+/* Random-rollout controller on the device (BASELINE.json configs #3 / #4: "batched random controls ... generated on
+ * device"): ctrl[a, e] ~ U(lo, hi), i.i.d. per call, env and actuator (Philox4x32-10 keyed by (seed, env); the per-env
+ * draw counter lives in the batch, so a captured CUDA graph replays with fresh numbers).  With reset_qpos != NULL the
+ * same launch applies a rollout driver's episode reset first: an env whose qpos[watch_row] < watch_min restarts from its
+ * column of reset_qpos (nq, nenv) / reset_qvel (nv, nenv; NULL = zeros).  Fills the role of a reference Controller
+ * (control.py:18-32) for a batch; writes state.ctrl (and the reset states) in place. */
+int b2_random_controls(b2_batch* batch, const b2_state* state, double lo, double hi, unsigned long long seed, int watch_row,
+                       double watch_min, const void* reset_qpos, const void* reset_qvel, void* stream);
+
 /* Batched discrete-time LQR synthesis on the device: for every env e the stabilising solution P_e of the DARE
  *     P = A'PA - A'PB (R + B'PB)^-1 B'PA + Q
  * and the gain K_e = (R + B'PB)^-1 B'PA (u = -K x) from that env's own (A_e, B_e) -- what the reference's example

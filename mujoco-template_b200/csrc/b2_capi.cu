@@ -84,6 +84,7 @@ struct b2_batch {
   void* d_shadow = nullptr;        // shadow state of the FD launch that also advances the envs (b2_control_tick)
   bool shadow_has_prestep = false;
   void* d_gain = nullptr;  // LQR gain block: K, qpos_ref, ctrl_ref
+  void* d_rng_ctr = nullptr;  // b2_random_controls: draw counter per env
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // copy/compute pipeline of b2_step_host
   cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
   bool pipe_ready = false;
@@ -178,7 +179,7 @@ int b2_batch_create(const b2_model* model, int nenv, int device, int precision, 
 }
 void b2_batch_destroy(b2_batch* b) {
   if (!b) return;
-  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch, b->d_gain, b->d_shadow};
+  void* p[] = {b->d_qpos, b->d_qvel, b->d_ctrl, b->d_warm, b->d_A, b->d_B, b->d_jscratch, b->d_gain, b->d_shadow, b->d_rng_ctr};
   for (void* q : p) if (q) cudaFree(q);
   if (b->host_graph) cudaGraphExecDestroy(b->host_graph);
   if (b->pipe_ready) { for (cudaStream_t st : b->pipe) cudaStreamDestroy(st); for (cudaEvent_t ev : b->pipe_ev) cudaEventDestroy(ev); }
@@ -677,6 +678,25 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   g_launches += b->host_graph_launches;
   e = cudaStreamSynchronize(s0);
   return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
+}
+
+int b2_random_controls(b2_batch* b, const b2_state* st, double lo, double hi, unsigned long long seed, int watch_row, double watch_min,
+                       const void* reset_qpos, const void* reset_qvel, void* stream) {
+  B2_CHECK_STATE("b2_random_controls");
+  const b2m_view& v = b->model->v;
+  if (v.nu == 0) return fail(B2_ERR_ARG, "b2_random_controls: model has no actuators");
+  if (reset_qpos && (watch_row < 0 || watch_row >= v.nq)) return fail(B2_ERR_ARG, "b2_random_controls: watch_row out of range");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  if (!b->d_rng_ctr) {
+    if ((e = cudaMalloc(&b->d_rng_ctr, sizeof(unsigned) * (size_t)b->nenv)) || (e = cudaMemset(b->d_rng_ctr, 0, sizeof(unsigned) * (size_t)b->nenv)))
+      return cuda_fail(e, "b2_random_controls: draw counters");
+  }
+  const int rc = b->precision == B2_F64
+                     ? b2::b2k_random_controls_f64(st, b->nenv, v.nq, v.nv, v.nu, lo, hi, seed, b->d_rng_ctr, watch_row, watch_min, reset_qpos, reset_qvel, stream)
+                     : b2::b2k_random_controls_f32(st, b->nenv, v.nq, v.nv, v.nu, lo, hi, seed, b->d_rng_ctr, watch_row, watch_min, reset_qpos, reset_qvel, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_random_controls launch") : B2_OK;
 }
 
 // Batched discrete LQR synthesis (see include/b2mj.h).  Q, R are host arrays shared by all envs; R is inverted here.

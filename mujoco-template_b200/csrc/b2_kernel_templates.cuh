@@ -267,8 +267,15 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // thread takes a group of up to B2_FD_GROUP of them, runs that stage once and then their rollouts (tasks 0..groups-1,
 // launched first: they are the longest); each position column is a thread of its own (two full rollouts).  RK4 models
 // have nothing to share between columns: one thread per (env, column).
+// register budget of the FD kernel: either through the resident-blocks hint or, with B2_LIN_MAXNREG, as an explicit cap
+// (ptxas settles on 168 registers for any hint between 3 x 128 and 5 x 64 threads per SM)
+#ifdef B2_LIN_MAXNREG
+#define B2_LIN_BOUNDS __maxnreg__(B2_LIN_MAXNREG)
+#else
+#define B2_LIN_BOUNDS __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS)
+#endif
 template <typename T, class D, class M>
-__global__ void __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow,
+__global__ void B2_LIN_BOUNDS k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow,
                                                                                  const void* image = nullptr) {
   model_load<M>(image, 0);
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
@@ -421,6 +428,43 @@ __global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, 
   for (int k = 0; k < M::nv(); k++) v[k] = st.qvel[(size_t)k * N + e];
   lqr_law(env, q, v, gain, u);
   for (int a = 0; a < M::nu(); a++) st.ctrl[(size_t)a * N + e] = u[a];
+}
+
+// Random-rollout controller (BASELINE configs #3 / #4: controls U(lo, hi) i.i.d. per step, env and actuator, drawn on the
+// device) fused with the episode reset a batched rollout driver applies: an env whose qpos[watch_row] has dropped below
+// watch_min starts again from its row of reset_qpos / reset_qvel.  Philox4x32-10 keyed by (seed, env), counter = the env's
+// own draw count (kept in ctr[], so a captured graph replays with fresh numbers).  One launch instead of five tensor ops.
+B2_DEV void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1, unsigned* out) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0, hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) k_random_controls(StateDev<T> st, int N, int nq, int nv, int nu, T lo, T hi, unsigned long long seed,
+                                                         unsigned* __restrict__ ctr, int watch_row, T watch_min,
+                                                         const T* __restrict__ reset_qpos, const T* __restrict__ reset_qvel) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  if (reset_qpos && st.qpos[(size_t)watch_row * N + e] < watch_min) {
+    for (int k = 0; k < nq; k++) st.qpos[(size_t)k * N + e] = reset_qpos[(size_t)k * N + e];
+    for (int k = 0; k < nv; k++) st.qvel[(size_t)k * N + e] = reset_qvel ? reset_qvel[(size_t)k * N + e] : T(0);
+  }
+  const unsigned draw = ctr[e];
+  ctr[e] = draw + 1;
+  for (int a = 0; a < nu; a += 2) {
+    unsigned r[4];
+    philox4x32_10(draw, (unsigned)(a >> 1), (unsigned)e, 0u, (unsigned)seed, (unsigned)(seed >> 32), r);
+    // 53-bit uniform in [0, 1) from two words each
+    const double u0 = ((double)(((unsigned long long)(r[0] >> 5) << 26) | (r[1] >> 6))) * (1.0 / 9007199254740992.0);
+    const double u1 = ((double)(((unsigned long long)(r[2] >> 5) << 26) | (r[3] >> 6))) * (1.0 / 9007199254740992.0);
+    st.ctrl[(size_t)a * N + e] = lo + (hi - lo) * (T)u0;
+    if (a + 1 < nu) st.ctrl[(size_t)(a + 1) * N + e] = lo + (hi - lo) * (T)u1;
+  }
 }
 
 // Recorder gather (reference logging.py:81-247 rows for a selection of envs): blockIdx.y = column, x = selected envs.

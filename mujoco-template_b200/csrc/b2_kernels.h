@@ -26,6 +26,8 @@ namespace b2 {
   int b2k_lqr_control##SUF(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \
   int b2k_dare##SUF(const void* A, const void* B, const void* qr, int nx, int nu, int N, int max_doublings, double tol, void* K, void* P, \
                     int* status, void* stream);                                                                            \
+  int b2k_random_controls##SUF(const b2_state* st, int N, int nq, int nv, int nu, double lo, double hi, unsigned long long seed, void* ctr, \
+                               int watch_row, double watch_min, const void* reset_qpos, const void* reset_qvel, void* stream);             \
   int b2k_record_rows##SUF(const void* cols, int ncol, const int* env_index, int nsel, int N, double time, void* out, void* stream); \
   int b2k_integrate_pos##SUF(const void* image, int cls, void* qpos, const void* qvel, double dt, int N, void* stream);                       \
   int b2k_differentiate_pos##SUF(const void* image, int cls, void* out, double dt, const void* q1, const void* q2, int N, void* stream);

@@ -284,6 +284,13 @@ int B2_FN(b2k_dare)(const void* A, const void* B, const void* qr /* device: Q, R
       (const real*)A, (const real*)B, q, q + nx * nx, q + nx * nx + nu * nu, nx, nu, N, max_doublings, (real)tol, (real*)K, (real*)P, status);
   return (int)cudaGetLastError();
 }
+int B2_FN(b2k_random_controls)(const b2_state* st, int N, int nq, int nv, int nu, double lo, double hi, unsigned long long seed, void* ctr,
+                               int watch_row, double watch_min, const void* reset_qpos, const void* reset_qvel, void* stream) {
+  k_random_controls<real><<<(N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(to_dev<real>(st), N, nq, nv, nu, (real)lo, (real)hi, seed,
+                                                                             (unsigned*)ctr, watch_row, (real)watch_min,
+                                                                             (const real*)reset_qpos, (const real*)reset_qvel);
+  return (int)cudaGetLastError();
+}
 int B2_FN(b2k_record_rows)(const void* cols, int ncol, const int* env_index, int nsel, int N, double time, void* out, void* stream) {
   const int threads = 128;
   k_record_rows<real><<<dim3((nsel + threads - 1) / threads, ncol), threads, 0, (cudaStream_t)stream>>>(

@@ -39,9 +39,12 @@ REAL_ARRAYS = ("gravity", "wind", "body_pos", "body_quat", "body_ipos", "body_iq
                "actuator_forcerange", "actuator_gainprm", "actuator_biasprm", "pair_margin", "pair_gap", "pair_friction",
                "pair_solref", "pair_solimp", "sensor_cutoff")
 
-# FD kernel block shape for small models: (threads per block, min resident blocks per SM)
+# FD kernel block shape for small models: (threads per block, min resident blocks per SM).  64 x 4 lets ptxas use 253
+# registers -- the cartpole FD kernel then has no spills at all -- at 8 warps per SM, in blocks small enough that the last
+# wave of the launch is short: 36.4 us against 38.6 us for 128 x 3 (168 registers, 320 B of spills, 12 warps); explicit caps
+# in between (184 / 200 / 216 registers at 9-11 warps) are all slower (round 2, profiles/ab_cartpole_lin_shapes_r02k.txt).
 import os as _os
-LIN_SHAPE = tuple(int(x) for x in _os.environ.get("B2_LIN_SHAPE", "128,3").split(","))
+LIN_SHAPE = tuple(int(x) for x in _os.environ.get("B2_LIN_SHAPE", "64,4").split(","))
 
 _MAX_CONTACTS = {(0, 2): 1, (0, 3): 2, (0, 6): 4, (0, 4): 1, (2, 2): 1, (2, 3): 1, (3, 3): 2}
 

@@ -164,4 +164,36 @@ class BatchedLQRController:
         data.ctrl.copy_(u)
 
 
-__all__ = ["BatchedLQRController", "batched_dlqr_gain", "dlqr_gain"]
+class BatchedRandomController:
+    """Random-rollout controller of BASELINE.json configs #3 / #4 ("batched random controls", drawn on the device every
+    step): ``ctrl ~ U(lo, hi)`` i.i.d. per step, env and actuator, in ONE library launch (``b2_random_controls``, Philox
+    keyed by ``(seed, env)``).  ``reset_below=(qpos_row, threshold)`` adds a rollout driver's episode reset to the same
+    launch: an env whose ``qpos[qpos_row]`` has dropped below the threshold restarts from the state it had when
+    ``prepare()`` (i.e. ``reset()``) last ran, or from ``set_reset_state(qpos, qvel)``."""
+
+    def __init__(self, lo: float, hi: float, seed: int = 0, reset_below: tuple[int, float] | None = None):
+        self.lo, self.hi, self.seed = float(lo), float(hi), int(seed)
+        self.reset_below = reset_below
+        self.capabilities = ControllerCapabilities(control_space=ControlSpace.TORQUE)
+        self._reset = None
+
+    def prepare(self, model: Any, data: Any) -> None:
+        if model.nu == 0:
+            raise ConfigError("BatchedRandomController requires nu>0")
+        if not hasattr(data.qpos, "device"):
+            raise ConfigError("BatchedRandomController drives a BatchedEnv (device tensors)")
+        if self.reset_below is not None:
+            self.set_reset_state(data.qpos, data.qvel)
+
+    def set_reset_state(self, qpos: Any, qvel: Any) -> None:
+        self._reset = (qpos.clone(), qvel.clone())
+
+    def __call__(self, model: Any, data: Any, t: float) -> None:
+        b = data.backend
+        row, thr = self.reset_below if self.reset_below is not None else (-1, 0.0)
+        rq = self._reset[0].data_ptr() if self._reset is not None else None
+        rv = self._reset[1].data_ptr() if self._reset is not None else None
+        b._launch("random_controls", b.batch.random_controls, b.state_struct(), self.lo, self.hi, self.seed, row, thr, rq, rv)
+
+
+__all__ = ["BatchedLQRController", "BatchedRandomController", "batched_dlqr_gain", "dlqr_gain"]

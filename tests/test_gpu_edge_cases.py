@@ -376,3 +376,46 @@ def test_graph_replay_keeps_its_model_when_another_model_runs_in_between(monkeyp
                 od.step()
             ref[e] = od.qpos
         assert _rel(env.data.qpos.cpu().numpy().T, ref) <= 1e-8
+
+
+def test_random_controller_kernel_statistics_reset_and_graph_replay():
+    """b2_random_controls: U(lo, hi) per env, actuator and call (fresh numbers on every call, also when the call is replayed
+    from a captured CUDA graph), reproducible per (seed, env), and the fused episode reset."""
+    import torch
+    import mujoco_template as mt
+    from mujoco_template.batched_controllers import BatchedRandomController
+
+    model = load_model("drone")
+    n = 4096
+    draws = {}
+    for seed in (0, 0, 1):
+        env = mt.BatchedEnv(model, n, controller=BatchedRandomController(0.0, 13.0, seed=seed, reset_below=(2, 0.5)))
+        env.reset(0)
+        z0 = env.data.qpos[2].clone()
+        env.data.qpos[2, :7] = 0.2          # seven drones below the reset height, moving
+        env.data.qvel[:, :7] = 1.0
+        out = []
+        for _ in range(3):
+            env.controller(model, env.data, 0.0)
+            out.append(env.data.ctrl.clone())
+        torch.cuda.synchronize()
+        assert torch.equal(env.data.qpos[2], z0) and float(env.data.qvel[:, :7].abs().max()) == 0.0  # reset to the prepare() state
+        draws.setdefault(seed, []).append(torch.stack(out))
+    a, b, c = draws[0][0], draws[0][1], draws[1][0]
+    assert torch.equal(a, b) and not torch.equal(a, c)                       # per-seed reproducible, seeds differ
+    assert not torch.equal(a[0], a[1]) and not torch.equal(a[1], a[2])       # fresh numbers every call
+    u = a.flatten().cpu().numpy()
+    assert u.min() >= 0.0 and u.max() < 13.0
+    assert abs(u.mean() - 6.5) < 0.05 and abs(u.std() - 13.0 / np.sqrt(12.0)) < 0.05
+    assert abs(np.corrcoef(a[0, 0].cpu().numpy(), a[0, 1].cpu().numpy())[0, 1]) < 0.05   # actuators independent
+    assert abs(np.corrcoef(a[0, 0].cpu().numpy(), a[1, 0].cpu().numpy())[0, 1]) < 0.05   # calls independent
+    # graph replay: the per-env draw counter lives on the device, so replays keep drawing fresh controls
+    env = mt.BatchedEnv(model, n, controller=BatchedRandomController(0.0, 13.0, seed=3))
+    env.reset(0)
+    env.enable_cuda_graph(True)
+    seen = []
+    for _ in range(5):
+        env.step(return_obs=False)
+        seen.append(env.data.ctrl.clone())
+    torch.cuda.synchronize()
+    assert all(not torch.equal(seen[i], seen[i + 1]) for i in range(4))
