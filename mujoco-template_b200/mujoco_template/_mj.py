@@ -305,7 +305,6 @@ class NativeBackend:
         """Materialise the derived arrays of the last control tick that deferred them (``b2_refresh_derived``)."""
         if self.derived_stale:
             self.derived_stale = False
-            self.refresh_count = getattr(self, "refresh_count", 0) + 1  # BatchedEnv: somebody does read derived arrays
             self._launch("refresh_derived", self.batch.refresh_derived, self.derived_struct())
 
     def control_tick(self, eps: float, centered: bool, use_lqr: bool, out=None, derived: bool = True):

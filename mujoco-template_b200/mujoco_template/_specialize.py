@@ -214,25 +214,45 @@ def jit_specialize(model, name: str | None = None, cache_dir: str | None = None,
     if int(c["nv"]) > JIT_MAX_NV:
         return None
     blob = _layout.pack(c)
-    key = f"{fnv1a(blob):016x}_{len(blob)}"
-    name = name or f"jit_{key[:8]}"
+    csrc = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
+    flags = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
+             "--expt-relaxed-constexpr", "-shared"]
+    name_hint = name
+    # The cache key covers everything the object depends on: the model, the generated source (kernel launch shape, spec
+    # ABI), the engine headers it includes and the compiler flags -- an object built against an older library is never
+    # picked up after an update.
+    source = emit_spec(c, name or "jit")
+    h = fnv1a(blob)
+    for path in sorted(os.listdir(csrc)):
+        if path.endswith((".cuh", ".h")):
+            with open(os.path.join(csrc, path), "rb") as fh:
+                h = fnv1a(fh.read() + h.to_bytes(8, "little"))
+    h = fnv1a(source.encode() + " ".join(flags).encode() + h.to_bytes(8, "little"))
+    key = f"{fnv1a(blob):016x}_{len(blob)}_{h:016x}"
+    name = name_hint or f"jit_{key[:8]}"
     cache_dir = cache_dir or os.environ.get("B2_SPEC_CACHE") or os.path.join(os.path.expanduser("~"), ".cache", "b2mj")
     os.makedirs(cache_dir, exist_ok=True)
     so = os.path.join(cache_dir, f"spec_{key}.so")
     if not os.path.exists(so):
+        import tempfile
+
         nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-        csrc = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
-        cu = os.path.join(cache_dir, f"spec_{key}.cu")
-        with open(cu, "w") as fh:
+        # private temporaries (several ranks may compile the same model at once), published by an atomic rename
+        fd, cu = tempfile.mkstemp(prefix=f"spec_{key}_", suffix=".cu", dir=cache_dir)
+        with os.fdopen(fd, "w") as fh:
             fh.write(emit_spec(c, name))
-        cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
-               "--expt-relaxed-constexpr", "-shared", "-I", os.path.join(csrc, "generated"), cu, "-o", so + ".tmp"]
+        tmp_so = cu[:-3] + ".so.tmp"
+        cmd = [nvcc] + flags + ["-I", os.path.join(csrc, "generated"), cu, "-o", tmp_so]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             from .exceptions import ConfigError
 
+            for leftover in (cu, tmp_so):
+                if os.path.exists(leftover):
+                    os.remove(leftover)
             raise ConfigError("jit_specialize: nvcc failed\n" + r.stderr[-2000:])
-        os.replace(so + ".tmp", so)
+        os.replace(tmp_so, so)
+        os.remove(cu)
         if verbose:
             print(f"jit_specialize: built {so}")
     _capi.lib()  # libb2mj.so must be loaded (globally) first: the object's registrar calls b2::register_spec

@@ -119,7 +119,16 @@ class BatchedEnv:
     def __init__(self, model: mj.MjModel, nenv: int, *, controller: Controller | None = None,
                  obs_spec: ObservationSpec | None = None, control_decimation: int = 1, device: int | None = None,
                  precision: int = 64, reward_fn=None, done_fn=None, info_fn=None, lin_eps: float = 1e-6,
-                 data: mj.BatchData | None = None):
+                 data: mj.BatchData | None = None, derived: str = "lazy"):
+        """``derived``: what ``step(return_obs=False)`` does about the derived arrays (``xpos``, ``site_xpos``,
+        ``sensordata``, ...).  ``"lazy"`` (default): the step runs without them and parks its pre-step state; whoever reads
+        ``data.xpos`` etc. afterwards gets the same values through one extra forward pass (``b2_refresh_derived``) -- right
+        when nothing, or only an occasional hook, reads them.  ``"eager"``: every step exports them, as ``mj_step`` does --
+        right when a hook, reward function or recorder reads them after every step.  The choice is the caller's and does
+        not depend on call history."""
+        if derived not in ("lazy", "eager"):
+            raise ConfigError("derived must be 'lazy' or 'eager'")
+        self.derived = derived
         if control_decimation < 1:
             raise ConfigError("control_decimation must be >= 1")
         if nenv < 1:
@@ -284,15 +293,8 @@ class BatchedEnv:
         if n < 1:
             raise ConfigError("BatchedEnv.step(n): n must be >= 1")
         info: InfoDict = {}
-        # derived arrays are produced on demand when the caller takes no observation -- unless it turns out that someone
-        # (a hook, a reward function, a recorder) reads them after such steps anyway: two lazy steps in a row that were
-        # each followed by a refresh switch this env back to eager derived outputs (a refresh costs a forward pass)
-        backend = self.data.backend
-        seen = getattr(backend, "refresh_count", 0)
-        if seen != getattr(self, "_refresh_seen", 0):
-            self._lazy_refreshes = getattr(self, "_lazy_refreshes", 0) + 1
-            self._refresh_seen = seen
-        lazy = not return_obs and getattr(self, "_lazy_refreshes", 0) < 2
+        # derived arrays are produced on demand when the caller takes no observation (see `derived` in __init__)
+        lazy = not return_obs and self.derived == "lazy"
         if getattr(self, "_graph_enabled", False) and n == 1 and self.controller is not None:
             lin_A, lin_B, jacs = self._graphed_work(lazy)
         else:

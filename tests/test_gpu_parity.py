@@ -754,9 +754,8 @@ def test_fused_control_tick_equals_three_launch_sequence(monkeypatch, name, n, p
             hist.append((res.info["A"].clone(), res.info["B"].clone(), benv.data.qpos.clone(), benv.data.qvel.clone(),
                          benv.data.ctrl.clone()) + derived)
         # FD(+step) + commit + lazy forward | FD + step | law + FD + step (+ the lazy forward: step(return_obs=False) on an
-        # Euler model leaves the derived arrays to b2_refresh_derived as well;
-        # the env switches back to eager derived outputs after two lazy steps whose derived arrays were read)
-        expect = 5 * (3 if euler else 2) if fused else (2 * 4 + 3 * 3 if euler else 5 * 3)
+        # Euler model leaves the derived arrays to b2_refresh_derived as well -- BatchedEnv(derived="lazy"), the default)
+        expect = 5 * (3 if euler else 2) if fused else (5 * 4 if euler else 5 * 3)
         assert mt._capi.launch_count() - c0 == expect
         out[fused] = hist
     tol = 1e-12 if precision == 64 else 2e-4
