@@ -201,6 +201,9 @@ typedef struct b2_record_col { const void* base; int row; int kind; } b2_record_
 int b2_recorder_create(b2_batch* batch, const b2_record_col* cols, int ncol, const int* env_index, int nsel, b2_recorder** out);
 int b2_recorder_record(b2_recorder* rec, double time, void* out_slot, void* stream);
 void b2_recorder_destroy(b2_recorder* rec);
+/* Diagnostic: histogram of the warp engine's queue keys of the last b2_step (16 bins: Newton rounds of the step before,
+ * capped at 7; + 8 when the env had constraint rows that couple two branches of the tree).  Synchronises `stream`. */
+int b2_warp_queue_histogram(b2_batch* batch, int* hist16, void* stream);
 /* number of kernels launched by this library in the calling process (bench gpu_launches) */
 long long b2_launch_count(void);
 /* size class the model was mapped to: 0 tiny, 1 small, 2 large */

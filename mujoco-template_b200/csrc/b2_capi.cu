@@ -784,6 +784,15 @@ void b2_recorder_destroy(b2_recorder* r) {
   delete r;
 }
 
+int b2_warp_queue_histogram(b2_batch* b, int* hist16, void* stream) {
+  if (!b || !hist16) return fail(B2_ERR_ARG, "b2_warp_queue_histogram: null pointer");
+  if (b->warp_mode != 1 || !b->d_warp_sort) return fail(B2_ERR_ARG, "b2_warp_queue_histogram: batch does not run on the warp engine's ordered queue");
+  cudaError_t e = cudaSetDevice(b->device);
+  if (!e) e = cudaStreamSynchronize((cudaStream_t)stream);
+  if (!e) e = cudaMemcpy(hist16, b->d_warp_sort, 16 * sizeof(int), cudaMemcpyDeviceToHost);
+  return e ? cuda_fail(e, "b2_warp_queue_histogram") : B2_OK;
+}
+
 int b2_fp_peak(int precision, int device, double* tflops) {
   if (!tflops || (precision != B2_F64 && precision != B2_F32)) return fail(B2_ERR_ARG, "b2_fp_peak: bad arguments");
   cudaError_t e = cudaSetDevice(device);

@@ -35,15 +35,10 @@ B2_DEV int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // packed lower tr
 // precision) and passed to the kernels by pointer -- no process-wide device symbols, so batches of different large models
 // can run concurrently on different streams.  Lanes read the model with lane-dependent indices, which the constant cache
 // would serialise (one address per cycle); read-only global loads are gathered by L1 instead.
-//  * ld_plan: work list of the tree-sparse L'DL factorisation (mj_factorM): for every pivot dof k the ancestor pairs (i, j),
-//    j <= i, packed as tri(i,j) | tri(k,j) << 10 | i << 20; ld_off[k] .. ld_off[k+1] delimits pivot k.
-//  * chol_plan: work list of the dense nv x nv Cholesky of the Newton Hessian: for pivot column j the trailing entries
-//    (i, c), j < c <= i, packed as tri(i,c) | tri(i,j) << 10 | tri(c,j) << 20; depends on nv only.
-//  * tri_row / tri_col: inverse of tri() for matrices up to 32 x 32.
+//  * tri_row / tri_col / tri_ij: inverse of tri() for matrices up to 32 x 32.
 template <typename T>
 struct WarpImage {
   DevModel<T, DimsLarge> model;
-  int ld_plan[5456], ld_off[33], chol_plan[5456], chol_off[33];
   unsigned char tri_row[528], tri_col[528];
   unsigned short tri_ij[544];  // per packed entry e: row | col << 8 | (col is row itself or an ancestor of it) << 15
 };
@@ -62,23 +57,6 @@ inline void fill_warp_image(WarpImage<T>& img, const b2m_view& v, const int* act
       if (i < v.nv) for (int a = i; a >= 0; a = v.dof_parentid[a]) if (a == j) { anc = true; break; }
       img.tri_ij[e++] = (unsigned short)(i | (j << 8) | (anc ? 0x8000 : 0));
     }
-  int n = 0;
-  for (int k = 0; k < v.nv && k < 32; k++) {
-    img.ld_off[k] = n;
-    for (int i = v.dof_parentid[k]; i >= 0; i = v.dof_parentid[i])
-      for (int j = i; j >= 0; j = v.dof_parentid[j]) img.ld_plan[n++] = tri_h(i, j) | (tri_h(k, j) << 10) | (i << 20);
-  }
-  for (int k = v.nv < 32 ? v.nv : 32; k <= 32; k++) img.ld_off[k] = n;
-  for (; n < 5456; n++) img.ld_plan[n] = 0;
-  n = 0;
-  const int nv = v.nv > 32 ? 32 : v.nv;
-  for (int j = 0; j < nv; j++) {
-    img.chol_off[j] = n;
-    for (int i = j + 1; i < nv; i++)
-      for (int c = j + 1; c <= i; c++) img.chol_plan[n++] = tri_h(i, c) | (tri_h(i, j) << 10) | (tri_h(c, j) << 20);
-  }
-  for (int j = nv; j <= 32; j++) img.chol_off[j] = n;
-  for (; n < 5456; n++) img.chol_plan[n] = 0;
 }
 
 // Model providers of the warp engine: an object that holds the image pointer; every field is a member accessor.
@@ -127,8 +105,9 @@ struct ImageModel<T, DimsRuntime> : ImageModelBase<T> { typedef DimsRuntime Dims
 struct WarpCaps { static constexpr int NCON = 32, NEFC = 128; };
 // reals of global scratch one resident warp owns: J (NEFC x nv), six row vectors, the contact records (dist, pos, frame) and
 // the int metadata of contacts and rows (counted as one real each)
+// ... and the env's merged ancestor lists (32 counts + 32 x 32 byte indices, see WarpEnv::merge_branches): 1152 B
 __host__ __device__ inline size_t warp_slot_reals(int nv) {
-  return (size_t)WarpCaps::NEFC * (nv + 6) + 13 * WarpCaps::NCON + WarpCaps::NCON + WarpCaps::NEFC;
+  return (size_t)WarpCaps::NEFC * (nv + 6) + 13 * WarpCaps::NCON + WarpCaps::NCON + WarpCaps::NEFC + 320;
 }
 
 // Shared-memory workspace of one env (offsets in reals).  How many warps an SM holds is decided by this size (and by the
@@ -169,24 +148,27 @@ __host__ __device__ inline int warp_ws_reals(int nq, int nv, int nu, int nb, int
 // coming from lane l+s by shuffle.  Nothing in the update loop waits on memory except its own read-modify-write, and the
 // next pivot's ancestor list is fetched while this one is being worked on (the kernel is latency-bound: the plan-driven
 // version of r01 spent 9 % of all stall samples on its load -> load -> FMA -> store chain).
-template <typename T, class M>
-__device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, int lane) {
+// The ancestor lists come either from the model image (the kinematic tree: int entries, read-only path) or from the env's
+// scratch slot (the tree with the branches its constraint rows couple merged: byte entries, WarpEnv::merge_branches).
+B2_DEV int anc_load(const int* p) { return __ldg(p); }
+B2_DEV int anc_load(const unsigned char* p) { return *p; }
+template <typename T, typename IDX>
+__device__ __noinline__ void factor_LD_impl(int nv, const int* __restrict__ nanc, const IDX* __restrict__ anclist, T* LDp, T* dinv, int lane) {
   // The (l, s) pairs of a pivot form a triangle, and chains are short (humanoid: m <= 14): the warp is folded into 32 / W
   // groups of W > m lanes, every group holds the same row-k registers, and group h takes the offsets s = h, h + 32 / W, ...
   // -- a quarter (m < 8) or half (m < 16) of the sweeps of the one-group form, every entry still updated exactly once per
   // pivot with the same operands (bit-identical).
-  const int nv = mdl.nv();
-  constexpr int LS = M::D::NV;  // stride of the ancestor lists in the model image
-  int m = mdl.dof_nanc(nv - 1);
+  constexpr int LS = DimsLarge::NV;  // stride of the ancestor lists
+  int m = anc_load(nanc + nv - 1);
   int wl = m < 8 ? 3 : (m < 16 ? 4 : 5);  // log2 W
-  int i = (lane & ((1 << wl) - 1)) < m ? mdl.dof_anclist((nv - 1) * LS + (lane & ((1 << wl) - 1))) : 0;
+  int i = (lane & ((1 << wl) - 1)) < m ? anc_load(anclist + (nv - 1) * LS + (lane & ((1 << wl) - 1))) : 0;
 #pragma unroll 1
   for (int k = nv - 1; k >= 0; k--) {
     // prefetch the next pivot's list (independent of this pivot's arithmetic)
-    const int mn = k > 0 ? mdl.dof_nanc(k - 1) : 0;
+    const int mn = k > 0 ? anc_load(nanc + k - 1) : 0;
     const int wln = mn < 8 ? 3 : (mn < 16 ? 4 : 5);
     const int ln = lane & ((1 << wln) - 1);
-    const int in = (k > 0 && ln < mn) ? mdl.dof_anclist((k - 1) * LS + ln) : 0;
+    const int in = (k > 0 && ln < mn) ? anc_load(anclist + (k - 1) * LS + ln) : 0;
     const int l = lane & ((1 << wl) - 1), h = lane >> wl, hs = 32 >> wl;
     const int kk = tri(k, 0);
     const T dkk = LDp[kk + k];
@@ -210,10 +192,9 @@ __device__ __noinline__ void factor_LD_impl(const M mdl, T* LDp, T* dinv, int la
 
 // x <- (L'DL)^-1 x with x_l in a register of lane l (nv <= 32): column sweeps by shuffle, no shared-memory traffic for x
 // and no warp barrier per column; the L entries of a column are loaded ahead of the value they multiply.
-template <typename T, class M>
-__device__ __noinline__ void solve_LD_impl(const M mdl, const T* LDp, const T* dinv, T* x, int lane) {
-  const int nv = mdl.nv();
-  const unsigned anc = lane < nv ? ((unsigned)mdl.dof_anc(lane)) & ~(1u << lane) : 0u;  // proper ancestors of dof `lane`
+// anc: this lane's proper-ancestor mask (kinematic tree or merged, matching the factor in LDp)
+template <typename T>
+__device__ __noinline__ void solve_LD_impl(int nv, unsigned anc, const T* LDp, const T* dinv, T* x, int lane) {
   const int rowbase = tri(lane < nv ? lane : 0, 0);
   T xl = lane < nv ? x[lane] : T(0);
   // x <- L^-T x : dof i (leaves first) pushes x_i into its ancestors j: x_j -= L[i,j] x_i.  Lane j needs bit j of anc(i),
@@ -295,7 +276,16 @@ struct WarpEnv {
   int ls_iter;
   unsigned active_sig[(WarpCaps::NEFC + 31) / 32];  // active-row bit set the factor in LDp was built for
   bool hess_valid;
-  bool rows_tree;  // every constraint row touches one root-to-leaf chain only: H = M + J'DJ keeps M's tree sparsity
+  // Sparsity of the Newton Hessian H = M + J' D J.  A row that touches one root-to-leaf chain (a limit, a contact with the
+  // world or between a body and its own ancestor) keeps M's tree pattern.  A row that couples two branches (foot against
+  // the other shin, hand on a thigh) adds fill between their chains: the env then factorises H over the MERGED tree --
+  // tree_mask / amask are this lane's proper-ancestor masks in the kinematic tree and in the merged one, dyn_nanc /
+  // dyn_list the merged ancestor lists in the scratch slot (merge_branches) -- instead of falling back to a dense
+  // Cholesky (round 1 and the first half of round 2: 17 % of the executed instructions once humanoids lie on the floor).
+  bool rows_cross;
+  unsigned tree_mask, amask;
+  int* dyn_nanc;
+  unsigned char* dyn_list;
 
   // base: this env's shared-memory workspace (WarpLayout); jscratch: the warp's global scratch slot
   B2_DEV void bind(const WarpImage<T>* image, T* base, T* jscratch) {
@@ -319,7 +309,12 @@ struct WarpEnv {
     T* cb = rv + 6 * WarpCaps::NEFC;  // contact records: written by collide, read by make_rows (once per step each)
     con_dist = cb; con_pos = cb + WarpCaps::NCON; con_frame = cb + 4 * WarpCaps::NCON;
     con_pair = reinterpret_cast<int*>(cb + 13 * WarpCaps::NCON); row_meta = con_pair + WarpCaps::NCON;
+    dyn_nanc = reinterpret_cast<int*>(cb + 13 * WarpCaps::NCON + WarpCaps::NCON + WarpCaps::NEFC);
+    dyn_list = reinterpret_cast<unsigned char*>(dyn_nanc + 32);
     lane = threadIdx.x & 31;
+    tree_mask = lane < nv ? ((unsigned)mdl.dof_anc(lane)) & ~(1u << lane) : 0u;
+    amask = tree_mask;
+    rows_cross = false;
     ncon = nefc = niter = flags = 0;
   }
   B2_DEV bool dof_is_anc(int i, int j) const { return (((unsigned)mdl.dof_anc(i)) >> j) & 1u; }
@@ -509,8 +504,37 @@ struct WarpEnv {
   }
 
   // in-place L'DL of the packed matrix in LDp (tree sparsity): per pivot k all ancestor pairs at once
-  B2_DEV void factor_LD() { factor_LD_impl<T, M>(mdl, LDp, dinv, lane); }
-  B2_DEV void solve_LD(T* x) { solve_LD_impl<T, M>(mdl, LDp, dinv, x, lane); }
+  B2_DEV void factor_LD() { factor_LD_impl<T, int>(mdl.nv(), mdl.img->model.dof_nanc, mdl.img->model.dof_anclist, LDp, dinv, lane); }
+  B2_DEV void solve_LD(T* x) { solve_LD_impl<T>(mdl.nv(), tree_mask, LDp, dinv, x, lane); }
+  // the Newton Hessian's factor and solve: over the merged tree when a row couples two branches
+  B2_DEV void factor_H(T* H) {
+    if (rows_cross) factor_LD_impl<T, unsigned char>(mdl.nv(), dyn_nanc, dyn_list, H, hdinv, lane);
+    else factor_LD_impl<T, int>(mdl.nv(), mdl.img->model.dof_nanc, mdl.img->model.dof_anclist, H, hdinv, lane);
+  }
+  B2_DEV void solve_H(const T* H, T* x) { solve_LD_impl<T>(mdl.nv(), rows_cross ? amask : tree_mask, H, hdinv, x, lane); }
+  // a constraint row couples the chains `chains` (bit set of dofs): every dof of the union gets the union's lower dofs as
+  // ancestors
+  B2_DEV void couple(unsigned chains) {
+    rows_cross = true;
+    if ((chains >> lane) & 1u) amask |= chains & ((1u << lane) - 1u);
+  }
+  // Symbolic factorisation of the merged pattern (eliminating dof k, leaves first, makes its ancestors a clique) and the
+  // compact ancestor lists the numeric factorisation walks (nearest ancestor first), written to the scratch slot.
+  B2_DEV void merge_branches() {
+    const int nv = mdl.nv();
+#pragma unroll 1
+    for (int k = nv - 1; k > 0; k--) {
+      const unsigned mk = __shfl_sync(0xffffffffu, amask, k);
+      if ((mk >> lane) & 1u) amask |= mk & ((1u << lane) - 1u);
+    }
+#pragma unroll 1
+    for (int k = 0; k < nv; k++) {
+      const unsigned mk = __shfl_sync(0xffffffffu, amask, k);
+      if (lane == 0) dyn_nanc[k] = __popc(mk);
+      if ((mk >> lane) & 1u) dyn_list[k * 32 + __popc(mk >> (lane + 1))] = (unsigned char)lane;  // bits set only below k <= 31
+    }
+    __syncwarp();
+  }
   B2_DEV void mul_M(T* r, const T* v) { mul_M_impl<T>(Mp, r, v, mdl.nv(), lane); }
 
   // Jacobian column of dof d for a point on `body` at offset `off` from the root's subtree CoM; false if d does not move body
@@ -644,7 +668,8 @@ struct WarpEnv {
   B2_DEV void make_rows() {
     const int nv = mdl.nv();
     nefc = 0;
-    rows_tree = true;
+    rows_cross = false;
+    amask = tree_mask;
     auto zero_row = [&](int r) { WFOR(k, nv) J[r * nv + k] = 0; };
     // joint limits: sequential over joints keeps upstream row order; the test itself is uniform
     for (int j = 0; j < mdl.njnt(); j++) {
@@ -670,11 +695,17 @@ struct WarpEnv {
           if (nefc >= WarpCaps::NEFC) { flags |= 8; continue; }
           const int r = nefc++;
           // a fixed tendon couples the dofs of its joints: chain-compatible if they are ancestors of one another
-          for (int w = mdl.tendon_adr(t) + 1; w < mdl.tendon_adr(t) + mdl.tendon_num(t); w++)
+          bool chain = true;
+          unsigned chains = 0;
+          for (int w = mdl.tendon_adr(t); w < mdl.tendon_adr(t) + mdl.tendon_num(t); w++) {
+            const int d1 = mdl.jnt_dofadr(mdl.wrap_jntid(w));
+            chains |= (unsigned)mdl.dof_anc(d1);
             for (int u = mdl.tendon_adr(t); u < w; u++) {
-              const int d1 = mdl.jnt_dofadr(mdl.wrap_jntid(w)), d2 = mdl.jnt_dofadr(mdl.wrap_jntid(u));
-              if (!(d1 >= d2 ? dof_is_anc(d1, d2) : dof_is_anc(d2, d1))) rows_tree = false;
+              const int d2 = mdl.jnt_dofadr(mdl.wrap_jntid(u));
+              if (!(d1 >= d2 ? dof_is_anc(d1, d2) : dof_is_anc(d2, d1))) chain = false;
             }
+          }
+          if (!chain) couple(chains);
           WFOR(k, nv) J[r * nv + k] = -side * ten_J[t * nv + k];
           if (lane == 0) { row_meta[r] = ROW_LIMIT_TENDON | (t << 8); row_pos[r] = dist; row_margin[r] = margin; }
         }
@@ -690,7 +721,8 @@ struct WarpEnv {
       nefc += nrow;
       const int b1 = mdl.geom_bodyid(mdl.pair_geom1(p)), b2 = mdl.geom_bodyid(mdl.pair_geom2(p));
       const int last1 = last_dof(b1), last2 = last_dof(b2);
-      if (last1 >= 0 && last2 >= 0 && !(last1 >= last2 ? dof_is_anc(last1, last2) : dof_is_anc(last2, last1))) rows_tree = false;
+      if (last1 >= 0 && last2 >= 0 && !(last1 >= last2 ? dof_is_anc(last1, last2) : dof_is_anc(last2, last1)))
+        couple((unsigned)mdl.dof_anc(last1) | (unsigned)mdl.dof_anc(last2));
       const T mu = mdl.pair_friction(2 * p);
       T fr[9], pos[3], off1[3], off2[3];
       for (int k = 0; k < 9; k++) fr[k] = con_frame[9 * c + k];
@@ -711,6 +743,7 @@ struct WarpEnv {
       if (lane < nrow) { row_meta[r0 + lane] = (dim == 1 ? ROW_CONTACT_1 : ROW_CONTACT_PYR) | (c << 8); row_pos[r0 + lane] = dist; row_margin[r0 + lane] = incl; }
     }
     __syncwarp();
+    if (rows_cross) merge_branches();
   }
 
   static B2_DEV T impedance(const T* si, T pos, T margin) {
@@ -1041,54 +1074,12 @@ struct WarpEnv {
       for (int t = 0; t < EPL; t++) if (lane + 32 * t < np) H[lane + 32 * t] = h[t];
     }
     __syncwarp();
-    if (rows_tree) {
-      // all active rows are chain rows (limits, contacts with the world or between a body and its own ancestor): H has the
-      // tree sparsity of M, so the tree-sparse L'DL of mj_factorM factorises it -- a third of the dense trailing updates
-      factor_LD_impl<T, M>(mdl, H, hdinv, lane);
-    } else {
-    // right-looking Cholesky: same per-entry subtraction order as the left-looking scalar loop; the trailing-block
-    // entries of every pivot column come from the host-built work list (no index inversion on the device)
-    for (int j = 0; j < nv; j++) {
-      T t = H[tri(j, j)];
-      if (t < Num<T>::minval()) t = Num<T>::minval();
-      const T djj = sqrt(t), inv = T(1) / djj;
-      __syncwarp();
-      for (int i = j + lane; i < nv; i += 32) H[tri(i, j)] = (i == j) ? djj : H[tri(i, j)] * inv;
-      if (lane == 0) hdinv[j] = inv;
-      __syncwarp();
-      // the trailing entries of one pivot column are independent of each other: four per lane are in flight at once
-      for (int e0 = __ldg(&mdl.img->chol_off[j]) + lane, end = __ldg(&mdl.img->chol_off[j + 1]); e0 < end; e0 += 128) {
-        int w[4];
-        T a[4], b[4], c[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) w[u] = e0 + 32 * u < end ? __ldg(&mdl.img->chol_plan[e0 + 32 * u]) : -1;
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (w[u] >= 0) { a[u] = H[w[u] & 1023]; b[u] = H[(w[u] >> 10) & 1023]; c[u] = H[w[u] >> 20]; }
-#pragma unroll
-        for (int u = 0; u < 4; u++) if (w[u] >= 0) H[w[u] & 1023] = a[u] - b[u] * c[u];
-      }
-      __syncwarp();
-    }
-    }  // dense
+    // H has the sparsity of the (merged) tree: the tree-sparse L'DL of mj_factorM factorises it
+    factor_H(H);
     }  // !same
     WFOR(k, nv) Mgrad[k] = grad[k];
     __syncwarp();
-    if (rows_tree) { solve_LD_impl<T, M>(mdl, H, hdinv, Mgrad, lane); return; }
-    // two triangular solves; the reciprocal pivots were stored by the factorisation
-    for (int j = 0; j < nv; j++) {
-      const T xj = Mgrad[j] * hdinv[j];
-      __syncwarp();
-      if (lane == 0) Mgrad[j] = xj;
-      for (int i = j + 1 + lane; i < nv; i += 32) Mgrad[i] -= H[tri(i, j)] * xj;
-      __syncwarp();
-    }
-    for (int j = nv - 1; j >= 0; j--) {
-      const T xj = Mgrad[j] * hdinv[j];
-      __syncwarp();
-      if (lane == 0) Mgrad[j] = xj;
-      WFOR(i, j) Mgrad[i] -= H[tri(j, i)] * xj;
-      __syncwarp();
-    }
+    solve_H(H, Mgrad);
   }
   // LS ("lock step"): the warps of a block run the same stage at the same time, separated by block barriers, so that
   // one instruction fetch from L2 serves all of them.  The kernel is bound by instruction-fetch bandwidth: its 276 KB of

@@ -138,9 +138,9 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
       if (st.warm) WFOR(k, env.mdl.nv()) st.warm[(size_t)k * N + e] = env.warm[k];  // by mj_forward too (mj_fwdConstraint saves it)
       if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
     }
-    // queue key of the next step: Newton rounds of this one, envs with dense (non-chain) rows -- three times the
-    // factorisation work per round -- in the upper half of the bins
-    if (mine && cost && lane == 0) cost[e] = frozen ? 0 : ((env.nefc && !env.rows_tree) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
+    // queue key of the next step: Newton rounds of this one, envs whose rows couple two branches of the tree (merged
+    // ancestor lists: longer factorisation sweeps) in the upper half of the bins
+    if (mine && cost && lane == 0) cost[e] = frozen ? 0 : ((env.nefc && env.rows_cross) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
     if (threadIdx.x == 0) s_next = nw + atomicAdd(queue, wpb);
     __syncthreads();
     first = s_next;

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
     "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
-    "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr", "b2_random_controls",
+    "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr", "b2_random_controls", "b2_warp_queue_histogram",
 )
 
 
@@ -90,6 +90,7 @@ def lib() -> C.CDLL:
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
     L.b2_stream_synchronize.argtypes = [vp, vp]
     L.b2_random_controls.argtypes = [vp, C.POINTER(State), C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_double, vp, vp, vp]
+    L.b2_warp_queue_histogram.argtypes = [vp, C.POINTER(C.c_int), vp]
     L.b2_dlqr.argtypes = [C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int,
                           C.c_double, vp, vp, vp, vp]
     L.b2_recorder_create.argtypes = [vp, C.POINTER(RecordCol), C.c_int, C.POINTER(C.c_int), C.c_int, C.POINTER(vp)]
@@ -211,6 +212,11 @@ class NativeBatch:
                         reset_qpos: int | None = None, reset_qvel: int | None = None, stream: int = 0) -> None:
         check(self._L.b2_random_controls(self.handle, C.byref(state), float(lo), float(hi), int(seed), int(watch_row), float(watch_min),
                                          reset_qpos, reset_qvel, stream))
+
+    def warp_queue_histogram(self, stream: int = 0) -> list[int]:
+        out = (C.c_int * 16)()
+        check(self._L.b2_warp_queue_histogram(self.handle, out, stream))
+        return list(out)
 
     def synchronize(self, stream: int = 0) -> None:
         check(self._L.b2_stream_synchronize(self.handle, stream))
