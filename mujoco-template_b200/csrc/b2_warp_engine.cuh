@@ -283,6 +283,7 @@ struct WarpEnv {
   // dyn_list the merged ancestor lists in the scratch slot (merge_branches) -- instead of falling back to a dense
   // Cholesky (round 1 and the first half of round 2: 17 % of the executed instructions once humanoids lie on the floor).
   bool rows_cross;
+  int solve_cycles;  // clock cycles this env spent in its last constraint stage: the work queue's sort key
   unsigned tree_mask, amask;
   int* dyn_nanc;
   unsigned char* dyn_list;
@@ -1062,12 +1063,24 @@ struct WarpEnv {
           const int r = w * 32 + __ffs(bits) - 1;
           const T* Jr = J + r * nv;
           const T d = row_D[r];
+#ifndef B2_WARP_HESS_GATHER
+          // the row is read once, one dof per lane, and its entries travel by shuffle instead of being gathered from the
+          // scratch slot entry by entry: +2 % at 4.7 contacts per env, +5 % at 7.7 (gpurun A/B, round 2)
+          const T jl = lane < nv ? Jr[lane] : T(0), djl = d * jl;
+#pragma unroll
+          for (int t = 0; t < EPL; t++) {
+            const int a = ij[t] >= 0 ? ij[t] & 255 : 0, b = ij[t] >= 0 ? ij[t] >> 8 : 0;
+            const T pa = __shfl_sync(0xffffffffu, djl, a), pb = __shfl_sync(0xffffffffu, jl, b);
+            if (ij[t] >= 0) h[t] += pa * pb;
+          }
+#else
 #pragma unroll
           for (int t = 0; t < EPL; t++) {
             if (ij[t] >= 0) {
               h[t] += (d * Jr[ij[t] & 255]) * Jr[ij[t] >> 8];
             }
           }
+#endif
         }
       }
 #pragma unroll
@@ -1095,11 +1108,15 @@ struct WarpEnv {
   template <int LS>
   B2_DEV void constrained_acceleration() {
     const int nv = mdl.nv();
+#ifdef B2_WARP_KEY_CYCLES
+    const long long t_begin = clock64();
+#endif
     niter = 0;
     bool done = false;
     if (!nefc) {
       WFOR(k, nv) { qacc[k] = a_smooth[k]; warm[k] = a_smooth[k]; f_con[k] = 0; }
       __syncwarp();
+      solve_cycles = 0;
       if (LS != 1) return;
       done = true;
     } else {
@@ -1160,6 +1177,9 @@ struct WarpEnv {
       WFOR(k, nv) warm[k] = qacc[k];
       __syncwarp();
     }
+#ifdef B2_WARP_KEY_CYCLES
+    solve_cycles = (int)(clock64() - t_begin);  // this env's own constraint-stage time (no block barrier inside when LS != 1)
+#endif
   }
 
   // ------------------------------------------------------------------ forward + Euler

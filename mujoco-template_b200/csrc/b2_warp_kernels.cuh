@@ -139,8 +139,14 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
       if (st.flags && env.flags && lane == 0) st.flags[e] |= env.flags;
     }
     // queue key of the next step: Newton rounds of this one, envs whose rows couple two branches of the tree (merged
-    // ancestor lists: longer factorisation sweeps) in the upper half of the bins
+    // ancestor lists: longer factorisation sweeps) in the upper half of the bins.  (The measured cycle count of the env's
+    // constraint stage as the key -- B2_WARP_KEY_CYCLES, 16 K / 32 K-cycle bins -- was 4 % slower: 7.7e6 against 8.0e6
+    // env-steps/s; the clock also counts the time the warp waits for its SM's other warps.)
+#ifdef B2_WARP_KEY_CYCLES
+    if (mine && cost && lane == 0) cost[e] = frozen ? 0 : (env.solve_cycles >> B2_WARP_KEY_CYCLES);
+#else
     if (mine && cost && lane == 0) cost[e] = frozen ? 0 : ((env.nefc && env.rows_cross) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
+#endif
     if (threadIdx.x == 0) s_next = nw + atomicAdd(queue, wpb);
     __syncthreads();
     first = s_next;
