@@ -789,8 +789,11 @@ int b2_warp_queue_histogram(b2_batch* b, int* hist16, void* stream) {
   if (b->warp_mode != 1 || !b->d_warp_sort) return fail(B2_ERR_ARG, "b2_warp_queue_histogram: batch does not run on the warp engine's ordered queue");
   cudaError_t e = cudaSetDevice(b->device);
   if (!e) e = cudaStreamSynchronize((cudaStream_t)stream);
-  if (!e) e = cudaMemcpy(hist16, b->d_warp_sort, 16 * sizeof(int), cudaMemcpyDeviceToHost);
-  return e ? cuda_fail(e, "b2_warp_queue_histogram") : B2_OK;
+  int bins[64] = {0};
+  if (!e) e = cudaMemcpy(bins, b->d_warp_sort, 64 * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e) return cuda_fail(e, "b2_warp_queue_histogram");
+  for (int k = 0; k < 16; k++) hist16[k] = bins[4 * k] + bins[4 * k + 1] + bins[4 * k + 2] + bins[4 * k + 3];  // row-count buckets folded
+  return B2_OK;
 }
 
 int b2_fp_peak(int precision, int device, double* tflops) {

@@ -194,8 +194,8 @@ int B2_FN(b2k_warp_plan)(const b2m_view* v, int N, int* out_wpb, int* out_blocks
 size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
   return (size_t)slots * warp_slot_reals(v->nv) * sizeof(real);
 }
-// bytes of the cost-ordered queue's buffers behind the work-queue counter: [hist | cursor] (64 ints), cost[N], perm[N]
-size_t B2_FN(b2k_warp_sort_bytes)(int N) { return (64 + 2 * (size_t)N) * sizeof(int); }
+// bytes of the cost-ordered queue's buffers behind the work-queue counter: [hist | cursor] (2 kCostBins ints), cost[N], perm[N]
+size_t B2_FN(b2k_warp_sort_bytes)(int N) { return (2 * kCostBins + 2 * (size_t)N) * sizeof(int); }
 int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
                          void* counter, void* sortbuf, int wpb, int blocks, void* stream) {
   const size_t smem = warp_block_smem(v, wpb, 0);
@@ -206,12 +206,12 @@ int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* s
   int *cost = nullptr, *perm = nullptr;
   if (sortbuf && wpb > 1 && nsteps > 0) {  // lock-step blocks: order the queue by the envs' last Newton iteration counts
     int* hist = (int*)sortbuf;
-    cost = hist + 64; perm = cost + N;
-    if ((e = cudaMemsetAsync(hist, 0, 64 * sizeof(int), s)) != cudaSuccess) return (int)e;
+    cost = hist + 2 * kCostBins; perm = cost + N;
+    if ((e = cudaMemsetAsync(hist, 0, 2 * kCostBins * sizeof(int), s)) != cudaSuccess) return (int)e;
     int sb = (N + 255) / 256;
     if (sb > 148 * 4) sb = 148 * 4;
     k_cost_hist<kCostBins><<<sb, 256, 0, s>>>(cost, N, hist);
-    k_cost_scatter<kCostBins><<<sb, 256, 0, s>>>(cost, N, hist, hist + 32, perm);
+    k_cost_scatter<kCostBins><<<sb, 256, 0, s>>>(cost, N, hist, hist + kCostBins, perm);
   }
   B2_WARP_DIMS(v, (k_warp_step_ls<real, WM, B2_WARP_LS_MODE><<<blocks, wpb * 32, smem, s>>>(
                       (const WarpImage<real>*)image, to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter,

@@ -45,7 +45,10 @@ B2_DEV void warp_store_solution(const WarpEnv<T, M>& env, const DerivedDev<T>& o
 // descending order of the count of their previous step (counting sort into kCostBins bins: histogram, then a scatter
 // that reserves a range per block and bin): block mates then need about the same number of rounds, and the expensive
 // envs start first.  Which env a warp runs has no effect on that env's result.
-constexpr int kCostBins = 16;
+#ifndef B2_WARP_COST_BINS
+#define B2_WARP_COST_BINS 64
+#endif
+constexpr int kCostBins = B2_WARP_COST_BINS;  // 16: (coupled rows?, Newton rounds); 64: ... x four buckets of the row count (+1 %)
 template <int BINS>
 __global__ void __launch_bounds__(256) k_cost_hist(const int* __restrict__ cost, int N, int* hist) {
   __shared__ int h[BINS];
@@ -145,7 +148,11 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
 #ifdef B2_WARP_KEY_CYCLES
     if (mine && cost && lane == 0) cost[e] = frozen ? 0 : (env.solve_cycles >> B2_WARP_KEY_CYCLES);
 #else
-    if (mine && cost && lane == 0) cost[e] = frozen ? 0 : ((env.nefc && env.rows_cross) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
+    if (mine && cost && lane == 0) {
+      int key = ((env.nefc && env.rows_cross) ? 8 : 0) + (env.niter < 7 ? env.niter : 7);
+      if (kCostBins == 64) key = key * 4 + (env.nefc < 12 ? 0 : (env.nefc < 24 ? 1 : (env.nefc < 36 ? 2 : 3)));
+      cost[e] = frozen ? 0 : key;
+    }
 #endif
     if (threadIdx.x == 0) s_next = nw + atomicAdd(queue, wpb);
     __syncthreads();
