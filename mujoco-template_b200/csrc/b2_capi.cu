@@ -275,8 +275,8 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
   if (b->warp_mode == 1 && count == b->nenv) {
     const void* image = nullptr;
     if ((rc = warp_image_of(b, &image))) return rc;
-    return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream)
-               : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, stream);
+    return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, park, stream)
+               : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, park, stream);
   }
   return f64 ? b2::b2k_step_f64(lane, b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream)
              : b2::b2k_step_f32(lane, b->model->cls, st, derived, count, b->nenv, nsteps, gain, park, stream);
@@ -444,23 +444,6 @@ static int shadow_state(b2_batch* b, b2_state* out) {
   return B2_OK;
 }
 
-// copy the state into the batch's shadow arrays: the pre-step state b2_refresh_derived works from
-static int park_state(b2_batch* b, const b2_state* st, void* stream) {
-  const b2m_view& v = b->model->v;
-  b2_state shadow;
-  int rc = shadow_state(b, &shadow);
-  if (rc) return rc;
-  const size_t N = (size_t)b->nenv, es = b->esz;
-  cudaStream_t s = (cudaStream_t)stream;
-  cudaError_t e = cudaMemcpyAsync(shadow.qpos, st->qpos, v.nq * N * es, cudaMemcpyDeviceToDevice, s);
-  if (!e) e = cudaMemcpyAsync(shadow.qvel, st->qvel, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
-  if (!e) e = cudaMemcpyAsync(shadow.qacc_warmstart, st->qacc_warmstart, v.nv * N * es, cudaMemcpyDeviceToDevice, s);
-  if (!e && v.nu) e = cudaMemcpyAsync(shadow.ctrl, st->ctrl, v.nu * N * es, cudaMemcpyDeviceToDevice, s);
-  if (e) return cuda_fail(e, "shadow copy of the pre-step state");
-  b->shadow_has_prestep = true;
-  return B2_OK;
-}
-
 // One control tick: [LQR law] -> (A, B) at the new controls -> one step (reference env.py:177-191 order).  The kernels
 // evaluate the control law themselves (no controller launch).
 //  * derived == NULL and an Euler model: ONE physics launch.  The FD thread that owns an env's velocity / control columns
@@ -486,7 +469,12 @@ int b2_control_tick(b2_batch* b, const b2_state* st, const b2_derived* derived, 
       // argument the pre-step state is parked in the shadow arrays for b2_refresh_derived, as in the fused form.
       if (gain && (rc = do_lqr_control(b, st, b->nenv, stream))) return rc;
       if ((rc = do_linearize(b, st, b->nenv, eps, centered, A, B, stream))) return rc;
-      if (!derived && st->qacc_warmstart && (rc = park_state(b, st, stream))) return rc;
+      if (!derived && st->qacc_warmstart) {  // the step kernel parks the pre-step state itself
+        b2_state shadow;
+        if ((rc = shadow_state(b, &shadow)) || (rc = do_step(b, st, b->nenv, 1, nullptr, stream, nullptr, &shadow))) return rc;
+        b->shadow_has_prestep = true;
+        return B2_OK;
+      }
       return do_step(b, st, b->nenv, 1, derived, stream);
     }
   }
@@ -513,12 +501,8 @@ int b2_step_lazy(b2_batch* b, const b2_state* st, void* stream) {
   int rc;
   if (!active_spec(b)) {
     if ((rc = prepare_warp(b))) return rc;
-    if (b->warp_mode == 1) {  // warp engine: park with device-to-device copies
-      if ((rc = park_state(b, st, stream))) return rc;
-      return do_step(b, st, b->nenv, 1, nullptr, stream);
-    }
   }
-  // lane engine: the step kernel has the pre-step state in registers and writes it to the shadow arrays itself
+  // the step kernel (lane or warp engine) has the pre-step state at hand and writes it to the shadow arrays itself
   b2_state shadow;
   if ((rc = shadow_state(b, &shadow))) return rc;
   if ((rc = do_step(b, st, b->nenv, 1, nullptr, stream, nullptr, &shadow))) return rc;

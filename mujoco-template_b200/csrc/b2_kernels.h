@@ -12,7 +12,7 @@ namespace b2 {
   void b2k_warp_image_fill##SUF(const b2m_view* v, const int* disabled, void* host);                                       \
   size_t b2k_warp_sort_bytes##SUF(int N);                                                                                  \
   int b2k_warp_step##SUF(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch, void* counter,  \
-                         void* sortbuf, int wpb, int blocks, void* stream);                                                                   \
+                         void* sortbuf, int wpb, int blocks, const b2_state* park, void* stream);                                                                   \
   int b2k_warp_linearize##SUF(const void* image, const b2m_view* v, const b2_state* st, int N, double eps, int centered, void* A, void* B, void* jscratch,  \
                               void* counter, int wpb, int blocks, void* stream);                                                        \
   size_t b2k_image_bytes##SUF(int cls);                                                                                    \

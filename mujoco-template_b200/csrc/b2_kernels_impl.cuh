@@ -197,7 +197,7 @@ size_t B2_FN(b2k_warp_scratch_bytes)(const b2m_view* v, int slots) {
 // bytes of the cost-ordered queue's buffers behind the work-queue counter: [hist | cursor] (2 kCostBins ints), cost[N], perm[N]
 size_t B2_FN(b2k_warp_sort_bytes)(int N) { return (2 * kCostBins + 2 * (size_t)N) * sizeof(int); }
 int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* st, const b2_derived* out, int N, int nsteps, void* jscratch,
-                         void* counter, void* sortbuf, int wpb, int blocks, void* stream) {
+                         void* counter, void* sortbuf, int wpb, int blocks, const b2_state* park, void* stream) {
   const size_t smem = warp_block_smem(v, wpb, 0);
   cudaStream_t s = (cudaStream_t)stream;
   // envs are handed out through a work queue: the first gridDim * wpb statically, the rest by atomic counter
@@ -215,7 +215,7 @@ int B2_FN(b2k_warp_step)(const void* image, const b2m_view* v, const b2_state* s
   }
   B2_WARP_DIMS(v, (k_warp_step_ls<real, WM, B2_WARP_LS_MODE><<<blocks, wpb * 32, smem, s>>>(
                       (const WarpImage<real>*)image, to_dev<real>(st), to_dev<real>(out), out != nullptr, N, nsteps, (real*)jscratch, (int*)counter,
-                      perm, cost)));
+                      perm, cost, to_dev<real>(park))));
   return (int)cudaGetLastError();
 }
 // FD linearisation on the warp engine: same scratch slots as the step plan (wpb warps per block)

@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256) k_cost_scatter(const int* __restrict__ co
 template <typename T, class M, int LS>
 __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* __restrict__ img, StateDev<T> st, DerivedDev<T> out,
                                                             int want_derived, int N, int nsteps, T* jscratch, int* queue,
-                                                            const int* __restrict__ perm, int* cost) {
+                                                            const int* __restrict__ perm, int* cost, StateDev<T> park) {
   extern __shared__ double b2_smem[];
   __shared__ int s_next;
   const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
@@ -115,6 +115,11 @@ __global__ void __maxnreg__(B2_WARP_REGS(M)) k_warp_step_ls(const WarpImage<T>* 
     WFOR(k, env.mdl.nu()) env.ctrl[k] = st.ctrl[(size_t)k * N + e];
     env.flags = 0;
     __syncwarp();
+    if (park.qpos && mine) {  // b2_step_lazy: keep the pre-step state for b2_refresh_derived (no copy launches)
+      WFOR(k, env.mdl.nq()) park.qpos[(size_t)k * N + e] = env.qpos[k];
+      WFOR(k, env.mdl.nv()) { park.qvel[(size_t)k * N + e] = env.qvel[k]; park.warm[(size_t)k * N + e] = env.warm[k]; }
+      WFOR(k, env.mdl.nu()) park.ctrl[(size_t)k * N + e] = env.ctrl[k];
+    }
     bool frozen = false;  // diverged env: flagged and left as it is (see k_step); its warp keeps pace on the rest pose
     for (int s = 0; s < total; s++) {
       env.check_state();

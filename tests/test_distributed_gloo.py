@@ -37,8 +37,12 @@ def _worker(rank, world, port, total, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_rollout_matches_single_process(tmp_path):
-    total, world = 16, 2
+import pytest
+
+
+@pytest.mark.parametrize("total", [16, 17])   # 17: shard_range hands out blocks of 8 and 9 envs (ragged gather)
+def test_two_rank_sharded_rollout_matches_single_process(tmp_path, total):
+    world = 2
     out = str(tmp_path / "gathered.pt")
     mp.spawn(_worker, args=(world, _free_port(), total, out), nprocs=world, join=True)
     gathered = torch.load(out).numpy()
