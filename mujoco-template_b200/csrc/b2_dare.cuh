@@ -18,13 +18,13 @@ namespace b2 {
 __host__ __device__ inline size_t dare_ws_reals(int nx, int nu) { return (size_t)8 * nx * nx + (size_t)2 * nx * nu + (size_t)2 * nu * nu + 32; }
 
 template <typename T>
-B2_DEV void dare_matmul(T* C, const T* X, bool tx, const T* Y, bool ty, int n, int lane, T beta) {
-  // C (n x n) = beta * C + op(X) op(Y), one entry per lane and sweep
+B2_DEV void dare_matmul(T* C, const T* X, bool tx, const T* Y, bool ty, int n, int lane) {
+  // C (n x n) = op(X) op(Y), one entry per lane and sweep (C is write-only: it may hold anything, NaN included)
   for (int e = lane; e < n * n; e += 32) {
     const int i = e / n, j = e - i * n;
     T s = 0;
     for (int k = 0; k < n; k++) s += (tx ? X[k * n + i] : X[i * n + k]) * (ty ? Y[j * n + k] : Y[k * n + j]);
-    C[e] = beta * C[e] + s;
+    C[e] = s;
   }
   __syncwarp();
 }
@@ -71,6 +71,10 @@ __global__ void __launch_bounds__(128) k_dare(const T* __restrict__ Ag, const T*
   T* ws = reinterpret_cast<T*>(b2_dare_smem) + (size_t)wib * dare_ws_reals(nx, nu);
   T *A = ws, *G = A + nn, *H = G + nn, *M = H + nn /* nx x 3nx */, *T1 = M + 3 * nn, *T2 = T1 + nn, *Bm = T2 + nn /* nx x nu */,
     *BR = Bm + nx * nu /* nx x nu: B Rinv, later P B */, *S = BR + nx * nu /* nu x 2nu */;
+#ifdef B2_DARE_POISON  // debugging aid: every read of workspace the kernel has not written shows up as a failed env
+  for (int k = lane; k < (int)dare_ws_reals(nx, nu); k += 32) ws[k] = T(__int_as_float(0x7fc00000));
+  __syncwarp();
+#endif
   for (int k = lane; k < nn; k += 32) { A[k] = Ag[(size_t)k * N + e]; H[k] = Q[k]; }
   for (int k = lane; k < nx * nu; k += 32) Bm[k] = Bg[(size_t)k * N + e];
   __syncwarp();
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(128) k_dare(const T* __restrict__ Ag, const T*
   bool ok = true;
   for (int it = 0; it < max_doublings; it++) {
     // M = [I + G H | A | G]
-    dare_matmul(T1, G, false, H, false, nx, lane, T(0));
+    dare_matmul(T1, G, false, H, false, nx, lane);
     for (int k = lane; k < nn; k += 32) {
       const int i = k / nx, j = k - i * nx;
       M[i * 3 * nx + j] = T1[k] + (i == j ? T(1) : T(0));
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(128) k_dare(const T* __restrict__ Ag, const T*
     for (int k = lane; k < nn; k += 32) { const int i = k / nx, j = k - i * nx; T1[k] = M[i * 3 * nx + nx + j]; T2[k] = M[i * 3 * nx + 2 * nx + j]; }
     __syncwarp();
     // H <- H + A' (H V1): M[0..nn) = H V1, then accumulate; track the change of H
-    dare_matmul(M, H, false, T1, false, nx, lane, T(0));
+    dare_matmul(M, H, false, T1, false, nx, lane);
     T dmax = 0, hmax = 0;
     for (int k = lane; k < nn; k += 32) {
       const int i = k / nx, j = k - i * nx;
@@ -126,11 +130,11 @@ __global__ void __launch_bounds__(128) k_dare(const T* __restrict__ Ag, const T*
     __syncwarp();
     for (int k = lane; k < nn; k += 32) H[k] = M[2 * nn + k];
     // G <- G + A V2 A': M[0..nn) = A V2, then (A V2) A' symmetrised
-    dare_matmul(M, A, false, T2, false, nx, lane, T(0));
-    dare_matmul(M + nn, M, false, A, true, nx, lane, T(0));
+    dare_matmul(M, A, false, T2, false, nx, lane);
+    dare_matmul(M + nn, M, false, A, true, nx, lane);
     for (int k = lane; k < nn; k += 32) { const int i = k / nx, j = k - i * nx; G[k] += T(0.5) * (M[nn + k] + M[nn + j * nx + i]); }
     // A <- A V1
-    dare_matmul(M, A, false, T1, false, nx, lane, T(0));
+    dare_matmul(M, A, false, T1, false, nx, lane);
     for (int k = lane; k < nn; k += 32) A[k] = M[k];
     __syncwarp();
     for (int o = 16; o > 0; o >>= 1) { dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o)); }

@@ -938,4 +938,19 @@ def test_dlqr_kernel_matches_scipy_dare():
     Kb, Pb = batched_dlqr_gain(res.info["A"], res.info["B"], np.diag([10.0, 100.0, 1.0, 1.0]), np.array([[0.01]]))
     assert tuple(Kb.shape) == (64, 1, 4)
     assert np.allclose(Kb[0].cpu().numpy(), ctl.K, rtol=1e-6, atol=1e-8)  # env 0 sits at the controller's setpoint
+    # a large batch right behind the FD kernel (whatever that left in shared memory must not matter: the first version of
+    # the kernel multiplied its uninitialised product buffers by zero, which failed 0.1 % of the envs of a 65,536 batch)
+    from mujoco_template import _mj as mj
+
+    drone = load_model("drone")
+    n = 32768
+    qpos, qvel, _ = random_states(drone, "drone", 4096, seed=8)
+    d = mj.BatchData(drone, n)
+    d.qpos.copy_(torch.as_tensor(np.tile(qpos, (8, 1)).T.copy(), device="cuda")); d.qvel.copy_(torch.as_tensor(np.tile(qvel, (8, 1)).T.copy(), device="cuda"))
+    d.ctrl.fill_(3.2495625)
+    for _ in range(3):
+        A, B = d.backend.linearize(1e-6, True)
+        Kd, Pd, st = batched_dlqr_gain(A.permute(2, 0, 1), B.permute(2, 0, 1), np.eye(12), np.eye(4), return_status=True)
+        assert int((st <= 0).sum()) == 0 and bool(torch.isfinite(Kd).all()) and bool(torch.isfinite(Pd).all())
+    assert torch.equal(Kd[:4096], Kd[4096:8192])  # tiled states: identical gains, whichever warp / block computed them
 
