@@ -275,6 +275,7 @@ static int launch_generic_step(b2_batch* b, const b2_state* st, const b2_derived
   if (b->warp_mode == 1 && count == b->nenv) {
     const void* image = nullptr;
     if ((rc = warp_image_of(b, &image))) return rc;
+    if (b->d_warp_sort && b->warp_wpb > 1 && nsteps > 0) g_launches += 2;  // the queue's histogram and scatter kernels
     return f64 ? b2::b2k_warp_step_f64(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, park, stream)
                : b2::b2k_warp_step_f32(image, &b->model->v, st, derived, b->nenv, nsteps, b->d_jscratch, b->d_warp_counter, b->d_warp_sort, b->warp_wpb, b->warp_blocks, park, stream);
   }
