@@ -419,3 +419,33 @@ def test_random_controller_kernel_statistics_reset_and_graph_replay():
         seen.append(env.data.ctrl.clone())
     torch.cuda.synchronize()
     assert all(not torch.equal(seen[i], seen[i + 1]) for i in range(4))
+
+
+def test_fp32_instantiations_of_the_auxiliary_kernels(tmp_path):
+    """b2_dlqr, b2_random_controls and the recorder gather in FP32 mode (B2_F32 batches / float32 tensors)."""
+    import torch
+    from scipy.linalg import solve_discrete_are
+
+    import mujoco_template as mt
+    from mujoco_template.batched_controllers import BatchedRandomController, batched_dlqr_gain
+
+    rng = np.random.default_rng(2)
+    A = rng.normal(0, 0.5, (16, 4, 4)); B = rng.normal(0, 1.0, (16, 4, 2))
+    K, P = batched_dlqr_gain(torch.as_tensor(A, device="cuda", dtype=torch.float32), torch.as_tensor(B, device="cuda", dtype=torch.float32),
+                             np.eye(4), np.eye(2), tol=1e-6)
+    assert K.dtype == torch.float32
+    for e in range(16):
+        Pe = solve_discrete_are(A[e], B[e], np.eye(4), np.eye(2))
+        assert np.max(np.abs(P[e].cpu().numpy() - Pe)) <= 2e-3 * np.max(np.abs(Pe))
+    model = load_model("drone")
+    env = mt.BatchedEnv(model, 512, controller=BatchedRandomController(0.0, 13.0, seed=5), precision=32)
+    env.reset(0)
+    imu = 0
+    with mt.BatchedStateControlRecorder(env, log_path=tmp_path / "f32.csv", env_indices=[3, 500], chunk_steps=4, store_rows=True,
+                                        probes=[mt.ArrayProbe("imu_z_m", "site_xpos", 3 * imu + 2)]) as rec:
+        mt.run_passive_headless(env, max_steps=6, hooks=rec, return_obs=False)
+    assert env.data.ctrl.dtype == torch.float32 and 0.0 <= float(env.data.ctrl.min()) and float(env.data.ctrl.max()) < 13.0
+    rows = np.array([r[1:] for r in rec.rows], dtype=float)
+    assert rows.shape == (12, 1 + model.nq + model.nv + model.nu + 1) and np.isfinite(rows).all()
+    assert abs(rows[-1, 0] - 6 * float(model.opt.timestep)) < 1e-6
+    assert np.allclose(rows[-2:, 1 + model.nq + model.nv: 1 + model.nq + model.nv + model.nu], env.data.ctrl[:, [3, 500]].T.cpu().numpy())
