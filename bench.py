@@ -312,7 +312,7 @@ def workload_name(name: str, nenv: int, lin: bool) -> str:
     return f"{name} batched rollout, N={nenv} envs/GPU, FP64, " + tail
 
 
-def make_controller(name: str, lin: bool, seed: int = 0):
+def make_controller(name: str, lin: bool, seed: int = 0, tv_lqr: bool = False):
     """The controller of a workload (counted as the controller, not as the path: SURVEY.md section 8d)."""
     import torch
 
@@ -321,6 +321,10 @@ def make_controller(name: str, lin: bool, seed: int = 0):
 
     if lin:
         if name == "cartpole":
+            if tv_lqr:  # gains of every env re-synthesised every tick from the env's own (A, B): b2_dlqr + b2_lqr_control_env
+                from mujoco_template.batched_controllers import BatchedTVLQRController
+
+                return BatchedTVLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
             return BatchedLQRController(Q=np.diag([10.0, 100.0, 1.0, 1.0]), R=np.array([[0.01]]))
 
         class HoldLin:
@@ -340,7 +344,7 @@ def make_controller(name: str, lin: bool, seed: int = 0):
 
 
 def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, *, use_graph: bool, want_e2e: bool,
-                 e2e_host_controller: bool, cpu_seconds: float) -> dict:
+                 e2e_host_controller: bool, cpu_seconds: float, tv_lqr: bool = False) -> dict:
     """Times one workload on this rank's GPU and returns the fields of its JSON line (rank 0's copy is printed)."""
     import torch
     import torch.distributed as dist
@@ -355,7 +359,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
         torch.cuda.synchronize()
 
     model = load_model(name)
-    controller = make_controller(name, lin, seed=rank)
+    controller = make_controller(name, lin, seed=rank, tv_lqr=tv_lqr)
     env = BatchedEnv(model, nenv, controller=controller, device=local)
     env.reset(0 if name == "drone" else (1 if name == "humanoid" else None))
     qpos, qvel = synth_states(model, name, nenv, seed=rank)  # each rank owns its own shard of envs
@@ -379,7 +383,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
             flush.zero_()
             env.step(return_obs=False)
         torch.cuda.synchronize()
-        for k in ("random_controls", "lqr_control", "linearize", "step", "control_tick"):
+        for k in ("random_controls", "lqr_control", "lqr_control_env", "linearize", "step", "control_tick"):
             v = env.data.backend.kernel_ms(k)[-10:]
             if v:
                 kernel_ms[k] = v
@@ -591,7 +595,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": max(warmup, 3),
         "ms_per_step": ms_step, "ms_per_step_per_rank": rank_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(name, nenv, lin), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
+        "config": {"workload": workload_name(name, nenv, lin) + (" -- time-varying LQR: every env's gain re-synthesised every tick from its own (A, B) (b2_dlqr)" if tv_lqr else ""), "model": name, "envs_per_gpu": nenv, "global_envs": nenv * world,
                    "l2": "flushed between timed iterations (192 MB memset outside the event pairs)",
                    "launch": "CUDA graph replay of one env.step()" if use_graph else "eager launches",
                    "timing": "CUDA event pair per step; steps queued 64 at a time behind a 4 ms spin kernel, so the pairs bracket "
@@ -673,6 +677,12 @@ def main():
             out["secondary"][sname] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_per_rank", "steps", "config", "roofline",
                                                            "roofline_fp64", "cpu_baseline", "e2e", "gpu_launches", "contact_stats",
                                                            "bad_env_flags", "kernel_variant", "clocks")}
+        # config #2 read literally ("per-step FD (A, B) linearisation for LQR"): the same workload with every env's gain
+        # re-synthesised every tick from its own latest (A, B) -- DARE + gain (b2_dlqr), per-env control law, FD, step
+        tv = run_workload(ctx, "cartpole", True, DEFAULT_NENV["cartpole"], args.steps, args.warmup, use_graph=not args.no_graph,
+                          want_e2e=False, e2e_host_controller=False, cpu_seconds=0.0, tv_lqr=True)
+        out["secondary"]["cartpole_tv_lqr"] = {k: tv[k] for k in ("value", "unit", "ms_per_step", "ms_per_step_per_rank", "steps", "config",
+                                                                  "gpu_launches", "bad_env_flags", "kernel_variant", "clocks")}
     if rank == 0:
         print(json.dumps(out))
     if world > 1:

@@ -169,6 +169,10 @@ int b2_fp_peak(int precision, int device, double* tflops);
 
 int b2_stream_synchronize(b2_batch* batch, void* stream);
 
+/* b2_lqr_control with a gain of its own for every env (time-varying LQR): K_env is a DEVICE array (nu, 2nv, nenv), env
+ * fastest -- the layout b2_dlqr writes -- and qpos_ref / ctrl_ref are those of b2_lqr_set_gain. */
+int b2_lqr_control_env(b2_batch* batch, const b2_state* state, const void* K_env, void* stream);
+
 /* Random-rollout controller on the device (BASELINE.json configs #3 / #4: "batched random controls ... generated on
  * device"): ctrl[a, e] ~ U(lo, hi), i.i.d. per call, env and actuator (Philox4x32-10 keyed by (seed, env); the per-env
  * draw counter lives in the batch, so a captured CUDA graph replays with fresh numbers).  With reset_qpos != NULL the

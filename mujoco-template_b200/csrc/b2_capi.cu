@@ -665,6 +665,19 @@ int b2_step_host(b2_batch* b, const b2_state* hs, int nsteps, int linearize, dou
   return e ? cuda_fail(e, "b2_step_host: synchronize") : B2_OK;
 }
 
+int b2_lqr_control_env(b2_batch* b, const b2_state* st, const void* K_env, void* stream) {
+  B2_CHECK_STATE("b2_lqr_control_env");
+  if (!b->d_gain) return fail(B2_ERR_ARG, "b2_lqr_control_env: call b2_lqr_set_gain first (qpos_ref / ctrl_ref come from it)");
+  if (!K_env) return fail(B2_ERR_ARG, "b2_lqr_control_env: K_env is NULL");
+  const void* lane = nullptr;
+  int rc = lane_image(b, &lane);
+  if (rc) return rc;
+  rc = b->precision == B2_F64 ? b2::b2k_lqr_control_env_f64(lane, b->model->cls, st, b->nenv, b->nenv, b->d_gain, K_env, stream)
+                              : b2::b2k_lqr_control_env_f32(lane, b->model->cls, st, b->nenv, b->nenv, b->d_gain, K_env, stream);
+  g_launches++;
+  return rc ? cuda_fail((cudaError_t)rc, "b2_lqr_control_env launch") : B2_OK;
+}
+
 int b2_random_controls(b2_batch* b, const b2_state* st, double lo, double hi, unsigned long long seed, int watch_row, double watch_min,
                        const void* reset_qpos, const void* reset_qvel, void* stream) {
   B2_CHECK_STATE("b2_random_controls");
@@ -711,13 +724,27 @@ int b2_dlqr(int device, int precision, const void* A, const void* B, const doubl
                                                    : aug[((i - (size_t)nx * nx - (size_t)nu * nu) / nu) * 2 * nu + nu + (i - (size_t)nx * nx - (size_t)nu * nu) % nu]);
     if (precision == B2_F64) ((double*)host.data())[i] = x; else ((float*)host.data())[i] = (float)x;
   }
-  cudaStream_t s = (cudaStream_t)stream;
+  // The (Q, R, R^-1) block lives on the device for as long as the process does, keyed by its contents: repeated calls with the
+  // same weights (a controller that re-synthesises its gains every tick) neither allocate nor copy, and the call can be
+  // captured into a CUDA graph once the block exists.
   void* dqr = nullptr;
-  if ((e = cudaMallocAsync(&dqr, nqr * esz, s)) != cudaSuccess) return cuda_fail(e, "b2_dlqr: cudaMallocAsync");
-  if ((e = cudaMemcpyAsync(dqr, host.data(), nqr * esz, cudaMemcpyHostToDevice, s)) != cudaSuccess) { cudaFreeAsync(dqr, s); return cuda_fail(e, "b2_dlqr: upload"); }
+  {
+    static std::mutex mu;
+    static std::vector<std::pair<std::vector<unsigned char>, void*>> cache;  // key: device, sizes, bytes
+    std::vector<unsigned char> key(host);
+    const int head[4] = {device, precision, nx, nu};
+    key.insert(key.end(), (const unsigned char*)head, (const unsigned char*)head + sizeof(head));
+    std::lock_guard<std::mutex> lock(mu);
+    for (auto& kv : cache) if (kv.first == key) { dqr = kv.second; break; }
+    if (!dqr) {
+      if ((e = cudaMalloc(&dqr, nqr * esz)) != cudaSuccess) return cuda_fail(e, "b2_dlqr: cudaMalloc");
+      if ((e = cudaMemcpy(dqr, host.data(), nqr * esz, cudaMemcpyHostToDevice)) != cudaSuccess) { cudaFree(dqr); return cuda_fail(e, "b2_dlqr: upload"); }
+      if (cache.size() >= 64) { cudaFree(cache.front().second); cache.erase(cache.begin()); }
+      cache.emplace_back(std::move(key), dqr);
+    }
+  }
   const int rc = precision == B2_F64 ? b2::b2k_dare_f64(A, B, dqr, nx, nu, nenv, max_doublings, tol, K, P, status, stream)
                                      : b2::b2k_dare_f32(A, B, dqr, nx, nu, nenv, max_doublings, tol, K, P, status, stream);
-  cudaFreeAsync(dqr, s);
   g_launches++;
   if (rc == (int)cudaErrorInvalidValue) return fail(B2_ERR_CAPACITY, "b2_dlqr: nx too large for the shared-memory workspace of one SM");
   return rc ? cuda_fail((cudaError_t)rc, "b2_dlqr launch") : B2_OK;

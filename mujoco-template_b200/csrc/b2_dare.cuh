@@ -173,3 +173,187 @@ __global__ void __launch_bounds__(128) k_dare(const T* __restrict__ Ag, const T*
 }
 
 }  // namespace b2
+
+namespace b2 {
+
+// Thread-per-env variant for small systems (pendulum 2 x 1, cartpole 4 x 1, ...): compile-time sizes, every matrix in
+// registers, same iteration and stopping rule as k_dare.  A warp per 4 x 4 system leaves 30 lanes idle; this form
+// synthesises the gains of 65,536 cartpoles in a fraction of a millisecond, which makes re-synthesis at every control tick
+// (time-varying LQR from the tick's own (A, B)) affordable.
+template <typename T, int N>
+B2_DEV void small_mul(T* C, const T* X, const T* Y) {  // C = X Y
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < N; k++) s += X[i * N + k] * Y[k * N + j];
+      C[i * N + j] = s;
+    }
+}
+template <typename T, int N>
+B2_DEV void small_mul_tn(T* C, const T* X, const T* Y) {  // C = X' Y
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < N; k++) s += X[k * N + i] * Y[k * N + j];
+      C[i * N + j] = s;
+    }
+}
+template <typename T, int N>
+B2_DEV void small_mul_nt(T* C, const T* X, const T* Y) {  // C = X Y'
+#pragma unroll
+  for (int i = 0; i < N; i++)
+#pragma unroll
+    for (int j = 0; j < N; j++) {
+      T s = 0;
+#pragma unroll
+      for (int k = 0; k < N; k++) s += X[i * N + k] * Y[j * N + k];
+      C[i * N + j] = s;
+    }
+}
+// Gauss-Jordan with partial pivoting on [W | R1 R2] (N x N and two N x N right-hand sides), fully unrolled: the row swap is a
+// chain of selects, so that no index is a run-time value and everything stays in registers.
+template <typename T, int N, int RHS>
+B2_DEV bool small_solve(T* W, T* R) {  // R: N x (RHS) row-major, overwritten by W^-1 R
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < N; c++) {
+    // bring the largest |W[r][c]|, r >= c, to row c
+#pragma unroll
+    for (int r = c + 1; r < N; r++) {
+      const bool sw = fabs(W[r * N + c]) > fabs(W[c * N + c]);
+#pragma unroll
+      for (int k = 0; k < N; k++) { const T a = W[c * N + k], b = W[r * N + k]; W[c * N + k] = sw ? b : a; W[r * N + k] = sw ? a : b; }
+#pragma unroll
+      for (int k = 0; k < RHS; k++) { const T a = R[c * RHS + k], b = R[r * RHS + k]; R[c * RHS + k] = sw ? b : a; R[r * RHS + k] = sw ? a : b; }
+    }
+    if (!(fabs(W[c * N + c]) > Num<T>::minval())) ok = false;
+    const T inv = T(1) / W[c * N + c];
+#pragma unroll
+    for (int k = 0; k < N; k++) W[c * N + k] *= inv;
+#pragma unroll
+    for (int k = 0; k < RHS; k++) R[c * RHS + k] *= inv;
+#pragma unroll
+    for (int r = 0; r < N; r++) {
+      if (r == c) continue;
+      const T f = W[r * N + c];
+#pragma unroll
+      for (int k = 0; k < N; k++) W[r * N + k] -= f * W[c * N + k];
+#pragma unroll
+      for (int k = 0; k < RHS; k++) R[r * RHS + k] -= f * R[c * RHS + k];
+    }
+  }
+  return ok;
+}
+
+template <typename T, int NX, int NU>
+__global__ void __launch_bounds__(64) k_dare_small(const T* __restrict__ Ag, const T* __restrict__ Bg, const T* __restrict__ Q,
+                                                   const T* __restrict__ R, const T* __restrict__ Rinv, int N, int max_doublings, T tol,
+                                                   T* Kg, T* Pg, int* status) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  constexpr int NN = NX * NX;
+  T A0[NN], A[NN], G[NN], H[NN], B[NX * NU];
+#pragma unroll
+  for (int k = 0; k < NN; k++) { A0[k] = Ag[(size_t)k * N + e]; A[k] = A0[k]; H[k] = Q[k]; }
+#pragma unroll
+  for (int k = 0; k < NX * NU; k++) B[k] = Bg[(size_t)k * N + e];
+  {  // G0 = B Rinv B'
+    T BR[NX * NU];
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int a = 0; a < NU; a++) { T s = 0;
+#pragma unroll
+        for (int b = 0; b < NU; b++) s += B[i * NU + b] * Rinv[b * NU + a];
+        BR[i * NU + a] = s; }
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int j = 0; j < NX; j++) { T s = 0;
+#pragma unroll
+        for (int a = 0; a < NU; a++) s += BR[i * NU + a] * B[j * NU + a];
+        G[i * NX + j] = s; }
+  }
+  int used = 0;
+  bool ok = true;
+#pragma unroll 1
+  for (int it = 0; it < max_doublings; it++) {
+    T W[NN], V[NX * 2 * NX];  // V = [A | G] -> W^-1 [A | G]
+    small_mul<T, NX>(W, G, H);
+#pragma unroll
+    for (int i = 0; i < NX; i++) {
+      W[i * NX + i] += T(1);
+#pragma unroll
+      for (int j = 0; j < NX; j++) { V[i * 2 * NX + j] = A[i * NX + j]; V[i * 2 * NX + NX + j] = G[i * NX + j]; }
+    }
+    ok = small_solve<T, NX, 2 * NX>(W, V);
+    if (!ok) break;
+    T V1[NN], V2[NN], t1[NN], t2[NN];
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int j = 0; j < NX; j++) { V1[i * NX + j] = V[i * 2 * NX + j]; V2[i * NX + j] = V[i * 2 * NX + NX + j]; }
+    small_mul<T, NX>(t1, H, V1);
+    small_mul_tn<T, NX>(t2, A, t1);  // A' H V1
+    T dmax = 0, hmax = 0;
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int j = 0; j < NX; j++) {
+        const T inc = T(0.5) * (t2[i * NX + j] + t2[j * NX + i]);
+        t1[i * NX + j] = H[i * NX + j] + inc;
+        dmax = fmax(dmax, fabs(inc)); hmax = fmax(hmax, fabs(t1[i * NX + j]));
+      }
+#pragma unroll
+    for (int k = 0; k < NN; k++) H[k] = t1[k];
+    small_mul<T, NX>(t1, A, V2);
+    small_mul_nt<T, NX>(t2, t1, A);  // A V2 A'
+#pragma unroll
+    for (int i = 0; i < NX; i++)
+#pragma unroll
+      for (int j = 0; j < NX; j++) t1[i * NX + j] = G[i * NX + j] + T(0.5) * (t2[i * NX + j] + t2[j * NX + i]);
+#pragma unroll
+    for (int k = 0; k < NN; k++) G[k] = t1[k];
+    small_mul<T, NX>(t1, A, V1);
+#pragma unroll
+    for (int k = 0; k < NN; k++) A[k] = t1[k];
+    used = it + 1;
+    if (it >= 3 && dmax <= tol * fmax(hmax, T(1))) break;
+  }
+#pragma unroll
+  for (int k = 0; k < NN; k++) Pg[(size_t)k * N + e] = H[k];
+  // K = (R + B'PB)^-1 B'P A0
+  T PB[NX * NU], S[NU * NU], RH[NU * NX];
+#pragma unroll
+  for (int i = 0; i < NX; i++)
+#pragma unroll
+    for (int a = 0; a < NU; a++) { T s = 0;
+#pragma unroll
+      for (int q = 0; q < NX; q++) s += H[i * NX + q] * B[q * NU + a];
+      PB[i * NU + a] = s; }
+#pragma unroll
+  for (int a = 0; a < NU; a++) {
+#pragma unroll
+    for (int b = 0; b < NU; b++) { T s = R[a * NU + b];
+#pragma unroll
+      for (int q = 0; q < NX; q++) s += B[q * NU + a] * PB[q * NU + b];
+      S[a * NU + b] = s; }
+#pragma unroll
+    for (int j = 0; j < NX; j++) { T s = 0;
+#pragma unroll
+      for (int q = 0; q < NX; q++) s += PB[q * NU + a] * A0[q * NX + j];
+      RH[a * NX + j] = s; }
+  }
+  ok = small_solve<T, NU, NX>(S, RH) && ok;
+#pragma unroll
+  for (int k = 0; k < NU * NX; k++) Kg[(size_t)k * N + e] = RH[k];
+  if (status) status[e] = ok ? used : -used - 1;
+}
+
+}  // namespace b2

@@ -430,6 +430,26 @@ __global__ void __launch_bounds__(128) k_lqr_control(StateDev<T> st, int count, 
   for (int a = 0; a < M::nu(); a++) st.ctrl[(size_t)a * N + e] = u[a];
 }
 
+// The same law with a gain of its own for every env (time-varying LQR: K_e re-synthesised from the env's latest (A, B) by
+// b2_dlqr): K_env (nu, 2nv, N) env fastest; qpos_ref / ctrl_ref from the shared gain block.
+template <typename T, class D, class M>
+__global__ void __launch_bounds__(128) k_lqr_control_env(StateDev<T> st, int count, int N, const T* __restrict__ gain, const T* __restrict__ K_env,
+                                                         const void* image = nullptr) {
+  model_load<M>(image, 0);
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= count) return;
+  RowStore<T, D> rows;
+  LaneEnv<T, D, M> env(rows);
+  const int nq = M::nq(), nv = M::nv(), nu = M::nu();
+  T q[D::NQ], v[D::NV], u[D::NU], g[D::NU * 2 * D::NV + D::NQ + D::NU];
+  for (int k = 0; k < nu * 2 * nv; k++) g[k] = K_env[(size_t)k * N + e];
+  for (int k = 0; k < nq + nu; k++) g[nu * 2 * nv + k] = gain[nu * 2 * nv + k];
+  for (int k = 0; k < nq; k++) q[k] = st.qpos[(size_t)k * N + e];
+  for (int k = 0; k < nv; k++) v[k] = st.qvel[(size_t)k * N + e];
+  lqr_law(env, q, v, g, u);
+  for (int a = 0; a < nu; a++) st.ctrl[(size_t)a * N + e] = u[a];
+}
+
 // Random-rollout controller (BASELINE configs #3 / #4: controls U(lo, hi) i.i.d. per step, env and actuator, drawn on the
 // device) fused with the episode reset a batched rollout driver applies: an env whose qpos[watch_row] has dropped below
 // watch_min starts again from its row of reset_qpos / reset_qvel.  Philox4x32-10 keyed by (seed, env), counter = the env's

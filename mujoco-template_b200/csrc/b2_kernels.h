@@ -26,6 +26,7 @@ namespace b2 {
   int b2k_lqr_control##SUF(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, void* stream);                           \
   int b2k_dare##SUF(const void* A, const void* B, const void* qr, int nx, int nu, int N, int max_doublings, double tol, void* K, void* P, \
                     int* status, void* stream);                                                                            \
+  int b2k_lqr_control_env##SUF(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, const void* K_env, void* stream); \
   int b2k_random_controls##SUF(const b2_state* st, int N, int nq, int nv, int nu, double lo, double hi, unsigned long long seed, void* ctr, \
                                int watch_row, double watch_min, const void* reset_qpos, const void* reset_qvel, void* stream);             \
   int b2k_record_rows##SUF(const void* cols, int ncol, const int* env_index, int nsel, int N, double time, void* out, void* stream); \

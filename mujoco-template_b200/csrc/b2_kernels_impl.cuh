@@ -270,6 +270,20 @@ int B2_FN(b2k_lqr_control)(const void* image, int cls, const b2_state* st, int c
 // batched DARE / LQR gains: one warp per env, as many warps per block as the shared-memory workspace allows (at most four)
 int B2_FN(b2k_dare)(const void* A, const void* B, const void* qr /* device: Q, R, Rinv */, int nx, int nu, int N, int max_doublings,
                     double tol, void* K, void* P, int* status, void* stream) {
+  const real* qd = (const real*)qr;
+  // small systems: one env per thread, compile-time sizes (B2_DARE_WARP=1 forces the warp kernel)
+  const char* force_warp = getenv("B2_DARE_WARP");
+  if (!(force_warp && force_warp[0] == '1')) {
+#define B2_DARE_SMALL(NX_, NU_)                                                                                                   \
+    if (nx == NX_ && nu == NU_) {                                                                                                 \
+      k_dare_small<real, NX_, NU_><<<(N + 63) / 64, 64, 0, (cudaStream_t)stream>>>((const real*)A, (const real*)B, qd, qd + nx * nx, \
+                                                                                  qd + nx * nx + nu * nu, N, max_doublings, (real)tol,   \
+                                                                                  (real*)K, (real*)P, status);                     \
+      return (int)cudaGetLastError();                                                                                             \
+    }
+    B2_DARE_SMALL(2, 1) B2_DARE_SMALL(4, 1) B2_DARE_SMALL(4, 2)
+#undef B2_DARE_SMALL
+  }
   int dev = 0, smem_max = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
@@ -282,6 +296,12 @@ int B2_FN(b2k_dare)(const void* A, const void* B, const void* qr /* device: Q, R
   const real* q = (const real*)qr;
   k_dare<real><<<(N + wpb - 1) / wpb, wpb * 32, per * wpb, (cudaStream_t)stream>>>(
       (const real*)A, (const real*)B, q, q + nx * nx, q + nx * nx + nu * nu, nx, nu, N, max_doublings, (real)tol, (real*)K, (real*)P, status);
+  return (int)cudaGetLastError();
+}
+int B2_FN(b2k_lqr_control_env)(const void* image, int cls, const b2_state* st, int count, int N, const void* gain, const void* K_env, void* stream) {
+  const int threads = 128, blocks = (count + threads - 1) / threads;
+  B2_DISPATCH(cls, (k_lqr_control_env<real, DD, RuntimeModel<DD>><<<blocks, threads, 0, (cudaStream_t)stream>>>(
+                       to_dev<real>(st), count, N, (const real*)gain, (const real*)K_env, image)));
   return (int)cudaGetLastError();
 }
 int B2_FN(b2k_random_controls)(const b2_state* st, int N, int nq, int nv, int nu, double lo, double hi, unsigned long long seed, void* ctr,

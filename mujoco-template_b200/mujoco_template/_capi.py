@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = (
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
     "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
-    "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr", "b2_random_controls", "b2_warp_queue_histogram",
+    "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr", "b2_random_controls", "b2_warp_queue_histogram", "b2_lqr_control_env",
 )
 
 
@@ -89,6 +89,7 @@ def lib() -> C.CDLL:
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
     L.b2_stream_synchronize.argtypes = [vp, vp]
+    L.b2_lqr_control_env.argtypes = [vp, C.POINTER(State), vp, vp]
     L.b2_random_controls.argtypes = [vp, C.POINTER(State), C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_double, vp, vp, vp]
     L.b2_warp_queue_histogram.argtypes = [vp, C.POINTER(C.c_int), vp]
     L.b2_dlqr.argtypes = [C.c_int, C.c_int, vp, vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.c_int, C.c_int, C.c_int,
@@ -184,6 +185,9 @@ class NativeBatch:
 
     def lqr_control(self, state: State, stream: int = 0) -> None:
         check(self._L.b2_lqr_control(self.handle, C.byref(state), stream))
+
+    def lqr_control_env(self, state: State, K_env: int, stream: int = 0) -> None:
+        check(self._L.b2_lqr_control_env(self.handle, C.byref(state), K_env, stream))
 
     def control_tick(self, state: State, derived: Derived | None, use_lqr: bool, eps: float, centered: bool, A: int, B: int,
                      stream: int = 0) -> None:

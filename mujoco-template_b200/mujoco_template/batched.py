@@ -191,8 +191,11 @@ class BatchedEnv:
 
     # ---- hot path
     def linearize(self, eps: float | None = None, centered: bool = True):
-        """(A, B) of every env: ``(nenv, 2nv, 2nv)`` and ``(nenv, 2nv, nu)`` views of fresh SoA buffers."""
-        A, B = self.data.backend.linearize(self.lin_eps if eps is None else float(eps), centered)
+        """(A, B) of every env: ``(nenv, 2nv, 2nv)`` and ``(nenv, 2nv, nu)`` views of fresh SoA buffers -- or of the
+        controller's own ``lin_out`` buffers when it provides them (a controller that consumes the linearisation on the
+        device, e.g. ``BatchedTVLQRController``, needs them at a fixed address from tick to tick)."""
+        out = getattr(self.controller, "lin_out", None)
+        A, B = self.data.backend.linearize(self.lin_eps if eps is None else float(eps), centered, out=out)
         return A.permute(2, 0, 1), B.permute(2, 0, 1)
 
     def jacobians(self, tokens: Iterable[str] | None = None):

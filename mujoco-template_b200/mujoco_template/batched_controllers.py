@@ -164,6 +164,74 @@ class BatchedLQRController:
         data.ctrl.copy_(u)
 
 
+class BatchedTVLQRController(BatchedLQRController):
+    """Time-varying LQR: every control tick re-synthesises the gain of EVERY env from that env's latest FD linearisation
+    ``(A_e, B_e)`` (``b2_dlqr``: DARE + gain on the device, one thread or warp per env) and applies it
+    (``b2_lqr_control_env``) -- BASELINE config #2 read literally: "per-step FD (A, B) linearisation for LQR".
+
+    The ``(A, B)`` are the ones the env computed for the previous tick (``needs_linearization=True``: ``BatchedEnv`` linearises
+    after every controller call, reference ``env.py:178-190``), so the gain lags the state by one step; the first tick uses the
+    setpoint gain of ``BatchedLQRController``.  No host round trip: three launches per tick (DARE, control law, FD) plus the
+    step."""
+
+    def __init__(self, *args, max_doublings: int = 40, tol: float = 1e-12, **kwargs):
+        kwargs["fused"] = False
+        super().__init__(*args, **kwargs)
+        self.max_doublings, self.tol = int(max_doublings), float(tol)
+        self._bufs = None
+        self.lin_out = None   # (A, B) buffers BatchedEnv.linearize writes into: fixed addresses (CUDA-graph replay)
+        self._have_lin = False
+
+    def prepare(self, model: Any, data: Any) -> None:
+        super().prepare(model, data)
+        if hasattr(data.qpos, "device"):
+            import torch
+
+            nx, n = 2 * model.nv, data.qpos.shape[1]
+            self.lin_out = (torch.zeros((nx, nx, n), dtype=data.qpos.dtype, device=data.qpos.device),
+                            torch.zeros((nx, model.nu, n), dtype=data.qpos.dtype, device=data.qpos.device))
+        self._have_lin = False
+
+    def device_law_ready(self, data: Any) -> bool:  # the gain differs per env: BatchedEnv must not fold the tick
+        return False
+
+    def __call__(self, model: Any, data: Any, t: float) -> None:
+        import torch
+
+        from . import _capi
+
+        b = data.backend
+        if not (hasattr(b, "batch") and hasattr(data.qpos, "device")):
+            raise ConfigError("BatchedTVLQRController drives a BatchedEnv (device tensors)")
+        if not self._gain_uploaded:
+            b.batch.lqr_set_gain(self.K, self._qref_np, self._uref_np)
+            self._gain_uploaded = True
+        if not self._have_lin or self.lin_out is None:   # first tick after prepare(): no linearisation yet
+            self._have_lin = True
+            b._launch("lqr_control", b.batch.lqr_control, b.state_struct())
+            return
+        A, B = self.lin_out
+        nx, nu, n = A.shape[0], B.shape[1], A.shape[2]
+        if self._bufs is None:
+            self._bufs = (torch.empty((nu, nx, n), dtype=A.dtype, device=A.device), torch.empty((nx, nx, n), dtype=A.dtype, device=A.device),
+                          torch.zeros(n, dtype=torch.int32, device=A.device))
+            self._Q = np.ascontiguousarray(np.eye(nx) if self.Q is None else np.asarray(self.Q, dtype=float)).reshape(-1)
+            self._R = np.ascontiguousarray(np.eye(nu) if self.R is None else np.asarray(self.R, dtype=float)).reshape(-1)
+        K_env, P_env, status = self._bufs
+        b._pre()
+        _capi.dlqr(A.device.index, 64 if A.dtype == torch.float64 else 32, A.data_ptr(), B.data_ptr(), self._Q, self._R, nx, nu, n,
+                   K_env.data_ptr(), P_env.data_ptr(), status.data_ptr(), self.max_doublings, self.tol, b.stream)
+        b._launch("lqr_control_env", b.batch.lqr_control_env, b.state_struct(), K_env.data_ptr())
+
+    @property
+    def gains(self):
+        """(K (N, nu, nx), P (N, nx, nx), status (N,)) of the last tick, or None before the first re-synthesis."""
+        if self._bufs is None:
+            return None
+        K_env, P_env, status = self._bufs
+        return K_env.permute(2, 0, 1), P_env.permute(2, 0, 1), status
+
+
 class BatchedRandomController:
     """Random-rollout controller of BASELINE.json configs #3 / #4 ("batched random controls", drawn on the device every
     step): ``ctrl ~ U(lo, hi)`` i.i.d. per step, env and actuator, in ONE library launch (``b2_random_controls``, Philox
@@ -196,4 +264,4 @@ class BatchedRandomController:
         b._launch("random_controls", b.batch.random_controls, b.state_struct(), self.lo, self.hi, self.seed, row, thr, rq, rv)
 
 
-__all__ = ["BatchedLQRController", "BatchedRandomController", "batched_dlqr_gain", "dlqr_gain"]
+__all__ = ["BatchedLQRController", "BatchedTVLQRController", "BatchedRandomController", "batched_dlqr_gain", "dlqr_gain"]
