@@ -185,7 +185,7 @@ struct NominalInMemory {
 // One column of the FD linearisation for env e -- c < nv: tangent-space position column, c < 2nv: velocity column, else
 // control column c - 2nv -- or, with nominal = true, the unperturbed step itself, which leaves the advanced state in
 // env.qpos / env.qvel / env.warm.  nom: accessor of the env's nominal state.
-template <typename T, class D, class M, class S>
+template <int PART, typename T, class D, class M, class S>
 B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
                       T eps, T inv_eps, int centered, int N, int e, T* A, T* B, bool& pos_valid, bool& vel_valid) {
   constexpr int NQ = D::NQ, NV = D::NV;
@@ -193,7 +193,8 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
   int kind, i;
   bool fwd = true, back = centered != 0;
-  if (nominal) { kind = 0; i = 0; fwd = back = false; }
+  if (PART == 2) { kind = 1; i = c; }  // position-column kernel: the column kind is a compile-time fact
+  else if (nominal) { kind = 0; i = 0; fwd = back = false; }
   else if (c < nv) { kind = 1; i = c; }
   else if (c < ndx) { kind = 2; i = c - nv; }
   else {
@@ -234,8 +235,8 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     B2_UNROLL
     for (int k = 0; k < nv; k++) if (!(fabs(env.qacc[k]) <= T(1e10))) env.flags |= 4;
     if (M::integrator() == 1) env.rk4(); else env.euler();
-    vel_valid = kind != 1 && kind != 2 && M::integrator() == 0;  // this rollout's velocity stage was the nominal one
-    pos_valid = kind != 1 && M::integrator() == 0;
+    vel_valid = PART != 2 && kind != 1 && kind != 2 && M::integrator() == 0;  // this rollout's velocity stage was the nominal one
+    pos_valid = PART != 2 && kind != 1 && M::integrator() == 0;
     // plus -> s2, minus -> s1, nominal -> whichever end the one-sided quotient is missing
     const bool to2 = phase == 0 || (phase == 2 && !fwd);
     B2_UNROLL
@@ -269,18 +270,30 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
 // have nothing to share between columns: one thread per (env, column).
 // register budget of the FD kernel: either through the resident-blocks hint or, with B2_LIN_MAXNREG, as an explicit cap
 // (ptxas settles on 168 registers for any hint between 3 x 128 and 5 x 64 threads per SM)
-#ifdef B2_LIN_MAXNREG
-#define B2_LIN_BOUNDS __maxnreg__(B2_LIN_MAXNREG)
-#else
-#define B2_LIN_BOUNDS __launch_bounds__(B2_LIN_THREADS, B2_LIN_MIN_BLOCKS)
+// PART: 0 = one kernel for all FD tasks of an env; 1 = the velocity / control groups (+ the env advance) only; 2 = the
+// position columns only.  The split exists for the register budget: a position-column thread runs two full rollouts and
+// keeps nothing across them -- 168 registers without a spill, 12 warps per SM -- while the group thread keeps the position
+// stage and both factorisations alive across up to seven rollouts and needs 253 (8 warps per SM); one kernel for both has
+// to take the larger budget for all its threads.
+#ifndef B2_LINP_THREADS
+#define B2_LINP_THREADS 128
 #endif
-template <typename T, class D, class M>
-__global__ void B2_LIN_BOUNDS k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow,
+#ifndef B2_LINP_MIN_BLOCKS
+#define B2_LINP_MIN_BLOCKS 3
+#endif
+#ifdef B2_LIN_MAXNREG
+#define B2_LIN_BOUNDS(PART) __maxnreg__(B2_LIN_MAXNREG)
+#else
+#define B2_LIN_BOUNDS(PART) __launch_bounds__((PART) == 2 ? B2_LINP_THREADS : B2_LIN_THREADS, (PART) == 2 ? B2_LINP_MIN_BLOCKS : B2_LIN_MIN_BLOCKS)
+#endif
+template <typename T, class D, class M, int PART = 0>
+__global__ void B2_LIN_BOUNDS(PART) k_linearize(StateDev<T> st, int count, int N, T eps, int centered, T* A, T* B, const T* __restrict__ gain, StateDev<T> shadow,
                                                                                  const void* image = nullptr) {
   model_load<M>(image, 0);
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)count * fd_tasks<M>()) return;
+  const int ntask = PART == 0 ? fd_tasks<M>() : (PART == 1 ? fd_group_count(nv, nu) : nv);
+  if (idx >= (long long)count * ntask) return;
   const int e = (int)(idx % count), task = (int)(idx / count);  // count envs, env stride N
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
@@ -300,14 +313,15 @@ __global__ void B2_LIN_BOUNDS k_linearize(StateDev<T> st, int count, int N, T ep
   const bool grouped = M::integrator() == 0;  // not a constant expression for the runtime provider
   const int groups = fd_group_count(nv, nu);
   int c0 = task, c1 = task + 1;
-  if (grouped) {
+  if (PART == 2) { c0 = task; c1 = task + 1; }
+  else if (grouped) {
     if (task < groups) { c0 = nv + task * B2_FD_GROUP; c1 = c0 + B2_FD_GROUP < ndx + nu ? c0 + B2_FD_GROUP : ndx + nu; }
     else { c0 = task - groups; c1 = c0 + 1; }
   }
   // shadow.qpos != null (grouped form only): the thread of the velocity / control columns also advances the env -- its
   // position stage is the step's -- and leaves the new state in the shadow arrays (the other threads of the env still
   // read the nominal state); k_commit_state swaps the two afterwards
-  const bool advance = grouped && task == 0 && shadow.qpos != nullptr;
+  const bool advance = PART != 2 && grouped && task == 0 && shadow.qpos != nullptr;
   bool pos_valid = false, vel_valid = false;
   const T inv_eps = T(1) / eps;
   // mj_checkPos / mj_checkVel once on the nominal state (an eps perturbation of a finite state is finite)
@@ -321,7 +335,7 @@ __global__ void B2_LIN_BOUNDS k_linearize(StateDev<T> st, int count, int N, T ep
   B2_NOUNROLL
   for (int c = c0; c < c1 + (advance ? 1 : 0) && !frozen; c++) {
     const bool nominal = c == c1;  // the advance comes after the group's columns, on the same position stage
-    fd_column(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid, vel_valid);
+    fd_column<PART>(env, nom, nominal ? ndx + nu : c, nominal, eps, inv_eps, centered, N, e, A, B, pos_valid, vel_valid);
   }
   if (advance) {
     B2_UNROLL

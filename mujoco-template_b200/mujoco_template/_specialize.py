@@ -45,6 +45,13 @@ REAL_ARRAYS = ("gravity", "wind", "body_pos", "body_quat", "body_ipos", "body_iq
 # in between (184 / 200 / 216 registers at 9-11 warps) are all slower (round 2, profiles/ab_cartpole_lin_shapes_r02k.txt).
 import os as _os
 LIN_SHAPE = tuple(int(x) for x in _os.environ.get("B2_LIN_SHAPE", "64,4").split(","))
+# B2_LIN_SPLIT=1 (build-time experiment, Euler models with nv <= 2): the FD launch as two kernels, the velocity / control
+# groups (LIN_SHAPE, 253 registers) and the position columns (LINP_SHAPE: 168 registers without a spill, 12 warps per SM).
+# Measured on the cartpole tick: +2 % device-timed when the two run back to back on one stream (1.65e9 against 1.62e9
+# env-steps/s), nothing when they overlap on two streams (the fork / join costs what the overlap gains), and -6 % end to end
+# (the PCIe write pipeline of the direct (A, B) stores drains between the launches).  Off by default.
+LINP_SHAPE = tuple(int(x) for x in _os.environ.get("B2_LINP_SHAPE", "128,3").split(","))
+LIN_SPLIT = _os.environ.get("B2_LIN_SPLIT", "0") == "1"
 
 _MAX_CONTACTS = {(0, 2): 1, (0, 3): 2, (0, 6): 4, (0, 4): 1, (2, 2): 1, (2, 3): 1, (3, 3): 2}
 
@@ -119,8 +126,12 @@ def emit_spec(compiled: dict, name: str) -> str:
     A("#define B2_STATIC_MODEL 1")
     # small models: ask for >= 3 resident blocks/SM in the FD kernel (<= 168 registers, measured best on B200)
     lin_threads, lin_blocks = (LIN_SHAPE if nv <= 2 else (128, 1))
+    linp_threads, linp_blocks = LINP_SHAPE
+    lin_split = LIN_SPLIT and nv <= 2 and int(c["integrator"]) == 0
     A(f"#define B2_LIN_THREADS {lin_threads}")
     A(f"#define B2_LIN_MIN_BLOCKS {lin_blocks}")
+    A(f"#define B2_LINP_THREADS {linp_threads}")
+    A(f"#define B2_LINP_MIN_BLOCKS {linp_blocks}")
     ncol = 2 * nv + nu
     # k_linearize: Euler deals the velocity / control columns out in groups of B2_FD_GROUP = 4 (b2_kernel_templates.cuh)
     fd_tasks = (nv + nu + 3) // 4 + nv if int(c["integrator"]) == 0 else ncol
@@ -158,9 +169,19 @@ def emit_spec(compiled: dict, name: str) -> str:
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_linearize{suf}(const b2_state* st, int count, int N, double eps, int centered, void* A, void* B, const void* gain, const b2_state* shadow, void* stream) {{")
-        A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {fd_tasks};")
-        A("  const int blocks = (int)((total + threads - 1) / threads);")
-        A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain, to_dev<{T}>(shadow));")
+        if lin_split:
+            # two launches on the same stream: the velocity / control groups (253 registers, they also advance the env), then
+            # the position columns (168 registers without a spill: 12 warps per SM) -- see k_linearize's PART
+            groups = (nv + nu + 3) // 4
+            A("  cudaStream_t s = (cudaStream_t)stream, side = s;")
+            A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {groups};")
+            A(f"  k_linearize<{T}, SDims, SModel<{T}>, 1><<<(int)((total + threads - 1) / threads), threads, 0, s>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain, to_dev<{T}>(shadow));")
+            A(f"  const int threads_p = {linp_threads}; const long long total_p = (long long)count * {nv};")
+            A(f"  k_linearize<{T}, SDims, SModel<{T}>, 2><<<(int)((total_p + threads_p - 1) / threads_p), threads_p, 0, side>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain, to_dev<{T}>(shadow));")
+        else:
+            A(f"  const int threads = {lin_threads}; const long long total = (long long)count * {fd_tasks};")
+            A("  const int blocks = (int)((total + threads - 1) / threads);")
+            A(f"  k_linearize<{T}, SDims, SModel<{T}>><<<blocks, threads, 0, (cudaStream_t)stream>>>(to_dev<{T}>(st), count, N, ({T})eps, centered, ({T}*)A, ({T}*)B, (const {T}*)gain, to_dev<{T}>(shadow));")
         A("  return (int)cudaGetLastError();")
         A("}")
         A(f"int spec_jacobian{suf}(const b2_state* st, int N, int kind, int objid, void* jacp, void* jacr, void* stream) {{")
