@@ -13,9 +13,12 @@
  * Each function below names the upstream MuJoCo routine whose published algorithm it
  * restates (target: 3.1.x semantics).
  *
- * PARITY UNPINNED against a live MuJoCo (no golden vectors exist in the reference and
- * mujoco cannot be imported here).  The oracle is pinned by analytic known answers and
- * invariants instead: tests/test_oracle_analytic.py.
+ * PARITY UNPINNED against a live MuJoCo for mj_step, the Newton solver and mjd_transitionFD (no golden
+ * vectors exist in the reference and mujoco cannot be imported here).  One path IS pinned against the real
+ * engine: mj_inverse of the humanoid at the LQR tutorial's keyframe reproduces the output the upstream
+ * notebook publishes, digit for digit (tests/test_published_values.py: compile, kinematics, bias forces,
+ * foot contacts and constraint rows).  Everything else is pinned by analytic known answers, independent
+ * derivations and invariants: tests/test_oracle_analytic.py, tests/test_oracle_independent.py.
  *
  * Build: see oracle/Makefile (gcc -O2 -shared).  Loaded via ctypes by oracle/oracle.py.
  */

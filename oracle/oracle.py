@@ -3,7 +3,8 @@
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline legs may
 import this module; the product package (``mujoco-template_b200/``) never does.
 
-PARITY UNPINNED against a live MuJoCo (see mjstep_oracle.c header and DESIGN.md).
+PARITY UNPINNED against a live MuJoCo except for the humanoid's inverse dynamics (published tutorial output:
+tests/test_published_values.py); see the mjstep_oracle.c header and DESIGN.md section 5.
 """
 
 from __future__ import annotations
