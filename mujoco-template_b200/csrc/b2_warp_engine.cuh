@@ -177,11 +177,34 @@ __device__ __noinline__ void factor_LD_impl(int nv, const int* __restrict__ nanc
     if (lane == m) dinv[k] = q;
     if (m) {
       const int rowbase = tri(i, 0);
+#ifndef B2_WARP_PAIRFOLD  // measured 2.6 % slower than the plain sweeps (gpurun A/B, profiles/ab_hum_pairfold_r03g.txt): off
+      if (true) {
+#else
+      if (wl < 5) {
+#endif
 #pragma unroll 2
-      for (int s = h; s - h < m; s += hs) {
-        const T rks = __shfl_sync(0xffffffffu, rk, l + s);  // group 0 holds the row; l + s < m <= W there when it is used
-        const int js = __shfl_sync(0xffffffffu, i, l + s);
-        if (l + s < m) LDp[rowbase + js] -= q * rks;
+        for (int s = h; s - h < m; s += hs) {
+          const T rks = __shfl_sync(0xffffffffu, rk, l + s);  // group 0 holds the row; l + s < m <= W there when it is used
+          const int js = __shfl_sync(0xffffffffu, i, l + s);
+          if (l + s < m) LDp[rowbase + js] -= q * rks;
+        }
+      } else {
+        // Long ancestor sets (16 <= m <= 31: merged trees) leave no room for lane groups; instead sweep s (m - s pairs,
+        // lanes 0 .. m-s-1) runs together with sweep m-1-s (s + 1 pairs, lanes m-s .. m): m + 1 lanes busy, half the sweeps.
+        // A lane of the second group works for row l' = lane - (m - s) at offset m-1-s, i.e. on column lane - 1; the row's
+        // quotient and base come by shuffle.
+        const int half = (m + 1) >> 1;
+#pragma unroll 1
+        for (int s = 0; s < half; s++) {
+          const int nA = m - s;
+          const bool inA = lane < nA, inB = (m - 1 - s != s) && lane >= nA && lane <= m;
+          const int lrow = inA ? lane : (lane - nA) & 31, lcol = (inA ? lane + s : lane - 1) & 31;
+          const T rks = __shfl_sync(0xffffffffu, rk, lcol);
+          const int js = __shfl_sync(0xffffffffu, i, lcol);
+          const T ql = __shfl_sync(0xffffffffu, q, lrow);
+          const int rb = __shfl_sync(0xffffffffu, rowbase, lrow);
+          if (inA || inB) LDp[rb + js] -= ql * rks;
+        }
       }
       if (lane < m) LDp[kk + i] = q;
     }
