@@ -272,18 +272,24 @@ def run_reference(args):
     lin = not args.no_linearize
     om = _cpu_model(model)
     cores = os.cpu_count() or 1
-    # bounded sample: about 1.5 s of all-core work per step, sized from a measured probe
+    # bounded sample: about 1.5 s of all-core work per step (about 20 s for the whole run), sized from a measured probe
     rate = _cpu_probe_rate(om, model, name, lin, cores, 5)
-    n = int(max(cores, min(1 << 18, 1.5 * rate)))
+    n = int(max(cores, min(1 << 18, 1.5 * rate, 20.0 * rate / max(args.steps + args.warmup, 1))))
     qpos, qvel = synth_states(model, name, n, 7)
     ctrl = np.zeros((n, model.nu))
     warm = np.zeros((n, model.nv))
-    for _ in range(args.warmup):
+    # every step is one pass of the hot path (FD linearisation + mj_step of every env of the sample) from the configured
+    # initial-state distribution -- the GPU arm's envs are held there by their controller, an uncontrolled CPU rollout
+    # would drift into the floor and time the contact solver instead.  The median step counts (the host is a shared VM).
+    q0, v0 = qpos.copy(), qvel.copy()
+    times = []
+    for i in range(args.warmup + args.steps):
+        np.copyto(qpos, q0); np.copyto(qvel, v0); warm[:] = 0
+        t0 = time.perf_counter()
         om.batch_rollout(qpos, qvel, ctrl, warm, nsteps=1, lin=lin, nthreads=cores)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        om.batch_rollout(qpos, qvel, ctrl, warm, nsteps=1, lin=lin, nthreads=cores)
-    dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.median(times)) * args.steps
     value = n * args.steps / dt
     sample = (f"{n} envs per step (bounded sample of the {DEFAULT_NENV[name]}-env workload), all {cores} host threads; " + CPU_KIND_NOTE)
     print(json.dumps({
