@@ -69,6 +69,15 @@ struct LaneEnv {
   static constexpr bool kKeepFactors = false;
 #endif
   T LDe[kKeepFactors ? D::NV * D::NV : 1], dinve[kKeepFactors ? D::NV : 1], Hs[kKeepFactors ? D::NV * D::NV : 1];
+  // The static models that do not keep factors (4 < nv <= 8: the drone) are short of registers instead.  k_step runs
+  // them with LATE = true: the mass matrix and the actuator moments -- functions of qpos that nothing reads before the
+  // acceleration stage -- are computed there, so that neither is live across collision, velocities and bias forces
+  // (same inputs, same arithmetic: bit-identical).  The FD kernel keeps them in the position stage its rollouts share.
+#if defined(B2_STATIC_MODEL) && !defined(B2_EARLY_POSITION)
+  static constexpr bool kLateMass = !kKeepFactors;
+#else
+  static constexpr bool kLateMass = false;
+#endif
   T ten_len[D::NT], ten_J[D::NT * D::NV], act_len[D::NU], act_moment[D::NU * D::NV];
   // ---- velocity-dependent
   T cvel[6 * D::NB], cdof_dot[6 * D::NV], spat[6 * D::NB], spat2[10 * D::NB];  // scratch: cacc / crb, cfrc
@@ -1137,15 +1146,16 @@ struct LaneEnv {
   // position-dependent part of mj_forward: poses, inertias, mass matrix, limit and contact rows,
   // actuator moments.  Depends on qpos only, so the FD kernel reuses it across rollouts that
   // perturb velocities or controls (upstream's mjSTAGE_POS skip, bit-identical by construction).
+  template <bool LATE = false>
   B2_STAGE void forward_position() {
     kinematics();
     com_frame();
     tendons();
-    mass_matrix();
+    if (!LATE) mass_matrix();
     if (kKeepFactors) factor_mass();
     limit_rows();
     collide();
-    transmission();
+    if (!LATE) transmission();
   }
   // velocity-dependent part (depends on qpos and qvel only): reused by FD rollouts that perturb a control
   // (upstream's mjSTAGE_VEL skip)
@@ -1154,7 +1164,9 @@ struct LaneEnv {
     passive_forces();
     bias_forces();
   }
+  template <bool LATE = false>
   B2_STAGE void forward_acc() {
+    if (LATE) { mass_matrix(); transmission(); }
     if (!kKeepFactors) factor_mass();
     smooth_dynamics();
     constrained_acceleration();

@@ -122,6 +122,37 @@ def test_drone_landing_contacts_per_step():
     assert seen >= 4
 
 
+def test_drone_landing_contacts_fused_launches():
+    """The same landing with eight steps per launch: within a fused launch the drone's kernel hands the state -- the
+    warm start included -- from step to step through the SoA arrays (state streaming), so every launch must land where
+    eight oracle steps from the same state and warm start do."""
+    from mujoco_template import _mj as mj
+
+    model = load_model("drone")
+    n = 16
+    qpos, qvel, ctrl = random_states(model, "drone", n, seed=8)
+    qpos[:, 2] = np.linspace(0.12, 0.4, n)
+    ctrl[:] = 0.0
+    warm = np.zeros((n, model.nv))
+    data = _batch(model, n)
+    om, od = oracle_for(model)
+    seen = 0
+    for s in range(15):
+        _upload(data, qpos, qvel, ctrl, warm)
+        mj.mj_step(model, data, 8)
+        for e in range(n):
+            od.reset(); od.qpos[:] = qpos[e]; od.qvel[:] = qvel[e]; od.ctrl[:] = ctrl[e]; od.qacc_warmstart[:] = warm[e]
+            for _ in range(8):
+                od.step()
+                seen = max(seen, od.ncon)
+            qpos[e] = od.qpos; qvel[e] = od.qvel; warm[e] = od.qacc_warmstart
+        assert _rel(data.qpos.cpu().numpy().T, qpos) <= 1e-8, s
+        assert _rel(data.qvel.cpu().numpy().T, qvel) <= 1e-7, s
+        assert _rel(data.qacc_warmstart.cpu().numpy().T, warm) <= 1e-6, s
+    assert seen >= 4
+    assert int(data.flags.max().item()) == 0
+
+
 def test_bad_state_is_flagged_not_reset():
     """Upstream silently resets mjData on NaN/huge values; we flag the env instead."""
     from mujoco_template import _capi, _mj as mj
