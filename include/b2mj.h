@@ -159,8 +159,15 @@ int b2_differentiate_pos(b2_batch* batch, void* qvel_out, double dt, const void*
  * HBM; any other host memory goes through a staged device buffer.  Used by bench.py's e2e leg. */
 #define B2_HOST_LINEARIZE 1
 #define B2_HOST_LQR 2
+#define B2_HOST_ASYNC 4
 int b2_step_host(b2_batch* batch, const b2_state* host_state, int nsteps, int linearize, double eps, void* host_A,
                  void* host_B, void* stream);
+/* With B2_HOST_ASYNC in `linearize`, b2_step_host returns as soon as its copy / compute pipeline is queued (on streams the
+ * batch owns); the host buffers belong to the library until b2_step_host_wait(batch) returns, which is also when their
+ * contents are the step's results.  One call in flight per batch.  Two batches driven alternately -- wait(a), submit(a),
+ * wait(b), submit(b), ... -- keep the device-to-host link busy with one batch's (A, B) while the other computes
+ * (bench.py's e2e leg: the env batch as two half-batches, each a closed loop through its own host buffers). */
+int b2_step_host_wait(b2_batch* batch);
 
 /* Measured CUDA-core FMA throughput (TFLOP/s, 2 flops per FMA) of `device` for B2_F64 / B2_F32:
  * the FP-pipe roofline denominator (MEASURED_PEAKS.json only has HBM and bf16 tensor peaks).

@@ -24,7 +24,7 @@ _lib: C.CDLL | None = None
 EXPORTED_SYMBOLS = (
     "b2_model_create", "b2_model_destroy", "b2_model_set_actuator_disabled", "b2_batch_create",
     "b2_batch_destroy", "b2_step", "b2_forward", "b2_linearize", "b2_jacobian", "b2_integrate_pos",
-    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_stream_synchronize", "b2_launch_count",
+    "b2_differentiate_pos", "b2_inverse", "b2_lqr_set_gain", "b2_lqr_control", "b2_control_tick", "b2_refresh_derived", "b2_step_lazy", "b2_step_host", "b2_step_host_wait", "b2_stream_synchronize", "b2_launch_count",
     "b2_batch_size_class", "b2_last_error", "b2_version", "b2_fp_peak", "b2_batch_kernel_variant",
     "b2_recorder_create", "b2_recorder_record", "b2_recorder_destroy", "b2_dlqr", "b2_random_controls", "b2_warp_queue_histogram", "b2_lqr_control_env",
 )
@@ -88,6 +88,7 @@ def lib() -> C.CDLL:
     L.b2_integrate_pos.argtypes = [vp, vp, vp, d, vp]
     L.b2_differentiate_pos.argtypes = [vp, vp, d, vp, vp, vp]
     L.b2_step_host.argtypes = [vp, C.POINTER(State), i, i, d, vp, vp, vp]
+    L.b2_step_host_wait.argtypes = [vp]
     L.b2_stream_synchronize.argtypes = [vp, vp]
     L.b2_lqr_control_env.argtypes = [vp, C.POINTER(State), vp, vp]
     L.b2_random_controls.argtypes = [vp, C.POINTER(State), C.c_double, C.c_double, C.c_ulonglong, C.c_int, C.c_double, vp, vp, vp]
@@ -207,10 +208,15 @@ class NativeBatch:
         check(self._L.b2_differentiate_pos(self.handle, out, float(dt), qpos1, qpos2, stream))
 
     def step_host(self, state: State, nsteps: int, linearize: bool, eps: float, A: int | None, B: int | None, stream: int = 0,
-                  device_lqr: bool = False) -> None:
-        """Host-buffer step; ``device_lqr`` evaluates the ``lqr_set_gain`` law on the device (``state.ctrl`` becomes an output)."""
-        flags = (1 if linearize else 0) | (2 if device_lqr else 0)
+                  device_lqr: bool = False, wait: bool = True) -> None:
+        """Host-buffer step; ``device_lqr`` evaluates the ``lqr_set_gain`` law on the device (``state.ctrl`` becomes an output).
+        ``wait=False`` queues the step and returns (B2_HOST_ASYNC); ``step_host_wait`` completes it."""
+        flags = (1 if linearize else 0) | (2 if device_lqr else 0) | (0 if wait else 4)
         check(self._L.b2_step_host(self.handle, C.byref(state), int(nsteps), flags, float(eps), A, B, stream))
+
+    def step_host_wait(self) -> None:
+        """Completes a ``step_host(..., wait=False)``: the host buffers hold the step's results when this returns."""
+        check(self._L.b2_step_host_wait(self.handle))
 
     def random_controls(self, state: State, lo: float, hi: float, seed: int, watch_row: int = -1, watch_min: float = 0.0,
                         reset_qpos: int | None = None, reset_qvel: int | None = None, stream: int = 0) -> None:

@@ -556,6 +556,49 @@ def test_step_host_pipeline_matches_device_path(name, n):
             assert np.array_equal(hA.numpy(), A.cpu().numpy()) and np.array_equal(hB.numpy(), B.cpu().numpy()), rep
 
 
+def test_step_host_async_half_batches_equal_the_synchronous_call():
+    """B2_HOST_ASYNC + b2_step_host_wait: two half-batches, each a closed loop through its own pinned buffers and driven
+    alternately (wait, submit), land bit for bit where one synchronous b2_step_host over the whole batch does."""
+    import torch
+    from mujoco_template import _capi, _mj as mj
+
+    model = load_model("cartpole")
+    n, half = 512, 256
+    qpos, qvel, ctrl = random_states(model, "cartpole", n, seed=33)
+    nv, nu = model.nv, model.nu
+
+    def buffers(sl):
+        hq = torch.as_tensor(qpos[sl].T.copy()).pin_memory(); hv = torch.as_tensor(qvel[sl].T.copy()).pin_memory()
+        hu = torch.as_tensor(ctrl[sl].T.copy()).pin_memory(); m = hq.shape[1]
+        hw = torch.zeros((nv, m), dtype=torch.float64).pin_memory()
+        hA = torch.zeros((2 * nv, 2 * nv, m), dtype=torch.float64).pin_memory(); hB = torch.zeros((2 * nv, nu, m), dtype=torch.float64).pin_memory()
+        return hq, hv, hu, hw, hA, hB
+
+    whole = buffers(slice(0, n))
+    data = _batch(model, n)
+    st = _capi.State(*(t.data_ptr() for t in whole[:4]), None)
+    parts = []
+    for sl in (slice(0, half), slice(half, n)):
+        bufs = buffers(sl)
+        parts.append((_capi.NativeBatch(data.backend.batch.model, half, 0), _capi.State(*(t.data_ptr() for t in bufs[:4]), None), bufs))
+    nsteps = 6
+    for _ in range(nsteps):
+        data.backend.batch.step_host(st, 1, True, 1e-6, whole[4].data_ptr(), whole[5].data_ptr(), 0)
+    for b, s, bufs in parts:
+        b.step_host(s, 1, True, 1e-6, bufs[4].data_ptr(), bufs[5].data_ptr(), 0, wait=False)
+    for _ in range(nsteps - 1):
+        for b, s, bufs in parts:
+            b.step_host_wait()
+            b.step_host(s, 1, True, 1e-6, bufs[4].data_ptr(), bufs[5].data_ptr(), 0, wait=False)
+    for b, s, bufs in parts:
+        b.step_host_wait()
+        b.step_host_wait()  # idempotent
+    for k in range(6):
+        got = torch.cat([parts[0][2][k], parts[1][2][k]], dim=-1).numpy()
+        assert np.array_equal(got, whole[k].numpy()), k
+    assert np.abs(whole[4].numpy()).max() > 0
+
+
 @pytest.mark.parametrize("name,graph", [("drone", False), ("drone", True), ("cartpole", False), ("humanoid", False)])
 def test_lazy_derived_outputs_equal_eager_ones(name, graph):
     """step(return_obs=False) runs without derived outputs (b2_step_lazy: the pre-step state is parked); reading
