@@ -291,7 +291,8 @@ def run_reference(args):
             times.append(time.perf_counter() - t0)
     dt = float(np.median(times)) * args.steps
     value = n * args.steps / dt
-    sample = (f"{n} envs per step (bounded sample of the {DEFAULT_NENV[name]}-env workload), all {cores} host threads; " + CPU_KIND_NOTE)
+    sample = (f"{n} envs per timed step, drawn from the state distribution of the {DEFAULT_NENV[name]}-env workload and sized for ~20 s "
+              f"of CPU work over the run, all {cores} host threads; " + CPU_KIND_NOTE)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -614,14 +615,20 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
                 dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             sp = float(tt.item()) / e2e_steps
             finite = all(bool(torch.isfinite(sub[2][0]).all()) for sub in subs)
-            e2e["synchronous"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "pcie_gbs_per_gpu": e2e["pcie_gbs_per_gpu"],
-                                  "api": e2e["api"], "note": "one b2_step_host call per step over the whole batch, returning when the "
-                                                             "results are in the host buffers"}
-            e2e.update({"value": nenv * world / sp, "ms_per_step": sp * 1e3,
-                        "pcie_gbs_per_gpu": {"h2d": h2d / sp / 1e9, "d2h": d2h / sp / 1e9}, "pcie_d2h_frac_of_55gbs": d2h / sp / 1e9 / 55.0,
-                        "parts": parts, "results_finite": finite,
-                        "api": e2e["api"] + "; the batch as %d sub-batches of %d envs, each a closed loop through its own pinned host "
-                               "buffers, submitted with B2_HOST_ASYNC and completed by b2_step_host_wait one step later" % (parts, npart)})
+            api_parts = ("; the batch as %d sub-batches of %d envs, each a closed loop through its own pinned host buffers, submitted "
+                         "with B2_HOST_ASYNC and completed by b2_step_host_wait one step later" % (parts, npart))
+            piped = {"value": nenv * world / sp, "ms_per_step": sp * 1e3,
+                     "pcie_gbs_per_gpu": {"h2d": h2d / sp / 1e9, "d2h": d2h / sp / 1e9}, "parts": parts, "results_finite": finite}
+            if piped["value"] > e2e["value"] and finite:  # the faster of the two ways to drive the same exchange is the headline
+                e2e["synchronous"] = {"value": e2e["value"], "ms_per_step": e2e["ms_per_step"], "pcie_gbs_per_gpu": e2e["pcie_gbs_per_gpu"],
+                                      "api": e2e["api"], "note": "one b2_step_host call per step over the whole batch, returning when the "
+                                                                 "results are in the host buffers"}
+                e2e.update(piped)
+                e2e["pcie_d2h_frac_of_55gbs"] = d2h / sp / 1e9 / 55.0
+                e2e["api"] += api_parts
+            else:
+                piped["api"] = e2e["api"] + api_parts
+                e2e["async_parts"] = piped
             del subs
         if lin:
             # the same tick when the consumer of (A, B) lives on the device (a device-side gain synthesis such as b2_dlqr, or
