@@ -488,7 +488,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
                                      "linearising controller that is b2_control_tick (control law + FD + the env advance in one "
                                      "launch, then the state commit); kernel_ms_launched_separately lists the same work as "
                                      "individual launches (the roofline kernel is timed there)",
-                "note": "FP64 CUDA-core bound, not HBM bound: see roofline_fp64 (SURVEY.md section 8d)"}
+                "note": "not HBM bound: a CUDA-core kernel bound by FP64 issue and dependency latency, see roofline_fp64 (SURVEY.md section 8d)"}
     # executed FP64 work: rollouts per launch x flops per step-evaluation
     evals = nenv * ((2 * (2 * model.nv + model.nu)) if lin else 1)
     flops_per_eval, flops_src = flops_per_step_eval(name, lin)
@@ -504,6 +504,7 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
         roofline_fp64["algorithmic_flops_per_launch_unit"] = alg
         roofline_fp64["algorithmic_unit"] = "one mjd_transitionFD (1 + 2(2nv+nu) serial mj_steps upstream)" if lin else "one mj_step"
         roofline_fp64["algorithmic_tflops"] = alg * nenv / (dom_ms * 1e-3) / 1e12
+        roofline_fp64["algorithmic_frac"] = roofline_fp64["algorithmic_tflops"] / ctx["fp64_peak"]
         roofline_fp64["algorithmic_note"] = ("oracle op count (add/mul/div/sqrt = 1, transcendental call = 20) of the scalar algorithm on this "
                                              "workload's states; the kernels execute fewer flops than that where they reuse stages across "
                                              "rollouts or fold the model into the instruction stream")
@@ -683,13 +684,15 @@ def run_workload(ctx, name: str, lin: bool, nenv: int, steps: int, warmup: int, 
 
 def flops_per_step_eval(name: str, lin: bool):
     """Executed FP64 flops per step-evaluation (2*dfma + dadd + dmul thread instructions), counted by ncu on the kernels
-    themselves (profiles/): cartpole k_linearize 3.847e8 flops per 655,360 rollouts = 587 -- one thread per env runs the
-    shared position stage once for all velocity / control columns, control columns skip the velocity stage too -- and
-    k_step 962 per step; drone k_step 7.43e8 / 262,144 = 2,835; humanoid k_warp_step_ls 3.70e9 / 16,384 = 226,000 in the
-    round-2 capture (profiles/ncu_hum_step_r02d.txt: 100 steps into the fall, ~5 contacts, 3.5 Newton iterations; 182,000
-    in round 1's lighter state).  The oracle's op counter (oracle.op_count) gives the ALGORITHMIC count of one
-    mj_step for the same states; the executed count is what the pipe-utilisation figure needs."""
-    table = {"pendulum": 1000.0, "cartpole": 587.0 if lin else 962.0, "drone": 2835.0, "humanoid": 226000.0}
+    themselves (profiles/ncu_*_r03q.txt, source-page sums): cartpole k_linearize 1.157e8 flops per 655,360 rollouts = 176.5
+    -- one thread per env runs the shared position stage once for all velocity / control columns, control columns skip
+    the velocity stage too, and the exact zeros / ones of the model are folded out of the instruction stream (ptx_fold.py;
+    587 before that pass) -- and k_step 277 per step (962 before); drone k_step 5.25e8 / 262,144 = 2,002 (2,835 before);
+    humanoid k_warp_step_ls 3.70e9 / 16,384 = 226,000 in the round-2 capture (profiles/ncu_hum_step_r02d.txt: 100 steps
+    into the fall, ~5 contacts, 3.5 Newton iterations; 182,000 in round 1's lighter state).  The oracle's op counter
+    (oracle.op_count) gives the ALGORITHMIC count of one mj_step for the same states; the executed
+    count is what the pipe-utilisation figure needs."""
+    table = {"pendulum": 1000.0, "cartpole": 176.5 if lin else 277.0, "drone": 2002.0, "humanoid": 226000.0}
     src = "ncu-counted executed flops (profiles/)" if name != "pendulum" else "a-priori estimate (BASELINE.md section 4)"
     return table[name], src
 

@@ -245,7 +245,7 @@ def jit_specialize(model, name: str | None = None, cache_dir: str | None = None,
     source = emit_spec(c, name or "jit")
     h = fnv1a(blob)
     for path in sorted(os.listdir(csrc)):
-        if path.endswith((".cuh", ".h")):
+        if path.endswith((".cuh", ".h")) or path in ("ptx_fold.py", "fold_build.py"):
             with open(os.path.join(csrc, path), "rb") as fh:
                 h = fnv1a(fh.read() + h.to_bytes(8, "little"))
     h = fnv1a(source.encode() + " ".join(flags).encode() + h.to_bytes(8, "little"))
@@ -262,18 +262,25 @@ def jit_specialize(model, name: str | None = None, cache_dir: str | None = None,
         fd, cu = tempfile.mkstemp(prefix=f"spec_{key}_", suffix=".cu", dir=cache_dir)
         with os.fdopen(fd, "w") as fh:
             fh.write(emit_spec(c, name))
-        tmp_so = cu[:-3] + ".so.tmp"
-        cmd = [nvcc] + flags + ["-I", os.path.join(csrc, "generated"), cu, "-o", tmp_so]
-        r = subprocess.run(cmd, capture_output=True, text=True)
+        tmp_so, obj = cu[:-3] + ".so.tmp", cu[:-3] + ".o"
+        # compile through fold_build.py (exact zeros / ones of the model folded on the PTX, as for the built-in models),
+        # then link
+        import sys
+
+        cflags = [f for f in flags if f != "-shared"] + ["-I", os.path.join(csrc, "generated")]
+        r = subprocess.run([sys.executable, os.path.join(csrc, "fold_build.py"), nvcc, cu, obj] + cflags, capture_output=True, text=True)
+        if r.returncode == 0:
+            r = subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", tmp_so, obj], capture_output=True, text=True)
         if r.returncode != 0:
             from .exceptions import ConfigError
 
-            for leftover in (cu, tmp_so):
+            for leftover in (cu, tmp_so, obj):
                 if os.path.exists(leftover):
                     os.remove(leftover)
             raise ConfigError("jit_specialize: nvcc failed\n" + r.stderr[-2000:])
         os.replace(tmp_so, so)
         os.remove(cu)
+        os.remove(obj)
         if verbose:
             print(f"jit_specialize: built {so}")
     _capi.lib()  # libb2mj.so must be loaded (globally) first: the object's registrar calls b2::register_spec
