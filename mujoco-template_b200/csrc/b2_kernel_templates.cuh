@@ -198,6 +198,12 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
   constexpr int NQ = D::NQ, NV = D::NV;
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   T s1[NQ + NV], s2[NQ + NV], col[2 * NV];  // the two end points of the difference quotient
+  // Without quaternion coordinates (nq == nv) the tangent difference is a plain subtraction: the end points are summed with
+  // their signs as they arrive (fma with +-1: the same value as s2 - s1) instead of being kept apart by selects.
+  const bool scalar_only = nq == nv;
+  T dacc[2 * NV];
+  B2_UNROLL
+  for (int k = 0; k < 2 * nv; k++) dacc[k] = 0;
   int kind, i;
   bool fwd = true, back = centered != 0;
   if (PART == 2) { kind = 1; i = c; }  // position-column kernel: the column kind is a compile-time fact
@@ -246,19 +252,30 @@ B2_DEV void fd_column(LaneEnv<T, D, M>& env, const S& nom, int c, bool nominal,
     pos_valid = PART != 2 && kind != 1 && M::integrator() == 0;
     // plus -> s2, minus -> s1, nominal -> whichever end the one-sided quotient is missing
     const bool to2 = phase == 0 || (phase == 2 && !fwd);
-    B2_UNROLL
-    for (int k = 0; k < nq + nv; k++) {
-      const T val = k < nq ? env.qpos[k < nq ? k : 0] : env.qvel[k >= nq ? k - nq : 0];
-      if (to2) s2[k] = val; else s1[k] = val;
+    if (scalar_only) {
+      const T sg = to2 ? T(1) : T(-1);
+      B2_UNROLL
+      for (int k = 0; k < 2 * nv; k++) dacc[k] = fma(sg, k < nv ? env.qpos[k < nv ? k : 0] : env.qvel[k >= nv ? k - nv : 0], dacc[k]);
+    } else {
+      B2_UNROLL
+      for (int k = 0; k < nq + nv; k++) {
+        const T val = k < nq ? env.qpos[k < nq ? k : 0] : env.qvel[k >= nq ? k - nq : 0];
+        if (to2) s2[k] = val; else s1[k] = val;
+      }
     }
   }
   if (nominal) return;
   if (fwd || back) {
     // difference quotient with the reciprocal step (1 / (2 eps) = 0.5 / eps exactly): no division per entry
     const T ih = (fwd && back) ? T(0.5) * inv_eps : inv_eps;
-    env.differentiate_pos(col, T(1), s1, s2);
-    B2_UNROLL
-    for (int k = 0; k < nv; k++) { col[k] *= ih; col[nv + k] = (s2[nq + k] - s1[nq + k]) * ih; }
+    if (scalar_only) {
+      B2_UNROLL
+      for (int k = 0; k < 2 * nv; k++) col[k] = dacc[k] * ih;
+    } else {
+      env.differentiate_pos(col, T(1), s1, s2);
+      B2_UNROLL
+      for (int k = 0; k < nv; k++) { col[k] *= ih; col[nv + k] = (s2[nq + k] - s1[nq + k]) * ih; }
+    }
   } else {
     B2_UNROLL
     for (int k = 0; k < ndx; k++) col[k] = 0;
@@ -300,8 +317,12 @@ __global__ void B2_LIN_BOUNDS(PART) k_linearize(StateDev<T> st, int count, int N
   const int nq = M::nq(), nv = M::nv(), nu = M::nu(), ndx = 2 * nv;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ntask = PART == 0 ? fd_tasks<M>() : (PART == 1 ? fd_group_count(nv, nu) : nv);
-  if (idx >= (long long)count * ntask) return;
-  const int e = (int)(idx % count), task = (int)(idx / count);  // count envs, env stride N
+  const long long total = (long long)count * ntask;
+  if (idx >= total) return;
+  // count envs, env stride N; task-major.  32-bit division when the launch fits (a 64-bit one is ~100 instructions)
+  int e, task;
+  if (total <= 0x7fffffffLL) { const unsigned u = (unsigned)idx; task = (int)(u / (unsigned)count); e = (int)(u - (unsigned)task * (unsigned)count); }
+  else { task = (int)(idx / count); e = (int)(idx % count); }
   RowStore<T, D> rows;
   LaneEnv<T, D, M> env(rows);
   T u0[D::NU];
