@@ -2,7 +2,7 @@
 
 Step-only throughput (zero/hover control, one mj_step per launch, CUDA events, L2 flushed between
 launches) and FP64 linearizations/s.  Prints one JSON object per line; the committed output lives in
-profiles/sweep_r03.jsonl.   python tools/sweep.py [--quick]
+profiles/sweep_r04.jsonl.   python tools/sweep.py [--quick]
 """
 import json
 import os
